@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- SIDE DLA-34 stereo inference throughput (pairs/s at 384x1280) on N B200s + kernel rooflines.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            one JSON line on rank 0
+  python bench.py --impl reference ...                     the reference's CPU path (port) on the host cores
+
+A step = one pass of the hot path (DLA-34 + DCN neck, heads, decode, instance depth branch, ddd_decode) over
+`--pairs` synthetic stereo pairs per GPU in micro-batches of `--micro-batch`; ranks are sharded by pair
+(weak scaling: fixed pairs per GPU), the only collective is the all-gather of the fixed-shape detections.
+  value : pairs/s with inputs resident in HBM       e2e : same through host buffers (H2D + D2H inside the timing)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+H_IN, W_IN = 384, 1280
+METRIC = "stereo pairs/sec (384x1280, DLA-34)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per GPU per step (config #4: batch 32)")
+    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "fp32"), choices=["fp32", "3xtf32", "tf32"])
+    ap.add_argument("--allow-tf32", action="store_true", help="let cuDNN use TF32 for the out-of-scope convolutions")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline microbenchmarks")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-pairs", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, "/tmp/side_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model():
+    from side_b200.networks import get_pose_net
+    from side_b200.utils.synthetic import HEADS, realistic_init
+    torch.manual_seed(0)
+    return realistic_init(get_pose_net(34, HEADS, 256), seed=1).eval()
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference-style port on the host cores (oracle/torch_port.py)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_s(model_cpu, n_pairs, warmup, seed=100):
+    from oracle import torch_port
+    from side_b200.engine import StereoDetector
+    from side_b200.utils.synthetic import make_batch
+    det = StereoDetector(model_cpu)
+    times = []
+    with torch_port.reference_ops():
+        for i in range(warmup + n_pairs):
+            batch = make_batch(1, H_IN, W_IN, seed=seed + i)
+            t0 = time.perf_counter()
+            det.process(batch)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return len(times) / sum(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = build_model()
+    cores = torch.get_num_threads()
+    val, times = cpu_reference_pairs_per_s(model, args.steps, args.warmup)
+    sample = "%d steps of 1 pair (batch 1, 384x1280, K=100 RoIs) after %d warm-up, torch CPU ops + torchvision deform_conv2d/roi_align" % (
+        args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "SIDE DLA-34 stereo inference, 384x1280, random-init (calibrated) weights, K=100", "pairs_per_step": 1},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-kernel rooflines (standalone launches at the BASELINE config shapes)
+# ----------------------------------------------------------------------------------------------------
+def time_op(fn, iters=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def kernel_rooflines(pk, precision):
+    from side_b200 import ops
+    from side_b200.utils.synthetic import make_boxes
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    out = {}
+    torch.manual_seed(0)
+    # config #2: instance volume, 64 RoIs x 48 candidates x 64 ch, P=16  (604 MB written + 15.7 MB read)
+    fL, fR = torch.randn(1, 64, 96, 320, device=dev), torch.randn(1, 64, 96, 320, device=dev)
+    left, right, _ = make_boxes(1, 64, seed=0)
+    left, right, fb = left.to(dev), right.to(dev), torch.tensor([384.38], device=dev)
+    for gate in (False, True):
+        ms = time_op(lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=gate), flush=flush)
+        byts = 64 * 192 * 48 * 256 * 4 + 2 * 64 * 96 * 320 * 4
+        out["inst_costvol_fwd" + ("_gate" if gate else "")] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"],
+                                                             "alg_bytes": byts}
+    # reference-shaped volume: 100 RoIs x 16 x 32 ch
+    l2, r2, _ = make_boxes(1, 100, seed=1)
+    f32L, f32R = fL[:, :32].contiguous(), fR[:, :32].contiguous()
+    ms = time_op(lambda: ops.inst_costvol(f32L, f32R, l2.to(dev), r2.to(dev), fb, 16, 16, 319.0, gate=True), flush=flush)
+    byts = 100 * 96 * 16 * 256 * 4 + 2 * 32 * 96 * 320 * 4
+    out["inst_costvol_fwd_gate_ref_shape"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    # full-image concat / gwc volumes: C=64, D=48, 96x320
+    ms = time_op(lambda: ops.concat_volume(fL, fR, 48), flush=flush)
+    byts = 128 * 48 * 96 * 320 * 4 + 2 * 64 * 96 * 320 * 4
+    out["concat_volume_fwd"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    ms = time_op(lambda: ops.gwc_volume(fL, fR, 48, 8), flush=flush)
+    byts = 8 * 48 * 96 * 320 * 4 + 2 * 64 * 96 * 320 * 4
+    out["gwc_volume_fwd"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    # soft-argmin and decode are latency bound: report microseconds
+    lg, db = torch.randn(64, 48, 4, 4, device=dev), torch.rand(64, 48, device=dev) * 80
+    out["softargmin_fwd"] = {"us": 1000 * time_op(lambda: ops.softargmin(lg, db))}
+    hm = torch.randn(4, 3, 96, 320, device=dev); wh = torch.rand(4, 3, 96, 320, device=dev); reg = torch.rand(4, 3, 96, 320, device=dev)
+    out["bbox_decode_B4"] = {"us": 1000 * time_op(lambda: ops.bbox_decode_raw(hm, wh, reg, K=100))}
+    # config #3: DCN sweep over the DLA-34 up-path shapes, B=2 (left+right of one pair)
+    shapes = [(512, 256, 12, 40), (256, 256, 24, 80), (256, 128, 24, 80), (128, 128, 48, 160), (128, 64, 48, 160), (64, 64, 96, 320),
+              (256, 64, 24, 80)]
+    dcn = {}
+    for (Cin, Cout, H, W) in shapes:
+        B = 2
+        x = torch.randn(B, Cin, H, W, device=dev); off = torch.randn(B, 18, H, W, device=dev) * 2
+        mask = torch.sigmoid(torch.randn(B, 9, H, W, device=dev)); w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
+        b = torch.rand(Cout, device=dev)
+        try:
+            ms = time_op(lambda: ops.dcn_forward_raw(x, off, mask, w, b, 1, 1, 1, 1, precision=precision), flush=flush, iters=5)
+        except RuntimeError as e:
+            dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = {"error": str(e)[:80]}
+            continue
+        fl = 2.0 * B * Cout * Cin * 9 * H * W
+        dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = {"ms": ms, "TFLOPs": fl / ms / 1e9, "frac_tensor": fl / ms / 1e9 / pk["tf_burst"]}
+    out["dcn_fwd_" + precision] = dcn
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    from side_b200 import _lib, ops
+    from side_b200.engine import OpTimer, StereoDetector, gather_detections
+    from side_b200.utils.synthetic import KITTI_FB
+
+    lib = _lib.load()
+    if lib.side_device_ok() != 1:
+        raise RuntimeError("libside_b200.so cannot run on this device (needs sm_100a)")
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(args.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.allow_tf32)
+    ops.set_dcn_precision(args.dcn_precision)
+    pk = peaks()
+
+    cpu_model = build_model()
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, times = cpu_reference_pairs_per_s(cpu_model, args.cpu_pairs, 1)
+        cpu_base = {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": "%d pairs (batch 1, 384x1280, K=100 RoIs) after 1 warm-up; reference-style torch CPU ops "
+                              "(torchvision deform_conv2d / roi_align loop, torch.topk decode)" % args.cpu_pairs}
+    model = cpu_model.to(dev)
+    det = StereoDetector(model, grid_size=28, K=100)
+
+    P, mb = args.pairs, args.micro_batch
+    assert P % mb == 0, "--pairs must be a multiple of --micro-batch"
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_l = torch.randn(P, 3, H_IN, W_IN, generator=g).pin_memory()
+    host_r = torch.randn(P, 3, H_IN, W_IN, generator=g).pin_memory()
+    dev_l, dev_r = host_l.to(dev), host_r.to(dev)
+    fb = torch.full((mb,), KITTI_FB, device=dev)
+    out_host = [torch.empty((P, 100, 6)).pin_memory(), torch.empty((P, 100, 6)).pin_memory(), torch.empty((P, 100, 10)).pin_memory()]
+
+    def step_resident():
+        outs = []
+        for i in range(0, P, mb):
+            outs.append(det.process({'input': dev_l[i:i + mb], 'input_right': dev_r[i:i + mb], 'fb': fb}))
+        d, dr, info = (torch.cat([o[j] for o in outs], 0) for j in range(3))
+        return gather_detections(d, dr, info)
+
+    stage = [torch.empty((mb, 3, H_IN, W_IN), device=dev) for _ in range(2)]
+
+    def step_e2e():
+        outs = []
+        for i in range(0, P, mb):
+            stage[0].copy_(host_l[i:i + mb], non_blocking=True)
+            stage[1].copy_(host_r[i:i + mb], non_blocking=True)
+            outs.append(det.process({'input': stage[0], 'input_right': stage[1], 'fb': fb}))
+        d, dr, info = (torch.cat([o[j] for o in outs], 0) for j in range(3))
+        res = gather_detections(d, dr, info)
+        for dst, src in zip(out_host, (d, dr, info)):
+            dst.copy_(src, non_blocking=True)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    barrier()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.launch_count(reset=True)
+
+    def dcn_work(out, x, *a, **k):
+        w = a[2]
+        return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+
+    with OpTimer("dcn_forward_raw", dcn_work) as tm:
+        ms_res = timed(step_resident, args.steps)
+    dcn = tm.summary()
+    launches = _lib.launch_count(reset=True)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop()
+
+    total_pairs = world * P * args.steps
+    value = total_pairs / (ms_res / 1000.0)
+    e2e = total_pairs / (ms_e2e / 1000.0)
+    dcn_tf = dcn["work"] / (dcn["ms"] / 1000.0) / 1e12 if dcn["ms"] > 0 else 0.0
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32" if not args.allow_tf32 else "fp32 (cuDNN convs TF32)", "data": "synthetic",
+            "config": {"workload": "SIDE DLA-34 stereo inference (config #4), %d pairs/GPU/step, micro-batch %d, 384x1280, K=100 RoIs/pair, "
+                                   "random-init weights with calibrated BatchNorm" % (P, mb),
+                       "pairs_per_gpu_per_step": P, "micro_batch": mb, "parallelism": "pair-sharded x%d, all_gather(detections)" % world,
+                       "dcn_precision": args.dcn_precision, "cudnn_tf32": bool(args.allow_tf32),
+                       "l2": "inputs larger than L2 (%.0f MB of images per step)" % (2 * P * 3 * H_IN * W_IN * 4 / 1e6)},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * H_IN * W_IN * 4,
+                    "d2h_bytes_per_step": P * 100 * 22 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "dcn_fwd (%s), %d launches in the timed region" % (args.dcn_precision, dcn["calls"]),
+                         "bound": "tensor", "achieved": dcn_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": dcn_tf / pk["tf_sust"],
+                         "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                         "share_of_step": dcn["ms"] / ms_res},
+            "cpu_baseline": cpu_base,
+        }
+        if not args.no_kernels and world == 1:
+            line["kernels"] = kernel_rooflines(pk, args.dcn_precision)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,193 @@
+/*
+ * side_b200.h -- C ABI of libside_b200.so: the B200 (sm_100a) implementation of SIDE's stereo hot path.
+ *
+ * This is the drop-in boundary.  The reference's only native boundary is the pybind11 module `_ext`
+ * (DCNv2/src/vision.cpp:4-9) with dcn_v2_forward / dcn_v2_backward (DCNv2/src/dcn_v2.h:9-73); everything
+ * else on the path is Python calling ATen/torchvision ops.  Each entry point below names the reference
+ * interface it replaces.  No torch / ATen types appear here: plain device pointers, ints and a stream.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to C-contiguous float32 (or the stated integer type) unless
+ *     marked "host"; tensors are NCHW as in the reference;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued
+ *     on it, nothing synchronises the host, the library is re-entrant (no global mutable state except
+ *     one-time cudaFuncSetAttribute calls) -- see SURVEY.md section 8b "Threading / streams";
+ *   - return value: 0 (SIDE_OK) or a negative SIDE_ERR_* code; side_last_error() gives a
+ *     thread-local message.  The Python layer maps non-zero to RuntimeError like AT_ASSERTM/AT_ERROR
+ *     do in the reference (dcn_v2_cuda.cu:61-85);
+ *   - there is NO CPU implementation: host pointers are rejected (SIDE_ERR_NOT_DEVICE), mirroring
+ *     AT_ERROR("Not implemented on the CPU") (dcn_v2.h:38).
+ */
+#ifndef SIDE_B200_H_
+#define SIDE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIDE_ABI_VERSION 1
+
+enum {
+    SIDE_OK = 0,
+    SIDE_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported parameter combination */
+    SIDE_ERR_NOT_DEVICE = -2,    /* a tensor pointer is not device memory */
+    SIDE_ERR_WORKSPACE = -3,     /* workspace missing or too small */
+    SIDE_ERR_CUDA = -4,          /* a CUDA runtime call or kernel launch failed */
+    SIDE_ERR_UNSUPPORTED = -5    /* valid request this build cannot serve (e.g. tcgen05 path for Cin % 32 != 0) */
+};
+
+/* flags for side_dcn_fwd / side_dcn_bwd */
+enum {
+    SIDE_DCN_MASK_IS_LOGIT = 1 << 0, /* `mask` holds pre-sigmoid logits: sigmoid is fused (DCN.forward, dcn_v2.py:122) */
+    SIDE_DCN_FUSE_AFFINE   = 1 << 1, /* y = y*scale[o] + shift[o]  (eval-mode BatchNorm of DeformConv.actf,
+                                        feature_extraction_dla34.py:348-351) */
+    SIDE_DCN_FUSE_RELU     = 1 << 2, /* y = max(y, 0) after the affine */
+    SIDE_DCN_PREC_FP32     = 0 << 4, /* SIMT fp32 FMA implicit GEMM (default; <=1e-5 rel vs the reference) */
+    SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel) */
+    SIDE_DCN_PREC_TF32     = 2 << 4, /* tcgen05 kind::tf32 single pass (~1e-3 rel, opt-in) */
+    SIDE_DCN_PREC_MASK     = 3 << 4
+};
+
+/* flags for side_inst_costvol_fwd / _bwd */
+enum {
+    SIDE_VOL_GATE = 1 << 0 /* multiply every (roi, depth) slice by the cosine gate x_cross
+                              (cost_volume.forward, stereo_network_old.py:197-203) */
+};
+
+/* decode flavour */
+enum {
+    SIDE_DECODE_HEAT_IS_LOGIT = 1 << 0 /* apply sigmoid to the heat-map first (bbox_decode, decode.py:93) */
+};
+
+int side_abi_version(void);
+const char *side_last_error(void);
+/* 1 when the shared object carries sm_100a device code and device 0 can run it; never fails. */
+int side_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * DCNv2 modulated deformable convolution.
+ * Replaces _ext.dcn_v2_forward (DCNv2/src/dcn_v2.h:9-39 -> dcn_v2_cuda_forward, dcn_v2_cuda.cu:43-173
+ * + modulated_deformable_im2col_gpu_kernel, dcn_v2_im2col_cuda.cu:125-195).  No `columns` buffer is
+ * materialised: the modulated bilinear gather feeds the contraction tile by tile.
+ *   x      [B, Cin, H, W]
+ *   offset [B, dg*2*kh*kw, Ho, Wo]  batch stride offset_bs floats (0 = dense); channel 2k = dy, 2k+1 = dx
+ *   mask   [B, dg*kh*kw,   Ho, Wo]  batch stride mask_bs floats (0 = dense); logits if MASK_IS_LOGIT
+ *          (offset / mask may alias the 27-channel conv_offset_mask output: offset = om, mask = om + 18*Ho*Wo,
+ *           both with batch stride 27*Ho*Wo -- the chunk/cat of dcn_v2.py:120-121 is a no-op on memory)
+ *   w      [Cout, Cin, kh, kw], bias [Cout] (may be NULL)
+ *   scale/shift [Cout] used only with SIDE_DCN_FUSE_AFFINE
+ *   y      [B, Cout, Ho, Wo]
+ *   ws     workspace of side_dcn_fwd_ws_bytes(...) bytes (re-laid-out weights); may be NULL when that is 0.
+ * Supported: dg == 1, any kh/kw/stride/pad/dilation for the fp32 path; the tcgen05 paths additionally
+ * need Cin % 32 == 0, Cout % 16 == 0, Cout <= 256.
+ * --------------------------------------------------------------------------------------------- */
+size_t side_dcn_fwd_ws_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw, int flags);
+int side_dcn_fwd(const float *x, const float *offset, const float *mask, const float *w, const float *bias,
+                 const float *scale, const float *shift, float *y, int B, int Cin, int H, int W, int Cout, int kh,
+                 int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg, long long offset_bs,
+                 long long mask_bs, int flags, void *ws, size_t ws_bytes, void *stream);
+
+/* Replaces _ext.dcn_v2_backward (dcn_v2.h:41-73 -> dcn_v2_cuda_backward, dcn_v2_cuda.cu:207-336 and the
+ * col2im / col2im_coord kernels, dcn_v2_im2col_cuda.cu:197-327).  All five gradients are OVERWRITTEN
+ * (the reference zero-initialises them, :252-256).  grad_mask is w.r.t. the post-sigmoid mask unless
+ * MASK_IS_LOGIT is set, in which case it is w.r.t. the logits.  Any output pointer may be NULL to skip it. */
+size_t side_dcn_bwd_ws_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw, int flags);
+int side_dcn_bwd(const float *x, const float *offset, const float *mask, const float *w, const float *gy,
+                 float *gx, float *goffset, float *gmask, float *gw, float *gbias, int B, int Cin, int H, int W,
+                 int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
+                 long long offset_bs, long long mask_bs, int flags, void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth-candidate / shifted-RoI generation.  Replaces get_proposal_shift (stereo_network_old.py:34-133).
+ *   left, right [N,5] = (b, x1, y1, x2, y2), grouped by image in ascending b;  fb [B]
+ *   pro_left, pro_right [D, N, 5], depth_bin [N, D];  x_clamp = input_w//4 - 1 (319 for 1280-wide input)
+ * --------------------------------------------------------------------------------------------- */
+int side_proposal_shift(const float *left, const float *right, const float *fb, int N, int B, int D,
+                        float x_clamp, float *pro_left, float *pro_right, float *depth_bin, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Instance-level depth cost volume with RoIAlign sampling fused in.
+ * Replaces the loop stereo_network_old.py:368-376 (2*D torchvision RoIAlign launches + 3*D slice copies)
+ * and, with SIDE_VOL_GATE, the cosine gate of cost_volume.forward (:197-203).
+ *   featL, featR [B, C, H, W];  left, right [N,5] boxes (as for side_proposal_shift);  fb [B]
+ *   valid        [N] uint8 or NULL: rows with valid==0 produce an all-zero volume slice, depth_bin = 0
+ *   cost         [N, 3C, D, P, P];  depth_bin [N, D];  xcross [N, D] (NULL allowed; written only with GATE)
+ * RoIAlign semantics: torchvision legacy aligned=False, spatial_scale 1, sampling_ratio 2 (:271).
+ * --------------------------------------------------------------------------------------------- */
+int side_inst_costvol_fwd(const float *featL, const float *featR, const float *left, const float *right,
+                          const float *fb, const uint8_t *valid, float *cost, float *depth_bin, float *xcross,
+                          int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *stream);
+
+/* Backward of the above w.r.t. featL / featR (autograd of RoIAlign + CopySlices + gate in the reference).
+ * gfeatL / gfeatR [B,C,H,W] are ACCUMULATED into (caller zero-fills); fp32 atomics => summation order is not
+ * deterministic, as in torchvision's roi_align backward. */
+int side_inst_costvol_bwd(const float *featL, const float *featR, const float *left, const float *right,
+                          const float *fb, const uint8_t *valid, const float *gcost, float *gfeatL, float *gfeatR,
+                          int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *stream);
+
+/* Stand-alone cosine gate on an already built volume (drop-in cost_volume.forward(cost, ...) entry,
+ * stereo_network_old.py:194-203).  out may alias cost.  bwd: gcost = d loss / d cost. */
+int side_xcross_gate_fwd(const float *cost, float *out, float *xcross, int N, int C, int D, int P, void *stream);
+int side_xcross_gate_bwd(const float *cost, const float *gout, float *gcost, int N, int C, int D, int P,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft-argmin tail.  Replaces stereo_network_old.py:228-236 (AvgPool2d(S) -> softmax over D -> sum p*depth_bin).
+ *   logits [N, D, S, S] (squeezed classify output, S = 4);  depth_bin [N, D];  depth [N];  prob [N, D] (NULL ok)
+ * --------------------------------------------------------------------------------------------- */
+int side_softargmin_fwd(const float *logits, const float *depth_bin, float *depth, float *prob, int N, int D,
+                        int S, void *stream);
+int side_softargmin_bwd(const float *prob, const float *depth_bin, const float *depth, const float *gdepth,
+                        float *glogits, float *gdepth_bin, int N, int D, int S, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CenterNet decode: 3x3 max-pool NMS + per-class top-K + cross-class top-K + head gathers, ONE launch.
+ * Replaces _nms/_topk/_gather_feat/_transpose_and_gather_feat (decode.py:9-33, utils.py:12-26) and the
+ * box / detection assembly of bbox_decode (decode.py:91-126) and ddd_decode (:35-89).
+ * Tie rule: larger score first, then lower flat index (torch.topk leaves ties unspecified).
+ *   heat [B, Cat, H, W]; K <= 1024; Cat*K <= 8192
+ *   ws: side_decode_ws_bytes(B, Cat, K) bytes of scratch (zero-initialised by the call itself)
+ * bbox flavour:  wh, reg [B,3,H,W] -> bbox, bbox_right [B,K,5] = (b, x1,y1,x2,y2); keep [B*K] uint8 = (sum of the
+ *                4 coords > 0, decode.py:123); slot [B*K] int32 = rank of the row among its image's kept rows;
+ *                count [B] int32 = kept rows per image.  wh is multiplied by wh_scale (stereo_network_old.py:360).
+ * ddd flavour:   kept [B,6*grid,H,W], dim [B,3,..], orien [B,2,..], wh, reg -> det, det_right [B,K,6], info [B,K,9]
+ *                info[...,8] = floor(argmax / grid).
+ * Both also return score [B,K], ind [B,K] int32 (flat y*W+x), cls [B,K] int32 (any may be NULL).
+ * --------------------------------------------------------------------------------------------- */
+size_t side_decode_ws_bytes(int B, int Cat, int K);
+int side_bbox_decode(const float *heat, const float *wh, const float *reg, float *bbox, float *bbox_right,
+                     uint8_t *keep, int32_t *slot, int32_t *count, float *score, int32_t *ind, int32_t *cls, int B,
+                     int Cat, int H, int W, int K, float wh_scale, int flags, void *ws, size_t ws_bytes,
+                     void *stream);
+int side_ddd_decode(const float *heat, const float *kept, const float *dim, const float *orien, const float *wh,
+                    const float *reg, float *det, float *det_right, float *info, float *score, int32_t *ind,
+                    int32_t *cls, int B, int Cat, int H, int W, int grid, int K, int flags, void *ws,
+                    size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-image disparity-sweep volumes (north_star item 1; no call site in the reference, SURVEY.md F3/A6;
+ * the reference's stereo-head concat torch.cat((L,R),1), stereo_network_old.py:348, is the D=1 case).
+ *   concat [B, 2C, D, H, W]: [:, 0:C, d, y, x] = L[.., x]*[x>=d];  [:, C:2C, d, y, x] = R[.., x-d]*[x>=d]
+ *   gwc    [B, G,  D, H, W]: mean over the C/G channels of group g of L[.., x]*R[.., x-d], 0 where x<d
+ * Backward entry points OVERWRITE gL, gR [B,C,H,W] (deterministic gather formulation, no atomics).
+ * --------------------------------------------------------------------------------------------- */
+int side_concat_volume_fwd(const float *L, const float *R, float *vol, int B, int C, int H, int W, int D,
+                           void *stream);
+int side_concat_volume_bwd(const float *gvol, float *gL, float *gR, int B, int C, int H, int W, int D,
+                           void *stream);
+int side_gwc_volume_fwd(const float *L, const float *R, float *vol, int B, int C, int H, int W, int D, int G,
+                        void *stream);
+int side_gwc_volume_bwd(const float *L, const float *R, const float *gvol, float *gL, float *gR, int B, int C,
+                        int H, int W, int D, int G, void *stream);
+
+/* Number of kernels launched by this library in the calling thread since the last reset
+ * (bench.py's "gpu_launches"). */
+long long side_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIDE_B200_H_ */

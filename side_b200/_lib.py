@@ -1,0 +1,82 @@
+"""ctypes binding of ``libside_b200.so`` (the C ABI declared in ``include/side_b200.h``).
+
+There is deliberately no fallback: if the shared object is missing or an entry point
+returns an error, a ``RuntimeError`` is raised -- the same way the reference's ``_ext``
+raises through ``AT_ASSERTM`` / ``AT_ERROR`` (DCNv2/src/cuda/dcn_v2_cuda.cu:61-85,
+DCNv2/src/dcn_v2.h:35-39 "Not implemented on the CPU").
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libside_b200.so")
+
+_vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/side_b200.h one to one
+SIGNATURES = {
+    "side_abi_version": (_i, []),
+    "side_last_error": (C.c_char_p, []),
+    "side_device_ok": (_i, []),
+    "side_launch_count": (_ll, [_i]),
+    "side_dcn_fwd_ws_bytes": (_sz, [_i] * 8),
+    "side_dcn_fwd": (_i, [_vp] * 8 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
+    "side_dcn_bwd_ws_bytes": (_sz, [_i] * 8),
+    "side_dcn_bwd": (_i, [_vp] * 10 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
+    "side_proposal_shift": (_i, [_vp] * 3 + [_i] * 3 + [_f] + [_vp] * 4),
+    "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
+    "side_inst_costvol_bwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
+    "side_xcross_gate_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "side_xcross_gate_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "side_softargmin_fwd": (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
+    "side_softargmin_bwd": (_i, [_vp] * 6 + [_i] * 3 + [_vp]),
+    "side_decode_ws_bytes": (_sz, [_i] * 3),
+    "side_bbox_decode": (_i, [_vp] * 11 + [_i] * 5 + [_f, _i, _vp, _sz, _vp]),
+    "side_ddd_decode": (_i, [_vp] * 12 + [_i] * 7 + [_vp, _sz, _vp]),
+    "side_concat_volume_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "side_concat_volume_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "side_gwc_volume_fwd": (_i, [_vp] * 3 + [_i] * 6 + [_vp]),
+    "side_gwc_volume_bwd": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+}
+
+# flag values (include/side_b200.h)
+DCN_MASK_IS_LOGIT = 1 << 0
+DCN_FUSE_AFFINE = 1 << 1
+DCN_FUSE_RELU = 1 << 2
+DCN_PREC_FP32 = 0 << 4
+DCN_PREC_3XTF32 = 1 << 4
+DCN_PREC_TF32 = 2 << 4
+VOL_GATE = 1 << 0
+DECODE_HEAT_IS_LOGIT = 1 << 0
+
+_lib = None
+
+
+def load():
+    """Loads the shared object (once).  Raises RuntimeError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            "side_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C side_b200/csrc`).  There is no CPU / PyTorch fallback." % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.side_abi_version() != 1:
+        raise RuntimeError("side_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().side_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count(reset=False):
+    return int(load().side_launch_count(1 if reset else 0))

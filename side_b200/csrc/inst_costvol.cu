@@ -1,0 +1,544 @@
+// inst_costvol.cu -- structure-aware instance depth cost volume.
+//
+// Reference behaviour replaced (all torch/torchvision ops, one launch each):
+//   get_proposal_shift                      stereo_network_old.py:34-133
+//   2*D RoIAlign launches + 3*D slice copies stereo_network_old.py:368-376   (RoIAlign((P,P),1,2), :271)
+//   cosine gate x_cross                     stereo_network_old.py:197-203
+//
+// B200 design: one CTA per (RoI n, depth candidate d).  The CTA derives its two shifted RoIs from the
+// boxes itself (no [D,N,5] proposal tensor round trip), builds separable sample tables once in shared
+// memory (the y table is shared by the left and the right RoI), gathers L and R tiles [C,P,P] into shared
+// memory, reduces the three gate sums with warp shuffles, and streams the gated [3C,P,P] slice to HBM with
+// 16-byte evict-first stores -- the volume is written exactly once and never re-read by this kernel.
+//
+// Numerics: the sample coordinates, bilinear weights and the 4-tap / 4-sample sums are evaluated with
+// explicitly rounded __f*_rn intrinsics in exactly the order torchvision's CPU kernel uses, so L, R and
+// L-R are bit-identical to the oracle (oracle/side_oracle.c: roi_align_one); only the gate scalar differs
+// (float32 reduction order), <= 1e-6 relative.
+#include "common.cuh"
+
+namespace side {
+
+struct AxisSample {
+    int lo, hi;   // lo < 0  => sample outside the image (contributes 0)
+    float l, h;   // fractional weight towards hi, and 1 - l
+};
+
+// Depth candidate i of RoI (l, r): stereo_network_old.py:53-77, one rounded float op per torch op.
+__device__ __forceinline__ void proposal_for(const float *__restrict__ l, const float *__restrict__ r, float fb,
+                                             int i, int D, float x_clamp, float &dbin, float &lx1, float &lx2,
+                                             float &rx1, float &rx2, float &y1, float &y2)
+{
+    const float xmin = fminf(l[1], r[1]);
+    const float xmax = fmaxf(l[3], r[3]);
+    y1 = fminf(l[2], r[2]);
+    y2 = fmaxf(l[4], r[4]);
+    float t = __fsub_rn(xmax, xmin);
+    t = __fmul_rn(t, 0.9f);
+    t = __fmul_rn(t, 4.0f);
+    float dmin = __fdiv_rn(fb, t);
+    dmin = fminf(fmaxf(dmin, 1.0f), 87.0f);
+    const float rate = (float)((double)i / (double)(D - 1));
+    const float u = __fmul_rn(__fsub_rn(87.0f, dmin), rate);
+    dbin = __fsub_rn(87.0f, u);
+    const float disp = __fdiv_rn(__fdiv_rn(fb, dbin), 8.0f);
+    lx1 = fminf(__fadd_rn(xmin, disp), x_clamp);
+    lx2 = fminf(__fadd_rn(xmax, disp), x_clamp);
+    rx1 = fmaxf(__fsub_rn(xmin, disp), 0.0f);
+    rx2 = fmaxf(__fsub_rn(xmax, disp), 0.0f);
+}
+
+// One axis of torchvision's pre_calc_for_bilinear_interpolate (legacy aligned=False, sampling_ratio 2).
+__device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p, int i, int size)
+{
+    float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
+                        __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), 2.0f));
+    AxisSample s;
+    if (c < -1.0f || c > (float)size) {
+        s.lo = -1; s.hi = -1; s.l = 0.f; s.h = 0.f;
+        return s;
+    }
+    if (c <= 0.f) c = 0.f;
+    int lo = (int)c, hi;
+    if (lo >= size - 1) {
+        hi = lo = size - 1;
+        c = (float)lo;
+    } else {
+        hi = lo + 1;
+    }
+    s.lo = lo; s.hi = hi;
+    s.l = __fsub_rn(c, (float)lo);
+    s.h = __fsub_rn(1.0f, s.l);
+    return s;
+}
+
+// sum over the 2x2 sample grid of one bin, torchvision order (iy outer, ix inner), then / 4
+__device__ __forceinline__ float roi_bin(const float *__restrict__ im, int W, const AxisSample *__restrict__ ys,
+                                         const AxisSample *__restrict__ xs)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+        const AxisSample y = ys[iy];
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            const AxisSample x = xs[ix];
+            float val = 0.f;
+            if (y.lo >= 0 && x.lo >= 0) {
+                const float w1 = __fmul_rn(y.h, x.h), w2 = __fmul_rn(y.h, x.l);
+                const float w3 = __fmul_rn(y.l, x.h), w4 = __fmul_rn(y.l, x.l);
+                const float v1 = __ldg(im + y.lo * W + x.lo), v2 = __ldg(im + y.lo * W + x.hi);
+                const float v3 = __ldg(im + y.hi * W + x.lo), v4 = __ldg(im + y.hi * W + x.hi);
+                val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1), __fmul_rn(w2, v2)), __fmul_rn(w3, v3)),
+                                __fmul_rn(w4, v4));
+            }
+            acc = __fadd_rn(acc, val);
+        }
+    }
+    return __fdiv_rn(acc, 4.0f);
+}
+
+struct VolParams {
+    const float *featL, *featR, *left, *right, *fb;
+    const uint8_t *valid;
+    float *cost, *depth_bin, *xcross;
+    const float *gcost;
+    float *gfeatL, *gfeatR;
+    int N, B, C, H, W, D, P;
+    float x_clamp;
+};
+
+constexpr int kVolThreads = 512;
+
+// block-wide sum of up to 4 values; result broadcast to all threads.  red: >= 4*32 floats of smem
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float *red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) red[k * 32 + wid] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        float t = lane < nw ? red[k * 32 + lane] : 0.f;
+        v[k] = warp_sum(t);
+    }
+}
+
+// shared-memory carve-up: [tables 3*2P AxisSample][red 4*32 floats][Ls C*PP][Rs C*PP]
+__device__ __forceinline__ void build_tables(const VolParams &p, int n, int d, AxisSample *ytab, AxisSample *xl,
+                                             AxisSample *xr, int &b, float &dbin)
+{
+    const float *l = p.left + (size_t)n * 5, *r = p.right + (size_t)n * 5;
+    b = min(max((int)l[0], 0), p.B - 1);
+    float lx1, lx2, rx1, rx2, y1, y2;
+    proposal_for(l, r, p.fb[b], d, p.D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+    const int t = threadIdx.x;
+    const int P2 = 2 * p.P;
+    if (t < 3 * P2) {
+        const int which = t / P2, s = t % P2;
+        if (which == 0) {
+            const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
+            ytab[s] = axis_sample(y1, __fdiv_rn(rh, (float)p.P), s >> 1, s & 1, p.H);
+        } else if (which == 1) {
+            const float rw = fmaxf(__fsub_rn(lx2, lx1), 1.0f);
+            xl[s] = axis_sample(lx1, __fdiv_rn(rw, (float)p.P), s >> 1, s & 1, p.W);
+        } else {
+            const float rw = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
+            xr[s] = axis_sample(rx1, __fdiv_rn(rw, (float)p.P), s >> 1, s & 1, p.W);
+        }
+    }
+}
+
+// GATE: apply x_cross.  STAGE: L/R tiles fit in shared memory (single gather pass, vector stores).
+template <bool GATE, bool STAGE>
+__global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_kernel(VolParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p.P, PP = P * P, C = p.C, CPP = C * PP;
+    AxisSample *ytab = reinterpret_cast<AxisSample *>(smem_raw);
+    AxisSample *xl = ytab + 2 * P, *xr = xl + 2 * P;
+    float *red = reinterpret_cast<float *>(xr + 2 * P);
+    float *Ls = red + 4 * 32, *Rs = Ls + CPP;
+
+    const int n = blockIdx.x / p.D, d = blockIdx.x % p.D;
+    const size_t cs = (size_t)p.D * PP;                       // channel stride of cost
+    float *out = p.cost + (size_t)n * 3 * C * cs + (size_t)d * PP;
+
+    if (p.valid && !p.valid[n]) {                              // dropped RoI: zero slice
+        for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) st_cs(out + (size_t)(e / PP) * cs + e % PP, 0.f);
+        if (threadIdx.x == 0) {
+            p.depth_bin[(size_t)n * p.D + d] = 0.f;
+            if (GATE && p.xcross) p.xcross[(size_t)n * p.D + d] = 0.f;
+        }
+        return;
+    }
+
+    int b;
+    float dbin;
+    build_tables(p, n, d, ytab, xl, xr, b, dbin);
+    if (threadIdx.x == 0) p.depth_bin[(size_t)n * p.D + d] = dbin;
+    __syncthreads();
+
+    const float *fL = p.featL + (size_t)b * C * p.H * p.W;
+    const float *fR = p.featR + (size_t)b * C * p.H * p.W;
+    const int HW = p.H * p.W;
+
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+        const int c = e / PP, q = e - c * PP, ph = q / P, pw = q - ph * P;
+        const float l = roi_bin(fL + (size_t)c * HW, p.W, ytab + 2 * ph, xl + 2 * pw);
+        const float r = roi_bin(fR + (size_t)c * HW, p.W, ytab + 2 * ph, xr + 2 * pw);
+        if (GATE) {
+            s[0] = fmaf(l, l, s[0]);
+            s[1] = fmaf(r, r, s[1]);
+            s[2] = fmaf(l, r, s[2]);
+        }
+        if (STAGE) {
+            Ls[e] = l;
+            Rs[e] = r;
+        } else if (!GATE) {
+            st_cs(out + (size_t)c * cs + q, l);
+            st_cs(out + (size_t)(C + c) * cs + q, r);
+            st_cs(out + (size_t)(2 * C + c) * cs + q, __fsub_rn(l, r));
+        }
+    }
+    float g = 1.0f;
+    if (GATE) {
+        block_sum<3>(s, red);
+        const float den = fmaxf(__fmul_rn(sqrtf(s[0]), sqrtf(s[1])), 0.01f);
+        g = __fdiv_rn(s[2], den);
+        if (threadIdx.x == 0 && p.xcross) p.xcross[(size_t)n * p.D + d] = g;
+    }
+    if (STAGE) {
+        __syncthreads();
+        if ((PP & 3) == 0) {
+            const int PP4 = PP >> 2;
+            for (int e4 = threadIdx.x; e4 < 3 * C * PP4; e4 += blockDim.x) {
+                const int ch = e4 / PP4, q4 = e4 - ch * PP4;
+                float4 v;
+                if (ch < C) {
+                    v = *reinterpret_cast<const float4 *>(Ls + ch * PP + 4 * q4);
+                } else if (ch < 2 * C) {
+                    v = *reinterpret_cast<const float4 *>(Rs + (ch - C) * PP + 4 * q4);
+                } else {
+                    const float4 a = *reinterpret_cast<const float4 *>(Ls + (ch - 2 * C) * PP + 4 * q4);
+                    const float4 bq = *reinterpret_cast<const float4 *>(Rs + (ch - 2 * C) * PP + 4 * q4);
+                    v = make_float4(__fsub_rn(a.x, bq.x), __fsub_rn(a.y, bq.y), __fsub_rn(a.z, bq.z),
+                                    __fsub_rn(a.w, bq.w));
+                }
+                if (GATE) {
+                    v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g);
+                    v.z = __fmul_rn(v.z, g); v.w = __fmul_rn(v.w, g);
+                }
+                st_cs(reinterpret_cast<float4 *>(out + (size_t)ch * cs + 4 * q4), v);
+            }
+        } else {
+            for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) {
+                const int ch = e / PP, q = e - ch * PP;
+                float v = ch < C ? Ls[e] : (ch < 2 * C ? Rs[e - CPP] : __fsub_rn(Ls[e - 2 * CPP], Rs[e - 2 * CPP]));
+                if (GATE) v = __fmul_rn(v, g);
+                st_cs(out + (size_t)ch * cs + q, v);
+            }
+        }
+    } else if (GATE) {
+        // tiles do not fit in shared memory: second gather pass (features are L2 resident)
+        for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+            const int c = e / PP, q = e - c * PP, ph = q / P, pw = q - ph * P;
+            const float l = roi_bin(fL + (size_t)c * HW, p.W, ytab + 2 * ph, xl + 2 * pw);
+            const float r = roi_bin(fR + (size_t)c * HW, p.W, ytab + 2 * ph, xr + 2 * pw);
+            st_cs(out + (size_t)c * cs + q, __fmul_rn(l, g));
+            st_cs(out + (size_t)(C + c) * cs + q, __fmul_rn(r, g));
+            st_cs(out + (size_t)(2 * C + c) * cs + q, __fmul_rn(__fsub_rn(l, r), g));
+        }
+    }
+}
+
+// scatter g * w_i / 4 to the 4 corners of the 2x2 samples of one bin (torchvision roi_align backward)
+__device__ __forceinline__ void roi_bin_scatter(float *__restrict__ gim, int W, const AxisSample *__restrict__ ys,
+                                                const AxisSample *__restrict__ xs, float g)
+{
+    const float gq = g * 0.25f;
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+        const AxisSample y = ys[iy];
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            const AxisSample x = xs[ix];
+            if (y.lo >= 0 && x.lo >= 0) {
+                atomicAdd(gim + y.lo * W + x.lo, gq * (y.h * x.h));
+                atomicAdd(gim + y.lo * W + x.hi, gq * (y.h * x.l));
+                atomicAdd(gim + y.hi * W + x.lo, gq * (y.l * x.h));
+                atomicAdd(gim + y.hi * W + x.hi, gq * (y.l * x.l));
+            }
+        }
+    }
+}
+
+template <bool GATE, bool STAGE>
+__global__ void __launch_bounds__(kVolThreads) inst_costvol_bwd_kernel(VolParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p.P, PP = P * P, C = p.C, CPP = C * PP;
+    AxisSample *ytab = reinterpret_cast<AxisSample *>(smem_raw);
+    AxisSample *xl = ytab + 2 * P, *xr = xl + 2 * P;
+    float *red = reinterpret_cast<float *>(xr + 2 * P);
+    float *Ls = red + 4 * 32, *Rs = Ls + CPP;
+
+    const int n = blockIdx.x / p.D, d = blockIdx.x % p.D;
+    if (p.valid && !p.valid[n]) return;
+    const size_t cs = (size_t)p.D * PP;
+    const float *G = p.gcost + (size_t)n * 3 * C * cs + (size_t)d * PP;
+
+    int b;
+    float dbin;
+    build_tables(p, n, d, ytab, xl, xr, b, dbin);
+    __syncthreads();
+    const int HW = p.H * p.W;
+    const float *fL = p.featL + (size_t)b * C * HW;
+    const float *fR = p.featR + (size_t)b * C * HW;
+    float *gL = p.gfeatL + (size_t)b * C * HW;
+    float *gR = p.gfeatR + (size_t)b * C * HW;
+
+    float xc = 1.f, gxc = 0.f, inv_den = 0.f, al = 0.f, ar = 0.f;
+    if (GATE) {
+        // recompute L, R and the gate statistics, plus g_xc = sum(G * raw)
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+            const int c = e / PP, q = e - c * PP, ph = q / P, pw = q - ph * P;
+            const float l = roi_bin(fL + (size_t)c * HW, p.W, ytab + 2 * ph, xl + 2 * pw);
+            const float r = roi_bin(fR + (size_t)c * HW, p.W, ytab + 2 * ph, xr + 2 * pw);
+            if (STAGE) { Ls[e] = l; Rs[e] = r; }
+            s[0] = fmaf(l, l, s[0]);
+            s[1] = fmaf(r, r, s[1]);
+            s[2] = fmaf(l, r, s[2]);
+            const float g0 = G[(size_t)c * cs + q], g1 = G[(size_t)(C + c) * cs + q], g2 = G[(size_t)(2 * C + c) * cs + q];
+            s[3] += g0 * l + g1 * r + g2 * (l - r);
+        }
+        block_sum<4>(s, red);
+        const float nl = sqrtf(s[0]), nr = sqrtf(s[1]);
+        const float prod = nl * nr;
+        const bool active = prod > 0.01f;                    // clamp(min=0.01) passes gradient only above the floor
+        const float den = active ? prod : 0.01f;
+        xc = s[2] / den;
+        gxc = s[3];
+        inv_den = 1.0f / den;
+        if (active && nl > 0.f && nr > 0.f) {
+            al = s[2] * nr / (den * den * nl);
+            ar = s[2] * nl / (den * den * nr);
+        }
+        if (STAGE) __syncthreads();
+    }
+    for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+        const int c = e / PP, q = e - c * PP, ph = q / P, pw = q - ph * P;
+        const float g0 = G[(size_t)c * cs + q], g1 = G[(size_t)(C + c) * cs + q], g2 = G[(size_t)(2 * C + c) * cs + q];
+        float gl = g0 + g2, gr = g1 - g2;
+        if (GATE) {
+            float l, r;
+            if (STAGE) { l = Ls[e]; r = Rs[e]; }
+            else {
+                l = roi_bin(fL + (size_t)c * HW, p.W, ytab + 2 * ph, xl + 2 * pw);
+                r = roi_bin(fR + (size_t)c * HW, p.W, ytab + 2 * ph, xr + 2 * pw);
+            }
+            gl = xc * gl + gxc * (r * inv_den - al * l);
+            gr = xc * gr + gxc * (l * inv_den - ar * r);
+        }
+        roi_bin_scatter(gL + (size_t)c * HW, p.W, ytab + 2 * ph, xl + 2 * pw, gl);
+        roi_bin_scatter(gR + (size_t)c * HW, p.W, ytab + 2 * ph, xr + 2 * pw, gr);
+    }
+}
+
+__global__ void proposal_shift_kernel(const float *__restrict__ left, const float *__restrict__ right,
+                                      const float *__restrict__ fb, int N, int B, int D, float x_clamp,
+                                      float *__restrict__ pro_left, float *__restrict__ pro_right,
+                                      float *__restrict__ depth_bin)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * D) return;
+    const int n = t / D, i = t % D;
+    const float *l = left + (size_t)n * 5, *r = right + (size_t)n * 5;
+    float dbin, lx1, lx2, rx1, rx2, y1, y2;
+    proposal_for(l, r, fb[min(max((int)l[0], 0), B - 1)], i, D, x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+    depth_bin[(size_t)n * D + i] = dbin;
+    float *pl = pro_left + ((size_t)i * N + n) * 5, *pr = pro_right + ((size_t)i * N + n) * 5;
+    pl[0] = l[0]; pl[1] = lx1; pl[2] = y1; pl[3] = lx2; pl[4] = y2;
+    pr[0] = l[0]; pr[1] = rx1; pr[2] = y1; pr[3] = rx2; pr[4] = y2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone gate on a materialised volume (drop-in cost_volume.forward entry)
+// ------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) xcross_gate_kernel(const float *__restrict__ cost, const float *__restrict__ gout,
+                                                          float *__restrict__ out, float *__restrict__ xcross, int C,
+                                                          int D, int PP)
+{
+    __shared__ float red[4 * 32];
+    const int n = blockIdx.x / D, d = blockIdx.x % D;
+    const size_t cs = (size_t)D * PP;
+    const size_t base = (size_t)n * 3 * C * cs + (size_t)d * PP;
+    const float *cb = cost + base;
+    const int CPP = C * PP;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+        const int c = e / PP, q = e - c * PP;
+        const float l = cb[(size_t)c * cs + q], r = cb[(size_t)(C + c) * cs + q];
+        s[0] = fmaf(l, l, s[0]);
+        s[1] = fmaf(r, r, s[1]);
+        s[2] = fmaf(l, r, s[2]);
+        if (BWD) {
+            const float *gb = gout + base;
+            s[3] += gb[(size_t)c * cs + q] * l + gb[(size_t)(C + c) * cs + q] * r +
+                    gb[(size_t)(2 * C + c) * cs + q] * cb[(size_t)(2 * C + c) * cs + q];
+        }
+    }
+    block_sum<4>(s, red);
+    const float nl = sqrtf(s[0]), nr = sqrtf(s[1]);
+    const float prod = __fmul_rn(nl, nr);
+    const bool active = prod > 0.01f;
+    const float den = active ? prod : 0.01f;
+    const float xc = __fdiv_rn(s[2], den);
+    if (!BWD) {
+        if (threadIdx.x == 0 && xcross) xcross[(size_t)n * D + d] = xc;
+        float *ob = out + base;
+        for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) {
+            const int c = e / PP, q = e - c * PP;
+            ob[(size_t)c * cs + q] = __fmul_rn(cb[(size_t)c * cs + q], xc);
+        }
+    } else {
+        const float gxc = s[3], inv_den = 1.0f / den;
+        float al = 0.f, ar = 0.f;
+        if (active && nl > 0.f && nr > 0.f) {
+            al = s[2] * nr / (den * den * nl);
+            ar = s[2] * nl / (den * den * nr);
+        }
+        const float *gb = gout + base;
+        float *ob = out + base;
+        for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+            const int c = e / PP, q = e - c * PP;
+            const float l = cb[(size_t)c * cs + q], r = cb[(size_t)(C + c) * cs + q];
+            ob[(size_t)c * cs + q] = xc * gb[(size_t)c * cs + q] + gxc * (r * inv_den - al * l);
+            ob[(size_t)(C + c) * cs + q] = xc * gb[(size_t)(C + c) * cs + q] + gxc * (l * inv_den - ar * r);
+            ob[(size_t)(2 * C + c) * cs + q] = xc * gb[(size_t)(2 * C + c) * cs + q];
+        }
+    }
+}
+
+static size_t vol_smem_bytes(int C, int P, bool stage)
+{
+    size_t b = sizeof(AxisSample) * 6 * P + sizeof(float) * 4 * 32;
+    if (stage) b += sizeof(float) * 2 * (size_t)C * P * P;
+    return b;
+}
+
+static int check_vol_args(const VolParams &p)
+{
+    SIDE_REQUIRE(p.N >= 0 && p.B > 0 && p.C > 0 && p.H > 1 && p.W > 1, "inst_costvol: bad shape");
+    SIDE_REQUIRE(p.D >= 2, "inst_costvol: D (depth candidates) must be >= 2 (reference divides by D-1)");
+    SIDE_REQUIRE(p.P >= 1 && 6 * p.P <= kVolThreads, "inst_costvol: P out of range (1..%d)", kVolThreads / 6);
+    SIDE_REQUIRE((long long)p.N * p.D < (1ll << 31), "inst_costvol: N*D too large");
+    return SIDE_OK;
+}
+
+}  // namespace side
+
+using namespace side;
+
+extern "C" int side_proposal_shift(const float *left, const float *right, const float *fb, int N, int B, int D,
+                                   float x_clamp, float *pro_left, float *pro_right, float *depth_bin, void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && B > 0 && D >= 2, "side_proposal_shift: bad shape (N=%d B=%d D=%d)", N, B, D);
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right); SIDE_REQUIRE_DEV(fb);
+    SIDE_REQUIRE_DEV(pro_left); SIDE_REQUIRE_DEV(pro_right); SIDE_REQUIRE_DEV(depth_bin);
+    proposal_shift_kernel<<<ceil_div((long long)N * D, 128), 128, 0, (cudaStream_t)stream>>>(
+        left, right, fb, N, B, D, x_clamp, pro_left, pro_right, depth_bin);
+    SIDE_LAUNCH_CHECK("proposal_shift_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, const float *left, const float *right,
+                                     const float *fb, const uint8_t *valid, float *cost, float *depth_bin,
+                                     float *xcross, int N, int B, int C, int H, int W, int D, int P, float x_clamp,
+                                     int flags, void *stream)
+{
+    VolParams p{featL, featR, left, right, fb, valid, cost, depth_bin, xcross, nullptr, nullptr, nullptr,
+                N, B, C, H, W, D, P, x_clamp};
+    int rc = check_vol_args(p);
+    if (rc) return rc;
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right);
+    SIDE_REQUIRE_DEV(fb); SIDE_REQUIRE_DEV(cost); SIDE_REQUIRE_DEV(depth_bin);
+    const bool gate = flags & SIDE_VOL_GATE;
+    const bool stage = gate && vol_smem_bytes(C, P, true) <= 200 * 1024;
+    const size_t smem = vol_smem_bytes(C, P, stage);
+    const dim3 grid((unsigned)((long long)N * D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gate && stage) {
+        if ((rc = set_smem_attr((const void *)inst_costvol_fwd_kernel<true, true>, smem))) return rc;
+        inst_costvol_fwd_kernel<true, true><<<grid, kVolThreads, smem, st>>>(p);
+    } else if (gate) {
+        inst_costvol_fwd_kernel<true, false><<<grid, kVolThreads, smem, st>>>(p);
+    } else {
+        inst_costvol_fwd_kernel<false, false><<<grid, kVolThreads, smem, st>>>(p);
+    }
+    SIDE_LAUNCH_CHECK("inst_costvol_fwd_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_inst_costvol_bwd(const float *featL, const float *featR, const float *left, const float *right,
+                                     const float *fb, const uint8_t *valid, const float *gcost, float *gfeatL,
+                                     float *gfeatR, int N, int B, int C, int H, int W, int D, int P, float x_clamp,
+                                     int flags, void *stream)
+{
+    VolParams p{featL, featR, left, right, fb, valid, nullptr, nullptr, nullptr, gcost, gfeatL, gfeatR,
+                N, B, C, H, W, D, P, x_clamp};
+    int rc = check_vol_args(p);
+    if (rc) return rc;
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right);
+    SIDE_REQUIRE_DEV(fb); SIDE_REQUIRE_DEV(gcost); SIDE_REQUIRE_DEV(gfeatL); SIDE_REQUIRE_DEV(gfeatR);
+    const bool gate = flags & SIDE_VOL_GATE;
+    const bool stage = gate && vol_smem_bytes(C, P, true) <= 200 * 1024;
+    const size_t smem = vol_smem_bytes(C, P, stage);
+    const dim3 grid((unsigned)((long long)N * D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gate && stage) {
+        if ((rc = set_smem_attr((const void *)inst_costvol_bwd_kernel<true, true>, smem))) return rc;
+        inst_costvol_bwd_kernel<true, true><<<grid, kVolThreads, smem, st>>>(p);
+    } else if (gate) {
+        inst_costvol_bwd_kernel<true, false><<<grid, kVolThreads, smem, st>>>(p);
+    } else {
+        inst_costvol_bwd_kernel<false, false><<<grid, kVolThreads, smem, st>>>(p);
+    }
+    SIDE_LAUNCH_CHECK("inst_costvol_bwd_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_xcross_gate_fwd(const float *cost, float *out, float *xcross, int N, int C, int D, int P,
+                                    void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && C > 0 && D > 0 && P > 0, "side_xcross_gate_fwd: bad shape");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(cost); SIDE_REQUIRE_DEV(out);
+    xcross_gate_kernel<false><<<(unsigned)((long long)N * D), 256, 0, (cudaStream_t)stream>>>(cost, nullptr, out,
+                                                                                            xcross, C, D, P * P);
+    SIDE_LAUNCH_CHECK("xcross_gate_kernel<fwd>");
+    return SIDE_OK;
+}
+
+extern "C" int side_xcross_gate_bwd(const float *cost, const float *gout, float *gcost, int N, int C, int D, int P,
+                                    void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && C > 0 && D > 0 && P > 0, "side_xcross_gate_bwd: bad shape");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(cost); SIDE_REQUIRE_DEV(gout); SIDE_REQUIRE_DEV(gcost);
+    xcross_gate_kernel<true><<<(unsigned)((long long)N * D), 256, 0, (cudaStream_t)stream>>>(cost, gout, gcost,
+                                                                                           nullptr, C, D, P * P);
+    SIDE_LAUNCH_CHECK("xcross_gate_kernel<bwd>");
+    return SIDE_OK;
+}

@@ -1,0 +1,230 @@
+"""DLA-34 backbone + deformable up-sampling neck, state-dict compatible with the reference's
+``feature_extraction_dla34.py`` (module tree ``base.*``, ``dla_up.ida_{0,1,2}.{proj,up,node}_k.*``,
+``ida_up.{proj,up,node}_k.*``).
+
+Only ``DeformConv.conv`` (the 16 DCN layers per view) is on the hot path and runs on
+libside_b200.so; the DLA base, BatchNorms and the depth-wise bilinear ``ConvTranspose2d`` stay cuDNN/ATen
+exactly as in the reference (out of scope).  No pretrained download happens here
+(reference quirk Q4): ``pretrained`` may be a local ``.pth`` path or falsy.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..dcn_v2 import DCN
+
+BN_MOMENTUM = 0.1
+
+
+def _bn(c):
+    return nn.BatchNorm2d(c, momentum=BN_MOMENTUM)
+
+
+class BasicBlock(nn.Module):
+    def __init__(self, inplanes, planes, stride=1, dilation=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=dilation, bias=False, dilation=dilation)
+        self.bn1 = _bn(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=dilation, bias=False, dilation=dilation)
+        self.bn2 = _bn(planes)
+        self.stride = stride
+
+    def forward(self, x, residual=None):
+        residual = x if residual is None else residual
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        y += residual
+        return self.relu(y)
+
+
+class Root(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, residual):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, 1, stride=1, bias=False, padding=(kernel_size - 1) // 2)
+        self.bn = _bn(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.residual = residual
+
+    def forward(self, *xs):
+        y = self.bn(self.conv(torch.cat(xs, 1)))
+        if self.residual:
+            y += xs[0]
+        return self.relu(y)
+
+
+class Tree(nn.Module):
+    def __init__(self, levels, block, in_channels, out_channels, stride=1, level_root=False, root_dim=0,
+                 root_kernel_size=1, dilation=1, root_residual=False):
+        super().__init__()
+        if root_dim == 0:
+            root_dim = 2 * out_channels
+        if level_root:
+            root_dim += in_channels
+        if levels == 1:
+            self.tree1 = block(in_channels, out_channels, stride, dilation=dilation)
+            self.tree2 = block(out_channels, out_channels, 1, dilation=dilation)
+            self.root = Root(root_dim, out_channels, root_kernel_size, root_residual)
+        else:
+            self.tree1 = Tree(levels - 1, block, in_channels, out_channels, stride, root_dim=0,
+                              root_kernel_size=root_kernel_size, dilation=dilation, root_residual=root_residual)
+            self.tree2 = Tree(levels - 1, block, out_channels, out_channels, root_dim=root_dim + out_channels,
+                              root_kernel_size=root_kernel_size, dilation=dilation, root_residual=root_residual)
+        self.level_root = level_root
+        self.root_dim = root_dim
+        self.levels = levels
+        self.downsample = nn.MaxPool2d(stride, stride=stride) if stride > 1 else None
+        self.project = None
+        if in_channels != out_channels:
+            self.project = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1, stride=1, bias=False), _bn(out_channels))
+
+    def forward(self, x, residual=None, children=None):
+        children = [] if children is None else children
+        bottom = self.downsample(x) if self.downsample else x
+        residual = self.project(bottom) if self.project else bottom
+        if self.level_root:
+            children.append(bottom)
+        x1 = self.tree1(x, residual)
+        if self.levels == 1:
+            return self.root(self.tree2(x1), x1, *children)
+        children.append(x1)
+        return self.tree2(x1, children=children)
+
+
+class DLA(nn.Module):
+    def __init__(self, levels, channels, block=BasicBlock, residual_root=False):
+        super().__init__()
+        self.channels = channels
+        self.base_layer = nn.Sequential(nn.Conv2d(3, channels[0], 7, stride=1, padding=3, bias=False), _bn(channels[0]),
+                                        nn.ReLU(inplace=True))
+        self.level0 = self._conv_level(channels[0], channels[0], levels[0])
+        self.level1 = self._conv_level(channels[0], channels[1], levels[1], stride=2)
+        self.level2 = Tree(levels[2], block, channels[1], channels[2], 2, level_root=False, root_residual=residual_root)
+        self.level3 = Tree(levels[3], block, channels[2], channels[3], 2, level_root=True, root_residual=residual_root)
+        self.level4 = Tree(levels[4], block, channels[3], channels[4], 2, level_root=True, root_residual=residual_root)
+        self.level5 = Tree(levels[5], block, channels[4], channels[5], 2, level_root=True, root_residual=residual_root)
+
+    @staticmethod
+    def _conv_level(inplanes, planes, convs, stride=1, dilation=1):
+        mods = []
+        for i in range(convs):
+            mods += [nn.Conv2d(inplanes, planes, 3, stride=stride if i == 0 else 1, padding=dilation, bias=False,
+                               dilation=dilation), _bn(planes), nn.ReLU(inplace=True)]
+            inplanes = planes
+        return nn.Sequential(*mods)
+
+    def forward(self, x):
+        ys = []
+        x = self.base_layer(x)
+        for i in range(6):
+            x = getattr(self, "level%d" % i)(x)
+            ys.append(x)
+        return ys
+
+    def load_pretrained_model(self, path):
+        """Loads ImageNet DLA weights from a LOCAL file (the reference downloads them, Q4)."""
+        weights = torch.load(path, map_location="cpu")
+        weights = {k: v for k, v in weights.items() if not k.startswith("fc.")}
+        self.load_state_dict(weights, strict=False)
+
+
+def dla34(pretrained=None, **kwargs):
+    model = DLA([1, 1, 1, 2, 2, 1], [16, 32, 64, 128, 256, 512], block=BasicBlock, **kwargs)
+    if isinstance(pretrained, str):
+        model.load_pretrained_model(pretrained)
+    return model
+
+
+def fill_up_weights(up):
+    """Bilinear kernel for the depth-wise ConvTranspose2d (reference feature_extraction_dla34.py:333-342)."""
+    w = up.weight.data
+    k = w.size(2)
+    f = math.ceil(k / 2)
+    c = (2 * f - 1 - f % 2) / (2.0 * f)
+    for i in range(k):
+        for j in range(w.size(3)):
+            w[0, 0, i, j] = (1 - math.fabs(i / f - c)) * (1 - math.fabs(j / f - c))
+    w[1:, 0] = w[0, 0]
+
+
+class DeformConv(nn.Module):
+    """DCN -> BN -> ReLU (reference :345-357).  In eval / no-grad mode BN and ReLU are folded into the
+    DCN kernel's epilogue (SIDE_DCN_FUSE_AFFINE | SIDE_DCN_FUSE_RELU)."""
+
+    def __init__(self, chi, cho):
+        super().__init__()
+        self.actf = nn.Sequential(_bn(cho), nn.ReLU(inplace=True))
+        self.conv = DCN(chi, cho, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1)
+
+    def forward(self, x):
+        bn = self.actf[0]
+        if not bn.training and not torch.is_grad_enabled():
+            return self.conv(x, bn=bn, relu=True)
+        return self.actf(self.conv(x))
+
+
+class IDAUp(nn.Module):
+    def __init__(self, o, channels, up_f):
+        super().__init__()
+        for i in range(1, len(channels)):
+            c, f = channels[i], int(up_f[i])
+            setattr(self, "proj_%d" % i, DeformConv(c, o))
+            up = nn.ConvTranspose2d(o, o, f * 2, stride=f, padding=f // 2, output_padding=0, groups=o, bias=False)
+            fill_up_weights(up)
+            setattr(self, "up_%d" % i, up)
+            setattr(self, "node_%d" % i, DeformConv(o, o))
+
+    def forward(self, layers, startp, endp):
+        for i in range(startp + 1, endp):
+            k = i - startp
+            layers[i] = getattr(self, "up_%d" % k)(getattr(self, "proj_%d" % k)(layers[i]))
+            layers[i] = getattr(self, "node_%d" % k)(layers[i] + layers[i - 1])
+
+
+class DLAUp(nn.Module):
+    def __init__(self, startp, channels, scales, in_channels=None):
+        super().__init__()
+        self.startp = startp
+        in_channels = list(channels) if in_channels is None else in_channels
+        self.channels = channels
+        channels = list(channels)
+        scales = np.array(scales, dtype=int)
+        for i in range(len(channels) - 1):
+            j = -i - 2
+            setattr(self, "ida_%d" % i, IDAUp(channels[j], in_channels[j:], scales[j:] // scales[j]))
+            scales[j + 1:] = scales[j]
+            in_channels[j + 1:] = [channels[j] for _ in channels[j + 1:]]
+
+    def forward(self, layers):
+        out = [layers[-1]]
+        for i in range(len(layers) - self.startp - 1):
+            getattr(self, "ida_%d" % i)(layers, len(layers) - i - 2, len(layers))
+            out.insert(0, layers[-1])
+        return out
+
+
+class feature_extraction_dla34(nn.Module):
+    """x [B,3,H,W] -> [B,64,H/4,W/4]  (reference :416-453)."""
+
+    def __init__(self, base_name, pretrained, down_ratio, last_level, out_channel=0):
+        super().__init__()
+        assert down_ratio in [2, 4, 8, 16]
+        assert base_name == "dla34", "only the canonical DLA-34 base is built"
+        self.first_level = int(np.log2(down_ratio))
+        self.last_level = last_level
+        self.base = dla34(pretrained=pretrained)
+        self.channels = self.base.channels
+        scales = [2 ** i for i in range(len(self.channels[self.first_level:]))]
+        self.dla_up = DLAUp(self.first_level, self.channels[self.first_level:], scales)
+        if out_channel == 0:
+            out_channel = self.channels[self.first_level]
+        self.ida_up = IDAUp(out_channel, self.channels[self.first_level:self.last_level],
+                            [2 ** i for i in range(self.last_level - self.first_level)])
+
+    def forward(self, x):
+        x = self.dla_up(self.base(x))
+        y = [x[i].clone() for i in range(self.last_level - self.first_level)]
+        self.ida_up(y, 0, len(y))
+        return y[-1]

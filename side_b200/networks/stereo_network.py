@@ -1,0 +1,204 @@
+"""Canonical SIDE stereo network (reference ``stereo_network_old.py``) on the B200 kernels.
+
+Same public API and state-dict keys as the reference:
+``get_proposal_shift``, ``cost_volume(inChannel).forward(cost, maxdisp, depth_bin)``,
+``stereo_network.forward(batch, useCostVolume=True, target=None, wh_scale=1.0) -> [dict]``,
+``get_pose_net(num_layers, heads, head_conv=256, down_ratio=4)``.
+
+What changed underneath (hot path only):
+  * the 2*D RoIAlign launches + 3*D slice copies + host-zeroed volume upload (:369-376) and the
+    cosine gate (:197-203) are ONE kernel (``ops.inst_costvol(..., gate=True)``) that also derives the
+    shifted RoIs / depth bins from the boxes (``get_proposal_shift`` :34-133) -- no CPU tensors, no syncs;
+  * AvgPool + softmax + the D-step Python loop (:228-236) are one warp-shuffle kernel (``ops.softargmin``);
+  * box decoding is the single-launch NMS/top-K kernel; in inference the RoI set keeps the fixed shape
+    [B*K] with a validity mask, so the forward never synchronises the host and can be graph-captured;
+  * the plain convolutions / BatchNorms / 3-D CNN stay cuDNN exactly as in the reference.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..decode import bbox_decode  # noqa: F401  (same import the reference module exposes)
+from .feature_extraction_dla34 import feature_extraction_dla34
+
+BN_MOMENTUM = 0.1
+input_h, input_w = 384., 1280.   # reference module constants (stereo_network_old.py:21); x clamp = input_w//4 - 1
+
+
+def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
+    return nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=pad, bias=False)
+
+
+def get_proposal_shift(left_boxes, right_boxes, depth_rate, fbs, trans_invs=None):
+    """Reference :34-133.  Boxes [N,5] = (b, x1, y1, x2, y2) in stride-4 feature coordinates.
+    Returns (proposals_left [D,N,5], proposals_right [D,N,5], depth_bin [N,D]) grouped by image (ascending b)."""
+    order = torch.argsort(left_boxes[:, 0], stable=True)
+    left_boxes, right_boxes = left_boxes[order], right_boxes[order]
+    return ops.proposal_shift(left_boxes.float(), right_boxes.float(), fbs.float().reshape(-1), int(depth_rate),
+                              input_w // 4 - 1.)
+
+
+class cost_volume(nn.Module):
+    """3-D aggregation network + soft-argmin depth regression (reference :135-244)."""
+
+    def __init__(self, inChannel, reduced_channel=32):
+        super().__init__()
+        self.reduced_channel = reduced_channel
+        c3 = 3 * reduced_channel   # 96 in the reference (hard-coded, :139)
+
+        def block(cin, cmid, cout):
+            return nn.Sequential(convbn_3d(cin, cmid, 3, 1, 1), nn.BatchNorm3d(cmid), nn.ReLU(inplace=True),
+                                 convbn_3d(cmid, cout, 3, 1, 1), nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+        self.dres0 = block(c3, 64, 64)
+        self.strAM_2D = nn.Sequential(nn.Conv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64))
+        self.dres1 = block(64, 64, 128)
+        self.max_pool1 = nn.MaxPool3d((1, 2, 2))
+        self.dres2 = block(128, 128, 128)
+        self.max_pool2 = nn.MaxPool3d((1, 2, 2))
+        self.classify = nn.Sequential(convbn_3d(128, 64, 3, 1, 1), nn.BatchNorm3d(64), nn.ReLU(inplace=True),
+                                      nn.Conv3d(64, 1, kernel_size=3, padding=1, stride=1, bias=False))
+        self.avg_pool = nn.AvgPool2d(4, 4)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv3d)):
+                n = int(np.prod(m.kernel_size)) * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def aggregate(self, cost):
+        """Gated volume [N,3C,D,P,P] -> classify logits [N,D,P/4,P/4] (cuDNN, as in the reference :205-227)."""
+        cost = self.dres0(cost)
+        isp = torch.sigmoid(self.strAM_2D(torch.mean(cost, dim=3))).unsqueeze(3)
+        cost = isp * cost
+        cost = self.max_pool1(self.dres1(cost))
+        cost = self.dres2(cost) + cost
+        cost = self.max_pool2(cost)
+        return torch.squeeze(self.classify(cost), 1)
+
+    def forward(self, cost, maxdisp, depth_bin, gated=False):
+        """cost: raw [L, R, L-R] volume (drop-in path) or already gated (``gated=True``, fused builder)."""
+        if not gated:
+            cost = ops.xcross_gate(cost.contiguous(), cost.shape[1] // 3)
+        logits = self.aggregate(cost)
+        if logits.shape[1] != maxdisp:
+            raise RuntimeError("cost volume has %d depth candidates, maxdisp=%d" % (logits.shape[1], maxdisp))
+        if logits.shape[-1] != 4 or logits.shape[-2] != 4:
+            raise RuntimeError("soft-argmin tail expects a 4x4 map (RoI size 16), got %s" % (tuple(logits.shape[-2:]),))
+        return ops.softargmin(logits.contiguous(), depth_bin)
+
+
+def fill_fc_weights(layers):
+    for m in layers.modules():
+        if isinstance(m, nn.Conv2d) and m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+
+
+class stereo_network(nn.Module):
+    def __init__(self, base_name, heads, pretrained, down_ratio, final_kernel, last_level, head_conv, out_channel=0):
+        super().__init__()
+        self.down_ratio = down_ratio
+        self.first_level = int(np.log2(down_ratio))
+        self.feature_extraction = feature_extraction_dla34(base_name, pretrained=pretrained, down_ratio=down_ratio,
+                                                           last_level=5)
+        channels = self.feature_extraction.channels
+        cf = channels[self.first_level]
+        self.roiSize = 16          # RoIAlign output size AND number of depth candidates (reference :270, F6)
+        self.depth_candidates = None   # None -> roiSize (reference behaviour)
+        self.feaRuduce = nn.Sequential(nn.Conv2d(cf, 32, kernel_size=1, padding=0, bias=False),
+                                       nn.BatchNorm2d(32, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))
+        self.reduced_channel = 32
+        self.depth_estimator = cost_volume(cf)
+        self.left_only = ['kept_type']
+        self.heads = heads
+        self.K = 100               # bbox_decode default (decode.py:91)
+        for head in self.heads:
+            classes = self.heads[head]
+            if head in self.left_only:
+                mods = [nn.Conv2d(cf, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+                for _ in range(4):
+                    mods += [nn.Conv2d(256, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+            else:
+                mods = [nn.Conv2d(cf * 2, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+            mods.append(nn.Conv2d(256, classes, kernel_size=final_kernel, stride=1, padding=final_kernel // 2, bias=True))
+            fc = nn.Sequential(*mods)
+            if 'hm' in head:
+                fc[-1].bias.data.fill_(-2.19)
+            else:
+                fill_fc_weights(fc)
+            self.__setattr__(head, fc)
+
+    # ------------------------------------------------------------------------------------------
+    def _features(self, left, right):
+        if not self.training and not torch.is_grad_enabled():
+            # eval BatchNorm is per-sample: one batched pass over [left; right] is identical (quirk Q7)
+            f = self.feature_extraction(torch.cat((left, right), 0))
+            return f[:left.shape[0]], f[left.shape[0]:]
+        return self.feature_extraction(left), self.feature_extraction(right)
+
+    def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D):
+        cost, depth_bin = ops.inst_costvol(featL, featR, left, right, fb, D, self.roiSize, input_w // 4 - 1.,
+                                           gate=True, valid=valid)
+        return self.depth_estimator(cost, D, depth_bin, gated=True)
+
+    def forward(self, batch, useCostVolume=True, target=None, wh_scale=1.0):
+        left, right = batch['input'], batch['input_right']
+        imgfea_left, imgfea_right = self._features(left, right)
+
+        z = {}
+        both = None
+        for head in self.heads:
+            if head in self.left_only:
+                z[head] = self.__getattr__(head)(imgfea_left)
+            else:
+                if both is None:
+                    both = torch.cat((imgfea_left, imgfea_right), 1)
+                z[head] = self.__getattr__(head)(both)
+
+        if useCostVolume:
+            fb = batch['fb'].to(left.device, torch.float32).reshape(-1)
+            feaL = self.feaRuduce(imgfea_left).contiguous()
+            feaR = self.feaRuduce(imgfea_right).contiguous()
+            D = self.depth_candidates or self.roiSize
+            dev = left.device
+            if target is None and not self.training:
+                # fixed-shape path: all B*K decoded rows, validity mask instead of compaction (no host sync)
+                o = ops.bbox_decode_raw(z['hm'], z['wh'], z['reg'], K=self.K, wh_scale=float(wh_scale), heat_is_logit=True)
+                B, K = o['score'].shape
+                disp = self._depth_from_boxes(feaL, feaR, o['bbox'].view(-1, 5), o['bbox_right'].view(-1, 5), fb,
+                                              o['keep'], D)
+                keep = o['keep'].bool()
+                depth = torch.zeros((B, K + 1), device=dev, dtype=torch.float32)
+                slot = torch.where(keep.view(B, K), o['slot'].long(), torch.full_like(o['slot'], K, dtype=torch.long))
+                depth.scatter_(1, slot, disp.view(B, K))            # dropped rows land in the spare column K
+                depth = depth[:, :K].unsqueeze(2).contiguous()
+            else:
+                if target is not None:
+                    bbox_keep, bbox_right_keep, bboxShape = target
+                else:
+                    bbox_keep, bbox_right_keep, bboxShape = bbox_decode(z['hm'], z['wh'] * wh_scale, z['reg'])
+                batch_size, max_obj = int(bboxShape[0]), int(bboxShape[1])
+                depth = torch.zeros((batch_size, max_obj, 1), device=dev, dtype=torch.float32)
+                if bbox_keep.shape[0] != 0:
+                    bl = bbox_keep.to(dev, torch.float32)
+                    br = bbox_right_keep.to(dev, torch.float32)
+                    order = torch.argsort(bl[:, 0], stable=True)   # group by image (reference :44-82)
+                    bl, br = bl[order].contiguous(), br[order].contiguous()
+                    disp = self._depth_from_boxes(feaL, feaR, bl, br, fb, None, D)
+                    bi = bl[:, 0].long()
+                    onehot = bi.unsqueeze(1) == torch.arange(batch_size, device=dev).unsqueeze(0)
+                    slot = (torch.cumsum(onehot, 0) - 1).gather(1, bi.clamp(0, batch_size - 1).unsqueeze(1)).squeeze(1)
+                    depth = depth.index_put((bi, slot, torch.zeros_like(bi)), disp)
+            z.update({"depth": depth})
+        return [z]
+
+
+def get_pose_net(num_layers, heads, head_conv=256, down_ratio=4, pretrained=None):
+    """Reference :388-396 (there ``pretrained=True`` forces a download, Q4; here: optional local path)."""
+    return stereo_network('dla{}'.format(num_layers), heads, pretrained=pretrained, down_ratio=down_ratio,
+                          final_kernel=1, last_level=5, head_conv=head_conv)

@@ -1,0 +1,427 @@
+"""Torch-facing wrappers of the C ABI (``include/side_b200.h``): tensors in, tensors out.
+
+PyTorch is only plumbing here -- it owns device memory and the current stream; every
+operator below is one call into ``libside_b200.so``.  CPU tensors are rejected with
+``RuntimeError`` (the reference's ``_ext`` does the same: DCNv2/src/dcn_v2.h:38).
+"""
+import torch
+
+from . import _lib
+
+_F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=_F32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("side_b200: %s must be a CUDA tensor -- not implemented on the CPU" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("side_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _pair(v):
+    return (int(v[0]), int(v[1])) if isinstance(v, (tuple, list)) else (int(v), int(v))
+
+
+# ----------------------------------------------------------------------------------------------
+# DCNv2
+# ----------------------------------------------------------------------------------------------
+PRECISIONS = {"fp32": _lib.DCN_PREC_FP32, "3xtf32": _lib.DCN_PREC_3XTF32, "tf32": _lib.DCN_PREC_TF32}
+_default_precision = "fp32"
+
+
+def set_dcn_precision(name):
+    """Selects the arithmetic of the DCN contraction: 'fp32' (SIMT FMA), '3xtf32' (tcgen05, fp32-class
+    accuracy) or 'tf32' (tcgen05 single pass, ~1e-3 relative)."""
+    global _default_precision
+    if name not in PRECISIONS:
+        raise ValueError("unknown DCN precision %r" % (name,))
+    _default_precision = name
+
+
+def get_dcn_precision():
+    return _default_precision
+
+
+def dcn_forward_raw(x, offset_t, mask_t, weight, bias, stride, padding, dilation, dg, *, offset_bs=0, mask_bs=0,
+                    flags=0, scale=None, shift=None, offset_ptr=None, mask_ptr=None, precision=None):
+    """One call of side_dcn_fwd.  ``offset_ptr`` / ``mask_ptr`` override the tensors' data_ptr (aliasing
+    into the 27-channel conv_offset_mask output)."""
+    lib = _lib.load()
+    x = _chk(x, "input")
+    weight = _chk(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, Cin_w, kh, kw = weight.shape
+    if Cin_w != Cin:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (Cin, Cin_w))
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding)
+    dh, dw = _pair(dilation)
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    flags |= PRECISIONS[precision or _default_precision]
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=_F32)
+    nws = lib.side_dcn_fwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags)
+    ws = torch.empty((max(nws, 16),), device=x.device, dtype=torch.uint8)
+    rc = lib.side_dcn_fwd(x.data_ptr(), offset_ptr or offset_t.data_ptr(), mask_ptr or mask_t.data_ptr(),
+                          weight.data_ptr(), _p(bias), _p(scale), _p(shift), y.data_ptr(), B, Cin, H, W, Cout, kh, kw,
+                          sh, sw, ph, pw, dh, dw, dg, offset_bs, mask_bs, flags, ws.data_ptr(), nws, _stream())
+    _lib.check(rc, "side_dcn_fwd")
+    return y
+
+
+def dcn_backward_raw(x, offset_t, mask_t, weight, gy, stride, padding, dilation, dg, *, offset_bs=0, mask_bs=0,
+                     flags=0, offset_ptr=None, mask_ptr=None, goffset_ptr=None, gmask_ptr=None, goffset=None,
+                     gmask=None):
+    lib = _lib.load()
+    x = _chk(x, "input")
+    weight = _chk(weight, "weight")
+    gy = _chk(gy, "grad_output")
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding)
+    dh, dw = _pair(dilation)
+    gx = torch.empty_like(x)
+    gw = torch.empty_like(weight)
+    gb = torch.empty((Cout,), device=x.device, dtype=_F32)
+    if goffset_ptr is None:
+        goffset = torch.empty_like(offset_t)
+        gmask = torch.empty_like(mask_t)
+        goffset_ptr, gmask_ptr = goffset.data_ptr(), gmask.data_ptr()
+    P = gy.shape[2] * gy.shape[3]
+    per_sample = 4 * Cin * kh * kw * P
+    free, _ = torch.cuda.mem_get_info(x.device)
+    nb = max(1, min(B, int(free * 0.5) // per_sample))
+    ws = torch.empty((per_sample * nb,), device=x.device, dtype=torch.uint8)
+    rc = lib.side_dcn_bwd(x.data_ptr(), offset_ptr or offset_t.data_ptr(), mask_ptr or mask_t.data_ptr(),
+                          weight.data_ptr(), gy.data_ptr(), gx.data_ptr(), goffset_ptr, gmask_ptr, gw.data_ptr(),
+                          gb.data_ptr(), B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, offset_bs, mask_bs, flags,
+                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "side_dcn_bwd")
+    return gx, goffset, gmask, gw, gb
+
+
+class _DCNv2(torch.autograd.Function):
+    """Drop-in for the reference autograd Function (DCNv2/dcn_v2.py:16-51)."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups):
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ctx.dg = int(deformable_groups)
+        offset = _chk(offset, "offset")
+        mask = _chk(mask, "mask")
+        bias = _chk(bias, "bias") if bias is not None else None
+        out = dcn_forward_raw(input, offset, mask, weight, bias, ctx.stride, ctx.padding, ctx.dilation, ctx.dg)
+        ctx.save_for_backward(input, offset, mask, weight, bias)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, mask, weight, bias = ctx.saved_tensors
+        gx, go, gm, gw, gb = dcn_backward_raw(input, offset, mask, weight, grad_output, ctx.stride, ctx.padding,
+                                              ctx.dilation, ctx.dg)
+        return gx, go, gm, gw, (gb if bias is not None else None), None, None, None, None
+
+
+dcn_v2_conv = _DCNv2.apply
+
+
+class _DCNFused(torch.autograd.Function):
+    """DCN.forward (dcn_v2.py:118-128) with the chunk/cat/sigmoid folded away: ``om`` is the raw 27-channel
+    conv_offset_mask output; channels 0..17 are consumed as the interleaved offsets exactly as stored and
+    channels 18..26 are mask logits (sigmoid fused in the kernel)."""
+
+    @staticmethod
+    def forward(ctx, input, om, weight, bias, stride, padding, dilation):
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        om = _chk(om, "conv_offset_mask output")
+        kk = weight.shape[2] * weight.shape[3]
+        if om.shape[1] != 3 * kk:
+            raise RuntimeError("conv_offset_mask must have %d channels" % (3 * kk))
+        P = om.shape[2] * om.shape[3]
+        ctx.kk, ctx.P = kk, P
+        out = dcn_forward_raw(input, om, om, weight, bias, ctx.stride, ctx.padding, ctx.dilation, 1,
+                              offset_bs=3 * kk * P, mask_bs=3 * kk * P, flags=_lib.DCN_MASK_IS_LOGIT,
+                              mask_ptr=om.data_ptr() + 4 * 2 * kk * P)
+        ctx.save_for_backward(input, om, weight, bias)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, om, weight, bias = ctx.saved_tensors
+        kk, P = ctx.kk, ctx.P
+        gom = torch.empty_like(om)
+        gx, _, _, gw, gb = dcn_backward_raw(input, om, om, weight, grad_output, ctx.stride, ctx.padding, ctx.dilation, 1,
+                                            offset_bs=3 * kk * P, mask_bs=3 * kk * P, flags=_lib.DCN_MASK_IS_LOGIT,
+                                            mask_ptr=om.data_ptr() + 4 * 2 * kk * P, goffset_ptr=gom.data_ptr(),
+                                            gmask_ptr=gom.data_ptr() + 4 * 2 * kk * P)
+        return gx, gom, gw, (gb if bias is not None else None), None, None, None
+
+
+dcn_fused = _DCNFused.apply
+
+
+def dcn_fused_infer(input, om, weight, bias, stride, padding, dilation, scale=None, shift=None, relu=False):
+    """Inference-only DCN (+ folded eval-mode BatchNorm + ReLU of DeformConv) in one kernel."""
+    om = _chk(om, "conv_offset_mask output")
+    kk = weight.shape[2] * weight.shape[3]
+    P = om.shape[2] * om.shape[3]
+    flags = _lib.DCN_MASK_IS_LOGIT
+    if scale is not None:
+        flags |= _lib.DCN_FUSE_AFFINE
+    if relu:
+        flags |= _lib.DCN_FUSE_RELU
+    return dcn_forward_raw(input, om, om, weight, bias, stride, padding, dilation, 1, offset_bs=3 * kk * P,
+                           mask_bs=3 * kk * P, flags=flags, scale=scale, shift=shift,
+                           mask_ptr=om.data_ptr() + 4 * 2 * kk * P)
+
+
+# ----------------------------------------------------------------------------------------------
+# instance cost volume, gate, soft-argmin
+# ----------------------------------------------------------------------------------------------
+def proposal_shift(left, right, fb, D, x_clamp):
+    lib = _lib.load()
+    left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
+    N = left.shape[0]
+    pl = torch.empty((D, N, 5), device=left.device, dtype=_F32)
+    pr = torch.empty((D, N, 5), device=left.device, dtype=_F32)
+    db = torch.empty((N, D), device=left.device, dtype=_F32)
+    _lib.check(lib.side_proposal_shift(left.data_ptr(), right.data_ptr(), fb.data_ptr(), N, fb.numel(), D,
+                                       float(x_clamp), pl.data_ptr(), pr.data_ptr(), db.data_ptr(), _stream()),
+               "side_proposal_shift")
+    return pl, pr, db
+
+
+class _InstCostVol(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, featL, featR, left, right, fb, valid, D, P, x_clamp, gate):
+        lib = _lib.load()
+        featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
+        left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
+        if valid is not None:
+            valid = _chk(valid, "valid", torch.uint8)
+        B, C, H, W = featL.shape
+        N = left.shape[0]
+        cost = torch.empty((N, 3 * C, D, P, P), device=featL.device, dtype=_F32)
+        depth_bin = torch.empty((N, D), device=featL.device, dtype=_F32)
+        xc = torch.empty((N, D), device=featL.device, dtype=_F32) if gate else None
+        flags = _lib.VOL_GATE if gate else 0
+        _lib.check(lib.side_inst_costvol_fwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
+                                             fb.data_ptr(), _p(valid), cost.data_ptr(), depth_bin.data_ptr(), _p(xc),
+                                             N, B, C, H, W, D, P, float(x_clamp), flags, _stream()),
+                   "side_inst_costvol_fwd")
+        ctx.save_for_backward(featL, featR, left, right, fb, valid)
+        ctx.cfg = (D, P, float(x_clamp), flags)
+        ctx.mark_non_differentiable(depth_bin)
+        return cost, depth_bin
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcost, _gdb):
+        lib = _lib.load()
+        featL, featR, left, right, fb, valid = ctx.saved_tensors
+        D, P, x_clamp, flags = ctx.cfg
+        B, C, H, W = featL.shape
+        N = left.shape[0]
+        gcost = _chk(gcost, "grad_cost")
+        gL = torch.zeros_like(featL)
+        gR = torch.zeros_like(featR)
+        _lib.check(lib.side_inst_costvol_bwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
+                                             fb.data_ptr(), _p(valid), gcost.data_ptr(), gL.data_ptr(), gR.data_ptr(),
+                                             N, B, C, H, W, D, P, x_clamp, flags, _stream()), "side_inst_costvol_bwd")
+        return gL, gR, None, None, None, None, None, None, None, None
+
+
+def inst_costvol(featL, featR, left, right, fb, D, P, x_clamp, gate=False, valid=None):
+    """-> (cost [N,3C,D,P,P], depth_bin [N,D]); boxes [N,5] grouped by image in ascending b."""
+    return _InstCostVol.apply(featL, featR, left, right, fb, valid, int(D), int(P), float(x_clamp), bool(gate))
+
+
+class _XCrossGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cost, C):
+        lib = _lib.load()
+        cost = _chk(cost, "cost")
+        N, C3, D, P, P2 = cost.shape
+        if C3 != 3 * C or P != P2:
+            raise RuntimeError("cost must be [N, 3*C, D, P, P]")
+        out = torch.empty_like(cost)
+        _lib.check(lib.side_xcross_gate_fwd(cost.data_ptr(), out.data_ptr(), None, N, C, D, P, _stream()),
+                   "side_xcross_gate_fwd")
+        ctx.save_for_backward(cost)
+        ctx.C = C
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (cost,) = ctx.saved_tensors
+        gout = _chk(gout, "grad_out")
+        N, _, D, P, _ = cost.shape
+        g = torch.empty_like(cost)
+        _lib.check(lib.side_xcross_gate_bwd(cost.data_ptr(), gout.data_ptr(), g.data_ptr(), N, ctx.C, D, P, _stream()),
+                   "side_xcross_gate_bwd")
+        return g, None
+
+
+def xcross_gate(cost, C):
+    return _XCrossGate.apply(cost, int(C))
+
+
+class _SoftArgmin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, depth_bin):
+        lib = _lib.load()
+        logits, depth_bin = _chk(logits, "logits"), _chk(depth_bin, "depth_bin")
+        N, D, S, S2 = logits.shape
+        if S != S2 or tuple(depth_bin.shape) != (N, D):
+            raise RuntimeError("softargmin: logits [N,D,S,S], depth_bin [N,D] expected")
+        depth = torch.empty((N,), device=logits.device, dtype=_F32)
+        prob = torch.empty((N, D), device=logits.device, dtype=_F32)
+        _lib.check(lib.side_softargmin_fwd(logits.data_ptr(), depth_bin.data_ptr(), depth.data_ptr(), prob.data_ptr(),
+                                           N, D, S, _stream()), "side_softargmin_fwd")
+        ctx.save_for_backward(prob, depth_bin, depth)
+        ctx.S = S
+        return depth
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        prob, depth_bin, depth = ctx.saved_tensors
+        g = _chk(g, "grad_depth")
+        N, D = prob.shape
+        S = ctx.S
+        gl = torch.empty((N, D, S, S), device=prob.device, dtype=_F32)
+        gdb = torch.empty((N, D), device=prob.device, dtype=_F32)
+        _lib.check(lib.side_softargmin_bwd(prob.data_ptr(), depth_bin.data_ptr(), depth.data_ptr(), g.data_ptr(),
+                                           gl.data_ptr(), gdb.data_ptr(), N, D, S, _stream()), "side_softargmin_bwd")
+        return gl, gdb
+
+
+def softargmin(logits, depth_bin):
+    """logits [N,D,S,S] (classify output squeezed), depth_bin [N,D] -> depth [N]."""
+    return _SoftArgmin.apply(logits, depth_bin)
+
+
+# ----------------------------------------------------------------------------------------------
+# decode
+# ----------------------------------------------------------------------------------------------
+def bbox_decode_raw(heat, wh, reg, K=100, wh_scale=1.0, heat_is_logit=True):
+    """-> dict(bbox [B,K,5], bbox_right [B,K,5], keep [B*K] uint8, slot [B,K] i32, count [B] i32,
+    score [B,K], ind [B,K] i32, cls [B,K] i32).  Fixed shapes, no host sync."""
+    lib = _lib.load()
+    heat, wh, reg = _chk(heat, "heat"), _chk(wh, "wh"), _chk(reg, "reg")
+    B, Cat, H, W = heat.shape
+    dev = heat.device
+    o = dict(bbox=torch.empty((B, K, 5), device=dev, dtype=_F32), bbox_right=torch.empty((B, K, 5), device=dev, dtype=_F32),
+             keep=torch.empty((B * K,), device=dev, dtype=torch.uint8), slot=torch.empty((B, K), device=dev, dtype=torch.int32),
+             count=torch.empty((B,), device=dev, dtype=torch.int32), score=torch.empty((B, K), device=dev, dtype=_F32),
+             ind=torch.empty((B, K), device=dev, dtype=torch.int32), cls=torch.empty((B, K), device=dev, dtype=torch.int32))
+    nws = lib.side_decode_ws_bytes(B, Cat, K)
+    ws = torch.empty((nws,), device=dev, dtype=torch.uint8)
+    flags = _lib.DECODE_HEAT_IS_LOGIT if heat_is_logit else 0
+    _lib.check(lib.side_bbox_decode(heat.data_ptr(), wh.data_ptr(), reg.data_ptr(), o["bbox"].data_ptr(),
+                                    o["bbox_right"].data_ptr(), o["keep"].data_ptr(), o["slot"].data_ptr(),
+                                    o["count"].data_ptr(), o["score"].data_ptr(), o["ind"].data_ptr(), o["cls"].data_ptr(),
+                                    B, Cat, H, W, K, float(wh_scale), flags, ws.data_ptr(), nws, _stream()),
+               "side_bbox_decode")
+    return o
+
+
+def ddd_decode_raw(heat, kept, dim, orien, wh, reg, grid_size, K=40, heat_is_logit=False):
+    lib = _lib.load()
+    heat, kept, dim = _chk(heat, "heat"), _chk(kept, "kept"), _chk(dim, "dim")
+    orien, wh, reg = _chk(orien, "orien"), _chk(wh, "wh"), _chk(reg, "reg")
+    B, Cat, H, W = heat.shape
+    if kept.shape[1] != 6 * grid_size:
+        raise RuntimeError("kept must have 6*grid_size channels")
+    dev = heat.device
+    det = torch.empty((B, K, 6), device=dev, dtype=_F32)
+    detr = torch.empty((B, K, 6), device=dev, dtype=_F32)
+    info = torch.empty((B, K, 9), device=dev, dtype=_F32)
+    nws = lib.side_decode_ws_bytes(B, Cat, K)
+    ws = torch.empty((nws,), device=dev, dtype=torch.uint8)
+    flags = _lib.DECODE_HEAT_IS_LOGIT if heat_is_logit else 0
+    _lib.check(lib.side_ddd_decode(heat.data_ptr(), kept.data_ptr(), dim.data_ptr(), orien.data_ptr(), wh.data_ptr(),
+                                   reg.data_ptr(), det.data_ptr(), detr.data_ptr(), info.data_ptr(), None, None, None, B,
+                                   Cat, H, W, int(grid_size), K, flags, ws.data_ptr(), nws, _stream()), "side_ddd_decode")
+    return det, detr, info
+
+
+# ----------------------------------------------------------------------------------------------
+# full-image volumes
+# ----------------------------------------------------------------------------------------------
+class _ConcatVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, R, D):
+        lib = _lib.load()
+        L, R = _chk(L, "left"), _chk(R, "right")
+        B, C, H, W = L.shape
+        vol = torch.empty((B, 2 * C, D, H, W), device=L.device, dtype=_F32)
+        _lib.check(lib.side_concat_volume_fwd(L.data_ptr(), R.data_ptr(), vol.data_ptr(), B, C, H, W, D, _stream()),
+                   "side_concat_volume_fwd")
+        ctx.shape = (B, C, H, W, D)
+        return vol
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        B, C, H, W, D = ctx.shape
+        g = _chk(g, "grad_volume")
+        gL = torch.empty((B, C, H, W), device=g.device, dtype=_F32)
+        gR = torch.empty((B, C, H, W), device=g.device, dtype=_F32)
+        _lib.check(lib.side_concat_volume_bwd(g.data_ptr(), gL.data_ptr(), gR.data_ptr(), B, C, H, W, D, _stream()),
+                   "side_concat_volume_bwd")
+        return gL, gR, None
+
+
+def concat_volume(L, R, D):
+    return _ConcatVolume.apply(L, R, int(D))
+
+
+class _GwcVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, R, D, G):
+        lib = _lib.load()
+        L, R = _chk(L, "left"), _chk(R, "right")
+        B, C, H, W = L.shape
+        vol = torch.empty((B, G, D, H, W), device=L.device, dtype=_F32)
+        _lib.check(lib.side_gwc_volume_fwd(L.data_ptr(), R.data_ptr(), vol.data_ptr(), B, C, H, W, D, G, _stream()),
+                   "side_gwc_volume_fwd")
+        ctx.save_for_backward(L, R)
+        ctx.cfg = (D, G)
+        return vol
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        L, R = ctx.saved_tensors
+        D, G = ctx.cfg
+        B, C, H, W = L.shape
+        g = _chk(g, "grad_volume")
+        gL = torch.empty_like(L)
+        gR = torch.empty_like(R)
+        _lib.check(lib.side_gwc_volume_bwd(L.data_ptr(), R.data_ptr(), g.data_ptr(), gL.data_ptr(), gR.data_ptr(), B, C, H,
+                                           W, D, G, _stream()), "side_gwc_volume_bwd")
+        return gL, gR, None, None
+
+
+def gwc_volume(L, R, D, G):
+    return _GwcVolume.apply(L, R, int(D), int(G))

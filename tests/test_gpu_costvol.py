@@ -1,0 +1,160 @@
+"""GPU parity: proposal generation, fused instance cost volume (+gate), soft-argmin -- vs the oracle and goldens."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle as co  # noqa: E402
+from oracle import torch_port as tp  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("D", [16, 48])
+def test_proposal_shift_golden_bit_exact(lib, D):
+    from side_b200.networks import get_proposal_shift
+    g = golden("proposal_shift_D%d" % D)
+    pl, pr, db = get_proposal_shift(dev(g["left"]), dev(g["right"]), D, dev(g["fb"]), None)
+    assert np.array_equal(db.cpu().numpy(), g["depth_bin"])
+    assert np.array_equal(pl.cpu().numpy(), g["pro_left"])
+    assert np.array_equal(pr.cpu().numpy(), g["pro_right"])
+
+
+def test_inst_costvol_golden(lib):
+    """The reference loop stereo_network_old.py:366-376 + gate :197-203 + tail :228-236 (golden from the reference)."""
+    from side_b200 import ops
+    g = golden("inst_costvol")
+    fL, fR = dev(g["featL"].astype(np.float32)), dev(g["featR"].astype(np.float32))
+    left, right, fb = dev(g["left"]), dev(g["right"]), dev(g["fb"])
+    cost, db = ops.inst_costvol(fL, fR, left, right, fb, 16, 16, 319.0)
+    c = cost.cpu().numpy()
+    assert hashlib.sha256(c.tobytes()).hexdigest() == str(g["cost_sha256"]), "raw [L,R,L-R] volume must be bit-exact"
+    assert np.array_equal(db.cpu().numpy(), g["depth_bin"])
+    gated, _ = ops.inst_costvol(fL, fR, left, right, fb, 16, 16, 319.0, gate=True)
+    assert rel_err(gated.cpu().numpy().reshape(-1)[::97], g["gated_sample"]) < 1e-4
+    gated2 = ops.xcross_gate(cost, 32)                       # stand-alone gate == fused gate
+    assert rel_err(gated2.cpu().numpy(), gated.cpu().numpy()) < 1e-5
+    depth = ops.softargmin(dev(g["logits"][:, 0]), db)
+    assert rel_err(depth.cpu().numpy(), g["disp"]) < 1e-4   # north_star: 1e-4 relative for soft-argmin depth
+
+
+def _random_case(rng, B, C, H, W, N):
+    fL = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    fR = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    b = np.sort(rng.integers(0, B, N)).astype(np.float32)
+    x1 = rng.uniform(-6, W - 4, N); w = rng.uniform(0.2, W / 3, N)
+    y1 = rng.uniform(-4, H - 3, N); h = rng.uniform(0.2, H / 2, N)
+    sh = rng.uniform(0, 12, N)
+    left = np.stack([b, x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+    right = np.stack([b, x1 - sh, y1 + rng.uniform(-1, 1, N), x1 + w - sh, y1 + h], 1).astype(np.float32)
+    fb = rng.uniform(300, 450, B).astype(np.float32)
+    return fL, fR, left, right, fb
+
+
+@pytest.mark.parametrize("cfg", [(2, 8, 24, 80, 9, 16, 16), (1, 3, 10, 33, 4, 2, 7), (3, 32, 17, 61, 11, 5, 16), (1, 64, 24, 80, 3, 48, 16)])
+def test_inst_costvol_random_bit_exact(lib, cfg):
+    """Boxes partly outside the image, sub-pixel boxes, P != 16, C not a power of two, D = 2 .. 48."""
+    from side_b200 import ops
+    B, C, H, W, N, D, P = cfg
+    rng = np.random.default_rng(B * 100 + C)
+    fL, fR, left, right, fb = _random_case(rng, B, C, H, W, N)
+    pl, pr, db = co.proposal_shift(left, right, fb, D, x_clamp=W - 1.0)
+    ref = co.inst_costvol(fL, fR, pl, pr, P)
+    cost, dbin = ops.inst_costvol(dev(fL), dev(fR), dev(left), dev(right), dev(fb), D, P, W - 1.0)
+    c = cost.cpu().numpy()
+    assert np.array_equal(dbin.cpu().numpy(), db)
+    assert np.array_equal(c, ref), "max abs diff %g" % np.abs(c - ref).max()
+    assert np.array_equal(c[:, 2 * C:], c[:, :C] - c[:, C:2 * C])       # L-R is computed from the kernel's own L, R
+    gref, xref = co.xcross_gate(ref, C)
+    gated, _ = ops.inst_costvol(dev(fL), dev(fR), dev(left), dev(right), dev(fb), D, P, W - 1.0, gate=True)
+    assert rel_err(gated.cpu().numpy(), gref) < 1e-4          # north_star: 1e-4 relative for the correlation/gate
+
+
+def test_inst_costvol_valid_mask_and_empty(lib):
+    from side_b200 import ops
+    rng = np.random.default_rng(1)
+    fL, fR, left, right, fb = _random_case(rng, 2, 8, 12, 40, 6)
+    valid = np.array([1, 0, 1, 1, 0, 1], np.uint8)
+    cost, db = ops.inst_costvol(dev(fL), dev(fR), dev(left), dev(right), dev(fb), 4, 16, 39.0, gate=True, valid=dev(valid))
+    full, dbf = ops.inst_costvol(dev(fL), dev(fR), dev(left), dev(right), dev(fb), 4, 16, 39.0, gate=True)
+    c, f = cost.cpu().numpy(), full.cpu().numpy()
+    assert np.all(c[valid == 0] == 0) and np.all(db.cpu().numpy()[valid == 0] == 0)
+    assert np.array_equal(c[valid == 1], f[valid == 1])
+    e, edb = ops.inst_costvol(dev(fL), dev(fR), dev(left[:0]), dev(right[:0]), dev(fb), 4, 16, 39.0)
+    assert tuple(e.shape) == (0, 24, 4, 16, 16) and tuple(edb.shape) == (0, 4)
+
+
+@pytest.mark.parametrize("gate", [False, True])
+def test_inst_costvol_backward_vs_autograd_of_port(lib, gate):
+    """Gradients w.r.t. the feature maps vs torch.autograd through the reference-style RoIAlign loop (CPU)."""
+    from side_b200 import ops
+    rng = np.random.default_rng(7)
+    fL, fR, left, right, fb = _random_case(rng, 2, 6, 14, 44, 5)
+    D, P = 5, 16
+    tl = [torch.from_numpy(a).requires_grad_(True) for a in (fL, fR)]
+    cref, _ = tp.inst_costvol(tl[0], tl[1], torch.from_numpy(left), torch.from_numpy(right), torch.from_numpy(fb), D, P, 43.0, gate=gate)
+    gc = torch.from_numpy(rng.standard_normal(tuple(cref.shape)).astype(np.float32))
+    gref = torch.autograd.grad(cref, tl, gc)
+    tg = [dev(a).requires_grad_(True) for a in (fL, fR)]
+    cost, _ = ops.inst_costvol(tg[0], tg[1], dev(left), dev(right), dev(fb), D, P, 43.0, gate=gate)
+    g = torch.autograd.grad(cost, tg, gc.cuda())
+    for mine, r, n in zip(g, gref, ("gfeatL", "gfeatR")):
+        assert rel_err(mine.cpu().numpy(), r.numpy()) < 1e-4, n
+
+
+def test_gate_and_softargmin_backward(lib):
+    from side_b200 import ops
+    torch.manual_seed(2)
+    cost = torch.randn(3, 12, 5, 4, 4)
+    a = cost.clone().requires_grad_(True)
+    ref = tp.xcross_gate(a, 4)
+    go = torch.randn_like(ref)
+    gr, = torch.autograd.grad(ref, a, go)
+    b = cost.cuda().requires_grad_(True)
+    out = ops.xcross_gate(b, 4)
+    gm, = torch.autograd.grad(out, b, go.cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert rel_err(gm.cpu().numpy(), gr.numpy()) < 1e-4
+    for (N, D) in [(7, 16), (64, 48), (3, 200), (1, 1)]:
+        lg = torch.randn(N, D, 4, 4); db = torch.rand(N, D) * 80 + 1
+        l1 = lg.clone().requires_grad_(True); d1 = db.clone().requires_grad_(True)
+        r = tp.softargmin(l1, d1)
+        gd = torch.randn(N)
+        grl, grd = torch.autograd.grad(r, (l1, d1), gd)
+        l2 = lg.cuda().requires_grad_(True); d2 = db.cuda().requires_grad_(True)
+        o = ops.softargmin(l2, d2)
+        gl, gdb = torch.autograd.grad(o, (l2, d2), gd.cuda())
+        dref, _ = co.softargmin(lg.numpy(), db.numpy())
+        assert rel_err(o.detach().cpu().numpy(), dref) < 1e-5, (N, D)
+        assert rel_err(gl.cpu().numpy(), grl.numpy()) < 1e-4 and rel_err(gdb.cpu().numpy(), grd.numpy()) < 1e-4, (N, D)
+
+
+def test_config2_full_size_properties(lib):
+    """BASELINE config #2: 64 RoIs, 48 candidates, 64 channels (604 MB volume).  Size-independent checks:
+    a seeded subset of RoIs against the oracle (bit-exact), L-R identity on the whole volume, gate scaling."""
+    from side_b200 import ops
+    from side_b200.utils.synthetic import make_boxes
+    torch.manual_seed(0)
+    fL, fR = torch.randn(1, 64, 96, 320), torch.randn(1, 64, 96, 320)
+    left, right, _ = make_boxes(1, 64, seed=0)
+    fb = torch.tensor([384.38])
+    cost, db = ops.inst_costvol(fL.cuda(), fR.cuda(), left.cuda(), right.cuda(), fb.cuda(), 48, 16, 319.0)
+    assert tuple(cost.shape) == (64, 192, 48, 16, 16)
+    assert torch.equal(cost[:, 128:], cost[:, :64] - cost[:, 64:128])
+    sub = [0, 17, 63]
+    pl, pr, dbo = co.proposal_shift(left.numpy()[sub], right.numpy()[sub], fb.numpy(), 48)
+    ref = co.inst_costvol(fL.numpy(), fR.numpy(), pl, pr, 16)
+    assert np.array_equal(cost[sub].cpu().numpy(), ref)
+    assert np.array_equal(db[sub].cpu().numpy(), dbo)
+    gated, _ = ops.inst_costvol(fL.cuda(), fR.cuda(), left.cuda(), right.cuda(), fb.cuda(), 48, 16, 319.0, gate=True)
+    ratio = (gated[:, :64] * cost[:, :64]).sum((1, 3, 4)) / (cost[:, :64] ** 2).sum((1, 3, 4))
+    l, r = cost[:, :64].double(), cost[:, 64:128].double()
+    xc = (l * r).sum((1, 3, 4)) / torch.clamp(torch.sqrt((l * l).sum((1, 3, 4))) * torch.sqrt((r * r).sum((1, 3, 4))), min=0.01)
+    assert (ratio.double() - xc).abs().max().item() < 1e-5

@@ -1,0 +1,111 @@
+"""CPU: the oracle (oracle/side_oracle.c + oracle/torch_port.py) against the golden vectors that were produced by
+executing the reference itself (oracle/gen_golden.py).  This is what pins the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+from oracle import c_oracle as co
+from oracle import torch_port as tp
+
+
+def test_dcn_zero_offset_kat():
+    """The reference's own KAT, DCNv2/test.py:32-67: identity-centre weight, zero offsets, mask 0.5 => 2*y == x."""
+    g = golden("dcn_kat_zero_offset")
+    y = co.dcn_forward(g["x"], g["offset"], g["mask"], g["weight"], g["bias"])
+    assert np.abs(g["x"] - 2 * y).max() < 1e-10
+    assert np.array_equal(y, g["y"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e"])
+def test_dcn_forward_backward_vs_reference(tag):
+    g = golden("dcn_conv_" + tag)
+    stride, pad, dil, dg = [int(v) for v in g["cfg"]]
+    y = co.dcn_forward(g["x"], g["offset"], g["mask"], g["weight"], g["bias"], stride, pad, dil, dg)
+    assert rel_err(y, g["y"]) < 1e-5
+    gx, go, gm, gw, gb = co.dcn_backward(g["x"], g["offset"], g["mask"], g["weight"], g["gy"], stride, pad, dil, dg)
+    for mine, ref in ((gx, "gx"), (go, "goffset"), (gm, "gmask"), (gw, "gweight"), (gb, "gbias")):
+        assert rel_err(mine, g[ref]) < 1e-5, ref
+
+
+def test_dcn_module_port():
+    g = golden("dcn_module")
+    om = torch.nn.functional.conv2d(torch.from_numpy(g["x"]), torch.from_numpy(g["p_conv_offset_mask.weight"]),
+                                    torch.from_numpy(g["p_conv_offset_mask.bias"]), padding=1)
+    y = tp.dcn_module_forward(torch.from_numpy(g["x"]), om, torch.from_numpy(g["p_weight"]), torch.from_numpy(g["p_bias"]),
+                              1, 1, 1)
+    assert rel_err(y.numpy(), g["y"]) < 1e-6
+    # C oracle on the same offsets / sigmoid(mask)
+    o = om.numpy()
+    yc = co.dcn_forward(g["x"], o[:, :18], 1.0 / (1.0 + np.exp(-o[:, 18:].astype(np.float64))).astype(np.float32),
+                        g["p_weight"], g["p_bias"])
+    assert rel_err(yc, g["y"]) < 1e-5
+
+
+@pytest.mark.parametrize("D", [16, 48])
+def test_proposal_shift_bit_exact(D):
+    g = golden("proposal_shift_D%d" % D)
+    pl, pr, db = co.proposal_shift(g["left"], g["right"], g["fb"], D)
+    assert np.array_equal(db.view(np.uint32), g["depth_bin"].view(np.uint32))
+    assert np.array_equal(pl.view(np.uint32), g["pro_left"].view(np.uint32))
+    assert np.array_equal(pr.view(np.uint32), g["pro_right"].view(np.uint32))
+    # edge cases present in the fixture: x clamp at 319, right clamp at 0, zero-width box -> depth_min 87
+    assert g["pro_left"][:, 0, 3].max() == 319.0 and g["pro_right"][:, 1, 1].min() == 0.0
+    assert np.all(g["depth_bin"][2] == 87.0)
+    tl, tr, tdb = tp.proposal_shift(torch.from_numpy(g["left"]), torch.from_numpy(g["right"]), torch.from_numpy(g["fb"]), D, 319.)
+    assert np.array_equal(tdb.numpy(), g["depth_bin"]) and np.array_equal(tl.numpy(), g["pro_left"])
+
+
+def test_inst_costvol_bit_exact_and_gate_and_softargmin():
+    g = golden("inst_costvol")
+    fL, fR = g["featL"].astype(np.float32), g["featR"].astype(np.float32)
+    D = P = 16
+    pl, pr, db = co.proposal_shift(g["left"], g["right"], g["fb"], D)
+    cost = co.inst_costvol(fL, fR, pl, pr, P)
+    assert list(cost.shape) == list(g["cost_shape"])
+    assert hashlib.sha256(cost.tobytes()).hexdigest() == str(g["cost_sha256"])      # bit-exact vs the reference loop
+    assert np.array_equal(cost.reshape(-1)[::97], g["cost_sample"])
+    gated, xc = co.xcross_gate(cost, 32)
+    assert rel_err(xc, g["xcross"]) < 1e-4
+    assert rel_err(gated.reshape(-1)[::97], g["gated_sample"]) < 1e-5
+    depth, _ = co.softargmin(g["logits"][:, 0], g["depth_bin"])
+    assert rel_err(depth, g["disp"]) < 1e-5
+    # torch port of the same sequence
+    c2, db2 = tp.inst_costvol(torch.from_numpy(fL), torch.from_numpy(fR), torch.from_numpy(g["left"]),
+                              torch.from_numpy(g["right"]), torch.from_numpy(g["fb"]), D, P, 319.)
+    assert np.array_equal(c2.numpy(), cost) and np.array_equal(db2.numpy(), db)
+    d2 = tp.softargmin(torch.from_numpy(g["logits"][:, 0]), torch.from_numpy(g["depth_bin"]))
+    assert rel_err(d2.numpy(), g["disp"]) < 1e-6
+
+
+def test_decode_vs_reference():
+    g = golden("decode")
+    grid, K = [int(v) for v in g["cfg"]]
+    bbox, bbr, keep = co.bbox_decode(g["hm"], g["wh"], g["reg"], K)
+    assert not keep.all()                                   # the fixture drops rows (decode.py:122-124)
+    bk, brk = bbox.reshape(-1, 5)[keep], bbr.reshape(-1, 5)[keep]
+    assert bk.shape == g["bbox_keep"].shape
+    assert np.abs(bk - g["bbox_keep"]).max() < 1e-4 and np.abs(brk - g["bbox_right_keep"]).max() < 1e-4
+    assert np.array_equal(bk[:, 0], g["bbox_keep"][:, 0])
+    heat = (1.0 / (1.0 + np.exp(-g["hm"].astype(np.float64)))).astype(np.float32)
+    det, detr, info = co.ddd_decode(heat, g["kept"], g["dim"], g["orien"], g["wh"], g["reg"], grid, K)
+    assert np.abs(det - g["det"]).max() < 1e-5 and np.abs(detr - g["det_right"]).max() < 1e-5
+    ref_info = g["info"].copy()
+    ref_info[..., 8] = np.floor(ref_info[..., 8])           # torch>=1.5 true division in the reference
+    assert np.abs(info - ref_info).max() < 1e-6
+    # class ids and integer pixel centres are exact
+    assert np.array_equal(det[..., 5], g["det"][..., 5])
+
+
+def test_volume_builders_against_torch_restatement():
+    """PARITY UNPINNED by the reference (no call site): C oracle vs the torch restatement only."""
+    rng = np.random.default_rng(0)
+    L = rng.standard_normal((2, 8, 5, 24)).astype(np.float32)
+    R = rng.standard_normal((2, 8, 5, 24)).astype(np.float32)
+    v = co.concat_volume(L, R, 6)
+    assert np.array_equal(v, tp.concat_volume(torch.from_numpy(L), torch.from_numpy(R), 6).numpy())
+    assert np.array_equal(v[:, :8, 0], L) and np.array_equal(v[:, 8:, 0], R)     # D=1 slice == torch.cat((L,R),1) (:348)
+    w = co.gwc_volume(L, R, 6, 4)
+    assert rel_err(w, tp.gwc_volume(torch.from_numpy(L), torch.from_numpy(R), 6, 4).numpy()) < 1e-6
