@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline microbenchmarks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=2)
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the resident timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -306,8 +308,12 @@ def main():
         w = a[2]
         return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
 
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     with OpTimer("dcn_forward_raw", dcn_work) as tm:
         ms_res = timed(step_resident, args.steps)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     dcn = tm.summary()
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)

@@ -69,6 +69,12 @@ __device__ __forceinline__ DcnTap dcn_tap(const DcnShape &s, const float *__rest
     return t;
 }
 
+struct DcnFwdArgs {
+    const float *x, *offset, *mask, *wt, *bias, *scale, *shift;
+    float *y;
+    DcnShape s;
+};
+
 inline int dcn_fill_shape(DcnShape &s, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
                           int pw, int dh, int dw, int dg, long long offset_bs, long long mask_bs, int flags)
 {

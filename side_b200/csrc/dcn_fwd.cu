@@ -12,6 +12,7 @@
 // [tap][Cin][Cout] so B tiles are read with coalesced 16-byte loads.  8x8 register micro-tiles, register-staged
 // double buffering (the gather loads for block k+1 are in flight while block k is multiplied).
 // Epilogue fuses bias, optional eval-mode BatchNorm affine and ReLU (DeformConv, feature_extraction_dla34.py:345-357).
+#include <algorithm>
 #include "dcn_common.cuh"
 
 namespace side {
@@ -32,12 +33,6 @@ __global__ void dcn_weight_relayout_kernel(const float *__restrict__ w, float *_
         wt[i] = __ldg(w + ((size_t)o * Cin + c) * KK + t);
     }
 }
-
-struct DcnFwdArgs {
-    const float *x, *offset, *mask, *wt, *bias, *scale, *shift;
-    float *y;
-    DcnShape s;
-};
 
 __global__ void __launch_bounds__(kDcnThreads, 3) dcn_fwd_simt_kernel(DcnFwdArgs a)
 {
@@ -180,8 +175,10 @@ __global__ void __launch_bounds__(kDcnThreads, 3) dcn_fwd_simt_kernel(DcnFwdArgs
     }
 }
 
-int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st);  // dcn_fwd_tc.cu
+// dcn_fwd_tc.cu (tcgen05 / TMEM path)
+int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st);
 size_t dcn_fwd_tc_ws_bytes(int Cin, int Cout, int KK, int flags);
+bool dcn_fwd_tc_supported(int Cin, int Cout, int dg);
 
 }  // namespace side
 
@@ -191,8 +188,10 @@ extern "C" size_t side_dcn_fwd_ws_bytes(int B, int Cin, int H, int W, int Cout, 
 {
     (void)B; (void)H; (void)W;
     if (Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0) return 0;
-    if ((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32) return dcn_fwd_tc_ws_bytes(Cin, Cout, kh * kw, flags);
-    return sizeof(float) * (size_t)Cin * Cout * kh * kw;
+    const size_t simt = sizeof(float) * (size_t)Cin * Cout * kh * kw;
+    if ((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32 && dcn_fwd_tc_supported(Cin, Cout, 1))
+        return std::max(simt, dcn_fwd_tc_ws_bytes(Cin, Cout, kh * kw, flags));
+    return simt;
 }
 
 extern "C" int side_dcn_fwd(const float *x, const float *offset, const float *mask, const float *w, const float *bias,
@@ -214,7 +213,9 @@ extern "C" int side_dcn_fwd(const float *x, const float *offset, const float *ma
     SIDE_REQUIRE_DEV(ws);
     a.x = x; a.offset = offset; a.mask = mask; a.bias = bias; a.scale = scale; a.shift = shift; a.y = y;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32) return dcn_fwd_tc(a, w, ws, ws_bytes, st);
+    // tensor-core precisions fall back to the (more accurate) fp32 SIMT kernel for shapes tcgen05 cannot tile
+    if ((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32 && dcn_fwd_tc_supported(Cin, Cout, dg))
+        return dcn_fwd_tc(a, w, ws, ws_bytes, st);
 
     SIDE_REQUIRE((Cin / dg) % kCK == 0 || dg == 1, "side_dcn_fwd: with deformable_groups>1, Cin/dg must be a multiple of %d",
                  kCK);

@@ -1,16 +1,311 @@
-// dcn_fwd_tc.cu -- tcgen05 / TMEM path of the DCNv2 forward (placeholder until the kernel lands).
+// dcn_fwd_tc.cu -- DCNv2 forward on the 5th-gen tensor cores: tcgen05.mma (kind::tf32) with the accumulator in TMEM.
+//
+// The contraction y[pixel, o] = sum_{tap, c} col[pixel, tap, c] * W[o, c, tap] is a dense GEMM
+// (M = B*Ho*Wo pixels, N = Cout, K = kh*kw*Cin) whose A operand does not exist in memory: it is the modulated
+// bilinear gather of the reference's im2col kernel (dcn_v2_im2col_cuda.cu:125-195).  Warp-specialised CTA, one
+// 128-pixel tile per CTA:
+//   warps 0-7  producers : thread = (pixel row, half of the 32-channel K block).  Computes the tap geometry once
+//                          per tap, gathers 16 channels (coalesced along W across the warp), multiplies by the mask
+//                          and writes the values STRAIGHT INTO THE UMMA OPERAND LAYOUT in shared memory
+//                          (K-major, 128-byte swizzle: one 128-byte row = 32 tf32 of one pixel, 16-byte chunk index
+//                          XOR (row & 7)), then fence.proxy.async + mbarrier arrive.  No `columns` tensor in HBM.
+//   warp 8     MMA issuer: one elected thread issues tcgen05.mma cta_group::1, M=128, N=Cout, K=8 per instruction,
+//                          D in TMEM (128 lanes x Cout fp32 columns); tcgen05.commit releases the smem stage.
+//   warp 9     weight loader: the weights were re-laid-out once into per-K-block tiles that ARE the shared-memory
+//                          image (swizzle included), so each stage is ONE TMA bulk copy (cp.async.bulk, UBLKCP)
+//                          completing on the stage's mbarrier.
+//   epilogue   (warps 0-7 again) tcgen05.ld 32x32b -> bias / folded BatchNorm / ReLU -> coalesced NCHW stores
+//              (a warp's 32 lanes are 32 consecutive pixels of one output channel).
+//
+// Precision.  tcgen05 has no fp32 MMA.  SIDE_DCN_PREC_3XTF32 splits both operands into hi = top 19 bits and
+// lo = x - hi (exact in fp32) and issues hi*hi + lo*hi + hi*lo into the same fp32 accumulator: the dropped lo*lo
+// term is 2^-20 relative, so the result meets the reference's fp32 tolerance (<= 1e-4 relative; measured ~1e-6).
+// SIDE_DCN_PREC_TF32 is the single-pass opt-in (~1e-3).
+#include <algorithm>
 #include "dcn_common.cuh"
 
 namespace side {
-struct DcnFwdArgs;
+
+constexpr int kTcBM = 128;            // UMMA M (pixels per tile)
+constexpr int kTcBK = 32;             // tf32 elements per stage row (= 128 bytes, one swizzle row)
+constexpr int kTcProducerThreads = 256;
+constexpr int kTcThreads = kTcProducerThreads + 64;
+constexpr int kTcMaxStages = 8;
+constexpr uint32_t kATileBytes = kTcBM * 128;   // 16 KB
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: 8-row groups are 1024 bytes apart (SBO), LBO is unused for swizzled K-major
+// (encoded as 1 like CUTLASS does), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+// byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int row, int chunk)
+{
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// w [Cout, Cin, KK] -> per-K-block tiles: wp[kb][part][Cout x 32] in the swizzled shared-memory image.
+// kb = tap * (Cin/32) + cb;  part 0 = hi (or the full value when !split), part 1 = lo.
+__global__ void dcn_tc_weight_prep_kernel(const float *__restrict__ w, float *__restrict__ wp, int Cout, int Cin, int KK,
+                                          int split)
+{
+    const long long total = (long long)KK * Cin * Cout;
+    const int ncb = Cin / kTcBK;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % kTcBK);
+        const int n = (int)((i / kTcBK) % Cout);
+        const int kb = (int)(i / ((long long)kTcBK * Cout));
+        const int tap = kb / ncb, cb = kb - tap * ncb;
+        const float v = __ldg(w + ((size_t)n * Cin + cb * kTcBK + kk) * KK + tap);
+        const size_t tile = (size_t)kb * (split ? 2 : 1) * Cout * kTcBK;
+        const uint32_t off = (sw128(n, kk >> 2) >> 2) + (kk & 3);
+        if (split) {
+            const float hi = tf32_hi(v);
+            wp[tile + off] = hi;
+            wp[tile + (size_t)Cout * kTcBK + off] = v - hi;
+        } else {
+            wp[tile + off] = v;
+        }
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp, int stages,
+                                                                  uint32_t idesc, uint32_t tmem_cols)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const DcnShape &s = a.s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = s.Cout;
+    const uint32_t b_part_bytes = (uint32_t)N * 128u;
+    const uint32_t a_bytes = SPLIT ? 2 * kATileBytes : kATileBytes;
+    const uint32_t b_bytes = SPLIT ? 2 * b_part_bytes : b_part_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    // SWIZZLE_128B tiles must start on a 1024-byte boundary of the SHARED address space
+    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+
+    const int ncb = s.Cin / kTcBK;
+    const int nkb = s.KK * ncb;
+
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], kTcProducerThreads + 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (tid < kTcProducerThreads) {
+        // ================= producers: modulated bilinear gather -> swizzled A tile =================
+        const int row = tid & 127, half = tid >> 7;
+        const long long Mtot = (long long)s.B * s.P;
+        const long long gp = (long long)blockIdx.x * kTcBM + row;
+        const bool pix_ok = gp < Mtot;
+        const int b = pix_ok ? (int)(gp / s.P) : 0;
+        const int p = pix_ok ? (int)(gp - (long long)b * s.P) : 0;
+        const int ho = p / s.Wo, wo = p - ho * s.Wo;
+        const int HWin = s.H * s.W;
+        const float *xb = a.x + (size_t)b * s.Cin * HWin;
+        DcnTap tap{};
+        int cur_tap = -1;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % stages, it = kb / stages;
+            const int tp = kb / ncb, c0 = (kb - tp * ncb) * kTcBK + half * 16;
+            if (tp != cur_tap) {
+                cur_tap = tp;
+                if (pix_ok) tap = dcn_tap(s, a.offset, a.mask, b, 0, tp, ho, wo);
+                else { tap.o1 = tap.o2 = tap.o3 = tap.o4 = 0; tap.w1 = tap.w2 = tap.w3 = tap.w4 = 0.f; tap.m = 0.f; }
+            }
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float *xc = xb + (size_t)(c0 + k) * HWin;
+                v[k] = (tap.w1 * __ldg(xc + tap.o1) + tap.w2 * __ldg(xc + tap.o2) + tap.w3 * __ldg(xc + tap.o3) +
+                        tap.w4 * __ldg(xc + tap.o4)) * tap.m;
+            }
+            if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
+            unsigned char *sa = tiles + (size_t)st * stage_bytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t off = sw128(row, half * 4 + j);
+                if (SPLIT) {
+                    float4 hi, lo;
+                    hi.x = tf32_hi(v[4 * j + 0]); lo.x = v[4 * j + 0] - hi.x;
+                    hi.y = tf32_hi(v[4 * j + 1]); lo.y = v[4 * j + 1] - hi.y;
+                    hi.z = tf32_hi(v[4 * j + 2]); lo.z = v[4 * j + 2] - hi.z;
+                    hi.w = tf32_hi(v[4 * j + 3]); lo.w = v[4 * j + 3] - hi.w;
+                    *reinterpret_cast<float4 *>(sa + off) = hi;
+                    *reinterpret_cast<float4 *>(sa + kATileBytes + off) = lo;
+                } else {
+                    *reinterpret_cast<float4 *>(sa + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[st]);
+        }
+
+        // ================= epilogue: TMEM -> registers -> NCHW =================
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int lg = warp & 3, chalf = warp >> 2;          // TMEM lane group of this warp, column half
+        const bool affine = s.flags & SIDE_DCN_FUSE_AFFINE, relu = s.flags & SIDE_DCN_FUSE_RELU;
+        float *yp = a.y + (size_t)b * s.Cout * s.P + p;
+        const int cbeg = chalf * (N / 2), cend = cbeg + N / 2;
+        for (int c = cbeg; c < cend; c += 8) {
+            float acc[8];
+            tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, acc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = c + j;
+                float o = acc[j] + (a.bias ? __ldg(a.bias + n) : 0.f);
+                if (affine) o = fmaf(o, __ldg(a.scale + n), __ldg(a.shift + n));
+                if (relu) o = fmaxf(o, 0.f);
+                if (pix_ok) yp[(size_t)n * s.P] = o;
+            }
+        }
+    } else if (warp == 8) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages, it = kb / stages;
+                mbar_wait(&full_bar[st], (uint32_t)(it & 1));
+                tc_fence_after();
+                const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {
+                    const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
+                    tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (SPLIT) {
+                        const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
+                        const uint64_t b_lo = tc_smem_desc(sb + b_part_bytes + k * 32);
+                        tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
+                        tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                    }
+                }
+                tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
+            }
+            tc_commit(&tmem_full_bar);         // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ================= weight loader (TMA bulk copies) =================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % stages, it = kb / stages;
+                if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
+                mbar_expect_tx(&full_bar[st], b_bytes);
+                bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)kb * (b_bytes / 4), b_bytes, &full_bar[st]);
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
+bool dcn_fwd_tc_supported(int Cin, int Cout, int dg)
+{
+    return dg == 1 && Cin % kTcBK == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
+}
+
 size_t dcn_fwd_tc_ws_bytes(int Cin, int Cout, int KK, int flags)
 {
-    (void)flags;
-    return sizeof(float) * 2 * (size_t)Cin * Cout * KK;
+    const bool split = (flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
+    return sizeof(float) * (split ? 2 : 1) * (size_t)Cin * Cout * KK;
 }
-int dcn_fwd_tc(const DcnFwdArgs &, const float *, void *, size_t, cudaStream_t)
+
+int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    set_error("side_dcn_fwd: tcgen05 path not built in this version");
-    return SIDE_ERR_UNSUPPORTED;
+    const DcnShape &s = a.s;
+    const bool split = (s.flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
+    if (!dcn_fwd_tc_supported(s.Cin, s.Cout, s.dg)) {
+        set_error("side_dcn_fwd: tcgen05 path needs dg == 1, Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
+        return SIDE_ERR_UNSUPPORTED;
+    }
+    if (ws_bytes < dcn_fwd_tc_ws_bytes(s.Cin, s.Cout, s.KK, s.flags)) {
+        set_error("side_dcn_fwd: workspace too small for the tcgen05 weight tiles");
+        return SIDE_ERR_WORKSPACE;
+    }
+    float *wp = reinterpret_cast<float *>(ws);
+    const long long nW = (long long)s.Cout * s.Cin * s.KK;
+    dcn_tc_weight_prep_kernel<<<(unsigned)std::min<long long>(1184, (nW + 255) / 256), 256, 0, st>>>(w, wp, s.Cout, s.Cin, s.KK,
+                                                                                                   split ? 1 : 0);
+    SIDE_LAUNCH_CHECK("dcn_tc_weight_prep_kernel");
+
+    const uint32_t stage_bytes = (split ? 2u : 1u) * (kATileBytes + (uint32_t)s.Cout * 128u);
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    stages = std::max(2, std::min(stages, kTcMaxStages));
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < s.Cout) tmem_cols <<= 1;
+    // instruction descriptor: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(s.Cout >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+    const unsigned grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
+    int rc;
+    if (split) {
+        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;
+        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, stages, idesc, tmem_cols);
+    } else {
+        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false>, smem))) return rc;
+        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, stages, idesc, tmem_cols);
+    }
+    SIDE_LAUNCH_CHECK("dcn_fwd_tc_kernel");
+    return SIDE_OK;
 }
+
 }  // namespace side
