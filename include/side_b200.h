@@ -116,10 +116,15 @@ int side_proposal_shift(const float *left, const float *right, const float *fb, 
  *   valid        [N] uint8 or NULL: rows with valid==0 produce an all-zero volume slice, depth_bin = 0
  *   cost         [N, 3C, D, P, P];  depth_bin [N, D];  xcross [N, D] (NULL allowed; written only with GATE)
  * RoIAlign semantics: torchvision legacy aligned=False, spatial_scale 1, sampling_ratio 2 (:271).
+ *   ws           optional workspace of side_inst_costvol_ws_bytes(B,C,H,W) bytes: enables the channels-last gather
+ *                (the features are transposed once to NHWC so each bilinear tap is one 16-byte load for 4 channels);
+ *                NULL selects the slower NCHW gather.  Results are bit-identical either way.
  * --------------------------------------------------------------------------------------------- */
+size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W);
 int side_inst_costvol_fwd(const float *featL, const float *featR, const float *left, const float *right,
                           const float *fb, const uint8_t *valid, float *cost, float *depth_bin, float *xcross,
-                          int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *stream);
+                          int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *ws,
+                          size_t ws_bytes, void *stream);
 
 /* Backward of the above w.r.t. featL / featR (autograd of RoIAlign + CopySlices + gate in the reference).
  * gfeatL / gfeatR [B,C,H,W] are ACCUMULATED into (caller zero-fills); fp32 atomics => summation order is not
@@ -183,7 +188,19 @@ int side_gwc_volume_fwd(const float *L, const float *R, float *vol, int B, int C
 int side_gwc_volume_bwd(const float *L, const float *R, const float *gvol, float *gL, float *gR, int B, int C,
                         int H, int W, int D, int G, void *stream);
 
-/* Number of kernels launched by this library in the calling thread since the last reset
+/* ---------------------------------------------------------------------------------------------
+ * Depth-wise transposed convolution of the DLA up-sampling neck.
+ * Replaces IDAUp.up_k = nn.ConvTranspose2d(o, o, 2f, stride=f, padding=f//2, groups=o, bias=False)
+ * (feature_extraction_dla34.py:370-373), which cuDNN serves with a generic grouped direct kernel.
+ *   x [B,C,H,W], w [C,1,k,k] -> y [B,C,Ho,Wo], Ho = (H-1)*stride - 2*pad + k
+ * bwd OVERWRITES gx [B,C,H,W] and gw [C,1,k,k] (either may be NULL).
+ * --------------------------------------------------------------------------------------------- */
+int side_dw_deconv_fwd(const float *x, const float *w, float *y, int B, int C, int H, int W, int k, int stride, int pad,
+                       void *stream);
+int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *gx, float *gw, int B, int C, int H, int W,
+                       int k, int stride, int pad, void *stream);
+
+/* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);
 

@@ -199,6 +199,11 @@ def gwc_volume(L, R, D, G):
     return vol
 
 
+def dw_deconv(x, w, stride, pad):
+    """IDAUp.up_k, feature_extraction_dla34.py:370-373: the ATen/cuDNN call the reference makes."""
+    return F.conv_transpose2d(x, w, None, stride=stride, padding=pad, groups=x.shape[1])
+
+
 # ---------------------------------------------------------------------------------------------
 @contextlib.contextmanager
 def reference_ops():
@@ -212,7 +217,7 @@ def reference_ops():
     repl = dict(dcn_v2_conv=dcn_v2_conv, dcn_fused=fused, dcn_fused_infer=dcn_fused_infer, proposal_shift=proposal_shift,
                 inst_costvol=inst_costvol, xcross_gate=xcross_gate, softargmin=softargmin,
                 bbox_decode_raw=bbox_decode_raw, ddd_decode_raw=ddd_decode_raw, concat_volume=concat_volume,
-                gwc_volume=gwc_volume)
+                gwc_volume=gwc_volume, dw_deconv=dw_deconv)
     saved = {k: getattr(ops, k) for k in repl}
     saved_dcn = dcn_mod.dcn_v2_conv
     try:

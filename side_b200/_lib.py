@@ -24,7 +24,8 @@ SIGNATURES = {
     "side_dcn_bwd_ws_bytes": (_sz, [_i] * 8),
     "side_dcn_bwd": (_i, [_vp] * 10 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
     "side_proposal_shift": (_i, [_vp] * 3 + [_i] * 3 + [_f] + [_vp] * 4),
-    "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
+    "side_inst_costvol_ws_bytes": (_sz, [_i] * 4),
+    "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
     "side_inst_costvol_bwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
     "side_xcross_gate_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "side_xcross_gate_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "side_concat_volume_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "side_gwc_volume_fwd": (_i, [_vp] * 3 + [_i] * 6 + [_vp]),
     "side_gwc_volume_bwd": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "side_dw_deconv_fwd": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
+    "side_dw_deconv_bwd": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
 }
 
 # flag values (include/side_b200.h)

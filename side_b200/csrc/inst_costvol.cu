@@ -258,6 +258,160 @@ __global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_kernel(VolParams
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// channels-last gather path (default when a workspace is supplied).
+// The 16 bilinear taps per output make the NCHW gather L1-issue bound (one 4-byte load per tap).  With the feature
+// maps transposed once to NHWC (B*H*W*C, a 2 x 7.8 MB pass against a 604 MB volume at config #2) every tap is ONE
+// 16-byte load that serves 4 channels, a warp reads 4 x 128 contiguous bytes per instruction, and taps shared by the
+// 2x2 sub-samples of a bin (same integer cell) are loaded once.  Arithmetic is unchanged (same rounded ops, same
+// order), so the result stays bit-identical to the oracle.
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float *ip = in + (size_t)b * C * HW;
+    float *op = out + (size_t)b * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(ip + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) op[(size_t)p * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+struct Tap4 { float4 v1, v2, v3, v4; };
+
+__device__ __forceinline__ Tap4 load_tap4(const float *__restrict__ base, int W, int C, const AxisSample &y, const AxisSample &x)
+{
+    Tap4 t;
+    t.v1 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.lo * W + x.lo) * C));
+    t.v2 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.lo * W + x.hi) * C));
+    t.v3 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.hi * W + x.lo) * C));
+    t.v4 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.hi * W + x.hi) * C));
+    return t;
+}
+
+__device__ __forceinline__ float tap_val(float w1, float w2, float w3, float w4, float a, float b, float c, float d)
+{
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, a), __fmul_rn(w2, b)), __fmul_rn(w3, c)), __fmul_rn(w4, d));
+}
+
+// one bin, 4 consecutive channels; base already points at channel 4*c4 of pixel (0,0) of image b (NHWC)
+__device__ __forceinline__ float4 roi_bin4(const float *__restrict__ base, int W, int C, const AxisSample *__restrict__ ys,
+                                           const AxisSample *__restrict__ xs)
+{
+    const AxisSample y0 = ys[0], y1 = ys[1], x0 = xs[0], x1 = xs[1];
+    const bool same_x = x0.lo == x1.lo && x0.hi == x1.hi, same_y = y0.lo == y1.lo && y0.hi == y1.hi;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    Tap4 t00, t01, t10, t11;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    t00.v1 = t00.v2 = t00.v3 = t00.v4 = z;
+    t01 = t00; t10 = t00; t11 = t00;
+    const bool vy0 = y0.lo >= 0, vy1 = y1.lo >= 0, vx0 = x0.lo >= 0, vx1 = x1.lo >= 0;
+    if (vy0 && vx0) t00 = load_tap4(base, W, C, y0, x0);
+    if (vy0 && vx1) t01 = (same_x && vx0) ? t00 : load_tap4(base, W, C, y0, x1);
+    if (vy1 && vx0) t10 = (same_y && vy0) ? t00 : load_tap4(base, W, C, y1, x0);
+    if (vy1 && vx1) t11 = (same_y && vy0) ? t01 : ((same_x && vx0) ? t10 : load_tap4(base, W, C, y1, x1));
+#define SIDE_ACC(T, Y, X, OK)                                                                                   \
+    {                                                                                                           \
+        float4 val = z;                                                                                         \
+        if (OK) {                                                                                               \
+            const float w1 = __fmul_rn(Y.h, X.h), w2 = __fmul_rn(Y.h, X.l), w3 = __fmul_rn(Y.l, X.h),           \
+                        w4 = __fmul_rn(Y.l, X.l);                                                               \
+            val.x = tap_val(w1, w2, w3, w4, T.v1.x, T.v2.x, T.v3.x, T.v4.x);                                    \
+            val.y = tap_val(w1, w2, w3, w4, T.v1.y, T.v2.y, T.v3.y, T.v4.y);                                    \
+            val.z = tap_val(w1, w2, w3, w4, T.v1.z, T.v2.z, T.v3.z, T.v4.z);                                    \
+            val.w = tap_val(w1, w2, w3, w4, T.v1.w, T.v2.w, T.v3.w, T.v4.w);                                    \
+        }                                                                                                       \
+        acc.x = __fadd_rn(acc.x, val.x); acc.y = __fadd_rn(acc.y, val.y);                                       \
+        acc.z = __fadd_rn(acc.z, val.z); acc.w = __fadd_rn(acc.w, val.w);                                       \
+    }
+    SIDE_ACC(t00, y0, x0, vy0 && vx0)
+    SIDE_ACC(t01, y0, x1, vy0 && vx1)
+    SIDE_ACC(t10, y1, x0, vy1 && vx0)
+    SIDE_ACC(t11, y1, x1, vy1 && vx1)
+#undef SIDE_ACC
+    return make_float4(__fdiv_rn(acc.x, 4.0f), __fdiv_rn(acc.y, 4.0f), __fdiv_rn(acc.z, 4.0f), __fdiv_rn(acc.w, 4.0f));
+}
+
+template <bool GATE>
+__global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_nhwc_kernel(VolParams p, const float *__restrict__ nhwcL,
+                                                                            const float *__restrict__ nhwcR)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p.P, PP = P * P, C = p.C, PPs = PP + 1;
+    AxisSample *ytab = reinterpret_cast<AxisSample *>(smem_raw);
+    AxisSample *xl = ytab + 2 * P, *xr = xl + 2 * P;
+    float *red = reinterpret_cast<float *>(xr + 2 * P);
+    float *Ls = red + 4 * 32, *Rs = Ls + (size_t)C * PPs;
+
+    const int n = blockIdx.x / p.D, d = blockIdx.x % p.D;
+    const size_t cs = (size_t)p.D * PP;
+    float *out = p.cost + (size_t)n * 3 * C * cs + (size_t)d * PP;
+
+    if (p.valid && !p.valid[n]) {
+        for (int e = threadIdx.x; e < 3 * C * PP; e += blockDim.x) st_cs(out + (size_t)(e / PP) * cs + e % PP, 0.f);
+        if (threadIdx.x == 0) {
+            p.depth_bin[(size_t)n * p.D + d] = 0.f;
+            if (GATE && p.xcross) p.xcross[(size_t)n * p.D + d] = 0.f;
+        }
+        return;
+    }
+    int b;
+    float dbin;
+    build_tables(p, n, d, ytab, xl, xr, b, dbin);
+    if (threadIdx.x == 0) p.depth_bin[(size_t)n * p.D + d] = dbin;
+    __syncthreads();
+
+    const float *fL = nhwcL + (size_t)b * p.H * p.W * C;
+    const float *fR = nhwcR + (size_t)b * p.H * p.W * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int c4l = lane & 7, ql = lane >> 3;
+    const int nc4 = C >> 2, ncblk = (nc4 + 7) >> 3, nqblk = PP >> 2;
+
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int t = warp; t < ncblk * nqblk; t += nwarps) {
+        const int cblk = t % ncblk, qblk = t / ncblk;
+        const int c4 = cblk * 8 + c4l, q = qblk * 4 + ql;
+        if (c4 >= nc4) continue;
+        const int ph = q / P, pw = q - ph * P;
+        const float4 l = roi_bin4(fL + 4 * c4, p.W, C, ytab + 2 * ph, xl + 2 * pw);
+        const float4 r = roi_bin4(fR + 4 * c4, p.W, C, ytab + 2 * ph, xr + 2 * pw);
+        if (GATE) {
+            s[0] = fmaf(l.x, l.x, fmaf(l.y, l.y, fmaf(l.z, l.z, fmaf(l.w, l.w, s[0]))));
+            s[1] = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, s[1]))));
+            s[2] = fmaf(l.x, r.x, fmaf(l.y, r.y, fmaf(l.z, r.z, fmaf(l.w, r.w, s[2]))));
+        }
+        float *lp = Ls + (size_t)(4 * c4) * PPs + q, *rp = Rs + (size_t)(4 * c4) * PPs + q;
+        lp[0] = l.x; lp[PPs] = l.y; lp[2 * PPs] = l.z; lp[3 * PPs] = l.w;
+        rp[0] = r.x; rp[PPs] = r.y; rp[2 * PPs] = r.z; rp[3 * PPs] = r.w;
+    }
+    float g = 1.0f;
+    if (GATE) {
+        block_sum<3>(s, red);
+        const float den = fmaxf(__fmul_rn(sqrtf(s[0]), sqrtf(s[1])), 0.01f);
+        g = __fdiv_rn(s[2], den);
+        if (threadIdx.x == 0 && p.xcross) p.xcross[(size_t)n * p.D + d] = g;
+    }
+    __syncthreads();
+    const int CPP = C * PP;
+    for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) {
+        const int ch = e / PP, q = e - ch * PP;
+        float v;
+        if (ch < C) v = Ls[(size_t)ch * PPs + q];
+        else if (ch < 2 * C) v = Rs[(size_t)(ch - C) * PPs + q];
+        else v = __fsub_rn(Ls[(size_t)(ch - 2 * C) * PPs + q], Rs[(size_t)(ch - 2 * C) * PPs + q]);
+        if (GATE) v = __fmul_rn(v, g);
+        st_cs(out + (size_t)ch * cs + q, v);
+    }
+}
+
 // scatter g * w_i / 4 to the 4 corners of the 2x2 samples of one bin (torchvision roi_align backward)
 __device__ __forceinline__ void roi_bin_scatter(float *__restrict__ gim, int W, const AxisSample *__restrict__ ys,
                                                 const AxisSample *__restrict__ xs, float g)
@@ -448,6 +602,12 @@ static int check_vol_args(const VolParams &p)
 
 using namespace side;
 
+extern "C" size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(float) * 2 * (size_t)B * C * H * W;
+}
+
 extern "C" int side_proposal_shift(const float *left, const float *right, const float *fb, int N, int B, int D,
                                    float x_clamp, float *pro_left, float *pro_right, float *depth_bin, void *stream)
 {
@@ -464,7 +624,7 @@ extern "C" int side_proposal_shift(const float *left, const float *right, const 
 extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, const float *left, const float *right,
                                      const float *fb, const uint8_t *valid, float *cost, float *depth_bin,
                                      float *xcross, int N, int B, int C, int H, int W, int D, int P, float x_clamp,
-                                     int flags, void *stream)
+                                     int flags, void *ws, size_t ws_bytes, void *stream)
 {
     VolParams p{featL, featR, left, right, fb, valid, cost, depth_bin, xcross, nullptr, nullptr, nullptr,
                 N, B, C, H, W, D, P, x_clamp};
@@ -474,10 +634,31 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
     SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right);
     SIDE_REQUIRE_DEV(fb); SIDE_REQUIRE_DEV(cost); SIDE_REQUIRE_DEV(depth_bin);
     const bool gate = flags & SIDE_VOL_GATE;
-    const bool stage = gate && vol_smem_bytes(C, P, true) <= 200 * 1024;
-    const size_t smem = vol_smem_bytes(C, P, stage);
     const dim3 grid((unsigned)((long long)N * D));
     cudaStream_t st = (cudaStream_t)stream;
+    // channels-last fast path: needs the transposed copies (workspace), C % 4 == 0, P*P % 4 == 0 and the padded
+    // L/R tiles in shared memory
+    const size_t nhwc_smem = sizeof(AxisSample) * 6 * P + sizeof(float) * 4 * 32 + sizeof(float) * 2 * (size_t)C * (P * P + 1);
+    if (ws != nullptr && ws_bytes >= side_inst_costvol_ws_bytes(B, C, H, W) && (C & 3) == 0 && ((P * P) & 3) == 0 &&
+        nhwc_smem <= 200 * 1024 && is_device_ptr(ws)) {
+        float *nl = reinterpret_cast<float *>(ws), *nr = nl + (size_t)B * C * H * W;
+        dim3 tg(ceil_div(H * W, 32), ceil_div(C, 32), B), tb(32, 8);
+        nchw_to_nhwc_kernel<<<tg, tb, 0, st>>>(featL, nl, C, H * W);
+        SIDE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+        nchw_to_nhwc_kernel<<<tg, tb, 0, st>>>(featR, nr, C, H * W);
+        SIDE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+        if (gate) {
+            if ((rc = set_smem_attr((const void *)inst_costvol_fwd_nhwc_kernel<true>, nhwc_smem))) return rc;
+            inst_costvol_fwd_nhwc_kernel<true><<<grid, kVolThreads, nhwc_smem, st>>>(p, nl, nr);
+        } else {
+            if ((rc = set_smem_attr((const void *)inst_costvol_fwd_nhwc_kernel<false>, nhwc_smem))) return rc;
+            inst_costvol_fwd_nhwc_kernel<false><<<grid, kVolThreads, nhwc_smem, st>>>(p, nl, nr);
+        }
+        SIDE_LAUNCH_CHECK("inst_costvol_fwd_nhwc_kernel");
+        return SIDE_OK;
+    }
+    const bool stage = gate && vol_smem_bytes(C, P, true) <= 200 * 1024;
+    const size_t smem = vol_smem_bytes(C, P, stage);
     if (gate && stage) {
         if ((rc = set_smem_attr((const void *)inst_costvol_fwd_kernel<true, true>, smem))) return rc;
         inst_costvol_fwd_kernel<true, true><<<grid, kVolThreads, smem, st>>>(p);

@@ -1,0 +1,137 @@
+// upsample.cu -- depth-wise ConvTranspose2d of the DLA up-sampling neck.
+//
+// Reference: IDAUp.up_k = nn.ConvTranspose2d(o, o, 2f, stride=f, padding=f//2, groups=o, bias=False) initialised to
+// bilinear interpolation (feature_extraction_dla34.py:333-342, 370-373), executed between every proj/node DCN pair.
+// cuDNN runs it through a generic grouped direct-convolution kernel that measured ~9 ms per call on B200 at
+// micro-batch 4 (41 % of the whole inference step, profiles/r1_launches_step_fp32.md) although the layer moves only
+// tens of MB.  Here: one thread per output pixel, at most ceil(k/s)^2 multiply-adds, fully coalesced along W;
+// HBM-bound (reads x once, writes y once).  Backward: gather form for grad_input, block reduction for grad_weight.
+#include "common.cuh"
+
+namespace side {
+
+__global__ void __launch_bounds__(256) dw_deconv_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                           float *__restrict__ y, int C, int H, int W, int Ho, int Wo, int k,
+                                                           int s, int p)
+{
+    const int bc = blockIdx.z, c = bc % C;
+    const int oy = blockIdx.y;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ox >= Wo) return;
+    const float *xp = x + (size_t)bc * H * W;
+    const float *wp = w + (size_t)c * k * k;
+    float acc = 0.f;
+    // taps with (oy + p - ky) % s == 0, visited in increasing ky (= decreasing iy)
+    for (int ky = (oy + p) % s; ky < k; ky += s) {
+        const int iy = (oy + p - ky) / s;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = (ox + p) % s; kx < k; kx += s) {
+            const int ix = (ox + p - kx) / s;
+            if (ix < 0 || ix >= W) continue;
+            acc = fmaf(__ldg(xp + iy * W + ix), __ldg(wp + ky * k + kx), acc);
+        }
+    }
+    y[((size_t)bc * Ho + oy) * Wo + ox] = acc;
+}
+
+// gx[b,c,iy,ix] = sum_{ky,kx} gy[b,c,iy*s-p+ky, ix*s-p+kx] * w[c,ky,kx]
+__global__ void __launch_bounds__(256) dw_deconv_bwd_input_kernel(const float *__restrict__ gy, const float *__restrict__ w,
+                                                                 float *__restrict__ gx, int C, int H, int W, int Ho, int Wo,
+                                                                 int k, int s, int p)
+{
+    const int bc = blockIdx.z, c = bc % C;
+    const int iy = blockIdx.y;
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= W) return;
+    const float *gp = gy + (size_t)bc * Ho * Wo;
+    const float *wp = w + (size_t)c * k * k;
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+        const int oy = iy * s - p + ky;
+        if (oy < 0 || oy >= Ho) continue;
+        for (int kx = 0; kx < k; ++kx) {
+            const int ox = ix * s - p + kx;
+            if (ox < 0 || ox >= Wo) continue;
+            acc = fmaf(__ldg(gp + oy * Wo + ox), __ldg(wp + ky * k + kx), acc);
+        }
+    }
+    gx[((size_t)bc * H + iy) * W + ix] = acc;
+}
+
+// gw[c,ky,kx] = sum_{b,iy,ix} x[b,c,iy,ix] * gy[b,c,iy*s-p+ky, ix*s-p+kx];  grid (k*k, C)
+__global__ void __launch_bounds__(256) dw_deconv_bwd_weight_kernel(const float *__restrict__ x, const float *__restrict__ gy,
+                                                                  float *__restrict__ gw, int B, int C, int H, int W, int Ho,
+                                                                  int Wo, int k, int s, int p)
+{
+    __shared__ float red[32];
+    const int tap = blockIdx.x, c = blockIdx.y;
+    const int ky = tap / k, kx = tap - ky * k;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float *xp = x + ((size_t)b * C + c) * H * W;
+        const float *gp = gy + ((size_t)b * C + c) * Ho * Wo;
+        for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+            const int iy = i / W, ix = i - iy * W;
+            const int oy = iy * s - p + ky, ox = ix * s - p + kx;
+            if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) acc = fmaf(__ldg(xp + i), __ldg(gp + oy * Wo + ox), acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) gw[(size_t)c * k * k + tap] = v;
+    }
+}
+
+static int dw_check(int B, int C, int H, int W, int k, int s, int p, int &Ho, int &Wo)
+{
+    SIDE_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && s > 0 && p >= 0, "dw_deconv: bad shape");
+    Ho = (H - 1) * s - 2 * p + k;
+    Wo = (W - 1) * s - 2 * p + k;
+    SIDE_REQUIRE(Ho > 0 && Wo > 0, "dw_deconv: empty output");
+    SIDE_REQUIRE((long long)B * C <= 65535 && Ho <= 65535 && H <= 65535, "dw_deconv: grid too large");
+    return SIDE_OK;
+}
+
+}  // namespace side
+
+using namespace side;
+
+extern "C" int side_dw_deconv_fwd(const float *x, const float *w, float *y, int B, int C, int H, int W, int k, int stride,
+                                  int pad, void *stream)
+{
+    int Ho, Wo;
+    int rc = dw_check(B, C, H, W, k, stride, pad, Ho, Wo);
+    if (rc) return rc;
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(y);
+    dim3 grid(ceil_div(Wo, 256), Ho, B * C);
+    dw_deconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, C, H, W, Ho, Wo, k, stride, pad);
+    SIDE_LAUNCH_CHECK("dw_deconv_fwd_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *gx, float *gw, int B, int C, int H,
+                                  int W, int k, int stride, int pad, void *stream)
+{
+    int Ho, Wo;
+    int rc = dw_check(B, C, H, W, k, stride, pad, Ho, Wo);
+    if (rc) return rc;
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(gy);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gx) {
+        SIDE_REQUIRE_DEV(gx);
+        dim3 grid(ceil_div(W, 256), H, B * C);
+        dw_deconv_bwd_input_kernel<<<grid, 256, 0, st>>>(gy, w, gx, C, H, W, Ho, Wo, k, stride, pad);
+        SIDE_LAUNCH_CHECK("dw_deconv_bwd_input_kernel");
+    }
+    if (gw) {
+        SIDE_REQUIRE_DEV(gw);
+        dim3 grid(k * k, C);
+        dw_deconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(x, gy, gw, B, C, H, W, Ho, Wo, k, stride, pad);
+        SIDE_LAUNCH_CHECK("dw_deconv_bwd_weight_kernel");
+    }
+    return SIDE_OK;
+}

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import ops
 from ..dcn_v2 import DCN
 
 BN_MOMENTUM = 0.1
@@ -149,6 +150,14 @@ def fill_up_weights(up):
     w[1:, 0] = w[0, 0]
 
 
+class DepthwiseUp(nn.ConvTranspose2d):
+    """IDAUp.up_k: depth-wise bilinear-initialised ConvTranspose2d (reference :370-373), same parameters / state-dict
+    key (``up_k.weight`` [o,1,2f,2f]); forward runs on side_dw_deconv_fwd instead of cuDNN's grouped direct kernel."""
+
+    def forward(self, x):
+        return ops.dw_deconv(x, self.weight, self.stride[0], self.padding[0])
+
+
 class DeformConv(nn.Module):
     """DCN -> BN -> ReLU (reference :345-357).  In eval / no-grad mode BN and ReLU are folded into the
     DCN kernel's epilogue (SIDE_DCN_FUSE_AFFINE | SIDE_DCN_FUSE_RELU)."""
@@ -171,7 +180,7 @@ class IDAUp(nn.Module):
         for i in range(1, len(channels)):
             c, f = channels[i], int(up_f[i])
             setattr(self, "proj_%d" % i, DeformConv(c, o))
-            up = nn.ConvTranspose2d(o, o, f * 2, stride=f, padding=f // 2, output_padding=0, groups=o, bias=False)
+            up = DepthwiseUp(o, o, f * 2, stride=f, padding=f // 2, output_padding=0, groups=o, bias=False)
             fill_up_weights(up)
             setattr(self, "up_%d" % i, up)
             setattr(self, "node_%d" % i, DeformConv(o, o))

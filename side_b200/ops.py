@@ -205,6 +205,9 @@ def proposal_shift(left, right, fb, D, x_clamp):
     return pl, pr, db
 
 
+USE_NHWC_GATHER = True   # False selects the NCHW gather kernel (same results, slower; kept for odd shapes / tests)
+
+
 class _InstCostVol(torch.autograd.Function):
     @staticmethod
     def forward(ctx, featL, featR, left, right, fb, valid, D, P, x_clamp, gate):
@@ -219,9 +222,12 @@ class _InstCostVol(torch.autograd.Function):
         depth_bin = torch.empty((N, D), device=featL.device, dtype=_F32)
         xc = torch.empty((N, D), device=featL.device, dtype=_F32) if gate else None
         flags = _lib.VOL_GATE if gate else 0
+        nws = lib.side_inst_costvol_ws_bytes(B, C, H, W) if USE_NHWC_GATHER else 0
+        ws = torch.empty((max(nws, 16),), device=featL.device, dtype=torch.uint8)
         _lib.check(lib.side_inst_costvol_fwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
                                              fb.data_ptr(), _p(valid), cost.data_ptr(), depth_bin.data_ptr(), _p(xc),
-                                             N, B, C, H, W, D, P, float(x_clamp), flags, _stream()),
+                                             N, B, C, H, W, D, P, float(x_clamp), flags, ws.data_ptr() if nws else None,
+                                             nws, _stream()),
                    "side_inst_costvol_fwd")
         ctx.save_for_backward(featL, featR, left, right, fb, valid)
         ctx.cfg = (D, P, float(x_clamp), flags)
@@ -425,3 +431,42 @@ class _GwcVolume(torch.autograd.Function):
 
 def gwc_volume(L, R, D, G):
     return _GwcVolume.apply(L, R, int(D), int(G))
+
+
+# ----------------------------------------------------------------------------------------------
+# depth-wise transposed convolution (IDAUp.up_k)
+# ----------------------------------------------------------------------------------------------
+class _DwDeconv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        lib = _lib.load()
+        x, w = _chk(x, "input"), _chk(w, "weight")
+        B, C, H, W = x.shape
+        k = w.shape[-1]
+        if tuple(w.shape) != (C, 1, k, k):
+            raise RuntimeError("depth-wise deconv weight must be [C,1,k,k]")
+        Ho, Wo = (H - 1) * stride - 2 * pad + k, (W - 1) * stride - 2 * pad + k
+        y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=_F32)
+        _lib.check(lib.side_dw_deconv_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), B, C, H, W, k, stride, pad, _stream()),
+                   "side_dw_deconv_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.cfg
+        gy = _chk(gy, "grad_output")
+        B, C, H, W = x.shape
+        gx, gw = torch.empty_like(x), torch.empty_like(w)
+        _lib.check(lib.side_dw_deconv_bwd(x.data_ptr(), w.data_ptr(), gy.data_ptr(), gx.data_ptr(), gw.data_ptr(), B, C, H, W,
+                                          w.shape[-1], stride, pad, _stream()), "side_dw_deconv_bwd")
+        return gx, gw, None, None
+
+
+def dw_deconv(x, w, stride, pad):
+    """Depth-wise ConvTranspose2d: x [B,C,H,W], w [C,1,k,k]."""
+    return _DwDeconv.apply(x, w, int(stride), int(pad))

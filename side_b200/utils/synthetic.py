@@ -59,10 +59,12 @@ def _calibrate_batchnorm(model, g):
     """
     import torch.nn.functional as F
     from ..dcn_v2 import DCN
+    from ..networks.feature_extraction_dla34 import DepthwiseUp
 
     bns = [m for m in model.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d))]
     saved = [(m.momentum, m.training) for m in bns]
     orig_forward = DCN.forward
+    orig_up = DepthwiseUp.forward
 
     def surrogate(self, input, bn=None, relu=False):
         return 0.5 * F.conv2d(input, self.weight, None, self.stride, self.padding, self.dilation) + \
@@ -70,6 +72,7 @@ def _calibrate_batchnorm(model, g):
 
     try:
         DCN.forward = surrogate
+        DepthwiseUp.forward = nn.ConvTranspose2d.forward      # plain ATen op for this CPU-side pass
         for m in bns:
             m.momentum = 1.0
             m.train()
@@ -82,6 +85,7 @@ def _calibrate_batchnorm(model, g):
             est.aggregate(cost)
     finally:
         DCN.forward = orig_forward
+        DepthwiseUp.forward = orig_up
         for m, (mom, tr) in zip(bns, saved):
             m.momentum = mom
             m.train(tr)

@@ -39,7 +39,7 @@ def test_no_compute_without_device_memory(lib):
     p = a.ctypes.data
     rc = lib.side_softargmin_fwd(p, p, p, None, 1, 1, 1, None)
     assert rc == -2 and b"device pointer" in lib.side_last_error()       # SIDE_ERR_NOT_DEVICE
-    assert lib.side_inst_costvol_fwd(p, p, p, p, p, None, p, p, None, 3, 1, 4, 8, 8, 1, 16, 7.0, 0, None) == -1  # D < 2
+    assert lib.side_inst_costvol_fwd(p, p, p, p, p, None, p, p, None, 3, 1, 4, 8, 8, 1, 16, 7.0, 0, None, 0, None) == -1  # D < 2
     assert lib.side_dcn_fwd(p, p, p, p, None, None, None, p, 1, 4, 4, 4, 4, 3, 3, 1, 1, 1, 1, 1, 1, 3, 0, 0, 0, None, 0, None) == -1
     assert lib.side_decode_ws_bytes(2, 3, 100) == 256 + 8 * 600
     assert lib.side_dcn_fwd_ws_bytes(1, 64, 96, 320, 64, 3, 3, 0) == 4 * 64 * 64 * 9

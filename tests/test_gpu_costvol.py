@@ -158,3 +158,22 @@ def test_config2_full_size_properties(lib):
     l, r = cost[:, :64].double(), cost[:, 64:128].double()
     xc = (l * r).sum((1, 3, 4)) / torch.clamp(torch.sqrt((l * l).sum((1, 3, 4))) * torch.sqrt((r * r).sum((1, 3, 4))), min=0.01)
     assert (ratio.double() - xc).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(2, 8, 24, 80, 9, 16, 16), (1, 64, 24, 80, 3, 48, 16), (3, 32, 17, 61, 11, 5, 16), (1, 4, 10, 33, 4, 2, 6)])
+def test_nchw_and_nhwc_gather_paths_identical(lib, cfg):
+    """The channels-last gather (default) and the NCHW gather produce the same bits, with and without the gate."""
+    from side_b200 import ops
+    B, C, H, W, N, D, P = cfg
+    rng = np.random.default_rng(C + N)
+    fL, fR, left, right, fb = _random_case(rng, B, C, H, W, N)
+    args = (dev(fL), dev(fR), dev(left), dev(right), dev(fb), D, P, W - 1.0)
+    res = {}
+    try:
+        for mode in (True, False):
+            ops.USE_NHWC_GATHER = mode
+            res[mode] = (ops.inst_costvol(*args)[0], ops.inst_costvol(*args, gate=True)[0])
+    finally:
+        ops.USE_NHWC_GATHER = True
+    assert torch.equal(res[True][0], res[False][0])
+    assert (res[True][1] - res[False][1]).abs().max().item() <= 1e-6 * res[False][1].abs().max().item()
