@@ -167,11 +167,11 @@ def kernel_rooflines(pk, precision):
     fL, fR = torch.randn(1, 64, 96, 320, device=dev), torch.randn(1, 64, 96, 320, device=dev)
     left, right, _ = make_boxes(1, 64, seed=0)
     left, right, fb = left.to(dev), right.to(dev), torch.tensor([384.38], device=dev)
-    for gate in (False, True):
-        ms = time_op(lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=gate), flush=flush)
+    for gate, fma in ((False, False), (True, False), (True, True)):
+        ms = time_op(lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=gate, fma=fma), flush=flush)
         byts = 64 * 192 * 48 * 256 * 4 + 2 * 64 * 96 * 320 * 4
-        out["inst_costvol_fwd" + ("_gate" if gate else "")] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"],
-                                                             "alg_bytes": byts}
+        out["inst_costvol_fwd" + ("_gate" if gate else "") + ("_fma" if fma else "")] = {
+            "ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
     # reference-shaped volume: 100 RoIs x 16 x 32 ch
     l2, r2, _ = make_boxes(1, 100, seed=1)
     f32L, f32R = fL[:, :32].contiguous(), fR[:, :32].contiguous()

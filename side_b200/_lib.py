@@ -50,6 +50,7 @@ DCN_PREC_FP32 = 0 << 4
 DCN_PREC_3XTF32 = 1 << 4
 DCN_PREC_TF32 = 2 << 4
 VOL_GATE = 1 << 0
+VOL_FMA = 1 << 1
 DECODE_HEAT_IS_LOGIT = 1 << 0
 
 _lib = None

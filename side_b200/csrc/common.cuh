@@ -18,6 +18,9 @@ inline int cuda_fail(cudaError_t e, const char *what)
     return SIDE_ERR_CUDA;
 }
 
+// NCHW -> NHWC staging copy (layout.cu)
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st);
+
 // true when p is device (or managed) memory of the current context; NULL is handled by callers
 bool is_device_ptr(const void *p);
 

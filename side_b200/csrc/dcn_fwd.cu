@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kDcnThreads, 3) dcn_fwd_simt_kernel(DcnFwdArgs
 
 // dcn_fwd_tc.cu (tcgen05 / TMEM path)
 int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st);
-size_t dcn_fwd_tc_ws_bytes(int Cin, int Cout, int KK, int flags);
+size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int flags);
 bool dcn_fwd_tc_supported(int Cin, int Cout, int dg);
 
 }  // namespace side
@@ -186,11 +186,10 @@ using namespace side;
 
 extern "C" size_t side_dcn_fwd_ws_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw, int flags)
 {
-    (void)B; (void)H; (void)W;
     if (Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0) return 0;
     const size_t simt = sizeof(float) * (size_t)Cin * Cout * kh * kw;
     if ((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32 && dcn_fwd_tc_supported(Cin, Cout, 1))
-        return std::max(simt, dcn_fwd_tc_ws_bytes(Cin, Cout, kh * kw, flags));
+        return std::max(simt, dcn_fwd_tc_ws_bytes(B, Cin, H, W, Cout, kh * kw, flags));
     return simt;
 }
 

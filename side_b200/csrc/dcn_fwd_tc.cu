@@ -103,15 +103,24 @@ __global__ void dcn_tc_weight_prep_kernel(const float *__restrict__ w, float *__
     }
 }
 
+// sample geometry of one (pixel, tap), ready for the channels-last gather: element offsets into the NHWC copy of x
+// (batch folded in) and bilinear weights pre-multiplied by the modulation mask
+struct TapRec {
+    int o1, o2, o3, o4;
+    float w1, w2, w3, w4;
+};
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp, int stages,
-                                                                  uint32_t idesc, uint32_t tmem_cols)
+__global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp,
+                                                                  const float *__restrict__ xt, int stages, uint32_t idesc,
+                                                                  uint32_t tmem_cols)
 {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) TapRec tapbuf[2][kTcBM];
 
     const DcnShape &s = a.s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,47 +156,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 
     if (tid < kTcProducerThreads) {
         // ================= producers: modulated bilinear gather -> swizzled A tile =================
-        const int row = tid & 127, half = tid >> 7;
+        // geometry: thread `row` (< 128) fills tapbuf once per tap; gather: thread = (c4 = tid & 7, rows (tid >> 3) + 32 i):
+        // a warp instruction reads 4 pixels x 128 contiguous bytes of the NHWC copy.
+        const int row = tid & 127;
         const long long Mtot = (long long)s.B * s.P;
         const long long gp = (long long)blockIdx.x * kTcBM + row;
         const bool pix_ok = gp < Mtot;
         const int b = pix_ok ? (int)(gp / s.P) : 0;
         const int p = pix_ok ? (int)(gp - (long long)b * s.P) : 0;
         const int ho = p / s.Wo, wo = p - ho * s.Wo;
-        const int HWin = s.H * s.W;
-        const float *xb = a.x + (size_t)b * s.Cin * HWin;
-        DcnTap tap{};
+        const int c4 = tid & 7, r0 = tid >> 3;
         int cur_tap = -1;
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % stages, it = kb / stages;
-            const int tp = kb / ncb, c0 = (kb - tp * ncb) * kTcBK + half * 16;
+            const int tp = kb / ncb, c0 = (kb - tp * ncb) * kTcBK + 4 * c4;
             if (tp != cur_tap) {
                 cur_tap = tp;
-                if (pix_ok) tap = dcn_tap(s, a.offset, a.mask, b, 0, tp, ho, wo);
-                else { tap.o1 = tap.o2 = tap.o3 = tap.o4 = 0; tap.w1 = tap.w2 = tap.w3 = tap.w4 = 0.f; tap.m = 0.f; }
+                if (tid < kTcBM) {
+                    TapRec tr;
+                    if (pix_ok) {
+                        const DcnTap g = dcn_tap(s, a.offset, a.mask, b, 0, tp, ho, wo);
+                        const int base = b * s.H * s.W;
+                        tr.o1 = (base + g.o1) * s.Cin; tr.o2 = (base + g.o2) * s.Cin;
+                        tr.o3 = (base + g.o3) * s.Cin; tr.o4 = (base + g.o4) * s.Cin;
+                        tr.w1 = g.w1 * g.m; tr.w2 = g.w2 * g.m; tr.w3 = g.w3 * g.m; tr.w4 = g.w4 * g.m;
+                    } else {
+                        tr.o1 = tr.o2 = tr.o3 = tr.o4 = 0;
+                        tr.w1 = tr.w2 = tr.w3 = tr.w4 = 0.f;
+                    }
+                    tapbuf[tp & 1][row] = tr;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
             }
-            float v[16];
+            float4 v[4];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float *xc = xb + (size_t)(c0 + k) * HWin;
-                v[k] = (tap.w1 * __ldg(xc + tap.o1) + tap.w2 * __ldg(xc + tap.o2) + tap.w3 * __ldg(xc + tap.o3) +
-                        tap.w4 * __ldg(xc + tap.o4)) * tap.m;
+            for (int i = 0; i < 4; ++i) {
+                const TapRec tr = tapbuf[tp & 1][r0 + 32 * i];
+                const float *xc = xt + c0;
+                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o1));
+                const float4 a2 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o2));
+                const float4 a3 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o3));
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o4));
+                v[i].x = fmaf(tr.w4, a4.x, fmaf(tr.w3, a3.x, fmaf(tr.w2, a2.x, tr.w1 * a1.x)));
+                v[i].y = fmaf(tr.w4, a4.y, fmaf(tr.w3, a3.y, fmaf(tr.w2, a2.y, tr.w1 * a1.y)));
+                v[i].z = fmaf(tr.w4, a4.z, fmaf(tr.w3, a3.z, fmaf(tr.w2, a2.z, tr.w1 * a1.z)));
+                v[i].w = fmaf(tr.w4, a4.w, fmaf(tr.w3, a3.w, fmaf(tr.w2, a2.w, tr.w1 * a1.w)));
             }
             if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
             unsigned char *sa = tiles + (size_t)st * stage_bytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t off = sw128(row, half * 4 + j);
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = sw128(r0 + 32 * i, c4);
                 if (SPLIT) {
                     float4 hi, lo;
-                    hi.x = tf32_hi(v[4 * j + 0]); lo.x = v[4 * j + 0] - hi.x;
-                    hi.y = tf32_hi(v[4 * j + 1]); lo.y = v[4 * j + 1] - hi.y;
-                    hi.z = tf32_hi(v[4 * j + 2]); lo.z = v[4 * j + 2] - hi.z;
-                    hi.w = tf32_hi(v[4 * j + 3]); lo.w = v[4 * j + 3] - hi.w;
+                    hi.x = tf32_hi(v[i].x); lo.x = v[i].x - hi.x;
+                    hi.y = tf32_hi(v[i].y); lo.y = v[i].y - hi.y;
+                    hi.z = tf32_hi(v[i].z); lo.z = v[i].z - hi.z;
+                    hi.w = tf32_hi(v[i].w); lo.w = v[i].w - hi.w;
                     *reinterpret_cast<float4 *>(sa + off) = hi;
                     *reinterpret_cast<float4 *>(sa + kATileBytes + off) = lo;
                 } else {
-                    *reinterpret_cast<float4 *>(sa + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    *reinterpret_cast<float4 *>(sa + off) = v[i];
                 }
             }
             fence_proxy_async_smem();
@@ -263,10 +292,16 @@ bool dcn_fwd_tc_supported(int Cin, int Cout, int dg)
     return dg == 1 && Cin % kTcBK == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
 }
 
-size_t dcn_fwd_tc_ws_bytes(int Cin, int Cout, int KK, int flags)
+static size_t tc_weight_bytes(int Cin, int Cout, int KK, int flags)
 {
     const bool split = (flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
-    return sizeof(float) * (split ? 2 : 1) * (size_t)Cin * Cout * KK;
+    return (sizeof(float) * (split ? 2 : 1) * (size_t)Cin * Cout * KK + 255) & ~(size_t)255;
+}
+
+// workspace = weight tiles + the channels-last copy of x
+size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int flags)
+{
+    return tc_weight_bytes(Cin, Cout, KK, flags) + sizeof(float) * (size_t)B * Cin * H * W;
 }
 
 int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st)
@@ -277,11 +312,18 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
         set_error("side_dcn_fwd: tcgen05 path needs dg == 1, Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
         return SIDE_ERR_UNSUPPORTED;
     }
-    if (ws_bytes < dcn_fwd_tc_ws_bytes(s.Cin, s.Cout, s.KK, s.flags)) {
-        set_error("side_dcn_fwd: workspace too small for the tcgen05 weight tiles");
+    if (ws_bytes < dcn_fwd_tc_ws_bytes(s.B, s.Cin, s.H, s.W, s.Cout, s.KK, s.flags)) {
+        set_error("side_dcn_fwd: workspace too small for the tcgen05 weight tiles + NHWC copy");
         return SIDE_ERR_WORKSPACE;
     }
+    if ((long long)s.B * s.H * s.W * s.Cin >= (1ll << 31)) {
+        set_error("side_dcn_fwd: input too large for 32-bit gather offsets");
+        return SIDE_ERR_UNSUPPORTED;
+    }
     float *wp = reinterpret_cast<float *>(ws);
+    float *xt = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws) + tc_weight_bytes(s.Cin, s.Cout, s.KK, s.flags));
+    int rc = launch_nchw_to_nhwc(a.x, xt, s.B, s.Cin, s.H * s.W, st);
+    if (rc) return rc;
     const long long nW = (long long)s.Cout * s.Cin * s.KK;
     dcn_tc_weight_prep_kernel<<<(unsigned)std::min<long long>(1184, (nW + 255) / 256), 256, 0, st>>>(w, wp, s.Cout, s.Cin, s.KK,
                                                                                                    split ? 1 : 0);
@@ -296,13 +338,12 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     // instruction descriptor: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(s.Cout >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
     const unsigned grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
-    int rc;
     if (split) {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;
-        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, stages, idesc, tmem_cols);
+        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols);
     } else {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false>, smem))) return rc;
-        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, stages, idesc, tmem_cols);
+        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols);
     }
     SIDE_LAUNCH_CHECK("dcn_fwd_tc_kernel");
     return SIDE_OK;

@@ -109,6 +109,7 @@ struct VolParams {
 };
 
 constexpr int kVolThreads = 512;
+constexpr int kNhwcThreads = 1024;   // 60 regs/thread: one CTA of 32 warps per SM next to its 133 KB of tiles
 
 // block-wide sum of up to 4 values; result broadcast to all threads.  red: >= 4*32 floats of smem
 template <int NV>
@@ -267,130 +268,130 @@ __global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_kernel(VolParams
 // 2x2 sub-samples of a bin (same integer cell) are loaded once.  Arithmetic is unchanged (same rounded ops, same
 // order), so the result stays bit-identical to the oracle.
 // ------------------------------------------------------------------------------------------------
-__global__ void nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW)
-{
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const float *ip = in + (size_t)b * C * HW;
-    float *op = out + (size_t)b * C * HW;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, p = p0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(ip + (size_t)c * HW + p) : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int p = p0 + i, c = c0 + threadIdx.x;
-        if (p < HW && c < C) op[(size_t)p * C + c] = tile[threadIdx.x][i];
-    }
-}
+// Per-axis sample with the NHWC element offset folded in (row*W*C for y, col*C for x).  Samples outside the image
+// keep offset 0 and get zero weights, which makes every tap product an exact zero without a branch
+// (finite features assumed: 0 * inf would differ from the reference's hard zero).
+struct AxisTap {
+    int olo, ohi;
+    float l, h;
+};
 
-struct Tap4 { float4 v1, v2, v3, v4; };
-
-__device__ __forceinline__ Tap4 load_tap4(const float *__restrict__ base, int W, int C, const AxisSample &y, const AxisSample &x)
-{
-    Tap4 t;
-    t.v1 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.lo * W + x.lo) * C));
-    t.v2 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.lo * W + x.hi) * C));
-    t.v3 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.hi * W + x.lo) * C));
-    t.v4 = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)y.hi * W + x.hi) * C));
-    return t;
-}
-
+template <bool FAST>
 __device__ __forceinline__ float tap_val(float w1, float w2, float w3, float w4, float a, float b, float c, float d)
 {
+    if (FAST) return fmaf(w4, d, fmaf(w3, c, fmaf(w2, b, w1 * a)));   // contracted, like nvcc compiles torchvision's CUDA kernel
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, a), __fmul_rn(w2, b)), __fmul_rn(w3, c)), __fmul_rn(w4, d));
 }
 
-// one bin, 4 consecutive channels; base already points at channel 4*c4 of pixel (0,0) of image b (NHWC)
-__device__ __forceinline__ float4 roi_bin4(const float *__restrict__ base, int W, int C, const AxisSample *__restrict__ ys,
-                                           const AxisSample *__restrict__ xs)
+// one bin, 4 consecutive channels; base points at channel 4*c4 of pixel (0,0) of image b (NHWC)
+template <bool FAST>
+__device__ __forceinline__ float4 roi_bin4(const float *__restrict__ base, const AxisTap *__restrict__ ys,
+                                           const AxisTap *__restrict__ xs)
 {
-    const AxisSample y0 = ys[0], y1 = ys[1], x0 = xs[0], x1 = xs[1];
-    const bool same_x = x0.lo == x1.lo && x0.hi == x1.hi, same_y = y0.lo == y1.lo && y0.hi == y1.hi;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    Tap4 t00, t01, t10, t11;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    t00.v1 = t00.v2 = t00.v3 = t00.v4 = z;
-    t01 = t00; t10 = t00; t11 = t00;
-    const bool vy0 = y0.lo >= 0, vy1 = y1.lo >= 0, vx0 = x0.lo >= 0, vx1 = x1.lo >= 0;
-    if (vy0 && vx0) t00 = load_tap4(base, W, C, y0, x0);
-    if (vy0 && vx1) t01 = (same_x && vx0) ? t00 : load_tap4(base, W, C, y0, x1);
-    if (vy1 && vx0) t10 = (same_y && vy0) ? t00 : load_tap4(base, W, C, y1, x0);
-    if (vy1 && vx1) t11 = (same_y && vy0) ? t01 : ((same_x && vx0) ? t10 : load_tap4(base, W, C, y1, x1));
-#define SIDE_ACC(T, Y, X, OK)                                                                                   \
-    {                                                                                                           \
-        float4 val = z;                                                                                         \
-        if (OK) {                                                                                               \
-            const float w1 = __fmul_rn(Y.h, X.h), w2 = __fmul_rn(Y.h, X.l), w3 = __fmul_rn(Y.l, X.h),           \
-                        w4 = __fmul_rn(Y.l, X.l);                                                               \
-            val.x = tap_val(w1, w2, w3, w4, T.v1.x, T.v2.x, T.v3.x, T.v4.x);                                    \
-            val.y = tap_val(w1, w2, w3, w4, T.v1.y, T.v2.y, T.v3.y, T.v4.y);                                    \
-            val.z = tap_val(w1, w2, w3, w4, T.v1.z, T.v2.z, T.v3.z, T.v4.z);                                    \
-            val.w = tap_val(w1, w2, w3, w4, T.v1.w, T.v2.w, T.v3.w, T.v4.w);                                    \
-        }                                                                                                       \
-        acc.x = __fadd_rn(acc.x, val.x); acc.y = __fadd_rn(acc.y, val.y);                                       \
-        acc.z = __fadd_rn(acc.z, val.z); acc.w = __fadd_rn(acc.w, val.w);                                       \
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+        const AxisTap y = ys[iy];
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            const AxisTap x = xs[ix];
+            const float w1 = __fmul_rn(y.h, x.h), w2 = __fmul_rn(y.h, x.l), w3 = __fmul_rn(y.l, x.h), w4 = __fmul_rn(y.l, x.l);
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(base + (y.olo + x.olo)));
+            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(base + (y.olo + x.ohi)));
+            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(base + (y.ohi + x.olo)));
+            const float4 v4 = __ldg(reinterpret_cast<const float4 *>(base + (y.ohi + x.ohi)));
+            acc.x = __fadd_rn(acc.x, tap_val<FAST>(w1, w2, w3, w4, v1.x, v2.x, v3.x, v4.x));
+            acc.y = __fadd_rn(acc.y, tap_val<FAST>(w1, w2, w3, w4, v1.y, v2.y, v3.y, v4.y));
+            acc.z = __fadd_rn(acc.z, tap_val<FAST>(w1, w2, w3, w4, v1.z, v2.z, v3.z, v4.z));
+            acc.w = __fadd_rn(acc.w, tap_val<FAST>(w1, w2, w3, w4, v1.w, v2.w, v3.w, v4.w));
+        }
     }
-    SIDE_ACC(t00, y0, x0, vy0 && vx0)
-    SIDE_ACC(t01, y0, x1, vy0 && vx1)
-    SIDE_ACC(t10, y1, x0, vy1 && vx0)
-    SIDE_ACC(t11, y1, x1, vy1 && vx1)
-#undef SIDE_ACC
-    return make_float4(__fdiv_rn(acc.x, 4.0f), __fdiv_rn(acc.y, 4.0f), __fdiv_rn(acc.z, 4.0f), __fdiv_rn(acc.w, 4.0f));
+    // x * 0.25 == x / 4 for every float (power-of-two scaling rounds identically)
+    return make_float4(__fmul_rn(acc.x, 0.25f), __fmul_rn(acc.y, 0.25f), __fmul_rn(acc.z, 0.25f), __fmul_rn(acc.w, 0.25f));
 }
 
-template <bool GATE>
-__global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_nhwc_kernel(VolParams p, const float *__restrict__ nhwcL,
+__device__ __forceinline__ AxisTap to_tap(const AxisSample &s, int stride)
+{
+    AxisTap t;
+    if (s.lo < 0) { t.olo = 0; t.ohi = 0; t.l = 0.f; t.h = 0.f; }
+    else { t.olo = s.lo * stride; t.ohi = s.hi * stride; t.l = s.l; t.h = s.h; }
+    return t;
+}
+
+// PT: compile-time RoI size (16 = the reference's roiSize) or 0 for the generic runtime-P version.
+template <bool GATE, bool FAST, int PT>
+__global__ void __launch_bounds__(kNhwcThreads) inst_costvol_fwd_nhwc_kernel(VolParams p, const float *__restrict__ nhwcL,
                                                                             const float *__restrict__ nhwcR)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P = p.P, PP = P * P, C = p.C, PPs = PP + 1;
-    AxisSample *ytab = reinterpret_cast<AxisSample *>(smem_raw);
-    AxisSample *xl = ytab + 2 * P, *xr = xl + 2 * P;
+    const int P = PT > 0 ? PT : p.P, PP = P * P, C = p.C, PPs = PP + 1;
+    AxisTap *ytab = reinterpret_cast<AxisTap *>(smem_raw);
+    AxisTap *xl = ytab + 2 * P, *xr = xl + 2 * P;
     float *red = reinterpret_cast<float *>(xr + 2 * P);
     float *Ls = red + 4 * 32, *Rs = Ls + (size_t)C * PPs;
 
-    const int n = blockIdx.x / p.D, d = blockIdx.x % p.D;
+    const int n = blockIdx.x / p.D, d = blockIdx.x - n * p.D;
     const size_t cs = (size_t)p.D * PP;
     float *out = p.cost + (size_t)n * 3 * C * cs + (size_t)d * PP;
+    const int CPP = C * PP;
 
     if (p.valid && !p.valid[n]) {
-        for (int e = threadIdx.x; e < 3 * C * PP; e += blockDim.x) st_cs(out + (size_t)(e / PP) * cs + e % PP, 0.f);
+        for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) st_cs(out + (size_t)(e / PP) * cs + e % PP, 0.f);
         if (threadIdx.x == 0) {
             p.depth_bin[(size_t)n * p.D + d] = 0.f;
             if (GATE && p.xcross) p.xcross[(size_t)n * p.D + d] = 0.f;
         }
         return;
     }
+    // sample tables (same arithmetic as the NCHW kernel / the oracle), converted to NHWC element offsets
     int b;
-    float dbin;
-    build_tables(p, n, d, ytab, xl, xr, b, dbin);
-    if (threadIdx.x == 0) p.depth_bin[(size_t)n * p.D + d] = dbin;
+    {
+        const float *l = p.left + (size_t)n * 5, *r = p.right + (size_t)n * 5;
+        b = min(max((int)l[0], 0), p.B - 1);
+        float dbin, lx1, lx2, rx1, rx2, y1, y2;
+        proposal_for(l, r, p.fb[b], d, p.D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+        if (threadIdx.x == 0) p.depth_bin[(size_t)n * p.D + d] = dbin;
+        const int t = threadIdx.x, P2 = 2 * P;
+        if (t < 3 * P2) {
+            const int which = t / P2, s = t - which * P2;
+            if (which == 0) {
+                const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
+                ytab[s] = to_tap(axis_sample(y1, __fdiv_rn(rh, (float)P), s >> 1, s & 1, p.H), p.W * C);
+            } else if (which == 1) {
+                const float rw = fmaxf(__fsub_rn(lx2, lx1), 1.0f);
+                xl[s] = to_tap(axis_sample(lx1, __fdiv_rn(rw, (float)P), s >> 1, s & 1, p.W), C);
+            } else {
+                const float rw = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
+                xr[s] = to_tap(axis_sample(rx1, __fdiv_rn(rw, (float)P), s >> 1, s & 1, p.W), C);
+            }
+        }
+    }
     __syncthreads();
 
     const float *fL = nhwcL + (size_t)b * p.H * p.W * C;
     const float *fR = nhwcR + (size_t)b * p.H * p.W * C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int c4l = lane & 7, ql = lane >> 3;
-    const int nc4 = C >> 2, ncblk = (nc4 + 7) >> 3, nqblk = PP >> 2;
+    const int nc4 = C >> 2, nqblk = PP >> 2;
 
     float s[3] = {0.f, 0.f, 0.f};
-    for (int t = warp; t < ncblk * nqblk; t += nwarps) {
-        const int cblk = t % ncblk, qblk = t / ncblk;
-        const int c4 = cblk * 8 + c4l, q = qblk * 4 + ql;
-        if (c4 >= nc4) continue;
-        const int ph = q / P, pw = q - ph * P;
-        const float4 l = roi_bin4(fL + 4 * c4, p.W, C, ytab + 2 * ph, xl + 2 * pw);
-        const float4 r = roi_bin4(fR + 4 * c4, p.W, C, ytab + 2 * ph, xr + 2 * pw);
-        if (GATE) {
-            s[0] = fmaf(l.x, l.x, fmaf(l.y, l.y, fmaf(l.z, l.z, fmaf(l.w, l.w, s[0]))));
-            s[1] = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, s[1]))));
-            s[2] = fmaf(l.x, r.x, fmaf(l.y, r.y, fmaf(l.z, r.z, fmaf(l.w, r.w, s[2]))));
+    for (int c4 = c4l; c4 < nc4; c4 += 8) {
+        const float *bl = fL + 4 * c4, *br = fR + 4 * c4;
+        float *lp0 = Ls + (size_t)(4 * c4) * PPs, *rp0 = Rs + (size_t)(4 * c4) * PPs;
+        for (int qblk = warp; qblk < nqblk; qblk += nwarps) {
+            const int q = qblk * 4 + ql;
+            const int ph = q / P, pw = q - ph * P;
+            const float4 l = roi_bin4<FAST>(bl, ytab + 2 * ph, xl + 2 * pw);
+            const float4 r = roi_bin4<FAST>(br, ytab + 2 * ph, xr + 2 * pw);
+            if (GATE) {
+                s[0] = fmaf(l.x, l.x, fmaf(l.y, l.y, fmaf(l.z, l.z, fmaf(l.w, l.w, s[0]))));
+                s[1] = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, s[1]))));
+                s[2] = fmaf(l.x, r.x, fmaf(l.y, r.y, fmaf(l.z, r.z, fmaf(l.w, r.w, s[2]))));
+            }
+            float *lp = lp0 + q, *rp = rp0 + q;
+            lp[0] = l.x; lp[PPs] = l.y; lp[2 * PPs] = l.z; lp[3 * PPs] = l.w;
+            rp[0] = r.x; rp[PPs] = r.y; rp[2 * PPs] = r.z; rp[3 * PPs] = r.w;
         }
-        float *lp = Ls + (size_t)(4 * c4) * PPs + q, *rp = Rs + (size_t)(4 * c4) * PPs + q;
-        lp[0] = l.x; lp[PPs] = l.y; lp[2 * PPs] = l.z; lp[3 * PPs] = l.w;
-        rp[0] = r.x; rp[PPs] = r.y; rp[2 * PPs] = r.z; rp[3 * PPs] = r.w;
     }
     float g = 1.0f;
     if (GATE) {
@@ -400,15 +401,29 @@ __global__ void __launch_bounds__(kVolThreads) inst_costvol_fwd_nhwc_kernel(VolP
         if (threadIdx.x == 0 && p.xcross) p.xcross[(size_t)n * p.D + d] = g;
     }
     __syncthreads();
-    const int CPP = C * PP;
-    for (int e = threadIdx.x; e < 3 * CPP; e += blockDim.x) {
-        const int ch = e / PP, q = e - ch * PP;
-        float v;
-        if (ch < C) v = Ls[(size_t)ch * PPs + q];
-        else if (ch < 2 * C) v = Rs[(size_t)(ch - C) * PPs + q];
-        else v = __fsub_rn(Ls[(size_t)(ch - 2 * C) * PPs + q], Rs[(size_t)(ch - 2 * C) * PPs + q]);
-        if (GATE) v = __fmul_rn(v, g);
-        st_cs(out + (size_t)ch * cs + q, v);
+    // write-out: thread owns column q = tid % PP (when blockDim % PP == 0) and strides over channels
+    if (PT > 0 && (kNhwcThreads % (PT * PT)) == 0) {
+        const int q = threadIdx.x % PP, c0 = threadIdx.x / PP, cstep = kNhwcThreads / PP;
+        const float *lq = Ls + q, *rq = Rs + q;
+        float *oq = out + q;
+        for (int c = c0; c < C; c += cstep) {
+            const float lv = lq[(size_t)c * PPs], rv = rq[(size_t)c * PPs];
+            float dv = __fsub_rn(lv, rv), l2 = lv, r2 = rv;
+            if (GATE) { l2 = __fmul_rn(lv, g); r2 = __fmul_rn(rv, g); dv = __fmul_rn(dv, g); }
+            st_cs(oq + (size_t)c * cs, l2);
+            st_cs(oq + (size_t)(C + c) * cs, r2);
+            st_cs(oq + (size_t)(2 * C + c) * cs, dv);
+        }
+    } else {
+        for (int e = threadIdx.x; e < CPP; e += blockDim.x) {
+            const int c = e / PP, q = e - c * PP;
+            const float lv = Ls[(size_t)c * PPs + q], rv = Rs[(size_t)c * PPs + q];
+            float dv = __fsub_rn(lv, rv), l2 = lv, r2 = rv;
+            if (GATE) { l2 = __fmul_rn(lv, g); r2 = __fmul_rn(rv, g); dv = __fmul_rn(dv, g); }
+            st_cs(out + (size_t)c * cs + q, l2);
+            st_cs(out + (size_t)(C + c) * cs + q, r2);
+            st_cs(out + (size_t)(2 * C + c) * cs + q, dv);
+        }
     }
 }
 
@@ -638,22 +653,30 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
     cudaStream_t st = (cudaStream_t)stream;
     // channels-last fast path: needs the transposed copies (workspace), C % 4 == 0, P*P % 4 == 0 and the padded
     // L/R tiles in shared memory
-    const size_t nhwc_smem = sizeof(AxisSample) * 6 * P + sizeof(float) * 4 * 32 + sizeof(float) * 2 * (size_t)C * (P * P + 1);
+    const size_t nhwc_smem = sizeof(AxisTap) * 6 * P + sizeof(float) * 4 * 32 + sizeof(float) * 2 * (size_t)C * (P * P + 1);
     if (ws != nullptr && ws_bytes >= side_inst_costvol_ws_bytes(B, C, H, W) && (C & 3) == 0 && ((P * P) & 3) == 0 &&
-        nhwc_smem <= 200 * 1024 && is_device_ptr(ws)) {
+        nhwc_smem <= 200 * 1024 && (long long)B * H * W * C < (1ll << 31) && is_device_ptr(ws)) {
         float *nl = reinterpret_cast<float *>(ws), *nr = nl + (size_t)B * C * H * W;
-        dim3 tg(ceil_div(H * W, 32), ceil_div(C, 32), B), tb(32, 8);
-        nchw_to_nhwc_kernel<<<tg, tb, 0, st>>>(featL, nl, C, H * W);
-        SIDE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
-        nchw_to_nhwc_kernel<<<tg, tb, 0, st>>>(featR, nr, C, H * W);
-        SIDE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
-        if (gate) {
-            if ((rc = set_smem_attr((const void *)inst_costvol_fwd_nhwc_kernel<true>, nhwc_smem))) return rc;
-            inst_costvol_fwd_nhwc_kernel<true><<<grid, kVolThreads, nhwc_smem, st>>>(p, nl, nr);
+        if ((rc = launch_nchw_to_nhwc(featL, nl, B, C, H * W, st))) return rc;
+        if ((rc = launch_nchw_to_nhwc(featR, nr, B, C, H * W, st))) return rc;
+#define SIDE_VOL_LAUNCH(G, F, PTV)                                                                                   \
+    do {                                                                                                             \
+        if ((rc = set_smem_attr((const void *)inst_costvol_fwd_nhwc_kernel<G, F, PTV>, nhwc_smem))) return rc;       \
+        inst_costvol_fwd_nhwc_kernel<G, F, PTV><<<grid, kNhwcThreads, nhwc_smem, st>>>(p, nl, nr);                    \
+    } while (0)
+        const bool fast = flags & SIDE_VOL_FMA;
+        if (P == 16) {
+            if (gate && fast) SIDE_VOL_LAUNCH(true, true, 16);
+            else if (gate) SIDE_VOL_LAUNCH(true, false, 16);
+            else if (fast) SIDE_VOL_LAUNCH(false, true, 16);
+            else SIDE_VOL_LAUNCH(false, false, 16);
         } else {
-            if ((rc = set_smem_attr((const void *)inst_costvol_fwd_nhwc_kernel<false>, nhwc_smem))) return rc;
-            inst_costvol_fwd_nhwc_kernel<false><<<grid, kVolThreads, nhwc_smem, st>>>(p, nl, nr);
+            if (gate && fast) SIDE_VOL_LAUNCH(true, true, 0);
+            else if (gate) SIDE_VOL_LAUNCH(true, false, 0);
+            else if (fast) SIDE_VOL_LAUNCH(false, true, 0);
+            else SIDE_VOL_LAUNCH(false, false, 0);
         }
+#undef SIDE_VOL_LAUNCH
         SIDE_LAUNCH_CHECK("inst_costvol_fwd_nhwc_kernel");
         return SIDE_OK;
     }

@@ -1,0 +1,36 @@
+// layout.cu -- NCHW -> NHWC staging copy shared by the gather kernels (instance cost volume, tcgen05 DCN).
+// Bilinear gathers fetch one pixel's channels at a time: channels-last makes every tap a contiguous 16-byte
+// (4-channel) load and every warp request a set of full 128-byte lines.
+#include "common.cuh"
+
+namespace side {
+
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float *ip = in + (size_t)b * C * HW;
+    float *op = out + (size_t)b * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(ip + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) op[(size_t)p * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+
+int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st)
+{
+    dim3 tg(ceil_div(HW, 32), ceil_div(C, 32), B), tb(32, 8);
+    SIDE_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, "nchw_to_nhwc: grid too large");
+    nchw_to_nhwc_kernel<<<tg, tb, 0, st>>>(in, out, C, HW);
+    SIDE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return SIDE_OK;
+}
+
+}  // namespace side

@@ -210,7 +210,7 @@ USE_NHWC_GATHER = True   # False selects the NCHW gather kernel (same results, s
 
 class _InstCostVol(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, featL, featR, left, right, fb, valid, D, P, x_clamp, gate):
+    def forward(ctx, featL, featR, left, right, fb, valid, D, P, x_clamp, gate, fma=False):
         lib = _lib.load()
         featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
         left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
@@ -221,7 +221,7 @@ class _InstCostVol(torch.autograd.Function):
         cost = torch.empty((N, 3 * C, D, P, P), device=featL.device, dtype=_F32)
         depth_bin = torch.empty((N, D), device=featL.device, dtype=_F32)
         xc = torch.empty((N, D), device=featL.device, dtype=_F32) if gate else None
-        flags = _lib.VOL_GATE if gate else 0
+        flags = (_lib.VOL_GATE if gate else 0) | (_lib.VOL_FMA if fma else 0)
         nws = lib.side_inst_costvol_ws_bytes(B, C, H, W) if USE_NHWC_GATHER else 0
         ws = torch.empty((max(nws, 16),), device=featL.device, dtype=torch.uint8)
         _lib.check(lib.side_inst_costvol_fwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
@@ -230,7 +230,7 @@ class _InstCostVol(torch.autograd.Function):
                                              nws, _stream()),
                    "side_inst_costvol_fwd")
         ctx.save_for_backward(featL, featR, left, right, fb, valid)
-        ctx.cfg = (D, P, float(x_clamp), flags)
+        ctx.cfg = (D, P, float(x_clamp), flags & _lib.VOL_GATE)
         ctx.mark_non_differentiable(depth_bin)
         return cost, depth_bin
 
@@ -248,12 +248,13 @@ class _InstCostVol(torch.autograd.Function):
         _lib.check(lib.side_inst_costvol_bwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
                                              fb.data_ptr(), _p(valid), gcost.data_ptr(), gL.data_ptr(), gR.data_ptr(),
                                              N, B, C, H, W, D, P, x_clamp, flags, _stream()), "side_inst_costvol_bwd")
-        return gL, gR, None, None, None, None, None, None, None, None
+        return gL, gR, None, None, None, None, None, None, None, None, None
 
 
-def inst_costvol(featL, featR, left, right, fb, D, P, x_clamp, gate=False, valid=None):
-    """-> (cost [N,3C,D,P,P], depth_bin [N,D]); boxes [N,5] grouped by image in ascending b."""
-    return _InstCostVol.apply(featL, featR, left, right, fb, valid, int(D), int(P), float(x_clamp), bool(gate))
+def inst_costvol(featL, featR, left, right, fb, D, P, x_clamp, gate=False, valid=None, fma=False):
+    """-> (cost [N,3C,D,P,P], depth_bin [N,D]); boxes [N,5] grouped by image in ascending b.
+    fma=True: FMA-contracted bilinear taps (<= 1e-6 relative to the bit-exact default)."""
+    return _InstCostVol.apply(featL, featR, left, right, fb, valid, int(D), int(P), float(x_clamp), bool(gate), bool(fma))
 
 
 class _XCrossGate(torch.autograd.Function):

@@ -177,3 +177,15 @@ def test_nchw_and_nhwc_gather_paths_identical(lib, cfg):
         ops.USE_NHWC_GATHER = True
     assert torch.equal(res[True][0], res[False][0])
     assert (res[True][1] - res[False][1]).abs().max().item() <= 1e-6 * res[False][1].abs().max().item()
+
+
+def test_fma_mode_within_1e6(lib):
+    """SIDE_VOL_FMA (opt-in): FMA-contracted taps; <= 1e-6 of the volume's range from the bit-exact default."""
+    from side_b200 import ops
+    rng = np.random.default_rng(11)
+    fL, fR, left, right, fb = _random_case(rng, 2, 32, 24, 80, 9)
+    args = (dev(fL), dev(fR), dev(left), dev(right), dev(fb), 16, 16, 79.0)
+    for gate in (False, True):
+        a = ops.inst_costvol(*args, gate=gate)[0]
+        b = ops.inst_costvol(*args, gate=gate, fma=True)[0]
+        assert (a - b).abs().max().item() <= 1e-6 * a.abs().max().item()
