@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kDecThreads) nms_topk_decode_kernel(DecParams 
     unsigned long long *merge = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned long long *comp = reinterpret_cast<unsigned long long *>(smem_raw + p.regionA_bytes);
     __shared__ unsigned int hist[256];
+    __shared__ unsigned int whist[kDecThreads / 32][256];   // per-warp private histograms: no cross-warp atomic contention
     __shared__ unsigned int sh_prefix, sh_remaining, sh_ngt, sh_running, sh_last;
     __shared__ unsigned int warp_cnt[32];
 
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kDecThreads) nms_topk_decode_kernel(DecParams 
     uint32_t mask = 0u;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0u;
+        for (int i = tid; i < (kDecThreads / 32) * 256; i += blockDim.x) (&whist[0][0])[i] = 0u;
         __syncthreads();
         const uint32_t prefix = sh_prefix;
         for (int base = 0; base < HW; base += blockDim.x) {
@@ -121,7 +122,14 @@ __global__ void __launch_bounds__(kDecThreads) nms_topk_decode_kernel(DecParams 
                 bin = (k >> shift) & 255u;
             }
             const unsigned peers = __match_any_sync(0xffffffffu, valid ? bin : (256u + lane));
-            if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+            if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&whist[wid][bin], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned h = 0;
+#pragma unroll 8
+            for (int w = 0; w < kDecThreads / 32; ++w) h += whist[w][tid];
+            hist[tid] = h;
         }
         __syncthreads();
         if (tid == 0) {
