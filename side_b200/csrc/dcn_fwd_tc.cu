@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 
     if (tid == 0) {
         for (int i = 0; i < stages; ++i) {
-            mbar_init(&full_bar[i], kTcProducerThreads + 1);
+            mbar_init(&full_bar[i], kTcProducerThreads / 32 + 1);
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(&tmem_full_bar, 1);
@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         const int ho = p / s.Wo, wo = p - ho * s.Wo;
         const int c4 = tid & 7, r0 = tid >> 3;
         int cur_tap = -1;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % stages, it = kb / stages;
+        float4 raw[16];
+        // issue the 16 tap loads of k-block kb (and publish the tap geometry when a new tap starts)
+        auto prefetch = [&](int kb) {
             const int tp = kb / ncb, c0 = (kb - tp * ncb) * kTcBK + 4 * c4;
             if (tp != cur_tap) {
                 cur_tap = tp;
@@ -188,20 +189,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
             }
+            const float *xc = xt + c0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int4 o = *reinterpret_cast<const int4 *>(&tapbuf[tp & 1][r0 + 32 * i]);
+                raw[4 * i + 0] = __ldg(reinterpret_cast<const float4 *>(xc + o.x));
+                raw[4 * i + 1] = __ldg(reinterpret_cast<const float4 *>(xc + o.y));
+                raw[4 * i + 2] = __ldg(reinterpret_cast<const float4 *>(xc + o.z));
+                raw[4 * i + 3] = __ldg(reinterpret_cast<const float4 *>(xc + o.w));
+            }
+        };
+        prefetch(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % stages, it = kb / stages;
+            const int tp = kb / ncb;
             float4 v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const TapRec tr = tapbuf[tp & 1][r0 + 32 * i];
-                const float *xc = xt + c0;
-                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o1));
-                const float4 a2 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o2));
-                const float4 a3 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o3));
-                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(xc + tr.o4));
-                v[i].x = fmaf(tr.w4, a4.x, fmaf(tr.w3, a3.x, fmaf(tr.w2, a2.x, tr.w1 * a1.x)));
-                v[i].y = fmaf(tr.w4, a4.y, fmaf(tr.w3, a3.y, fmaf(tr.w2, a2.y, tr.w1 * a1.y)));
-                v[i].z = fmaf(tr.w4, a4.z, fmaf(tr.w3, a3.z, fmaf(tr.w2, a2.z, tr.w1 * a1.z)));
-                v[i].w = fmaf(tr.w4, a4.w, fmaf(tr.w3, a3.w, fmaf(tr.w2, a2.w, tr.w1 * a1.w)));
+                const float4 w = *reinterpret_cast<const float4 *>(&tapbuf[tp & 1][r0 + 32 * i].w1);
+                const float4 a1 = raw[4 * i], a2 = raw[4 * i + 1], a3 = raw[4 * i + 2], a4 = raw[4 * i + 3];
+                v[i].x = fmaf(w.w, a4.x, fmaf(w.z, a3.x, fmaf(w.y, a2.x, w.x * a1.x)));
+                v[i].y = fmaf(w.w, a4.y, fmaf(w.z, a3.y, fmaf(w.y, a2.y, w.x * a1.y)));
+                v[i].z = fmaf(w.w, a4.z, fmaf(w.z, a3.z, fmaf(w.y, a2.z, w.x * a1.z)));
+                v[i].w = fmaf(w.w, a4.w, fmaf(w.z, a3.w, fmaf(w.y, a2.w, w.x * a1.w)));
             }
+            if (kb + 1 < nkb) prefetch(kb + 1);          // next block's loads fly while this one is stored
             if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
             unsigned char *sa = tiles + (size_t)st * stage_bytes;
 #pragma unroll
@@ -220,7 +232,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(&full_bar[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[st]);   // one arrival per producer warp
         }
 
         // ================= epilogue: TMEM -> registers -> NCHW =================
