@@ -202,6 +202,37 @@ int side_dw_deconv_fwd(const float *x, const float *w, float *y, int B, int C, i
 int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *gx, float *gw, int B, int C, int H, int W,
                        int k, int stride, int pad, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Aggregation network of the instance-depth branch on the tensor cores.
+ * Replaces the cuDNN calls behind cost_volume.dres0 / dres1 / dres2 / classify (stereo_network_old.py:139-171,
+ * 205-227): nn.Conv3d(k=3, stride 1, padding 1, bias=False) [+ BatchNorm3d (eval) + ReLU (+ residual)].
+ * Activations are channels-last (NDHWC) and kept as the exact tf32 split x = hi + lo (hi = top 19 bits) so that
+ * the 3xTF32 contraction (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM) matches fp32 to <= 1e-4 relative.
+ *   side_conv_tc_prep_weights: w [Cout, Cin, taps] (= nn.Conv3d.weight viewed [Cout, Cin, 27]) -> wp, the per-k-block
+ *       swizzled shared-memory image (hi and lo), side_conv_tc_weight_bytes(Cin, Cout, taps) bytes.  Once per layer.
+ *   side_conv3d_tc_fwd: x_hi, x_lo [N, D, H, W, Cin] -> y [N, D, H, W, Cout] (fp32, may be NULL) and / or its split
+ *       y_hi, y_lo (may be NULL); out = relu?(conv * scale[o] + shift[o]) + residual[.., o].
+ *       Needs Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 128, W | 128, (D, H) tiling into 128-voxel boxes
+ *       (16x16, 8x8 with even D, 4x4 with D % 8 == 0); kernel 3x3x3 or 1x3x3.
+ * Helpers (one pass over HBM each):
+ *   side_ncdhw_to_cl_split  x [N, C, S] -> hi, lo [N, S, C]                      (volume from side_inst_costvol_fwd)
+ *   side_tf32_split         x -> hi, lo, n elements (n % 4 == 0)
+ *   side_gate_mul_split     y [N,D,H,W,C] * gate [N,D,W,C] -> hi, lo              (isp * cost, :207-210)
+ *   side_maxpool_hw2_cl     x [N,D,H,W,C] -> MaxPool3d((1,2,2)) -> y and / or hi, lo  (:213, :218)
+ *   side_conv3d_c1_cl       x [N,D,H,W,C], w [1,C,3,3,3] -> out [N,D,H,W]         (classify.3, :170)
+ * --------------------------------------------------------------------------------------------- */
+size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps);
+int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int taps, void *stream);
+int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
+                       const float *residual, float *y, float *y_hi, float *y_lo, int N, int D, int H, int W, int Cin,
+                       int Cout, int kd, int kh, int kw, int relu, void *stream);
+int side_ncdhw_to_cl_split(const float *x, float *hi, float *lo, int N, int C, long long S, void *stream);
+int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);
+int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
+                        void *stream);
+int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream);
+int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

@@ -1,0 +1,207 @@
+// aggr_ops.cu -- the small HBM-bound steps between the tensor-core convolutions of the aggregation network
+// (cost_volume.forward, stereo_network_old.py:205-227), all on channels-last (NDHWC) activations:
+//   layout change NCDHW -> NDHWC with the tf32 hi/lo split          (input of dres0)
+//   structure-aware gate  cost = isp * cost  (:207-210)              fused with the split for dres1
+//   MaxPool3d((1,2,2))    (:213, :218)                               fused with the split for dres2 / classify
+//   classify's last Conv3d(64 -> 1) (:170)                           warp-per-voxel SIMT dot products
+// Every kernel reads its input once and writes each output once (vectorised 16-byte accesses).
+#include "tc_common.cuh"
+
+namespace side {
+
+__device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
+{
+    h.x = tf32_hi(v.x); l.x = v.x - h.x;
+    h.y = tf32_hi(v.y); l.y = v.y - h.y;
+    h.z = tf32_hi(v.z); l.z = v.z - h.z;
+    h.w = tf32_hi(v.w); l.w = v.w - h.w;
+}
+
+// in [N, C, S] -> hi, lo [N, S, C]
+__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, float *__restrict__ hi, float *__restrict__ lo, int C,
+                                         long long S)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const float *ip = in + (size_t)n * C * S;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < S) ? __ldg(ip + (size_t)c * S + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long p = p0 + i;
+        const int c = c0 + threadIdx.x;
+        if (p < S && c < C) {
+            const float v = tile[threadIdx.x][i];
+            const float h = tf32_hi(v);
+            const size_t o = ((size_t)n * S + p) * C + c;
+            hi[o] = h;
+            lo[o] = v - h;
+        }
+    }
+}
+
+__global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo, long long n4)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 h, l;
+        split4(__ldg(x + i), h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo
+__global__ void gate_mul_split_kernel(const float4 *__restrict__ y, const float4 *__restrict__ gate, float4 *__restrict__ hi,
+                                      float4 *__restrict__ lo, long long n4, int H, int WC4)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / WC4;             // (n, d, h)
+        const int wc = (int)(i - row * WC4);
+        const long long nd = row / H;
+        const float4 v = __ldg(y + i), g = __ldg(gate + nd * WC4 + wc);
+        float4 h, l;
+        split4(make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w), h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// x [ND, H, W, C] -> max over 2x2 (h, w) windows -> [ND, H/2, W/2, C]; y and/or (hi, lo)
+__global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, float4 *__restrict__ hi,
+                                      float4 *__restrict__ lo, long long n4out, int H, int W, int C4)
+{
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4out; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int wo = (int)(r % Wo);
+        r /= Wo;
+        const int ho = (int)(r % Ho);
+        const long long nd = r / Ho;
+        const float4 *p = x + ((nd * H + 2 * ho) * W + 2 * wo) * C4 + c;
+        const float4 a = __ldg(p), b = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
+        float4 m;
+        m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(cc.x, d.x));
+        m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(cc.y, d.y));
+        m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(cc.z, d.z));
+        m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(cc.w, d.w));
+        if (y) y[i] = m;
+        if (hi) {
+            float4 h, l;
+            split4(m, h, l);
+            hi[i] = h;
+            lo[i] = l;
+        }
+    }
+}
+
+// x [N, D, H, W, C], w [1, C, 3, 3, 3] -> out [N, D, H, W]   (Conv3d(C -> 1, 3, padding 1, bias=False)); one warp per voxel
+__global__ void __launch_bounds__(256) conv3d_c1_cl_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                           float *__restrict__ out, long long nvox, int D, int H, int W, int C)
+{
+    extern __shared__ float ws[];   // [27][C]
+    for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) {
+        const int tap = i / C, c = i - tap * C;
+        ws[i] = __ldg(w + (size_t)c * 27 + tap);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long v = warp0; v < nvox; v += nwarps) {
+        const int wq = (int)(v % W);
+        long long r = v / W;
+        const int hq = (int)(r % H);
+        r /= H;
+        const int dq = (int)(r % D);
+        const long long n = r / D;
+        float acc = 0.f;
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dd = dq + tap / 9 - 1, hh = hq + (tap / 3) % 3 - 1, ww = wq + tap % 3 - 1;
+            if (dd < 0 || dd >= D || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const float *xp = x + ((((size_t)n * D + dd) * H + hh) * W + ww) * C;
+            const float *wp = ws + tap * C;
+            for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(xp + c), wp[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[v] = acc;
+    }
+}
+
+}  // namespace side
+
+using namespace side;
+
+static inline unsigned ew_grid(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148 * 16); }
+
+extern "C" int side_ncdhw_to_cl_split(const float *x, float *hi, float *lo, int N, int C, long long S, void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && C > 0 && S > 0, "side_ncdhw_to_cl_split: bad shape");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "side_ncdhw_to_cl_split: grid too large");
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
+    dim3 g((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), b(32, 8);
+    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, hi, lo, C, S);
+    SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream)
+{
+    SIDE_REQUIRE(n >= 0 && n % 4 == 0, "side_tf32_split: element count must be a multiple of 4");
+    if (n == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
+    tf32_split_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo), n / 4);
+    SIDE_LAUNCH_CHECK("tf32_split_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
+                                   void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "side_gate_mul_split: bad shape (C %% 4 == 0)");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(y); SIDE_REQUIRE_DEV(gate); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
+    const long long n4 = (long long)N * D * H * W * C / 4;
+    gate_mul_split_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
+        reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
+    SIDE_LAUNCH_CHECK("gate_mul_split_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C,
+                                   void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
+                 "side_maxpool_hw2_cl: bad shape (even H, W; C %% 4 == 0)");
+    SIDE_REQUIRE(y || (hi && lo), "side_maxpool_hw2_cl: no output requested");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(x);
+    if (y) SIDE_REQUIRE_DEV(y);
+    if (hi) { SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo); }
+    const long long n4 = (long long)N * D * (H / 2) * (W / 2) * C / 4;
+    maxpool_hw2_cl_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
+        reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
+    SIDE_LAUNCH_CHECK("maxpool_hw2_cl_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream)
+{
+    SIDE_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && C > 0 && 27 * C * 4 <= 48 * 1024, "side_conv3d_c1_cl: bad shape");
+    if (N == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(out);
+    const long long nvox = (long long)N * D * H * W;
+    conv3d_c1_cl_kernel<<<ew_grid(nvox * 32, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W,
+                                                                                                      C);
+    SIDE_LAUNCH_CHECK("conv3d_c1_cl_kernel");
+    return SIDE_OK;
+}

@@ -1,0 +1,332 @@
+// conv_tc.cu -- 3x3x3 (and 3x3) stride-1 "same" convolutions of the instance-depth aggregation network on the
+// 5th-gen tensor cores (cost_volume.dres0/dres1/dres2/classify,
+// stereo_network_old.py:139-171, 205-227; nn.Conv3d(3, padding=1, bias=False) + BatchNorm3d + ReLU).
+//
+// cuDNN serves these fp32 convolutions with FFT / Winograd / SIMT-SGEMM kernels (about 70 % of an inference step,
+// profiles/r1_launches_step_3xtf32.md).  Here each one is an implicit GEMM on tcgen05:
+//     y[voxel, o] = sum_{tap, c} x[voxel + tap, c] * W[o, c, tap]        M = N*D*H*W voxels, N = Cout, K = 27*Cin
+// with channels-last activations (NDHWC), so that the A operand of one (tap, 32-channel block) for a tile of 128
+// voxels is ONE 5-D TMA box {32 ch, bw, bh, bd, 1} whose start coordinate is shifted by the tap: the hardware's
+// out-of-bound zero fill IS the convolution's zero padding, and the 128-byte-swizzled box lands in shared memory in
+// exactly the K-major SWIZZLE_128B layout tcgen05.mma reads.  No im2col, no gather warps.
+//
+//   warp 0   TMA producer : per k-block two tensor loads (hi and lo halves of the activations) + one bulk copy of the
+//                           pre-swizzled weight tile, all completing on the stage's mbarrier
+//   warp 1   MMA issuer   : one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128, N=Cout, accumulators in TMEM,
+//                           DOUBLE-BUFFERED (2 x Cout columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5 epilogue    : tcgen05.ld -> folded BatchNorm -> ReLU -> (+ residual) -> fp32 channels-last stores, and/or
+//                           the hi/lo tf32 split the next convolution consumes
+// Persistent grid (one CTA per SM, static round-robin over tiles).
+//
+// Precision: 3xTF32 as in dcn_fwd_tc.cu -- x = hi + lo with hi = top 19 bits (exact split), products hi*hi + lo*hi +
+// hi*lo accumulate in fp32; the dropped lo*lo term is 2^-22 relative.  Activations are kept pre-split in HBM
+// (the producer layer's epilogue writes both halves), so no warp touches the operands between TMA and the MMA.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace side {
+
+constexpr int kCvThreads = 192;
+constexpr int kCvMaxStages = 6;
+constexpr int kCvBM = 128;
+constexpr uint32_t kCvATile = kCvBM * 128;   // 16 KB: 128 voxels x 32 tf32
+
+struct ConvTcParams {
+    const float *wp;                  // [nkb][2][Cout x 32] swizzled weight tiles (hi, lo)
+    float *y, *y_hi, *y_lo;           // [M, Cout] channels-last outputs, any may be NULL
+    const float *scale, *shift;       // folded BatchNorm, NULL = identity
+    const float *residual;            // [M, Cout] added after the ReLU (dres2(cost) + cost), NULL = none
+    int relu;
+    int N, ncb, nkb, ntiles;
+    int D, H, W;                      // spatial extent of one sample
+    int bh, bd;                       // TMA box rows along h and d (bw = W); bd*bh*W == 128
+    int kd, kh, kw;                   // kernel extent (3,3,3) or (1,3,3)
+    int stages;
+};
+
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                                const __grid_constant__ CUtensorMap tm_lo, ConvTcParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[kCvMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kCvMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full[2];
+    __shared__ __align__(8) uint64_t tmem_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_scale[256], s_shift[256];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N;
+    const uint32_t b_part = (uint32_t)N * 128u;
+    const uint32_t stage_bytes = 2 * kCvATile + 2 * b_part;
+    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int stages = p.stages;
+
+    for (int i = tid; i < N; i += kCvThreads) {
+        s_scale[i] = p.scale ? p.scale[i] : 1.0f;
+        s_shift[i] = p.shift ? p.shift[i] : 0.0f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * N) tmem_cols <<= 1;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int S = p.D * p.H * p.W, HW = p.H * p.W;
+    const int khw = p.kh * p.kw;
+    const int pd = (p.kd - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_lo) : "memory");
+            int st = 0;
+            uint32_t phs = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int vox0 = tile * kCvBM;
+                const int n = vox0 / S, r = vox0 - n * S;
+                const int d0 = r / HW, h0 = (r - d0 * HW) / p.W;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
+                    const int kdi = tap / khw, r2 = tap - kdi * khw, khi = r2 / p.kw, kwi = r2 - khi * p.kw;
+                    mbar_wait(&empty_bar[st], phs ^ 1u);
+                    unsigned char *sa = tiles + (size_t)st * stage_bytes;
+                    mbar_expect_tx(&full_bar[st], stage_bytes);
+                    tma_load_5d(sa, &tm_hi, cb * 32, kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
+                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
+                    bulk_g2s(sa + 2 * kCvATile, p.wp + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
+                    if (++st == stages) { st = 0; phs ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_tf32(kCvBM, N);
+            int st = 0, acc = 0;
+            uint32_t phs = 0, acc_ph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&full_bar[st], phs);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
+                    const uint32_t sb = sa + 2 * kCvATile;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
+                        const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32), b_lo = tc_smem_desc(sb + b_part + k * 32);
+                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
+                        tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                    }
+                    tc_commit(&empty_bar[st]);
+                    if (++st == stages) { st = 0; phs ^= 1u; }
+                }
+                tc_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int m = lg * 32 + lane;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const size_t row = (size_t)tile * kCvBM + m;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * N);
+            for (int c = 0; c < N; c += 16) {
+                float v[16];
+                tc_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float o = fmaf(v[j], s_scale[c + j], s_shift[c + j]);
+                    if (p.relu) o = fmaxf(o, 0.f);
+                    v[j] = o;
+                }
+                if (p.residual) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row * N + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 rr = __ldg(rp + j);
+                        v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                    }
+                }
+                if (p.y) {
+                    float4 *yp = reinterpret_cast<float4 *>(p.y + row * N + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (p.y_hi) {
+                    float4 *hp = reinterpret_cast<float4 *>(p.y_hi + row * N + c);
+                    float4 *lp = reinterpret_cast<float4 *>(p.y_lo + row * N + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 h, l;
+                        h.x = tf32_hi(v[4 * j]);     l.x = v[4 * j] - h.x;
+                        h.y = tf32_hi(v[4 * j + 1]); l.y = v[4 * j + 1] - h.y;
+                        h.z = tf32_hi(v[4 * j + 2]); l.z = v[4 * j + 2] - h.z;
+                        h.w = tf32_hi(v[4 * j + 3]); l.w = v[4 * j + 3] - h.w;
+                        hp[j] = h;
+                        lp[j] = l;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// channels-last activation [Nn, D, H, W, C] fp32 -> box {32, bw, bh, bd, 1}, 128-byte swizzle, zero fill out of bounds
+static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw)
+{
+    PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
+    if (!enc) {
+        set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+        return SIDE_ERR_CUDA;
+    }
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Nn};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return SIDE_ERR_CUDA;
+    }
+    return SIDE_OK;
+}
+
+static int g_sm_count = 0;
+
+}  // namespace side
+
+using namespace side;
+
+extern "C" size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps)
+{
+    if (Cin <= 0 || Cout <= 0 || taps <= 0) return 0;
+    return sizeof(float) * 2 * (size_t)Cin * Cout * taps;
+}
+
+extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int taps, void *stream)
+{
+    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= 256 && taps > 0,
+                 "side_conv_tc_prep_weights: needs Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
+    SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(wp);
+    return launch_tc_weight_prep(w, wp, Cout, Cin, taps, 1, (cudaStream_t)stream);
+}
+
+extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale,
+                                  const float *shift, const float *residual, float *y, float *y_hi, float *y_lo, int Nn,
+                                  int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int relu, void *stream)
+{
+    SIDE_REQUIRE(Nn >= 0 && D > 0 && H > 0 && W > 0, "side_conv3d_tc_fwd: bad shape");
+    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= 128,
+                 "side_conv3d_tc_fwd: needs Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 128 (got %d -> %d)", Cin, Cout);
+    SIDE_REQUIRE((kd == 1 || kd == 3) && kh == 3 && kw == 3, "side_conv3d_tc_fwd: kernel must be 3x3x3 or 1x3x3");
+    SIDE_REQUIRE(W <= 128 && (128 % W) == 0, "side_conv3d_tc_fwd: W must divide 128 (got %d)", W);
+    if (Nn == 0) return SIDE_OK;
+    const int bh = std::min(H, 128 / W);
+    SIDE_REQUIRE(H % bh == 0 && (128 % (W * bh)) == 0, "side_conv3d_tc_fwd: H=%d does not tile into 128-voxel boxes", H);
+    const int bd = 128 / (W * bh);
+    SIDE_REQUIRE(D % bd == 0, "side_conv3d_tc_fwd: D=%d must be a multiple of %d for %dx%d maps", D, bd, H, W);
+    SIDE_REQUIRE((long long)Nn * D * H * W < (1ll << 31), "side_conv3d_tc_fwd: too many voxels");
+    SIDE_REQUIRE(y || (y_hi && y_lo), "side_conv3d_tc_fwd: no output requested");
+    SIDE_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "side_conv3d_tc_fwd: y_hi and y_lo go together");
+    SIDE_REQUIRE_DEV(x_hi); SIDE_REQUIRE_DEV(x_lo); SIDE_REQUIRE_DEV(wp);
+    if (y) SIDE_REQUIRE_DEV(y);
+    if (y_hi) { SIDE_REQUIRE_DEV(y_hi); SIDE_REQUIRE_DEV(y_lo); }
+
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, W))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, W))) return rc;
+
+    ConvTcParams p;
+    p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
+    p.relu = relu; p.N = Cout; p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
+    p.ntiles = (int)((long long)Nn * D * H * W / kCvBM);
+    p.D = D; p.H = H; p.W = W; p.bh = bh; p.bd = bd; p.kd = kd; p.kh = kh; p.kw = kw;
+    const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)Cout * 128u;
+    p.stages = std::max(2, std::min((int)((200u * 1024u) / stage_bytes), kCvMaxStages));
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
+    if (g_sm_count == 0) {
+        int dev = 0;
+        SIDE_CUDA(cudaGetDevice(&dev));
+        SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = (unsigned)std::min(p.ntiles, g_sm_count);
+    conv_tc_kernel<<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+    SIDE_LAUNCH_CHECK("conv_tc_kernel");
+    return SIDE_OK;
+}

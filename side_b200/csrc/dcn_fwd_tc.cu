@@ -22,61 +22,15 @@
 // term is 2^-20 relative, so the result meets the reference's fp32 tolerance (<= 1e-4 relative; measured ~1e-6).
 // SIDE_DCN_PREC_TF32 is the single-pass opt-in (~1e-3).
 #include <algorithm>
-#include "dcn_common.cuh"
+#include "tc_common.cuh"
 
 namespace side {
 
 constexpr int kTcBM = 128;            // UMMA M (pixels per tile)
-constexpr int kTcBK = 32;             // tf32 elements per stage row (= 128 bytes, one swizzle row)
 constexpr int kTcProducerThreads = 256;
 constexpr int kTcThreads = kTcProducerThreads + 64;
 constexpr int kTcMaxStages = 8;
 constexpr uint32_t kATileBytes = kTcBM * 128;   // 16 KB
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-// K-major, SWIZZLE_128B operand tile: 8-row groups are 1024 bytes apart (SBO), LBO is unused for swizzled K-major
-// (encoded as 1 like CUTLASS does), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
-{
-    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
-}
-
-// byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128(int row, int chunk)
-{
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // w [Cout, Cin, KK] -> per-K-block tiles: wp[kb][part][Cout x 32] in the swizzled shared-memory image.
 // kb = tap * (Cin/32) + cb;  part 0 = hi (or the full value when !split), part 1 = lo.
@@ -300,6 +254,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     }
 }
 
+int launch_tc_weight_prep(const float *w, float *wp, int Cout, int Cin, int KK, int split, cudaStream_t st)
+{
+    const long long nW = (long long)Cout * Cin * KK;
+    dcn_tc_weight_prep_kernel<<<(unsigned)std::min<long long>(1184, (nW + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin, KK, split);
+    SIDE_LAUNCH_CHECK("dcn_tc_weight_prep_kernel");
+    return SIDE_OK;
+}
+
 bool dcn_fwd_tc_supported(int Cin, int Cout, int dg)
 {
     return dg == 1 && Cin % kTcBK == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
@@ -337,10 +299,7 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     float *xt = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws) + tc_weight_bytes(s.Cin, s.Cout, s.KK, s.flags));
     int rc = launch_nchw_to_nhwc(a.x, xt, s.B, s.Cin, s.H * s.W, st);
     if (rc) return rc;
-    const long long nW = (long long)s.Cout * s.Cin * s.KK;
-    dcn_tc_weight_prep_kernel<<<(unsigned)std::min<long long>(1184, (nW + 255) / 256), 256, 0, st>>>(w, wp, s.Cout, s.Cin, s.KK,
-                                                                                                   split ? 1 : 0);
-    SIDE_LAUNCH_CHECK("dcn_tc_weight_prep_kernel");
+    if ((rc = launch_tc_weight_prep(w, wp, s.Cout, s.Cin, s.KK, split ? 1 : 0, st))) return rc;
 
     const uint32_t stage_bytes = (split ? 2u : 1u) * (kATileBytes + (uint32_t)s.Cout * 128u);
     int stages = (int)((200u * 1024u) / stage_bytes);
@@ -349,7 +308,7 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < s.Cout) tmem_cols <<= 1;
     // instruction descriptor: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(s.Cout >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+    const uint32_t idesc = tc_idesc_tf32(kTcBM, s.Cout);
     const unsigned grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
     if (split) {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;

@@ -1,0 +1,77 @@
+// tc_common.cuh -- tcgen05 / TMEM helpers shared by the tensor-core kernels (dcn_fwd_tc.cu, conv_tc.cu).
+#pragma once
+#include "dcn_common.cuh"
+
+namespace side {
+
+constexpr int kTcBK = 32;             // tf32 elements per stage row (= 128 bytes, one swizzle row)
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: 8-row groups are 1024 bytes apart (SBO), LBO is unused for swizzled K-major
+// (encoded as 1 like CUTLASS does), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+// byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int row, int chunk)
+{
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// instruction descriptor, kind::tf32: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ __forceinline__ uint32_t tc_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// w [Cout, Cin, KK] -> per-K-block tiles wp[kb][part][Cout x 32] in the swizzled shared-memory image (dcn_fwd_tc.cu)
+int launch_tc_weight_prep(const float *w, float *wp, int Cout, int Cin, int KK, int split, cudaStream_t st);
+
+}  // namespace side

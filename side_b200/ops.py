@@ -471,3 +471,99 @@ class _DwDeconv(torch.autograd.Function):
 def dw_deconv(x, w, stride, pad):
     """Depth-wise ConvTranspose2d: x [B,C,H,W], w [C,1,k,k]."""
     return _DwDeconv.apply(x, w, int(stride), int(pad))
+
+
+# ----------------------------------------------------------------------------------------------
+# aggregation network on the tensor cores (channels-last activations, tf32 hi/lo split)
+# ----------------------------------------------------------------------------------------------
+def conv_tc_prepare(weight):
+    """nn.Conv3d / nn.Conv2d weight [Cout, Cin, *k] -> swizzled per-k-block tiles (hi, lo) for side_conv3d_tc_fwd."""
+    lib = _lib.load()
+    weight = _chk(weight, "weight")
+    Cout, Cin = weight.shape[:2]
+    taps = weight[0, 0].numel()
+    nbytes = lib.side_conv_tc_weight_bytes(Cin, Cout, taps)
+    wp = torch.empty((nbytes // 4,), device=weight.device, dtype=_F32)
+    _lib.check(lib.side_conv_tc_prep_weights(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
+               "side_conv_tc_prep_weights")
+    return wp
+
+
+def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, relu=False, residual=None, full=False,
+              split=True):
+    """x_hi, x_lo [N, D, H, W, Cin] -> (y, y_hi, y_lo) [N, D, H, W, Cout] (entries not requested are None)."""
+    lib = _lib.load()
+    x_hi, x_lo = _chk(x_hi, "x_hi"), _chk(x_lo, "x_lo")
+    N, D, H, W, Cin = x_hi.shape
+    dev = x_hi.device
+    y = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if full else None
+    y_hi = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if split else None
+    y_lo = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if split else None
+    if residual is not None:
+        residual = _chk(residual, "residual")
+    _lib.check(lib.side_conv3d_tc_fwd(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
+                                      _p(y), _p(y_hi), _p(y_lo), N, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2],
+                                      1 if relu else 0, _stream()), "side_conv3d_tc_fwd")
+    return y, y_hi, y_lo
+
+
+def ncdhw_to_cl_split(x):
+    """x [N, C, D, H, W] -> hi, lo [N, D, H, W, C]."""
+    lib = _lib.load()
+    x = _chk(x, "x")
+    N, C = x.shape[:2]
+    sp = tuple(x.shape[2:])
+    S = 1
+    for s in sp:
+        S *= s
+    hi = torch.empty((N,) + sp + (C,), device=x.device, dtype=_F32)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.side_ncdhw_to_cl_split(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, C, S, _stream()),
+               "side_ncdhw_to_cl_split")
+    return hi, lo
+
+
+def tf32_split(x):
+    lib = _lib.load()
+    x = _chk(x, "x")
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(lib.side_tf32_split(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "side_tf32_split")
+    return hi, lo
+
+
+def gate_mul_split(y, gate):
+    """y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo."""
+    lib = _lib.load()
+    y, gate = _chk(y, "y"), _chk(gate, "gate")
+    N, D, H, W, C = y.shape
+    if tuple(gate.shape) != (N, D, W, C):
+        raise RuntimeError("gate must be [N, D, W, C]")
+    hi, lo = torch.empty_like(y), torch.empty_like(y)
+    _lib.check(lib.side_gate_mul_split(y.data_ptr(), gate.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, D, H, W, C, _stream()),
+               "side_gate_mul_split")
+    return hi, lo
+
+
+def maxpool_hw2_cl(x, full=False, split=True):
+    """MaxPool3d((1,2,2)) on channels-last x [N, D, H, W, C] -> (y, hi, lo) [N, D, H/2, W/2, C]."""
+    lib = _lib.load()
+    x = _chk(x, "x")
+    N, D, H, W, C = x.shape
+    shp = (N, D, H // 2, W // 2, C)
+    y = torch.empty(shp, device=x.device, dtype=_F32) if full else None
+    hi = torch.empty(shp, device=x.device, dtype=_F32) if split else None
+    lo = torch.empty(shp, device=x.device, dtype=_F32) if split else None
+    _lib.check(lib.side_maxpool_hw2_cl(x.data_ptr(), _p(y), _p(hi), _p(lo), N, D, H, W, C, _stream()), "side_maxpool_hw2_cl")
+    return y, hi, lo
+
+
+def conv3d_c1_cl(x, w):
+    """x [N, D, H, W, C], w [1, C, 3, 3, 3] -> [N, D, H, W]."""
+    lib = _lib.load()
+    x, w = _chk(x, "x"), _chk(w, "w")
+    N, D, H, W, C = x.shape
+    if tuple(w.shape) != (1, C, 3, 3, 3):
+        raise RuntimeError("conv3d_c1_cl: weight must be [1, C, 3, 3, 3]")
+    out = torch.empty((N, D, H, W), device=x.device, dtype=_F32)
+    _lib.check(lib.side_conv3d_c1_cl(x.data_ptr(), w.data_ptr(), out.data_ptr(), N, D, H, W, C, _stream()), "side_conv3d_c1_cl")
+    return out

@@ -1,0 +1,120 @@
+"""GPU parity: the aggregation network on the tensor cores.
+
+Reference = the reference module's own ops (``nn.Conv3d`` / ``BatchNorm3d`` / ``MaxPool3d``, cost_volume.forward,
+stereo_network_old.py:205-227) evaluated by PyTorch on the CPU in float64 -- a floating-point kernel, so the checker is
+the plain torch op; tolerance 1e-4 relative (north_star: fp32 correlation / depth outputs)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    """The strAM Conv2d stays cuDNN: keep it in true fp32 (torch lets cuDNN use TF32 by default)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _cl(x):      # NCDHW -> NDHWC
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, D, H, W, Cin, Cout, relu, affine, residual
+    (2, 16, 16, 16, 96, 64, True, True, False),      # dres0.0
+    (1, 8, 16, 16, 64, 128, True, True, False),      # dres1.3
+    (3, 16, 8, 8, 128, 128, True, True, True),       # dres2.3 + residual
+    (2, 16, 4, 4, 128, 64, True, True, False),       # classify.0
+    (1, 48, 16, 16, 32, 16, False, False, False),    # plain conv, D = 48
+    (5, 2, 8, 8, 64, 32, False, True, False),        # odd sample count, persistent tail
+])
+def test_conv3d_tc_matches_fp64(lib, cfg):
+    from side_b200 import ops
+    N, D, H, W, Cin, Cout, relu, affine, res = cfg
+    g = torch.Generator().manual_seed(N * 1000 + Cin + Cout)
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (2.0 / (27 * Cout)) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5 if affine else None
+    shift = torch.randn(Cout, generator=g) * 0.1 if affine else None
+    r = torch.randn(N, Cout, D, H, W, generator=g) if res else None
+    ref = F.conv3d(x.double(), w.double(), padding=1)
+    if affine:
+        ref = ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1)
+    if relu:
+        ref = ref.relu()
+    if res:
+        ref = ref + r.double()
+    ref = _cl(ref).numpy()
+
+    dev = torch.device("cuda")
+    wp = ops.conv_tc_prepare(w.to(dev))
+    hi, lo = ops.tf32_split(_cl(x).to(dev))
+    assert torch.equal(hi + lo, _cl(x).to(dev))                       # exact split
+    y, yh, yl = ops.conv3d_tc(hi, lo, wp, Cout, scale=None if scale is None else scale.to(dev),
+                              shift=None if shift is None else shift.to(dev), relu=relu,
+                              residual=None if r is None else _cl(r).to(dev), full=True, split=True)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4
+    assert torch.equal(yh + yl, y)                                    # split outputs reassemble the fp32 result exactly
+    assert torch.equal(yh, (y.view(torch.int32) & -8192).view(torch.float32))
+
+
+def test_layout_and_pool_helpers(lib):
+    from side_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    dev = torch.device("cuda")
+    x = torch.randn(3, 40, 4, 6, 10, generator=g)                    # NCDHW, ragged vs the 32x32 transpose tile
+    hi, lo = ops.ncdhw_to_cl_split(x.to(dev))
+    assert torch.equal((hi + lo).cpu(), _cl(x))
+    assert torch.equal(hi.cpu(), (_cl(x).view(torch.int32) & -8192).view(torch.float32))
+    y = torch.randn(2, 5, 6, 8, 12, generator=g)                     # NDHWC
+    gate = torch.rand(2, 5, 8, 12, generator=g)
+    hi, lo = ops.gate_mul_split(y.to(dev), gate.to(dev))
+    assert torch.equal((hi + lo).cpu(), y * gate.unsqueeze(2))
+    full, hi, lo = ops.maxpool_hw2_cl(y.to(dev), full=True, split=True)
+    ref = F.max_pool3d(y.permute(0, 4, 1, 2, 3), (1, 2, 2)).permute(0, 2, 3, 4, 1)
+    assert torch.equal(full.cpu(), ref) and torch.equal((hi + lo).cpu(), ref)
+    w = torch.randn(1, 12, 3, 3, 3, generator=g)
+    out = ops.conv3d_c1_cl(y.to(dev), w.to(dev))
+    ref = F.conv3d(y.permute(0, 4, 1, 2, 3).double(), w.double(), padding=1)[:, 0]
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("N,D", [(3, 16), (2, 48)])
+def test_aggregate_tc_matches_module_fp64(lib, N, D):
+    """cost_volume.aggregate on tcgen05 == the reference layer sequence in float64 on the CPU (<= 1e-4 of the logit range),
+    and the depth regressed from it agrees to 1e-4 relative."""
+    from side_b200 import ops
+    from side_b200.networks.stereo_network import cost_volume
+    torch.manual_seed(11)
+    m = cost_volume(64).eval()
+    for mod in m.modules():                                           # non-trivial eval BatchNorm statistics
+        if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2)
+            mod.bias.data.normal_(0, 0.1)
+    cost = torch.randn(N, 96, D, 16, 16)
+    with torch.no_grad():
+        ref = m.double().aggregate(cost.double()).float()
+    m = m.float().cuda()
+    with torch.no_grad():
+        c = cost.cuda()
+        assert m._tc_ok(c)
+        out = m.aggregate_tc(c)
+        assert tuple(out.shape) == (N, D, 4, 4)
+        scale = float(ref.abs().max())
+        assert float((out.cpu() - ref).abs().max()) < 1e-4 * scale
+        db = torch.linspace(87, 5, D).repeat(N, 1)
+        d_tc = ops.softargmin(out.contiguous(), db.cuda()).cpu()
+        d_ref = ops.softargmin(ref.cuda().contiguous(), db.cuda()).cpu()
+        assert float(((d_tc - d_ref).abs() / d_ref.abs()).max()) < 1e-4
+        # the module switches back to cuDNN under autograd / training
+        assert not m.train()._tc_ok(c)
