@@ -55,8 +55,15 @@ enum {
 enum {
     SIDE_VOL_GATE = 1 << 0, /* multiply every (roi, depth) slice by the cosine gate x_cross
                                (cost_volume.forward, stereo_network_old.py:197-203) */
-    SIDE_VOL_FMA = 1 << 1   /* opt-in: contract the 4-tap bilinear sum into FMAs (as nvcc does for torchvision's CUDA
+    SIDE_VOL_FMA = 1 << 1,  /* opt-in: contract the 4-tap bilinear sum into FMAs (as nvcc does for torchvision's CUDA
                                kernel).  <= 1e-6 relative to the bit-exact default, ~half the instructions. */
+    SIDE_VOL_SEPARABLE = 1 << 2, /* separable evaluation: the y interpolation (identical for all D candidates of a RoI)
+                               is computed once per RoI into shared memory, every bin is then 4 taps.  Values differ
+                               from torchvision's operation order by a few ulp (<= 1e-5 relative);
+                               channel placement and L-R stay exact.  Needs P == 16, C % 8 == 0, D <= 256 and
+                               side_inst_costvol_fast_ws_bytes(...) bytes of workspace. */
+    SIDE_VOL_XCROSS = 1 << 3 /* with SEPARABLE and without GATE: also return the gate scalar xcross[N, D] computed in the
+                               same pass, WITHOUT applying it (the consumer, side_ncdhw_to_cl_split, multiplies) */
 };
 
 /* decode flavour */
@@ -123,6 +130,7 @@ int side_proposal_shift(const float *left, const float *right, const float *fb, 
  *                NULL selects the slower NCHW gather.  Results are bit-identical either way.
  * --------------------------------------------------------------------------------------------- */
 size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W);
+size_t side_inst_costvol_fast_ws_bytes(int B, int C, int H, int W, int N, int D);
 int side_inst_costvol_fwd(const float *featL, const float *featR, const float *left, const float *right,
                           const float *fb, const uint8_t *valid, float *cost, float *depth_bin, float *xcross,
                           int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *ws,

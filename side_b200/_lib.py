@@ -25,6 +25,7 @@ SIGNATURES = {
     "side_dcn_bwd": (_i, [_vp] * 10 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
     "side_proposal_shift": (_i, [_vp] * 3 + [_i] * 3 + [_f] + [_vp] * 4),
     "side_inst_costvol_ws_bytes": (_sz, [_i] * 4),
+    "side_inst_costvol_fast_ws_bytes": (_sz, [_i] * 6),
     "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
     "side_inst_costvol_bwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
     "side_xcross_gate_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
@@ -59,6 +60,8 @@ DCN_PREC_3XTF32 = 1 << 4
 DCN_PREC_TF32 = 2 << 4
 VOL_GATE = 1 << 0
 VOL_FMA = 1 << 1
+VOL_SEPARABLE = 1 << 2
+VOL_XCROSS = 1 << 3
 DECODE_HEAT_IS_LOGIT = 1 << 0
 
 _lib = None

@@ -13,7 +13,7 @@
 //   warp 0   TMA producer : per k-block two tensor loads (hi and lo halves of the activations) + one bulk copy of the
 //                           pre-swizzled weight tile, all completing on the stage's mbarrier
 //   warp 1   MMA issuer   : one thread, tcgen05.mma.cta_group::1.kind::tf32, M=128, N=Cout, accumulators in TMEM,
-//                           DOUBLE-BUFFERED (2 x Cout columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//                           DOUBLE-BUFFERED (2 x 2 x Cout columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2-5 epilogue    : tcgen05.ld -> folded BatchNorm -> ReLU -> (+ residual) -> fp32 channels-last stores, and/or
 //                           the hi/lo tf32 split the next convolution consumes
 // Persistent grid (one CTA per SM, static round-robin over tiles).
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         mbar_fence_init();
     }
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < 2 * N) tmem_cols <<= 1;
+    while ((int)tmem_cols < 4 * N) tmem_cols <<= 1;   // 2 buffers x (main, cross) accumulators
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(tmem_cols)
@@ -141,7 +141,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                // Two accumulators per tile: hi*hi in `tmem_d`, the two small cross terms in `tmem_x`.  The tensor core
+                // adds into the fp32 accumulator with truncation (round toward zero), a bias of ~0.5 ulp of the
+                // accumulator per MMA; keeping the 2/3 of the MMAs that carry 2^-11-sized terms out of the main
+                // accumulator cuts that bias 3x (the cross accumulator is ~2^-10 of the main one, its ulp is negligible).
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
+                const uint32_t tmem_x = tmem_d + (uint32_t)N;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&full_bar[st], phs);
                     tc_fence_after();
@@ -152,8 +157,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                         const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32), b_lo = tc_smem_desc(sb + b_part + k * 32);
                         tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
-                        tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                        tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tmem_x, a_hi, b_lo, idesc, 1u);
                     }
                     tc_commit(&empty_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
@@ -173,13 +178,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
             const size_t row = (size_t)tile * kCvBM + m;
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
             for (int c = 0; c < N; c += 16) {
-                float v[16];
+                float v[16], vx[16];
                 tc_ld16(taddr + (uint32_t)c, v);
+                tc_ld16(taddr + (uint32_t)(N + c), vx);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float o = fmaf(v[j], s_scale[c + j], s_shift[c + j]);
+                    float o = fmaf(v[j] + vx[j], s_scale[c + j], s_shift[c + j]);
                     if (p.relu) o = fmaxf(o, 0.f);
                     v[j] = o;
                 }

@@ -200,6 +200,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         for (int c = cbeg; c < cend; c += 8) {
             float acc[8];
             tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, acc);
+            if (SPLIT) {                      // cross-term accumulator (see the MMA issuer)
+                float accx[8];
+                tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(N + c), accx);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += accx[j];
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int n = c + j;
@@ -223,10 +229,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                     const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                     tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
                     if (SPLIT) {
+                        // The two small cross terms go to a SECOND accumulator (columns N..2N): the tensor core adds
+                        // into fp32 with truncation, ~0.5 ulp of the accumulator per MMA, so keeping them out of the
+                        // main accumulator cuts that systematic bias 3x; the epilogue adds the two.
                         const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
                         const uint64_t b_lo = tc_smem_desc(sb + b_part_bytes + k * 32);
-                        tc_mma_tf32(tmem_d, a_lo, b_hi, idesc, 1u);
-                        tc_mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                        tc_mma_tf32(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tmem_d + (uint32_t)N, a_hi, b_lo, idesc, 1u);
                     }
                 }
                 tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
@@ -306,7 +315,7 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     stages = std::max(2, std::min(stages, kTcMaxStages));
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < s.Cout) tmem_cols <<= 1;
+    while ((int)tmem_cols < (split ? 2 : 1) * s.Cout) tmem_cols <<= 1;
     // instruction descriptor: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = tc_idesc_tf32(kTcBM, s.Cout);
     const unsigned grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);

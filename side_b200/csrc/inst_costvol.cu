@@ -19,6 +19,10 @@
 
 namespace side {
 
+// compiler-level scheduling barrier: keeps ptxas from hoisting the next batch of shared loads over this point
+// (bounds the live registers of the separable slice loop; it emits no instruction)
+#define SEP_SCHED_FENCE() asm volatile("" ::: "memory")
+
 struct AxisSample {
     int lo, hi;   // lo < 0  => sample outside the image (contributes 0)
     float l, h;   // fractional weight towards hi, and 1 - l
@@ -427,6 +431,355 @@ __global__ void __launch_bounds__(kNhwcThreads) inst_costvol_fwd_nhwc_kernel(Vol
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Separable fast path (SIDE_VOL_SEPARABLE).
+// The RoIAlign of depth candidate d samples the SAME 32 feature rows for every d of a RoI (the candidates only shift
+// the box along x, stereo_network_old.py:70-77), so the y half of the bilinear interpolation and the sum over the two
+// y sub-samples of a bin are shared by all D slices.  One CTA owns (RoI n, 8 channels): it builds
+//     U[side][ph][x][c] = sum_{iy} ( hy * f[ylo][x][c] + ly * f[yhi][x][c] )          (once per group of slices)
+// in shared memory for the window of columns the group's shifted boxes touch, and every output bin is then 4 taps
+//     bin = sum_{ix} ( 0.25*hx * U[ph][xlo] + 0.25*lx * U[ph][xhi] )
+// instead of 16 global taps and 33 rounded operations.  One warp per slice: lane = (channel, row of a pair, 4 consecutive
+// bins); the 32 x-sample table entries of the slice are computed one per lane and exchanged by shuffles; a quarter-warp's
+// 16-byte evict-first stores cover 128 contiguous bytes.  The gate statistics (sum L^2, sum R^2, sum L*R) are
+// accumulated in the same pass as per-(n, d, channel-chunk) partials, so the fused network path needs ONE pass over the
+// volume (the scalar gate is applied by the consumer, side_ncdhw_to_cl_split); SIDE_VOL_GATE on this path runs a
+// statistics pass first.
+// Numerics: same sample positions, validity rules and weights as the exact kernels; the products are re-associated
+// (y before x), so values differ from torchvision's order by a few ulp (<= 1e-6 relative, tests allow 1e-5); L-R is
+// still computed from the kernel's own L and R, channel placement is exact.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSepCC = 8;             // channels per CTA
+constexpr int kSepThreads = 512;
+constexpr int kSepXq = 22;            // window columns per (side, lane-quad)
+constexpr int kSepMaxD = 256;
+// U[side][ph][cell][8 channels]: cell = 4 * (x - win[quad]) + quad, i.e. the four lane-quads of a warp (bins 0-3, 4-7,
+// 8-11, 12-15) read from four interleaved sub-windows whose 32-byte cells sit in different bank octets BY CONSTRUCTION;
+// the row stride is = 4 (mod 32) floats so the two rows a warp instruction touches are 4 banks apart: every shared load
+// of the slice loop is conflict-free whatever the box geometry.
+constexpr int kSepRowF = 4 * (kSepXq + 2) * kSepCC + 4;     // floats per ph row (772): kSepXq real cells + 2 zero cells
+constexpr int kSepUSide = 16 * kSepRowF;                     // floats per side
+
+// first / last integer cell touched by x-samples e0..e1 of a box (clamped into the image like axis_sample does)
+__device__ __forceinline__ void sep_cells(float start, float bin, int e0, int e1, int W, int &c0, int &c1)
+{
+    const float a = __fadd_rn(__fadd_rn(start, __fmul_rn((float)(e0 >> 1), bin)),
+                              __fdiv_rn(__fmul_rn((float)(e0 & 1) + 0.5f, bin), 2.0f));
+    const float b = __fadd_rn(__fadd_rn(start, __fmul_rn((float)(e1 >> 1), bin)),
+                              __fdiv_rn(__fmul_rn((float)(e1 & 1) + 0.5f, bin), 2.0f));
+    c0 = min(max((int)floorf(fminf(fmaxf(a, -2.f), (float)W + 1.f)), 0), W - 1);
+    c1 = min(min(max((int)floorf(fminf(fmaxf(b, -2.f), (float)W + 1.f)), 0), W - 1) + 1, W - 1);
+}
+
+template <bool WRITE, bool STATS, bool APPLY>
+__global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolParams p, const float *__restrict__ nhwcL,
+                                                                         const float *__restrict__ nhwcR,
+                                                                         float *__restrict__ partial)
+{
+    extern __shared__ __align__(16) float U[];              // [2][16][kSepRowF]
+    __shared__ AxisTap ytab[32];
+    __shared__ float4 geo[kSepMaxD];                         // lx1, bin_w(left), rx1, bin_w(right) per slice
+    __shared__ short2 cellbuf[kSepMaxD][8];                  // (first, last) cell per slice and (side, quad)
+    __shared__ int g_d1, g_win[8], g_wr[8];                  // current slice group: last slice, window start / width
+    __shared__ int s_slow;
+
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x, c0 = chunk * kSepCC;
+    const int C = p.C, D = p.D, W = p.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSepThreads >> 5;
+    const size_t cs = (size_t)D * 256;
+    float *outn = p.cost + ((size_t)n * 3 * C + c0) * cs;
+
+    if (p.valid && !p.valid[n]) {
+        if (WRITE) {
+            for (int i = tid; i < 3 * kSepCC * D * 64; i += kSepThreads) {
+                const int q4 = i & 63, rest = i >> 6, d = rest % D, ch = rest / D;     // ch = which * 8 + cc
+                st_cs(reinterpret_cast<float4 *>(outn + ((size_t)(ch >> 3) * C + (ch & 7)) * cs + (size_t)d * 256) + q4,
+                      make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            if (chunk == 0)
+                for (int d = tid; d < D; d += kSepThreads) p.depth_bin[(size_t)n * D + d] = 0.f;
+        }
+        if (STATS)
+            for (int d = tid; d < D; d += kSepThreads)
+                *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+
+    const float *lb = p.left + (size_t)n * 5, *rb = p.right + (size_t)n * 5;
+    const int b = min(max((int)lb[0], 0), p.B - 1);
+    const float fb = p.fb[b];
+    if (tid == 0) s_slow = 0;
+    for (int d = tid; d < D; d += kSepThreads) {
+        float dbin, lx1, lx2, rx1, rx2, y1, y2;
+        proposal_for(lb, rb, fb, d, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+        const float rwl = fmaxf(__fsub_rn(lx2, lx1), 1.0f), rwr = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
+        geo[d] = make_float4(lx1, __fdiv_rn(rwl, 16.0f), rx1, __fdiv_rn(rwr, 16.0f));
+        if (WRITE && chunk == 0) p.depth_bin[(size_t)n * D + d] = dbin;
+    }
+    if (tid < 32) {
+        float dbin, lx1, lx2, rx1, rx2, y1, y2;
+        proposal_for(lb, rb, fb, 0, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+        const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
+        ytab[tid] = to_tap(axis_sample(y1, __fdiv_rn(rh, 16.0f), tid >> 1, tid & 1, p.H), W * C);
+    }
+    __syncthreads();
+    // cells touched by each lane-quad (x-samples 8q .. 8q+7) of each slice, both sides
+    for (int i = tid; i < D * 8; i += kSepThreads) {
+        const int d = i >> 3, sq = i & 7, q = sq & 3;
+        const float4 g4 = geo[d];
+        int a0, a1;
+        sep_cells(sq < 4 ? g4.x : g4.z, sq < 4 ? g4.y : g4.w, 8 * q, 8 * q + 7, W, a0, a1);
+        cellbuf[d][sq] = make_short2((short)a0, (short)a1);
+        if (a1 - a0 + 1 > kSepXq) s_slow = 1;               // one slice alone overflows a sub-window: box > ~90 columns wide
+    }
+    __syncthreads();
+
+    const float *fLb = nhwcL + (size_t)b * p.H * W * C + c0;
+    const float *fRb = nhwcR + (size_t)b * p.H * W * C + c0;
+
+    if (s_slow) {
+        // Very wide box (> ~90 feature columns, or garbage): the same formula evaluated straight from global memory,
+        // one slice at a time.  Results are identical to the fast path's.
+        float *red = U;
+        for (int d = 0; d < D; ++d) {
+            const float4 g4 = geo[d];
+            float sv[4] = {0.f, 0.f, 0.f, 0.f};
+            float g = 1.0f;
+            if (APPLY) {
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                for (int j = 0; j < nchunk; ++j) {
+                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nchunk + j) * 4);
+                    t0 += ps.x; t1 += ps.y; t2 += ps.z;
+                }
+                g = __fdiv_rn(t2, fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f));
+                if (chunk == 0 && tid == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+            }
+            for (int idx = tid; idx < 256 * kSepCC; idx += kSepThreads) {
+                const int c1 = idx & 7, q = idx >> 3, ph = q >> 4, pw = q & 15;
+                const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
+                float lr[2];
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const float *f = (side ? fRb : fLb) + c1;
+                    float t = 0.f;
+#pragma unroll
+                    for (int ix = 0; ix < 2; ++ix) {
+                        const AxisSample sx = axis_sample(side ? g4.z : g4.x, side ? g4.w : g4.y, pw, ix, W);
+                        float ulo = 0.f, uhi = 0.f, wq = 0.f;
+                        if (sx.lo >= 0) {
+                            const float *a = f + (size_t)sx.lo * C, *bq = f + (size_t)sx.hi * C;
+                            ulo = fmaf(t0.l, __ldg(a + t0.ohi), t0.h * __ldg(a + t0.olo)) + fmaf(t1.l, __ldg(a + t1.ohi), t1.h * __ldg(a + t1.olo));
+                            uhi = fmaf(t0.l, __ldg(bq + t0.ohi), t0.h * __ldg(bq + t0.olo)) + fmaf(t1.l, __ldg(bq + t1.ohi), t1.h * __ldg(bq + t1.olo));
+                            wq = 0.25f * sx.l;
+                        }
+                        t = ix == 0 ? (0.25f - wq) * ulo : fmaf(0.25f - wq, ulo, t);
+                        t = fmaf(wq, uhi, t);
+                    }
+                    lr[side] = t;
+                }
+                if (STATS) {
+                    sv[0] = fmaf(lr[0], lr[0], sv[0]); sv[1] = fmaf(lr[1], lr[1], sv[1]); sv[2] = fmaf(lr[0], lr[1], sv[2]);
+                }
+                if (WRITE) {
+                    float *o = outn + (size_t)c1 * cs + (size_t)d * 256 + q;
+                    float lv = lr[0], rv = lr[1], dv = __fsub_rn(lr[0], lr[1]);
+                    if (APPLY) { lv = __fmul_rn(lv, g); rv = __fmul_rn(rv, g); dv = __fmul_rn(dv, g); }
+                    st_cs(o, lv);
+                    st_cs(o + (size_t)C * cs, rv);
+                    st_cs(o + (size_t)2 * C * cs, dv);
+                }
+            }
+            if (STATS) {
+                block_sum<4>(sv, red);
+                if (tid == 0)
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(sv[0], sv[1], sv[2], 0.f);
+                __syncthreads();
+            }
+        }
+        return;
+    }
+
+    // lane = (channel-in-group ccl, row-in-pair phsel, quad): a quarter-warp's 16-byte stores cover 128 contiguous bytes
+    const int quad = lane & 3, phsel = (lane >> 2) & 1, ccl = lane >> 3;
+
+    int d0 = 0;
+    while (d0 < D) {
+        // ---- slice group [d0, d1]: grow while all 8 sub-windows stay within kSepXq columns (warp 0, one lane per window) ----
+        if (warp == 0) {
+            const int sq = lane & 7;
+            int lo = cellbuf[d0][sq].x, hi = cellbuf[d0][sq].y, dd = d0;
+            while (dd + 1 < D) {
+                const short2 c = cellbuf[dd + 1][sq];
+                const int nlo = min(lo, (int)c.x), nhi = max(hi, (int)c.y);
+                if (!__all_sync(0xffffffffu, nhi - nlo + 1 <= kSepXq)) break;
+                lo = nlo; hi = nhi; ++dd;
+            }
+            if (lane < 8) { g_win[sq] = lo; g_wr[sq] = hi - lo + 1; }
+            if (lane == 0) g_d1 = dd;
+        }
+        __syncthreads();
+        const int d1 = g_d1;
+        // ---- build U: local cells 0..wr-1 real, cells wr and wr+1 = zeros (invalid samples read (wr, wr+1); a sample
+        //      clamped at the right border reads (W-1, W) with weight 0 on the second) ----
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const float *f = side ? fRb : fLb;
+            float *Us = U + side * kSepUSide;
+            const int ncell = max(max(g_wr[4 * side], g_wr[4 * side + 1]), max(g_wr[4 * side + 2], g_wr[4 * side + 3])) + 2;
+            for (int it = tid; it < 16 * ncell * 8; it += kSepThreads) {
+                const int half = it & 1, q = (it >> 1) & 3, r2 = it >> 3, cell = r2 % ncell, ph = r2 / ncell;
+                const int wr = g_wr[4 * side + q];
+                if (cell > wr + 1) continue;
+                const int x = g_win[4 * side + q] + cell;
+                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cell < wr && x <= W - 1) {
+                    const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
+                    const float *fx = f + (size_t)x * C + 4 * half;
+                    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(fx + t0.olo));
+                    const float4 a1 = __ldg(reinterpret_cast<const float4 *>(fx + t0.ohi));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(fx + t1.olo));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(fx + t1.ohi));
+                    u.x = fmaf(t0.l, a1.x, t0.h * a0.x) + fmaf(t1.l, b1.x, t1.h * b0.x);
+                    u.y = fmaf(t0.l, a1.y, t0.h * a0.y) + fmaf(t1.l, b1.y, t1.h * b0.y);
+                    u.z = fmaf(t0.l, a1.z, t0.h * a0.z) + fmaf(t1.l, b1.z, t1.h * b0.z);
+                    u.w = fmaf(t0.l, a1.w, t0.h * a0.w) + fmaf(t1.l, b1.w, t1.h * b0.w);
+                }
+                *reinterpret_cast<float4 *>(Us + (size_t)ph * kSepRowF + (4 * cell + q) * kSepCC + 4 * half) = u;
+            }
+        }
+        __syncthreads();
+        // ---- one warp per slice ----
+        for (int d = d0 + warp; d <= d1; d += nwarps) {
+            const float4 g4 = geo[d];
+            // x-sample `lane` of this slice (it belongs to quad lane >> 3): byte offset of its first cell inside that quad's
+            // sub-window + 0.25 * fractional weight
+            uint32_t myoL, myoR;
+            float mybL = 0.f, mybR = 0.f;
+            {
+                const int sq = lane >> 3;
+                myoL = (uint32_t)((4 * g_wr[sq] + sq) * kSepCC * 4);         // invalid sample: the two zero cells
+                myoR = (uint32_t)((4 * g_wr[4 + sq] + sq) * kSepCC * 4);
+                const AxisSample sl = axis_sample(g4.x, g4.y, lane >> 1, lane & 1, W);
+                if (sl.lo >= 0) {
+                    myoL = (uint32_t)((4 * (sl.lo - g_win[sq]) + sq) * kSepCC * 4);
+                    mybL = 0.25f * sl.l;
+                }
+                const AxisSample sr = axis_sample(g4.z, g4.w, lane >> 1, lane & 1, W);
+                if (sr.lo >= 0) {
+                    myoR = (uint32_t)((4 * (sr.lo - g_win[4 + sq]) + sq) * kSepCC * 4);
+                    mybR = 0.25f * sr.l;
+                }
+            }
+            // the second cell of a sample is always the next one of the sub-window (+128 bytes): hi = lo + 1, or lo == W-1
+            // where the weight of the second cell is exactly 0 and the next cell holds zeros
+            uint32_t oL[4], oR[4];        // two samples' offsets per register
+            float bL[8], bR[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int src = (quad << 3) + j;
+                const uint32_t tl = __shfl_sync(0xffffffffu, myoL, src), tr = __shfl_sync(0xffffffffu, myoR, src);
+                if (j & 1) { oL[j >> 1] |= tl << 16; oR[j >> 1] |= tr << 16; }
+                else { oL[j >> 1] = tl; oR[j >> 1] = tr; }
+                bL[j] = __shfl_sync(0xffffffffu, mybL, src);
+                bR[j] = __shfl_sync(0xffffffffu, mybR, src);
+            }
+            float g = 1.0f;
+            if (APPLY) {
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                if (lane < nchunk) {
+                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nchunk + lane) * 4);
+                    t0 = ps.x; t1 = ps.y; t2 = ps.z;
+                }
+                t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+                const float den = fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f);
+                g = __fdiv_rn(t2, den);
+                if (chunk == 0 && lane == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+            }
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            constexpr int kRowBytes = kSepRowF * 4;
+            const size_t side_stride = (size_t)C * cs;                // L -> R -> L-R planes
+#pragma unroll 1
+            for (int cg = 0; cg < 2; ++cg) {                          // channel group (4 channels per warp instruction)
+                const char *uL = reinterpret_cast<const char *>(U + phsel * kSepRowF + 4 * cg + ccl);
+                const char *uR = uL + kSepUSide * 4;
+                float *o = outn + (size_t)(4 * cg + ccl) * cs + (size_t)d * 256 + phsel * 16 + 4 * quad;
+#pragma unroll 1
+                for (int rp2 = 0; rp2 < 4; ++rp2, uL += 4 * kRowBytes, uR += 4 * kRowBytes, o += 64) {
+#pragma unroll
+                    for (int rp = 0; rp < 2; ++rp) {                  // row pair within this iteration
+                        const int ub = 2 * rp * kRowBytes;            // immediate byte offset into U
+                        float l[4], r[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a0 = oL[j] & 0xffffu, a1 = oL[j] >> 16;
+                            const float w0 = bL[2 * j], w1 = bL[2 * j + 1];
+                            float t = (0.25f - w0) * *reinterpret_cast<const float *>(uL + ub + a0);
+                            t = fmaf(w0, *reinterpret_cast<const float *>(uL + ub + 128 + a0), t);
+                            t = fmaf(0.25f - w1, *reinterpret_cast<const float *>(uL + ub + a1), t);
+                            l[j] = fmaf(w1, *reinterpret_cast<const float *>(uL + ub + 128 + a1), t);
+                        }
+                        SEP_SCHED_FENCE();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t c0r = oR[j] & 0xffffu, c1r = oR[j] >> 16;
+                            const float v0 = bR[2 * j], v1 = bR[2 * j + 1];
+                            float q = (0.25f - v0) * *reinterpret_cast<const float *>(uR + ub + c0r);
+                            q = fmaf(v0, *reinterpret_cast<const float *>(uR + ub + 128 + c0r), q);
+                            q = fmaf(0.25f - v1, *reinterpret_cast<const float *>(uR + ub + c1r), q);
+                            r[j] = fmaf(v1, *reinterpret_cast<const float *>(uR + ub + 128 + c1r), q);
+                        }
+                        if (STATS) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                s0 = fmaf(l[j], l[j], s0);
+                                s1 = fmaf(r[j], r[j], s1);
+                                s2 = fmaf(l[j], r[j], s2);
+                            }
+                        }
+                        if (WRITE) {
+                            float4 lv = make_float4(l[0], l[1], l[2], l[3]), rv = make_float4(r[0], r[1], r[2], r[3]);
+                            float4 dv = make_float4(__fsub_rn(l[0], r[0]), __fsub_rn(l[1], r[1]), __fsub_rn(l[2], r[2]),
+                                                    __fsub_rn(l[3], r[3]));
+                            if (APPLY) {
+                                lv.x = __fmul_rn(lv.x, g); lv.y = __fmul_rn(lv.y, g); lv.z = __fmul_rn(lv.z, g); lv.w = __fmul_rn(lv.w, g);
+                                rv.x = __fmul_rn(rv.x, g); rv.y = __fmul_rn(rv.y, g); rv.z = __fmul_rn(rv.z, g); rv.w = __fmul_rn(rv.w, g);
+                                dv.x = __fmul_rn(dv.x, g); dv.y = __fmul_rn(dv.y, g); dv.z = __fmul_rn(dv.z, g); dv.w = __fmul_rn(dv.w, g);
+                            }
+                            float *oo = o + rp * 32;
+                            st_cs(reinterpret_cast<float4 *>(oo), lv);
+                            st_cs(reinterpret_cast<float4 *>(oo + side_stride), rv);
+                            st_cs(reinterpret_cast<float4 *>(oo + 2 * side_stride), dv);
+                        }
+                        SEP_SCHED_FENCE();
+                    }
+                }
+            }
+            if (STATS) {
+                s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+                if (lane == 0)
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(s0, s1, s2, 0.f);
+            }
+        }
+        __syncthreads();
+        d0 = d1 + 1;
+    }
+}
+
+// xcross[n, d] from the per-chunk partial sums (fused network path: the gate is applied by the consumer)
+__global__ void sep_finish_xcross_kernel(const float *__restrict__ partial, const uint8_t *__restrict__ valid,
+                                         float *__restrict__ xcross, int ND, int D, int nchunk)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ND) return;
+    if (valid && !valid[i / D]) { xcross[i] = 0.f; return; }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < nchunk; ++j) {
+        const float4 ps = *reinterpret_cast<const float4 *>(partial + ((size_t)i * nchunk + j) * 4);
+        s0 += ps.x; s1 += ps.y; s2 += ps.z;
+    }
+    xcross[i] = __fdiv_rn(s2, fmaxf(__fmul_rn(sqrtf(s0), sqrtf(s1)), 0.01f));
+}
+
 // scatter g * w_i / 4 to the 4 corners of the 2x2 samples of one bin (torchvision roi_align backward)
 __device__ __forceinline__ void roi_bin_scatter(float *__restrict__ gim, int W, const AxisSample *__restrict__ ys,
                                                 const AxisSample *__restrict__ xs, float g)
@@ -617,6 +970,12 @@ static int check_vol_args(const VolParams &p)
 
 using namespace side;
 
+extern "C" size_t side_inst_costvol_fast_ws_bytes(int B, int C, int H, int W, int N, int D)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0 || D <= 0) return 0;
+    return sizeof(float) * (2 * (size_t)B * C * H * W + 4 * (size_t)N * D * ((C + kSepCC - 1) / kSepCC));
+}
+
 extern "C" size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W)
 {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
@@ -651,6 +1010,40 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
     const bool gate = flags & SIDE_VOL_GATE;
     const dim3 grid((unsigned)((long long)N * D));
     cudaStream_t st = (cudaStream_t)stream;
+    if (flags & SIDE_VOL_SEPARABLE) {
+        SIDE_REQUIRE(P == 16 && C % kSepCC == 0 && D <= kSepMaxD && N <= 65535,
+                     "inst_costvol: the separable path needs P == 16, C %% 8 == 0, D <= %d, N <= 65535", kSepMaxD);
+        SIDE_REQUIRE((long long)B * H * W * C < (1ll << 31) && W < 32768, "inst_costvol: features too large for the separable path");
+        if (ws == nullptr || ws_bytes < side_inst_costvol_fast_ws_bytes(B, C, H, W, N, D) || !is_device_ptr(ws)) {
+            set_error("inst_costvol: the separable path needs side_inst_costvol_fast_ws_bytes(...) bytes of device workspace");
+            return SIDE_ERR_WORKSPACE;
+        }
+        float *nl = reinterpret_cast<float *>(ws), *nr = nl + (size_t)B * C * H * W, *partial = nr + (size_t)B * C * H * W;
+        if ((rc = launch_nchw_to_nhwc(featL, nl, B, C, H * W, st))) return rc;
+        if ((rc = launch_nchw_to_nhwc(featR, nr, B, C, H * W, st))) return rc;
+        const size_t smem = sizeof(float) * 2 * kSepUSide;
+        const dim3 sg((unsigned)(C / kSepCC), (unsigned)N);
+        const bool want_xc = (flags & SIDE_VOL_XCROSS) && xcross != nullptr;
+        if (gate) {
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<false, true, false>, smem))) return rc;
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, false, true>, smem))) return rc;
+            inst_costvol_sep_kernel<false, true, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
+            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<stats>");
+            inst_costvol_sep_kernel<true, false, true><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
+            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write, gate>");
+        } else if (want_xc) {
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, true, false>, smem))) return rc;
+            inst_costvol_sep_kernel<true, true, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
+            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write, stats>");
+            sep_finish_xcross_kernel<<<ceil_div((long long)N * D, 128), 128, 0, st>>>(partial, valid, xcross, N * D, D, C / kSepCC);
+            SIDE_LAUNCH_CHECK("sep_finish_xcross_kernel");
+        } else {
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, false, false>, smem))) return rc;
+            inst_costvol_sep_kernel<true, false, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
+            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write>");
+        }
+        return SIDE_OK;
+    }
     // channels-last fast path: needs the transposed copies (workspace), C % 4 == 0, P*P % 4 == 0 and the padded
     // L/R tiles in shared memory
     const size_t nhwc_smem = sizeof(AxisTap) * 6 * P + sizeof(float) * 4 * 32 + sizeof(float) * 2 * (size_t)C * (P * P + 1);

@@ -189,3 +189,57 @@ def test_fma_mode_within_1e6(lib):
         a = ops.inst_costvol(*args, gate=gate)[0]
         b = ops.inst_costvol(*args, gate=gate, fma=True)[0]
         assert (a - b).abs().max().item() <= 1e-6 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("cfg", [(2, 8, 24, 80, 9, 16), (1, 64, 24, 80, 3, 48), (3, 32, 17, 61, 11, 5), (1, 16, 96, 320, 7, 48)])
+def test_separable_path_vs_exact_oracle(lib, cfg):
+    """SIDE_VOL_SEPARABLE: same sample positions / validity rules, products re-associated (y first, shared by all D).
+    Interpolated values <= 1e-5 of the range from the bit-exact oracle (SURVEY 8(a) A5 bound); L-R from the kernel's own
+    L, R exactly; depth bins bit-exact; gate <= 1e-4; ungated + xcross single pass == gated."""
+    from side_b200 import ops
+    B, C, H, W, N, D = cfg
+    rng = np.random.default_rng(B * 7 + C + D)
+    fL, fR, left, right, fb = _random_case(rng, B, C, H, W, N)
+    if W == 320:   # boxes clamped at the right border, at 0, a sub-pixel box and one wider than the 96-column window
+        left[:4, 1:] = [[300., 5., 318., 40.], [2., 10., 30., 20.], [100.2, 50.1, 100.6, 50.4], [40., 3., 290., 90.]]
+        right[:4, 1:] = [[290., 5., 309., 41.], [-6., 10., 22., 20.], [97.2, 50.1, 97.7, 50.4], [20., 3., 270., 90.]]
+    pl, pr, db = co.proposal_shift(left, right, fb, D, x_clamp=W - 1.0)
+    ref = co.inst_costvol(fL, fR, pl, pr, 16)
+    args = (dev(fL), dev(fR), dev(left), dev(right), dev(fb), D, 16, W - 1.0)
+    cost, dbin = ops.inst_costvol(*args, separable=True)
+    c = cost.cpu().numpy()
+    assert np.array_equal(dbin.cpu().numpy(), db)
+    assert rel_err(c, ref) < 1e-5
+    assert np.array_equal(c[:, 2 * C:], c[:, :C] - c[:, C:2 * C])
+    gref, xref = co.xcross_gate(ref, C)
+    gated, _ = ops.inst_costvol(*args, gate=True, separable=True)
+    assert rel_err(gated.cpu().numpy(), gref) < 1e-4
+    raw, db2, xc = ops.inst_costvol_ungated(*args)
+    assert torch.equal(raw, cost) and torch.equal(db2, dbin)
+    assert rel_err(xc.cpu().numpy(), xref) < 1e-4
+    assert rel_err((raw * xc[:, None, :, None, None]).cpu().numpy(), gated.cpu().numpy()) < 1e-6
+    # deterministic: a second run gives the same bits
+    assert torch.equal(ops.inst_costvol(*args, gate=True, separable=True)[0], gated)
+
+
+def test_separable_path_valid_mask_and_absurd_boxes(lib):
+    from side_b200 import ops
+    rng = np.random.default_rng(5)
+    fL, fR, left, right, fb = _random_case(rng, 2, 8, 12, 40, 6)
+    left[2, 1:] = [-3000., 2., 39., 9.]          # > 1500 columns wide: slow path inside the kernel
+    right[2, 1:] = [-3010., 2., 30., 9.]
+    left[3, 1:] = [50., 2., 60., 9.]             # completely right of the 40-column image
+    right[3, 1:] = [45., 2., 55., 9.]
+    valid = np.array([1, 0, 1, 1, 0, 1], np.uint8)
+    args = (dev(fL), dev(fR), dev(left), dev(right), dev(fb), 4, 16, 39.0)
+    pl, pr, db = co.proposal_shift(left, right, fb, 4, x_clamp=39.0)
+    ref = co.inst_costvol(fL, fR, pl, pr, 16)
+    full, _ = ops.inst_costvol(*args, separable=True)
+    assert rel_err(full.cpu().numpy(), ref) < 1e-5
+    gref, _ = co.xcross_gate(ref, 8)
+    cost, dbm = ops.inst_costvol(*args, gate=True, valid=dev(valid), separable=True)
+    c = cost.cpu().numpy()
+    assert np.all(c[valid == 0] == 0) and np.all(dbm.cpu().numpy()[valid == 0] == 0)
+    assert rel_err(c[valid == 1], gref[valid == 1]) < 1e-4
+    raw, _, xc = ops.inst_costvol_ungated(*args, valid=dev(valid))
+    assert np.all(raw.cpu().numpy()[valid == 0] == 0) and np.all(xc.cpu().numpy()[valid == 0] == 0)
