@@ -147,7 +147,8 @@ def time_op(fn, iters=10, warm=3, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400000)      # ~0.2 ms of GPU idle spin: the host enqueues fn's launches behind it, so the
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # events time the GPU, not Python
         e0.record()
         fn()
         e1.record()
@@ -167,17 +168,26 @@ def kernel_rooflines(pk, precision):
     fL, fR = torch.randn(1, 64, 96, 320, device=dev), torch.randn(1, 64, 96, 320, device=dev)
     left, right, _ = make_boxes(1, 64, seed=0)
     left, right, fb = left.to(dev), right.to(dev), torch.tensor([384.38], device=dev)
-    for gate, fma in ((False, False), (True, False), (True, True)):
-        ms = time_op(lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=gate, fma=fma), flush=flush)
-        byts = 64 * 192 * 48 * 256 * 4 + 2 * 64 * 96 * 320 * 4
-        out["inst_costvol_fwd" + ("_gate" if gate else "") + ("_fma" if fma else "")] = {
-            "ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    byts = 64 * 192 * 48 * 256 * 4 + 2 * 64 * 96 * 320 * 4
+    variants = {
+        "inst_costvol_fwd_separable": lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, separable=True),
+        "inst_costvol_fwd_separable_xcross": lambda: ops.inst_costvol_ungated(fL, fR, left, right, fb, 48, 16, 319.0),
+        "inst_costvol_fwd_separable_gate_2pass": lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=True, separable=True),
+        "inst_costvol_fwd_exact": lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0),
+        "inst_costvol_fwd_exact_gate": lambda: ops.inst_costvol(fL, fR, left, right, fb, 48, 16, 319.0, gate=True),
+    }
+    for name, fn in variants.items():
+        ms = time_op(fn, flush=flush)
+        out[name] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
     # reference-shaped volume: 100 RoIs x 16 x 32 ch
     l2, r2, _ = make_boxes(1, 100, seed=1)
     f32L, f32R = fL[:, :32].contiguous(), fR[:, :32].contiguous()
-    ms = time_op(lambda: ops.inst_costvol(f32L, f32R, l2.to(dev), r2.to(dev), fb, 16, 16, 319.0, gate=True), flush=flush)
+    l2, r2 = l2.to(dev), r2.to(dev)
     byts = 100 * 96 * 16 * 256 * 4 + 2 * 32 * 96 * 320 * 4
-    out["inst_costvol_fwd_gate_ref_shape"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    ms = time_op(lambda: ops.inst_costvol_ungated(f32L, f32R, l2, r2, fb, 16, 16, 319.0), flush=flush)
+    out["inst_costvol_fwd_separable_xcross_ref_shape"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    ms = time_op(lambda: ops.inst_costvol(f32L, f32R, l2, r2, fb, 16, 16, 319.0, gate=True), flush=flush)
+    out["inst_costvol_fwd_exact_gate_ref_shape"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
     # full-image concat / gwc volumes: C=64, D=48, 96x320
     ms = time_op(lambda: ops.concat_volume(fL, fR, 48), flush=flush)
     byts = 128 * 48 * 96 * 320 * 4 + 2 * 64 * 96 * 320 * 4

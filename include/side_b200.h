@@ -223,7 +223,8 @@ int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *g
  *       Needs Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 128, W | 128, (D, H) tiling into 128-voxel boxes
  *       (16x16, 8x8 with even D, 4x4 with D % 8 == 0); kernel 3x3x3 or 1x3x3.
  * Helpers (one pass over HBM each):
- *   side_ncdhw_to_cl_split  x [N, C, S] -> hi, lo [N, S, C]                      (volume from side_inst_costvol_fwd)
+ *   side_ncdhw_to_cl_split  x [N, C, S] (* scale[N, D], D | S, or NULL) -> hi, lo [N, S, C]   (volume from
+ *                           side_inst_costvol_fwd; scale = xcross applies the gate deferred by SIDE_VOL_XCROSS)
  *   side_tf32_split         x -> hi, lo, n elements (n % 4 == 0)
  *   side_gate_mul_split     y [N,D,H,W,C] * gate [N,D,W,C] -> hi, lo              (isp * cost, :207-210)
  *   side_maxpool_hw2_cl     x [N,D,H,W,C] -> MaxPool3d((1,2,2)) -> y and / or hi, lo  (:213, :218)
@@ -234,7 +235,8 @@ int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int 
 int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                        const float *residual, float *y, float *y_hi, float *y_lo, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int relu, void *stream);
-int side_ncdhw_to_cl_split(const float *x, float *hi, float *lo, int N, int C, long long S, void *stream);
+int side_ncdhw_to_cl_split(const float *x, const float *scale, float *hi, float *lo, int N, int C, long long S, int D,
+                           void *stream);
 int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);
 int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
                         void *stream);

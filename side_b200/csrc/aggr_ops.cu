@@ -17,9 +17,9 @@ __device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
     h.w = tf32_hi(v.w); l.w = v.w - h.w;
 }
 
-// in [N, C, S] -> hi, lo [N, S, C]
-__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, float *__restrict__ hi, float *__restrict__ lo, int C,
-                                         long long S)
+// in [N, C, S] -> hi, lo [N, S, C]; optional scale[n, p / per_d] (the cosine gate of the slice the voxel belongs to)
+__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ hi,
+                                         float *__restrict__ lo, int C, long long S, int D, int per_d)
 {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -36,7 +36,8 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, float *__
         const long long p = p0 + i;
         const int c = c0 + threadIdx.x;
         if (p < S && c < C) {
-            const float v = tile[threadIdx.x][i];
+            float v = tile[threadIdx.x][i];
+            if (scale) v = __fmul_rn(v, __ldg(scale + (size_t)n * D + (int)(p / per_d)));
             const float h = tf32_hi(v);
             const size_t o = ((size_t)n * S + p) * C + c;
             hi[o] = h;
@@ -139,14 +140,17 @@ using namespace side;
 
 static inline unsigned ew_grid(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148 * 16); }
 
-extern "C" int side_ncdhw_to_cl_split(const float *x, float *hi, float *lo, int N, int C, long long S, void *stream)
+extern "C" int side_ncdhw_to_cl_split(const float *x, const float *scale, float *hi, float *lo, int N, int C, long long S,
+                                      int D, void *stream)
 {
     SIDE_REQUIRE(N >= 0 && C > 0 && S > 0, "side_ncdhw_to_cl_split: bad shape");
+    SIDE_REQUIRE(scale == nullptr || (D > 0 && S % D == 0), "side_ncdhw_to_cl_split: scale needs D | S");
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "side_ncdhw_to_cl_split: grid too large");
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
     dim3 g((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), b(32, 8);
-    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, hi, lo, C, S);
+    if (scale) SIDE_REQUIRE_DEV(scale);
+    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, scale, hi, lo, C, S, D, scale ? (int)(S / D) : 1);
     SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
     return SIDE_OK;
 }

@@ -11,6 +11,7 @@
 // workspace.  The last CTA of each image to finish (threadfence + ticket) merges the Cat*K candidates,
 // then gathers the regression heads at the K winning pixels directly from NCHW -- no transposed copies.
 // Tie rule everywhere: larger score first, then lower flat index (documented; torch.topk leaves it open).
+#include <algorithm>
 #include "common.cuh"
 
 namespace side {
@@ -332,11 +333,14 @@ static int launch_decode(DecParams &p, bool ddd, void *ws, size_t ws_bytes, void
     cudaStream_t st = (cudaStream_t)stream;
     SIDE_CUDA(cudaMemsetAsync(p.ws_ticket, 0, sizeof(unsigned int) * p.B, st));
     int rc;
+    // the kernel also has ~33 KB of STATIC shared memory (per-warp histograms): static + dynamic can exceed the 48 KB
+    // default even when the dynamic part alone does not, so always opt in
+    const size_t attr = std::max(smem, (size_t)64 * 1024);
     if (ddd) {
-        if ((rc = set_smem_attr((const void *)nms_topk_decode_kernel<true>, smem))) return rc;
+        if ((rc = set_smem_attr((const void *)nms_topk_decode_kernel<true>, attr))) return rc;
         nms_topk_decode_kernel<true><<<p.B * p.Cat, kDecThreads, smem, st>>>(p);
     } else {
-        if ((rc = set_smem_attr((const void *)nms_topk_decode_kernel<false>, smem))) return rc;
+        if ((rc = set_smem_attr((const void *)nms_topk_decode_kernel<false>, attr))) return rc;
         nms_topk_decode_kernel<false><<<p.B * p.Cat, kDecThreads, smem, st>>>(p);
     }
     SIDE_LAUNCH_CHECK("nms_topk_decode_kernel");

@@ -55,8 +55,9 @@ __device__ __forceinline__ void proposal_for(const float *__restrict__ l, const 
 // One axis of torchvision's pre_calc_for_bilinear_interpolate (legacy aligned=False, sampling_ratio 2).
 __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p, int i, int size)
 {
+    // (.. / 2) == (.. * 0.5f) bit for bit (power-of-two scaling); the multiply avoids the IEEE division subroutine
     float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                        __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), 2.0f));
+                        __fmul_rn(__fmul_rn((float)i + 0.5f, bin), 0.5f));
     AxisSample s;
     if (c < -1.0f || c > (float)size) {
         s.lo = -1; s.hi = -1; s.l = 0.f; s.h = 0.f;
@@ -439,8 +440,8 @@ __global__ void __launch_bounds__(kNhwcThreads) inst_costvol_fwd_nhwc_kernel(Vol
 //     U[side][ph][x][c] = sum_{iy} ( hy * f[ylo][x][c] + ly * f[yhi][x][c] )          (once per group of slices)
 // in shared memory for the window of columns the group's shifted boxes touch, and every output bin is then 4 taps
 //     bin = sum_{ix} ( 0.25*hx * U[ph][xlo] + 0.25*lx * U[ph][xhi] )
-// instead of 16 global taps and 33 rounded operations.  One warp per slice: lane = (channel, row of a pair, 4 consecutive
-// bins); the 32 x-sample table entries of the slice are computed one per lane and exchanged by shuffles; a quarter-warp's
+// instead of 16 global taps and 33 rounded operations.  One warp per slice: lane = (channel pair, row of a pair, 4
+// consecutive bins), 8-byte conflict-free shared loads; the 32 x-sample table entries of the slice are computed one per lane and exchanged by shuffles; a quarter-warp's
 // 16-byte evict-first stores cover 128 contiguous bytes.  The gate statistics (sum L^2, sum R^2, sum L*R) are
 // accumulated in the same pass as per-(n, d, channel-chunk) partials, so the fused network path needs ONE pass over the
 // volume (the scalar gate is applied by the consumer, side_ncdhw_to_cl_split); SIDE_VOL_GATE on this path runs a
@@ -451,28 +452,37 @@ __global__ void __launch_bounds__(kNhwcThreads) inst_costvol_fwd_nhwc_kernel(Vol
 // ------------------------------------------------------------------------------------------------
 constexpr int kSepCC = 8;             // channels per CTA
 constexpr int kSepThreads = 512;
-constexpr int kSepXq = 22;            // window columns per (side, lane-quad)
+constexpr int kSepXq = 46;            // window columns per (side, lane-quad)
 constexpr int kSepMaxD = 256;
 // U[side][ph][cell][8 channels]: cell = 4 * (x - win[quad]) + quad, i.e. the four lane-quads of a warp (bins 0-3, 4-7,
 // 8-11, 12-15) read from four interleaved sub-windows whose 32-byte cells sit in different bank octets BY CONSTRUCTION;
 // the row stride is = 4 (mod 32) floats so the two rows a warp instruction touches are 4 banks apart: every shared load
 // of the slice loop is conflict-free whatever the box geometry.
-constexpr int kSepRowF = 4 * (kSepXq + 2) * kSepCC + 4;     // floats per ph row (772): kSepXq real cells + 2 zero cells
+constexpr int kSepRowF = 4 * (kSepXq + 2) * kSepCC + 4;     // floats per ph row (1540): kSepXq real cells + 2 zero cells
 constexpr int kSepUSide = 16 * kSepRowF;                     // floats per side
+
+// shared-memory load through a 32-bit shared-space address + immediate byte offset
+template <int IMM>
+__device__ __forceinline__ float2 sep_lds2(uint32_t addr)
+{
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM));
+    return v;
+}
 
 // first / last integer cell touched by x-samples e0..e1 of a box (clamped into the image like axis_sample does)
 __device__ __forceinline__ void sep_cells(float start, float bin, int e0, int e1, int W, int &c0, int &c1)
 {
     const float a = __fadd_rn(__fadd_rn(start, __fmul_rn((float)(e0 >> 1), bin)),
-                              __fdiv_rn(__fmul_rn((float)(e0 & 1) + 0.5f, bin), 2.0f));
+                              __fmul_rn(__fmul_rn((float)(e0 & 1) + 0.5f, bin), 0.5f));
     const float b = __fadd_rn(__fadd_rn(start, __fmul_rn((float)(e1 >> 1), bin)),
-                              __fdiv_rn(__fmul_rn((float)(e1 & 1) + 0.5f, bin), 2.0f));
+                              __fmul_rn(__fmul_rn((float)(e1 & 1) + 0.5f, bin), 0.5f));
     c0 = min(max((int)floorf(fminf(fmaxf(a, -2.f), (float)W + 1.f)), 0), W - 1);
     c1 = min(min(max((int)floorf(fminf(fmaxf(b, -2.f), (float)W + 1.f)), 0), W - 1) + 1, W - 1);
 }
 
 template <bool WRITE, bool STATS, bool APPLY>
-__global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolParams p, const float *__restrict__ nhwcL,
+__global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolParams p, const float *__restrict__ nhwcL,
                                                                          const float *__restrict__ nhwcR,
                                                                          float *__restrict__ partial)
 {
@@ -513,14 +523,14 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
         float dbin, lx1, lx2, rx1, rx2, y1, y2;
         proposal_for(lb, rb, fb, d, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
         const float rwl = fmaxf(__fsub_rn(lx2, lx1), 1.0f), rwr = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
-        geo[d] = make_float4(lx1, __fdiv_rn(rwl, 16.0f), rx1, __fdiv_rn(rwr, 16.0f));
+        geo[d] = make_float4(lx1, __fmul_rn(rwl, 0.0625f), rx1, __fmul_rn(rwr, 0.0625f));   // == rw / 16 exactly
         if (WRITE && chunk == 0) p.depth_bin[(size_t)n * D + d] = dbin;
     }
     if (tid < 32) {
         float dbin, lx1, lx2, rx1, rx2, y1, y2;
         proposal_for(lb, rb, fb, 0, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
         const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
-        ytab[tid] = to_tap(axis_sample(y1, __fdiv_rn(rh, 16.0f), tid >> 1, tid & 1, p.H), W * C);
+        ytab[tid] = to_tap(axis_sample(y1, __fmul_rn(rh, 0.0625f), tid >> 1, tid & 1, p.H), W * C);
     }
     __syncthreads();
     // cells touched by each lane-quad (x-samples 8q .. 8q+7) of each slice, both sides
@@ -534,10 +544,9 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
     }
     __syncthreads();
 
-    const float *fLb = nhwcL + (size_t)b * p.H * W * C + c0;
-    const float *fRb = nhwcR + (size_t)b * p.H * W * C + c0;
-
     if (s_slow) {
+        const float *fLb = nhwcL + (size_t)b * p.H * W * C + c0;
+        const float *fRb = nhwcR + (size_t)b * p.H * W * C + c0;
         // Very wide box (> ~90 feature columns, or garbage): the same formula evaluated straight from global memory,
         // one slice at a time.  Results are identical to the fast path's.
         float *red = U;
@@ -599,7 +608,7 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
         return;
     }
 
-    // lane = (channel-in-group ccl, row-in-pair phsel, quad): a quarter-warp's 16-byte stores cover 128 contiguous bytes
+    // lane = (channel pair ccl, row-in-pair phsel, quad): a quarter-warp's 16-byte stores cover 128 contiguous bytes
     const int quad = lane & 3, phsel = (lane >> 2) & 1, ccl = lane >> 3;
 
     int d0 = 0;
@@ -621,30 +630,41 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
         const int d1 = g_d1;
         // ---- build U: local cells 0..wr-1 real, cells wr and wr+1 = zeros (invalid samples read (wr, wr+1); a sample
         //      clamped at the right border reads (W-1, W) with weight 0 on the second) ----
+        {
+            int ncell = 0;
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const float *f = side ? fRb : fLb;
-            float *Us = U + side * kSepUSide;
-            const int ncell = max(max(g_wr[4 * side], g_wr[4 * side + 1]), max(g_wr[4 * side + 2], g_wr[4 * side + 3])) + 2;
-            for (int it = tid; it < 16 * ncell * 8; it += kSepThreads) {
-                const int half = it & 1, q = (it >> 1) & 3, r2 = it >> 3, cell = r2 % ncell, ph = r2 / ncell;
+            for (int k = 0; k < 8; ++k) ncell = max(ncell, g_wr[k]);
+            ncell += 2;
+            const size_t img = (size_t)b * p.H * W * C + c0;
+            const int per_side = 16 * ncell * 8;
+            // branch-free body (clamped address, value selected afterwards) so that the unrolled iterations' 16 loads
+            // are all in flight together: the build is latency-bound, not bandwidth-bound
+#pragma unroll 4
+            for (int it = tid; it < 2 * per_side; it += kSepThreads) {
+                const int side = it >= per_side, i2 = it - side * per_side;
+                const int half = i2 & 1, q = (i2 >> 1) & 3, r2 = i2 >> 3, cell = r2 % ncell, ph = r2 / ncell;
                 const int wr = g_wr[4 * side + q];
-                if (cell > wr + 1) continue;
                 const int x = g_win[4 * side + q] + cell;
-                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cell < wr && x <= W - 1) {
-                    const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
-                    const float *fx = f + (size_t)x * C + 4 * half;
-                    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(fx + t0.olo));
-                    const float4 a1 = __ldg(reinterpret_cast<const float4 *>(fx + t0.ohi));
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(fx + t1.olo));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(fx + t1.ohi));
-                    u.x = fmaf(t0.l, a1.x, t0.h * a0.x) + fmaf(t1.l, b1.x, t1.h * b0.x);
-                    u.y = fmaf(t0.l, a1.y, t0.h * a0.y) + fmaf(t1.l, b1.y, t1.h * b0.y);
-                    u.z = fmaf(t0.l, a1.z, t0.h * a0.z) + fmaf(t1.l, b1.z, t1.h * b0.z);
-                    u.w = fmaf(t0.l, a1.w, t0.h * a0.w) + fmaf(t1.l, b1.w, t1.h * b0.w);
+                const bool real = cell < wr && x <= W - 1;
+                const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
+                const float *fx = (side ? nhwcR : nhwcL) + img + (size_t)min(x, W - 1) * C + 4 * half;
+                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(fx + t0.olo));
+                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(fx + t0.ohi));
+                // the two y sub-samples of a bin usually fall in the same cell or in adjacent ones: reuse the rows already
+                // loaded (ph is uniform across a warp except at row boundaries, so these branches do not diverge)
+                float4 b0 = a0, b1 = a1;
+                if (t1.olo != t0.olo || t1.ohi != t0.ohi) {
+                    b0 = (t1.olo == t0.ohi) ? a1 : __ldg(reinterpret_cast<const float4 *>(fx + t1.olo));
+                    b1 = __ldg(reinterpret_cast<const float4 *>(fx + t1.ohi));
                 }
-                *reinterpret_cast<float4 *>(Us + (size_t)ph * kSepRowF + (4 * cell + q) * kSepCC + 4 * half) = u;
+                float4 u;
+                u.x = fmaf(t0.l, a1.x, t0.h * a0.x) + fmaf(t1.l, b1.x, t1.h * b0.x);
+                u.y = fmaf(t0.l, a1.y, t0.h * a0.y) + fmaf(t1.l, b1.y, t1.h * b0.y);
+                u.z = fmaf(t0.l, a1.z, t0.h * a0.z) + fmaf(t1.l, b1.z, t1.h * b0.z);
+                u.w = fmaf(t0.l, a1.w, t0.h * a0.w) + fmaf(t1.l, b1.w, t1.h * b0.w);
+                if (!real) u = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cell <= wr + 1)
+                    *reinterpret_cast<float4 *>(U + side * kSepUSide + (size_t)ph * kSepRowF + (4 * cell + q) * kSepCC + 4 * half) = u;
             }
         }
         __syncthreads();
@@ -697,46 +717,48 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
             }
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
             constexpr int kRowBytes = kSepRowF * 4;
+            constexpr int kR = kSepUSide * 4;                         // byte distance of the right-view table
             const size_t side_stride = (size_t)C * cs;                // L -> R -> L-R planes
+            uint32_t uL = smem_u32(U + phsel * kSepRowF + 2 * ccl);   // this lane's channel pair (2 ccl, 2 ccl + 1)
+            float *o = outn + (size_t)(2 * ccl) * cs + (size_t)d * 256 + phsel * 16 + 4 * quad;
 #pragma unroll 1
-            for (int cg = 0; cg < 2; ++cg) {                          // channel group (4 channels per warp instruction)
-                const char *uL = reinterpret_cast<const char *>(U + phsel * kSepRowF + 4 * cg + ccl);
-                const char *uR = uL + kSepUSide * 4;
-                float *o = outn + (size_t)(4 * cg + ccl) * cs + (size_t)d * 256 + phsel * 16 + 4 * quad;
-#pragma unroll 1
-                for (int rp2 = 0; rp2 < 4; ++rp2, uL += 4 * kRowBytes, uR += 4 * kRowBytes, o += 64) {
+            for (int rp2 = 0; rp2 < 4; ++rp2, uL += 4 * kRowBytes, o += 64) {
 #pragma unroll
-                    for (int rp = 0; rp < 2; ++rp) {                  // row pair within this iteration
-                        const int ub = 2 * rp * kRowBytes;            // immediate byte offset into U
-                        float l[4], r[4];
+                for (int rp = 0; rp < 2; ++rp) {                      // row pair within this iteration
+                    float l0[4], l1[4], r0[4], r1[4];                 // [bin] for the two channels, left / right view
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t a0 = uL + (oL[j] & 0xffffu), a1 = uL + (oL[j] >> 16);
+                        const uint32_t c0r = uL + (oR[j] & 0xffffu), c1r = uL + (oR[j] >> 16);
+                        float2 p0, p1, p2, p3, q0, q1, q2, q3;
+                        if (rp == 0) {
+                            p0 = sep_lds2<0>(a0); p1 = sep_lds2<128>(a0); p2 = sep_lds2<0>(a1); p3 = sep_lds2<128>(a1);
+                            q0 = sep_lds2<kR>(c0r); q1 = sep_lds2<kR + 128>(c0r); q2 = sep_lds2<kR>(c1r); q3 = sep_lds2<kR + 128>(c1r);
+                        } else {
+                            p0 = sep_lds2<2 * kRowBytes>(a0); p1 = sep_lds2<2 * kRowBytes + 128>(a0);
+                            p2 = sep_lds2<2 * kRowBytes>(a1); p3 = sep_lds2<2 * kRowBytes + 128>(a1);
+                            q0 = sep_lds2<kR + 2 * kRowBytes>(c0r); q1 = sep_lds2<kR + 2 * kRowBytes + 128>(c0r);
+                            q2 = sep_lds2<kR + 2 * kRowBytes>(c1r); q3 = sep_lds2<kR + 2 * kRowBytes + 128>(c1r);
+                        }
+                        const float w0 = bL[2 * j], w1 = bL[2 * j + 1], wa0 = 0.25f - w0, wa1 = 0.25f - w1;
+                        l0[j] = fmaf(w1, p3.x, fmaf(wa1, p2.x, fmaf(w0, p1.x, wa0 * p0.x)));
+                        l1[j] = fmaf(w1, p3.y, fmaf(wa1, p2.y, fmaf(w0, p1.y, wa0 * p0.y)));
+                        const float v0 = bR[2 * j], v1 = bR[2 * j + 1], va0 = 0.25f - v0, va1 = 0.25f - v1;
+                        r0[j] = fmaf(v1, q3.x, fmaf(va1, q2.x, fmaf(v0, q1.x, va0 * q0.x)));
+                        r1[j] = fmaf(v1, q3.y, fmaf(va1, q2.y, fmaf(v0, q1.y, va0 * q0.y)));
+                    }
+                    if (STATS) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint32_t a0 = oL[j] & 0xffffu, a1 = oL[j] >> 16;
-                            const float w0 = bL[2 * j], w1 = bL[2 * j + 1];
-                            float t = (0.25f - w0) * *reinterpret_cast<const float *>(uL + ub + a0);
-                            t = fmaf(w0, *reinterpret_cast<const float *>(uL + ub + 128 + a0), t);
-                            t = fmaf(0.25f - w1, *reinterpret_cast<const float *>(uL + ub + a1), t);
-                            l[j] = fmaf(w1, *reinterpret_cast<const float *>(uL + ub + 128 + a1), t);
+                            s0 = fmaf(l0[j], l0[j], fmaf(l1[j], l1[j], s0));
+                            s1 = fmaf(r0[j], r0[j], fmaf(r1[j], r1[j], s1));
+                            s2 = fmaf(l0[j], r0[j], fmaf(l1[j], r1[j], s2));
                         }
-                        SEP_SCHED_FENCE();
+                    }
+                    if (WRITE) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t c0r = oR[j] & 0xffffu, c1r = oR[j] >> 16;
-                            const float v0 = bR[2 * j], v1 = bR[2 * j + 1];
-                            float q = (0.25f - v0) * *reinterpret_cast<const float *>(uR + ub + c0r);
-                            q = fmaf(v0, *reinterpret_cast<const float *>(uR + ub + 128 + c0r), q);
-                            q = fmaf(0.25f - v1, *reinterpret_cast<const float *>(uR + ub + c1r), q);
-                            r[j] = fmaf(v1, *reinterpret_cast<const float *>(uR + ub + 128 + c1r), q);
-                        }
-                        if (STATS) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                s0 = fmaf(l[j], l[j], s0);
-                                s1 = fmaf(r[j], r[j], s1);
-                                s2 = fmaf(l[j], r[j], s2);
-                            }
-                        }
-                        if (WRITE) {
+                        for (int k = 0; k < 2; ++k) {
+                            const float *l = k ? l1 : l0, *r = k ? r1 : r0;
                             float4 lv = make_float4(l[0], l[1], l[2], l[3]), rv = make_float4(r[0], r[1], r[2], r[3]);
                             float4 dv = make_float4(__fsub_rn(l[0], r[0]), __fsub_rn(l[1], r[1]), __fsub_rn(l[2], r[2]),
                                                     __fsub_rn(l[3], r[3]));
@@ -745,12 +767,11 @@ __global__ void __launch_bounds__(kSepThreads, 2) inst_costvol_sep_kernel(VolPar
                                 rv.x = __fmul_rn(rv.x, g); rv.y = __fmul_rn(rv.y, g); rv.z = __fmul_rn(rv.z, g); rv.w = __fmul_rn(rv.w, g);
                                 dv.x = __fmul_rn(dv.x, g); dv.y = __fmul_rn(dv.y, g); dv.z = __fmul_rn(dv.z, g); dv.w = __fmul_rn(dv.w, g);
                             }
-                            float *oo = o + rp * 32;
+                            float *oo = o + (size_t)k * cs + rp * 32;
                             st_cs(reinterpret_cast<float4 *>(oo), lv);
                             st_cs(reinterpret_cast<float4 *>(oo + side_stride), rv);
                             st_cs(reinterpret_cast<float4 *>(oo + 2 * side_stride), dv);
                         }
-                        SEP_SCHED_FENCE();
                     }
                 }
             }

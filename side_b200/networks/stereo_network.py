@@ -107,11 +107,12 @@ class cost_volume(nn.Module):
         return (self.tensor_core and not self.training and not torch.is_grad_enabled() and cost.is_cuda and P == 16 and
                 P2 == 16 and D % 8 == 0 and C3 % 32 == 0 and C3 == self.dres0[0].in_channels)
 
-    def aggregate_tc(self, cost):
-        """Same function as ``aggregate`` on tcgen05 (3xTF32): [N,3C,D,16,16] -> logits [N,D,4,4]."""
+    def aggregate_tc(self, cost, xcross=None):
+        """Same function as ``aggregate`` on tcgen05 (3xTF32): [N,3C,D,16,16] -> logits [N,D,4,4].
+        ``xcross`` [N,D]: cosine gate still to be applied to ``cost`` (folded into the layout change)."""
         L = self._tc_state()
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
-        hi, lo = ops.ncdhw_to_cl_split(cost)                                   # [N, D, 16, 16, 3C]
+        hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross)                     # [N, D, 16, 16, 3C]
         _, hi, lo = conv(0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
         isp = self.strAM_2D(y.mean(dim=2).permute(0, 3, 1, 2))                 # mean over H -> [N, 64, D, W]
@@ -186,10 +187,22 @@ class stereo_network(nn.Module):
             return f[:left.shape[0]], f[left.shape[0]:]
         return self.feature_extraction(left), self.feature_extraction(right)
 
+    fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream
+
     def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D):
+        est = self.depth_estimator
+        C = featL.shape[1]
+        if (self.fast_volume and est.tensor_core and featL.is_cuda and not self.training and not torch.is_grad_enabled() and self.roiSize == 16
+                and D % 8 == 0 and D <= 256 and C % 8 == 0 and (3 * C) % 32 == 0 and 3 * C == est.dres0[0].in_channels
+                and left.shape[0] <= 65535):
+            # one pass over the volume: [L, R, L-R] written ungated with the gate scalars on the side; the gate is applied
+            # while the volume is re-laid out channels-last for the tensor-core convolutions
+            cost, depth_bin, xc = ops.inst_costvol_ungated(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid)
+            logits = est.aggregate_tc(cost, xcross=xc)
+            return ops.softargmin(logits, depth_bin)
         cost, depth_bin = ops.inst_costvol(featL, featR, left, right, fb, D, self.roiSize, input_w // 4 - 1.,
                                            gate=True, valid=valid)
-        return self.depth_estimator(cost, D, depth_bin, gated=True)
+        return est(cost, D, depth_bin, gated=True)
 
     def forward(self, batch, useCostVolume=True, target=None, wh_scale=1.0):
         left, right = batch['input'], batch['input_right']

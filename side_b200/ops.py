@@ -536,8 +536,8 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     return y, y_hi, y_lo
 
 
-def ncdhw_to_cl_split(x):
-    """x [N, C, D, H, W] -> hi, lo [N, D, H, W, C]."""
+def ncdhw_to_cl_split(x, scale=None):
+    """x [N, C, D, H, W] (* scale [N, D] per depth slice) -> hi, lo [N, D, H, W, C]."""
     lib = _lib.load()
     x = _chk(x, "x")
     N, C = x.shape[:2]
@@ -545,9 +545,15 @@ def ncdhw_to_cl_split(x):
     S = 1
     for s in sp:
         S *= s
+    D = 0
+    if scale is not None:
+        scale = _chk(scale, "scale")
+        D = sp[0]
+        if tuple(scale.shape) != (N, D):
+            raise RuntimeError("scale must be [N, D]")
     hi = torch.empty((N,) + sp + (C,), device=x.device, dtype=_F32)
     lo = torch.empty_like(hi)
-    _lib.check(lib.side_ncdhw_to_cl_split(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, C, S, _stream()),
+    _lib.check(lib.side_ncdhw_to_cl_split(x.data_ptr(), _p(scale), hi.data_ptr(), lo.data_ptr(), N, C, S, D, _stream()),
                "side_ncdhw_to_cl_split")
     return hi, lo
 

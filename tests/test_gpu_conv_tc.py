@@ -74,6 +74,9 @@ def test_layout_and_pool_helpers(lib):
     hi, lo = ops.ncdhw_to_cl_split(x.to(dev))
     assert torch.equal((hi + lo).cpu(), _cl(x))
     assert torch.equal(hi.cpu(), (_cl(x).view(torch.int32) & -8192).view(torch.float32))
+    sc = torch.rand(3, 4, generator=g) + 0.5                          # per-(sample, depth slice) scale (deferred cosine gate)
+    hi, lo = ops.ncdhw_to_cl_split(x.to(dev), scale=sc.to(dev))
+    assert torch.equal((hi + lo).cpu(), _cl(x * sc[:, None, :, None, None]))
     y = torch.randn(2, 5, 6, 8, 12, generator=g)                     # NDHWC
     gate = torch.rand(2, 5, 8, 12, generator=g)
     hi, lo = ops.gate_mul_split(y.to(dev), gate.to(dev))

@@ -98,3 +98,14 @@ def test_ddd_decode_full_size_vs_oracle(lib):
     rd, rdr, ri = co.ddd_decode(heat, kept, dim, orien, wh, reg, grid, K)
     assert np.array_equal(det.cpu().numpy(), rd) and np.array_equal(detr.cpu().numpy(), rdr)
     assert np.array_equal(info.cpu().numpy(), ri)
+
+
+def test_small_map_in_a_fresh_process(lib):
+    """Regression: with a small H*W the kernel's static (33 KB) + dynamic shared memory exceeds the 48 KB default although the
+    dynamic part alone does not; in a fresh process (no earlier large launch to raise the attribute) the launch used to fail."""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r); import torch; from side_b200 import ops; "
+            "h = torch.randn(1, 3, 16, 320, device='cuda'); o = ops.bbox_decode_raw(h, torch.rand_like(h), torch.rand_like(h), K=100); "
+            "torch.cuda.synchronize(); print(int(o['count'].sum()))") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
