@@ -318,13 +318,17 @@ def main():
         w = a[2]
         return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
 
+    def conv_work(out, x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), **k):
+        return 2.0 * (x_hi.numel() // x_hi.shape[-1]) * Cout * x_hi.shape[-1] * ksize[0] * ksize[1] * ksize[2]
+
     if args.profiler_range:
         torch.cuda.profiler.start()
-    with OpTimer("dcn_forward_raw", dcn_work) as tm:
+    with OpTimer("dcn_forward_raw", dcn_work) as tm, OpTimer("conv3d_tc", conv_work) as tmc:
         ms_res = timed(step_resident, args.steps)
     if args.profiler_range:
         torch.cuda.profiler.stop()
     dcn = tm.summary()
+    cv = tmc.summary()
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop()
@@ -332,7 +336,22 @@ def main():
     total_pairs = world * P * args.steps
     value = total_pairs / (ms_res / 1000.0)
     e2e = total_pairs / (ms_e2e / 1000.0)
-    dcn_tf = dcn["work"] / (dcn["ms"] / 1000.0) / 1e12 if dcn["ms"] > 0 else 0.0
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")      # dram bytes per launch from the committed ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+
+    def roof(name, label, summ):
+        tf = summ["work"] / (summ["ms"] / 1000.0) / 1e12 if summ["ms"] > 0 else 0.0
+        return {"kernel": "%s, %d launches in the timed region" % (label, summ["calls"]), "bound": "tensor", "achieved": tf,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": traffic.get(name),
+                "peak_source": pk["src"] + " bf16 sustained (cuBLAS); this kernel is 3xTF32: tf32 rate is half of bf16 and every "
+                               "product takes 3 MMAs, so 1/6 = 0.167 is the ceiling of this fraction",
+                "share_of_step": summ["ms"] / ms_res, "algorithmic_flop_per_step": summ["work"] / max(args.steps, 1)}
+
+    r_dcn = roof("dcn_fwd_tc_kernel", "dcn_fwd (%s)" % args.dcn_precision, dcn)
+    r_cv = roof("conv_tc_kernel", "conv3d_tc (aggregation network, 3xtf32)", cv)
+    dominant, other = (r_cv, r_dcn) if cv["ms"] >= dcn["ms"] else (r_dcn, r_cv)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -347,10 +366,8 @@ def main():
                     "d2h_bytes_per_step": P * 100 * 22 * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "dcn_fwd (%s), %d launches in the timed region" % (args.dcn_precision, dcn["calls"]),
-                         "bound": "tensor", "achieved": dcn_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": dcn_tf / pk["tf_sust"],
-                         "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
-                         "share_of_step": dcn["ms"] / ms_res},
+            "roofline": dominant,
+            "roofline_second": other,
             "cpu_baseline": cpu_base,
         }
         if not args.no_kernels and world == 1:

@@ -220,8 +220,10 @@ int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *g
  *       swizzled shared-memory image (hi and lo), side_conv_tc_weight_bytes(Cin, Cout, taps) bytes.  Once per layer.
  *   side_conv3d_tc_fwd: x_hi, x_lo [N, D, H, W, Cin] -> y [N, D, H, W, Cout] (fp32, may be NULL) and / or its split
  *       y_hi, y_lo (may be NULL); out = relu?(conv * scale[o] + shift[o]) + residual[.., o].
- *       Needs Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 128, W | 128, (D, H) tiling into 128-voxel boxes
- *       (16x16, 8x8 with even D, 4x4 with D % 8 == 0); kernel 3x3x3 or 1x3x3.
+ *       Needs Cin % 32 == 0; Cout % 16 == 0 (<= 128) or Cout % 128 == 0 (<= 1536, processed as 128-wide n-tiles); a
+ *       (D, H, W) that tiles into 128-voxel boxes (box w = largest power of two <= 128 dividing W, then rows, then
+ *       slices: 16x16, 8x8 with even D, 4x4 with D % 8 == 0, 96x320 as 2 rows x 64 columns); kernel 3x3x3 or 1x3x3
+ *       (2-D convolutions are D = 1, kd = 1: the head convolutions of stereo_network.forward, :343-348).
  * Helpers (one pass over HBM each):
  *   side_ncdhw_to_cl_split  x [N, C, S] (* scale[N, D], D | S, or NULL) -> hi, lo [N, S, C]   (volume from
  *                           side_inst_costvol_fwd; scale = xcross applies the gate deferred by SIDE_VOL_XCROSS)

@@ -33,6 +33,7 @@ namespace side {
 constexpr int kCvThreads = 192;
 constexpr int kCvMaxStages = 6;
 constexpr int kCvBM = 128;
+constexpr int kCvMaxCout = 1536;       // all n-tiles' folded-BN vectors live in shared memory
 constexpr uint32_t kCvATile = kCvBM * 128;   // 16 KB: 128 voxels x 32 tf32
 
 struct ConvTcParams {
@@ -41,12 +42,26 @@ struct ConvTcParams {
     const float *scale, *shift;       // folded BatchNorm, NULL = identity
     const float *residual;            // [M, Cout] added after the ReLU (dres2(cost) + cost), NULL = none
     int relu;
-    int N, ncb, nkb, ntiles;
+    int N, ncb, nkb, ntiles;          // N = output channels of ONE n-tile (<= 128); ntiles = m-tiles * n_ntiles
+    int Ntot, n_ntiles;               // all output channels, number of n-tiles (Ntot = n_ntiles * N)
     int D, H, W;                      // spatial extent of one sample
-    int bh, bd;                       // TMA box rows along h and d (bw = W); bd*bh*W == 128
+    int bw, bh, bd;                   // TMA box extent along w, h, d; bd*bh*bw == 128
+    int wt, ht;                       // boxes per row (W / bw) and per column (H / bh)
     int kd, kh, kw;                   // kernel extent (3,3,3) or (1,3,3)
     int stages;
 };
+
+// m-tile -> first voxel coordinates of its box
+__device__ __forceinline__ void conv_tile_origin(const ConvTcParams &p, int mt, int &n, int &d0, int &h0, int &w0)
+{
+    const int tps = (p.D / p.bd) * p.ht * p.wt;        // tiles per sample
+    n = mt / tps;
+    int r = mt - n * tps;
+    const int wi = r % p.wt;
+    r /= p.wt;
+    const int hi = r % p.ht;
+    w0 = wi * p.bw; h0 = hi * p.bh; d0 = (r / p.ht) * p.bd;
+}
 
 __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4,
                                             uint64_t *bar)
@@ -66,7 +81,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ __align__(8) uint64_t tmem_full[2];
     __shared__ __align__(8) uint64_t tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_scale[256], s_shift[256];
+    __shared__ float s_scale[kCvMaxCout], s_shift[kCvMaxCout];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
@@ -75,7 +90,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int stages = p.stages;
 
-    for (int i = tid; i < N; i += kCvThreads) {
+    for (int i = tid; i < p.Ntot; i += kCvThreads) {
         s_scale[i] = p.scale ? p.scale[i] : 1.0f;
         s_shift[i] = p.shift ? p.shift[i] : 0.0f;
     }
@@ -103,7 +118,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int S = p.D * p.H * p.W, HW = p.H * p.W;
     const int khw = p.kh * p.kw;
     const int pd = (p.kd - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
 
@@ -115,18 +129,19 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             int st = 0;
             uint32_t phs = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int vox0 = tile * kCvBM;
-                const int n = vox0 / S, r = vox0 - n * S;
-                const int d0 = r / HW, h0 = (r - d0 * HW) / p.W;
+                const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+                int n, d0, h0, w0;
+                conv_tile_origin(p, mt, n, d0, h0, w0);
+                const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
                     const int kdi = tap / khw, r2 = tap - kdi * khw, khi = r2 / p.kw, kwi = r2 - khi * p.kw;
                     mbar_wait(&empty_bar[st], phs ^ 1u);
                     unsigned char *sa = tiles + (size_t)st * stage_bytes;
                     mbar_expect_tx(&full_bar[st], stage_bytes);
-                    tma_load_5d(sa, &tm_hi, cb * 32, kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
-                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
-                    bulk_g2s(sa + 2 * kCvATile, p.wp + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
+                    tma_load_5d(sa, &tm_hi, cb * 32, w0 + kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
+                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, w0 + kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
+                    bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
                 }
             }
@@ -177,7 +192,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
-            const size_t row = (size_t)tile * kCvBM + m;
+            const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+            int n, d0, h0, w0;
+            conv_tile_origin(p, mt, n, d0, h0, w0);
+            const int ww = m % p.bw, r1 = m / p.bw, hh = r1 % p.bh, dd = r1 / p.bh;
+            const size_t vox = (((size_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
+            const size_t row = vox * p.Ntot + (size_t)nt * N;            // float offset of this row's first channel
+            const int cbase = nt * N;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
             for (int c = 0; c < N; c += 16) {
                 float v[16], vx[16];
@@ -185,12 +206,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 tc_ld16(taddr + (uint32_t)(N + c), vx);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float o = fmaf(v[j] + vx[j], s_scale[c + j], s_shift[c + j]);
+                    float o = fmaf(v[j] + vx[j], s_scale[cbase + c + j], s_shift[cbase + c + j]);
                     if (p.relu) o = fmaxf(o, 0.f);
                     v[j] = o;
                 }
                 if (p.residual) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row * N + c);
+                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 rr = __ldg(rp + j);
@@ -198,13 +219,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     }
                 }
                 if (p.y) {
-                    float4 *yp = reinterpret_cast<float4 *>(p.y + row * N + c);
+                    float4 *yp = reinterpret_cast<float4 *>(p.y + row + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
                 if (p.y_hi) {
-                    float4 *hp = reinterpret_cast<float4 *>(p.y_hi + row * N + c);
-                    float4 *lp = reinterpret_cast<float4 *>(p.y_lo + row * N + c);
+                    float4 *hp = reinterpret_cast<float4 *>(p.y_hi + row + c);
+                    float4 *lp = reinterpret_cast<float4 *>(p.y_lo + row + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4 h, l;
@@ -277,6 +298,9 @@ static int g_sm_count = 0;
 
 using namespace side;
 
+// n-tile width: all of Cout when it fits one accumulator pair (<= 128), otherwise 128-wide tiles
+static int conv_ntile(int Cout) { return Cout <= 128 ? Cout : 128; }
+
 extern "C" size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps)
 {
     if (Cin <= 0 || Cout <= 0 || taps <= 0) return 0;
@@ -285,10 +309,19 @@ extern "C" size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps)
 
 extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int taps, void *stream)
 {
-    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= 256 && taps > 0,
-                 "side_conv_tc_prep_weights: needs Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
+    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && taps > 0 &&
+                     (Cout <= 128 || Cout % 128 == 0),
+                 "side_conv_tc_prep_weights: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (<= %d)",
+                 kCvMaxCout);
     SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(wp);
-    return launch_tc_weight_prep(w, wp, Cout, Cin, taps, 1, (cudaStream_t)stream);
+    // one swizzled tile set per n-tile: [n_tile][k-block][hi|lo][Nt x 32]
+    const int Nt = conv_ntile(Cout);
+    for (int nt = 0; nt < Cout / Nt; ++nt) {
+        int rc = launch_tc_weight_prep(w + (size_t)nt * Nt * Cin * taps, wp + (size_t)nt * 2 * Nt * Cin * taps, Nt, Cin, taps, 1,
+                                       (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return SIDE_OK;
 }
 
 extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale,
@@ -296,15 +329,18 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
                                   int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int relu, void *stream)
 {
     SIDE_REQUIRE(Nn >= 0 && D > 0 && H > 0 && W > 0, "side_conv3d_tc_fwd: bad shape");
-    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= 128,
-                 "side_conv3d_tc_fwd: needs Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 128 (got %d -> %d)", Cin, Cout);
+    SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && (Cout <= 128 || Cout % 128 == 0),
+                 "side_conv3d_tc_fwd: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (got %d -> %d)", Cin, Cout);
     SIDE_REQUIRE((kd == 1 || kd == 3) && kh == 3 && kw == 3, "side_conv3d_tc_fwd: kernel must be 3x3x3 or 1x3x3");
-    SIDE_REQUIRE(W <= 128 && (128 % W) == 0, "side_conv3d_tc_fwd: W must divide 128 (got %d)", W);
     if (Nn == 0) return SIDE_OK;
-    const int bh = std::min(H, 128 / W);
-    SIDE_REQUIRE(H % bh == 0 && (128 % (W * bh)) == 0, "side_conv3d_tc_fwd: H=%d does not tile into 128-voxel boxes", H);
-    const int bd = 128 / (W * bh);
-    SIDE_REQUIRE(D % bd == 0, "side_conv3d_tc_fwd: D=%d must be a multiple of %d for %dx%d maps", D, bd, H, W);
+    // 128-voxel box: bw = largest power of two <= 128 dividing W, then rows, then depth slices
+    int bw = 128;
+    while (bw > 1 && W % bw) bw >>= 1;
+    int bh = 128 / bw;
+    while (bh > 1 && H % bh) bh >>= 1;
+    const int bd = 128 / (bw * bh);
+    SIDE_REQUIRE(bd >= 1 && D % bd == 0, "side_conv3d_tc_fwd: %dx%dx%d does not tile into 128-voxel boxes (box %dx%dx%d)", D, H, W,
+                 bd, bh, bw);
     SIDE_REQUIRE((long long)Nn * D * H * W < (1ll << 31), "side_conv3d_tc_fwd: too many voxels");
     SIDE_REQUIRE(y || (y_hi && y_lo), "side_conv3d_tc_fwd: no output requested");
     SIDE_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "side_conv3d_tc_fwd: y_hi and y_lo go together");
@@ -314,16 +350,20 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
 
     CUtensorMap tm_hi, tm_lo;
     int rc;
-    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, W))) return rc;
-    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, W))) return rc;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw))) return rc;
 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
-    p.relu = relu; p.N = Cout; p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
-    p.ntiles = (int)((long long)Nn * D * H * W / kCvBM);
-    p.D = D; p.H = H; p.W = W; p.bh = bh; p.bd = bd; p.kd = kd; p.kh = kh; p.kw = kw;
-    const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)Cout * 128u;
-    p.stages = std::max(2, std::min((int)((200u * 1024u) / stage_bytes), kCvMaxStages));
+    p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N;
+    p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
+    const long long mtiles = (long long)Nn * D * H * W / kCvBM;
+    SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
+    p.ntiles = (int)(mtiles * p.n_ntiles);
+    p.D = D; p.H = H; p.W = W; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = W / bw; p.ht = H / bh;
+    p.kd = kd; p.kh = kh; p.kw = kw;
+    const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
+    p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
     if (g_sm_count == 0) {

@@ -187,6 +187,84 @@ class stereo_network(nn.Module):
             return f[:left.shape[0]], f[left.shape[0]:]
         return self.feature_extraction(left), self.feature_extraction(right)
 
+    # -- heads on the tensor cores (inference) -------------------------------------------------------------
+    heads_tensor_core = True   # False keeps the cuDNN head convolutions (training always does)
+
+    def _heads_tc_ok(self, f):
+        if not (self.heads_tensor_core and f.is_cuda and not self.training and not torch.is_grad_enabled()):
+            return False
+        B, C, H, W = f.shape
+        bw = 128
+        while bw > 1 and W % bw:
+            bw >>= 1
+        bh = 128 // bw
+        while bh > 1 and H % bh:
+            bh >>= 1
+        if bw * bh != 128 or C % 32:
+            return False
+        for head in self.heads:                        # 3x3 (no bias) + ReLU chains ending in a biased 1x1: the reference layout
+            mods = list(self.__getattr__(head))
+            convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+            if any(c.kernel_size != (3, 3) or c.bias is not None or c.out_channels % 128 for c in convs[:-1]):
+                return False
+            if convs[-1].kernel_size != (1, 1):
+                return False
+        return True
+
+    def _heads_state(self):
+        """Swizzled tf32 weight tiles of the 3x3 head convolutions.  The first convolutions of all stereo heads (same
+        input cat(left, right)) are stacked into ONE convolution; their 1x1 outputs become one block-diagonal matmul."""
+        stereo = [h for h in self.heads if h not in self.left_only]
+        mono = [h for h in self.heads if h in self.left_only]
+        params = [p for h in self.heads for p in self.__getattr__(h).parameters()]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        st = getattr(self, "_heads_cache", None)
+        if st is None or st[0] != key:
+            d = {"stereo": stereo, "mono": {}}
+            if stereo:
+                w0 = torch.cat([self.__getattr__(h)[0].weight.detach() for h in stereo], 0)          # [n*256, 2C, 3, 3]
+                d["stereo_w"] = (ops.conv_tc_prepare(w0), w0.shape[0])
+                outs = [self.__getattr__(h)[-1] for h in stereo]
+                hid = [c.in_channels for c in outs]
+                blk = torch.zeros((sum(hid), sum(c.out_channels for c in outs)), device=w0.device)
+                r = c0 = 0
+                for c, hdim in zip(outs, hid):
+                    blk[r:r + hdim, c0:c0 + c.out_channels] = c.weight.detach().view(c.out_channels, hdim).t()
+                    r += hdim
+                    c0 += c.out_channels
+                d["stereo_out"] = (blk.contiguous(), torch.cat([c.bias.detach() for c in outs]), [c.out_channels for c in outs])
+            for h in mono:
+                mods = [m for m in self.__getattr__(h) if isinstance(m, nn.Conv2d)]
+                d["mono"][h] = ([(ops.conv_tc_prepare(c.weight.detach()), c.out_channels) for c in mods[:-1]], mods[-1])
+            st = (key, d)
+            self._heads_cache = st
+        return st[1]
+
+    def _heads_tc(self, fl, fr):
+        """All head convolutions of forward (:343-348) as tcgen05 implicit GEMMs on channels-last activations."""
+        S = self._heads_state()
+        B, C, H, W = fl.shape
+        z = {}
+        if S["stereo"]:
+            hi, lo = ops.ncdhw_to_cl_split(torch.cat((fl, fr), 1).unsqueeze(2))                  # [B, 1, H, W, 2C]
+            wp, cout = S["stereo_w"]
+            y, _, _ = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=True, split=False)
+            blk, bias, widths = S["stereo_out"]
+            o = torch.addmm(bias, y.view(-1, cout), blk).view(B, H, W, -1).permute(0, 3, 1, 2)
+            c0 = 0
+            for h, wdt in zip(S["stereo"], widths):
+                z[h] = o[:, c0:c0 + wdt].contiguous()
+                c0 += wdt
+        for h, (chain, last) in S["mono"].items():
+            hi, lo = ops.ncdhw_to_cl_split(fl.unsqueeze(2))                                        # [B, 1, H, W, C]
+            y = None
+            for i, (wp, cout) in enumerate(chain):
+                final = i == len(chain) - 1
+                y, hi, lo = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=final, split=not final)
+            o = torch.addmm(last.bias.detach(), y.view(-1, y.shape[-1]), last.weight.detach().view(last.out_channels, -1).t())
+            z[h] = o.view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+        return {h: z[h] for h in self.heads}
+
     fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream
 
     def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D):
@@ -208,15 +286,18 @@ class stereo_network(nn.Module):
         left, right = batch['input'], batch['input_right']
         imgfea_left, imgfea_right = self._features(left, right)
 
-        z = {}
-        both = None
-        for head in self.heads:
-            if head in self.left_only:
-                z[head] = self.__getattr__(head)(imgfea_left)
-            else:
-                if both is None:
-                    both = torch.cat((imgfea_left, imgfea_right), 1)
-                z[head] = self.__getattr__(head)(both)
+        if self._heads_tc_ok(imgfea_left):
+            z = self._heads_tc(imgfea_left, imgfea_right)
+        else:
+            z = {}
+            both = None
+            for head in self.heads:
+                if head in self.left_only:
+                    z[head] = self.__getattr__(head)(imgfea_left)
+                else:
+                    if both is None:
+                        both = torch.cat((imgfea_left, imgfea_right), 1)
+                    z[head] = self.__getattr__(head)(both)
 
         if useCostVolume:
             fb = batch['fb'].to(left.device, torch.float32).reshape(-1)

@@ -121,3 +121,38 @@ def test_aggregate_tc_matches_module_fp64(lib, N, D):
         assert float(((d_tc - d_ref).abs() / d_ref.abs()).max()) < 1e-4
         # the module switches back to cuDNN under autograd / training
         assert not m.train()._tc_ok(c)
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 320), (1, 16, 320), (3, 8, 64)])
+def test_heads_tc_match_cudnn_heads(lib, shape):
+    """stereo_network heads (:343-348) on tcgen05 (stacked first convolutions, n-tiles of 128, 2 x 64 pixel boxes) vs the
+    module's own cuDNN fp32 path on the same weights: <= 1e-4 of each head's range."""
+    from side_b200.networks import get_pose_net
+    from side_b200.utils.synthetic import HEADS, realistic_init
+    B, H, W = shape
+    torch.manual_seed(2)
+    m = realistic_init(get_pose_net(34, HEADS, 256), seed=3).eval().cuda()
+    fl, fr = torch.randn(B, 64, H, W, device="cuda"), torch.randn(B, 64, H, W, device="cuda")
+    with torch.no_grad():
+        assert m._heads_tc_ok(fl)
+        z = m._heads_tc(fl, fr)
+        both = torch.cat((fl, fr), 1)
+        for h in m.heads:
+            ref = m.__getattr__(h)(fl if h in m.left_only else both)
+            assert z[h].shape == ref.shape and z[h].is_contiguous()
+            err = float((z[h] - ref).abs().max() / ref.abs().max())
+            assert err < 1e-4, (h, err)
+
+
+def test_conv2d_tc_wide_n_tiles(lib):
+    """2-D convolution through the same kernel: D = 1, kd = 1, W = 320 (boxes of 2 rows x 64 columns), Cout = 256 (2 n-tiles)."""
+    from side_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 8, 320, generator=g)
+    w = torch.randn(256, 64, 3, 3, generator=g) * 0.05
+    ref = F.conv2d(x.double(), w.double(), padding=1).relu().permute(0, 2, 3, 1).numpy()
+    dev = torch.device("cuda")
+    hi, lo = ops.ncdhw_to_cl_split(x.to(dev).unsqueeze(2))
+    y, yh, yl = ops.conv3d_tc(hi, lo, ops.conv_tc_prepare(w.to(dev)), 256, ksize=(1, 3, 3), relu=True, full=True, split=True)
+    assert rel_err(y.cpu().numpy()[:, 0], ref) < 1e-4
+    assert torch.equal(yh + yl, y)
