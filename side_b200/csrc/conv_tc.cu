@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = tc_idesc_tf32(kCvBM, N);
+            // hi*hi and hi*lo share their A operand: ONE MMA of width 2N against the adjacent [B_hi | B_lo] tiles writes
+            // main (columns 0..N) and the first cross term (N..2N) at once; lo*hi then accumulates onto N..2N.  The A tile
+            // is fetched from shared memory twice per k-step instead of three times (the kernel is smem-bandwidth bound:
+            // tf32 operands are 4 bytes, a 128 x N x 8 MMA reads (128 + N) * 32 bytes in 128 * N / 256 cycles).
+            const uint32_t idesc = tc_idesc_tf32(kCvBM, N), idesc2 = tc_idesc_tf32(kCvBM, 2 * N);
             int st = 0, acc = 0;
             uint32_t phs = 0, acc_ph = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -170,10 +174,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
-                        const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32), b_lo = tc_smem_desc(sb + b_part + k * 32);
-                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_x, a_hi, b_lo, idesc, 1u);
+                        const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32);
+                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);     // [hi*hi | hi*lo]
+                        tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, 1u);                          // + lo*hi
                     }
                     tc_commit(&empty_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
