@@ -27,9 +27,10 @@
 namespace side {
 
 constexpr int kTcBM = 128;            // UMMA M (pixels per tile)
-constexpr int kTcProducerThreads = 256;
+constexpr int kTcProducerThreads = 512;
 constexpr int kTcThreads = kTcProducerThreads + 64;
 constexpr int kTcMaxStages = 8;
+constexpr int kTcMaxTapGroup = 9;     // taps whose sample geometry is computed together (one exposed latency per group)
 constexpr uint32_t kATileBytes = kTcBM * 128;   // 16 KB
 
 // w [Cout, Cin, KK] -> per-K-block tiles: wp[kb][part][Cout x 32] in the swizzled shared-memory image.
@@ -60,21 +61,29 @@ __global__ void dcn_tc_weight_prep_kernel(const float *__restrict__ w, float *__
 // sample geometry of one (pixel, tap), ready for the channels-last gather: element offsets into the NHWC copy of x
 // (batch folded in) and bilinear weights pre-multiplied by the modulation mask
 struct TapRec {
-    int o1, o2, o3, o4;
+    uint32_t o1, o2, o3, o4;     // BYTE offsets of the four corners' pixels (channel 0) in the channels-last copy
     float w1, w2, w3, w4;
+};
+
+// Tile geometry: 128 pixels = th x tw.  8 x 16 tiles keep the footprint of the 9 deformed taps compact (for small
+// offsets ~10 x 18 source pixels x Cin channels), so that with only 2-3 operand stages in shared memory the rest of
+// the 228 KB stays L1 and most of the 36 corner reads per pixel hit it; maps that do not tile into 8 x 16 use 1 x 128
+// over the flattened (b, y, x) index.
+struct TcTiling {
+    int th, tw;          // tile extent (th * tw == 128); th == 1: flattened
+    int tiles_x, tiles_y;
 };
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp,
                                                                   const float *__restrict__ xt, int stages, uint32_t idesc,
-                                                                  uint32_t tmem_cols)
+                                                                  uint32_t tmem_cols, TcTiling tl, int tap_group)
 {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) TapRec tapbuf[2][kTcBM];
 
     const DcnShape &s = a.s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,6 +94,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     const uint32_t stage_bytes = a_bytes + b_bytes;
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the SHARED address space
     unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    TapRec *tapbuf = reinterpret_cast<TapRec *>(tiles + (size_t)stages * stage_bytes);      // [tap_group][128]
 
     const int ncb = s.Cin / kTcBK;
     const int nkb = s.KK * ncb;
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         mbar_init(&tmem_full_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 8) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(tmem_cols)
                      : "memory");
@@ -110,69 +120,101 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 
     if (tid < kTcProducerThreads) {
         // ================= producers: modulated bilinear gather -> swizzled A tile =================
-        // geometry: thread `row` (< 128) fills tapbuf once per tap; gather: thread = (c4 = tid & 7, rows (tid >> 3) + 32 i):
-        // a warp instruction reads 4 pixels x 128 contiguous bytes of the NHWC copy.
-        const int row = tid & 127;
-        const long long Mtot = (long long)s.B * s.P;
-        const long long gp = (long long)blockIdx.x * kTcBM + row;
-        const bool pix_ok = gp < Mtot;
-        const int b = pix_ok ? (int)(gp / s.P) : 0;
-        const int p = pix_ok ? (int)(gp - (long long)b * s.P) : 0;
-        const int ho = p / s.Wo, wo = p - ho * s.Wo;
-        const int c4 = tid & 7, r0 = tid >> 3;
-        int cur_tap = -1;
-        float4 raw[16];
-        // issue the 16 tap loads of k-block kb (and publish the tap geometry when a new tap starts)
-        auto prefetch = [&](int kb) {
-            const int tp = kb / ncb, c0 = (kb - tp * ncb) * kTcBK + 4 * c4;
-            if (tp != cur_tap) {
-                cur_tap = tp;
-                if (tid < kTcBM) {
-                    TapRec tr;
-                    if (pix_ok) {
-                        const DcnTap g = dcn_tap(s, a.offset, a.mask, b, 0, tp, ho, wo);
-                        const int base = b * s.H * s.W;
-                        tr.o1 = (base + g.o1) * s.Cin; tr.o2 = (base + g.o2) * s.Cin;
-                        tr.o3 = (base + g.o3) * s.Cin; tr.o4 = (base + g.o4) * s.Cin;
-                        tr.w1 = g.w1 * g.m; tr.w2 = g.w2 * g.m; tr.w3 = g.w3 * g.m; tr.w4 = g.w4 * g.m;
-                    } else {
-                        tr.o1 = tr.o2 = tr.o3 = tr.o4 = 0;
-                        tr.w1 = tr.w2 = tr.w3 = tr.w4 = 0.f;
-                    }
-                    tapbuf[tp & 1][row] = tr;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+        int tile_b = 0, tile_y0 = 0, tile_x0 = 0;
+        if (tl.th != 1) {
+            const int per_img = tl.tiles_x * tl.tiles_y;
+            tile_b = blockIdx.x / per_img;
+            const int t = blockIdx.x - tile_b * per_img, ty = t / tl.tiles_x;
+            tile_y0 = ty * 8; tile_x0 = (t - ty * tl.tiles_x) * 16;
+        }
+        // pixel of tile row m
+        auto pixel_of = [&](int m, int &b, int &ho, int &wo) -> bool {
+            if (tl.th == 1) {
+                const long long gp = (long long)blockIdx.x * kTcBM + m;
+                if (gp >= (long long)s.B * s.P) return false;
+                b = (int)(gp / s.P);
+                const int p = (int)(gp - (long long)b * s.P);
+                ho = p / s.Wo; wo = p - ho * s.Wo;
+                return true;
             }
-            const float *xc = xt + c0;
+            b = tile_b;
+            ho = tile_y0 + (m >> 4); wo = tile_x0 + (m & 15);       // 8 x 16 tiles
+            return ho < s.Ho && wo < s.Wo;
+        };
+        // gather: thread = (c4 = tid & 7 -> 4 channels, rows (tid >> 3) and (tid >> 3) + 64): a warp instruction reads 4 pixels x
+        // 128 contiguous bytes of the channels-last copy
+        const int c4 = tid & 7, r0 = tid >> 3;
+        float4 raw[8];
+        auto geometry = [&](int tap0) {         // sample geometry of taps tap0 .. tap0 + tap_group - 1 for all 128 pixels
+            const int ntap = min(tap_group, s.KK - tap0);
+            for (int i = tid; i < ntap * kTcBM; i += kTcProducerThreads) {
+                const int tt = i / kTcBM, m = i - tt * kTcBM;
+                int b, ho, wo;
+                TapRec tr;
+                if (pixel_of(m, b, ho, wo)) {
+                    const DcnTap g = dcn_tap(s, a.offset, a.mask, b, 0, tap0 + tt, ho, wo);
+                    const int base = b * s.H * s.W;
+                    const uint32_t pix = (uint32_t)s.Cin * 4u;
+                    tr.o1 = (uint32_t)(base + g.o1) * pix; tr.o2 = (uint32_t)(base + g.o2) * pix;
+                    tr.o3 = (uint32_t)(base + g.o3) * pix; tr.o4 = (uint32_t)(base + g.o4) * pix;
+                    tr.w1 = g.w1 * g.m; tr.w2 = g.w2 * g.m; tr.w3 = g.w3 * g.m; tr.w4 = g.w4 * g.m;
+                } else {
+                    tr.o1 = tr.o2 = tr.o3 = tr.o4 = 0u;
+                    tr.w1 = tr.w2 = tr.w3 = tr.w4 = 0.f;
+                }
+                tapbuf[tt * kTcBM + m] = tr;
+            }
+        };
+        // issue the 8 corner loads of k-block (tap slot `slot` of the table, channel block cb)
+        auto prefetch = [&](int slot, int cb) {
+            const TapRec *tb = tapbuf + slot * kTcBM;
+            const char *xc = reinterpret_cast<const char *>(xt + cb * kTcBK + 4 * c4);   // one 64-bit base per k-block,
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int4 o = *reinterpret_cast<const int4 *>(&tapbuf[tp & 1][r0 + 32 * i]);
+            for (int i = 0; i < 2; ++i) {                                                // unsigned 32-bit byte offsets per corner
+                const uint4 o = *reinterpret_cast<const uint4 *>(&tb[r0 + 64 * i]);
                 raw[4 * i + 0] = __ldg(reinterpret_cast<const float4 *>(xc + o.x));
                 raw[4 * i + 1] = __ldg(reinterpret_cast<const float4 *>(xc + o.y));
                 raw[4 * i + 2] = __ldg(reinterpret_cast<const float4 *>(xc + o.z));
                 raw[4 * i + 3] = __ldg(reinterpret_cast<const float4 *>(xc + o.w));
             }
         };
-        prefetch(0);
+        geometry(0);
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+        prefetch(0, 0);
+        // all loop state is carried incrementally: no integer division in the k loop
+        int st = 0, tp = 0, cb = 0, slot = 0;
+        uint32_t eph = 1;                        // parity to wait for on empty_bar[st] (first pass falls through)
         for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % stages, it = kb / stages;
-            const int tp = kb / ncb;
-            float4 v[4];
+            const TapRec *tb = tapbuf + slot * kTcBM;
+            float4 v[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 w = *reinterpret_cast<const float4 *>(&tapbuf[tp & 1][r0 + 32 * i].w1);
+            for (int i = 0; i < 2; ++i) {
+                const float4 w = *reinterpret_cast<const float4 *>(&tb[r0 + 64 * i].w1);
                 const float4 a1 = raw[4 * i], a2 = raw[4 * i + 1], a3 = raw[4 * i + 2], a4 = raw[4 * i + 3];
                 v[i].x = fmaf(w.w, a4.x, fmaf(w.z, a3.x, fmaf(w.y, a2.x, w.x * a1.x)));
                 v[i].y = fmaf(w.w, a4.y, fmaf(w.z, a3.y, fmaf(w.y, a2.y, w.x * a1.y)));
                 v[i].z = fmaf(w.w, a4.z, fmaf(w.z, a3.z, fmaf(w.y, a2.z, w.x * a1.z)));
                 v[i].w = fmaf(w.w, a4.w, fmaf(w.z, a3.w, fmaf(w.y, a2.w, w.x * a1.w)));
             }
-            if (kb + 1 < nkb) prefetch(kb + 1);          // next block's loads fly while this one is stored
-            if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
+            // advance (tap, channel block) to the next k-block and start its loads while this one is stored
+            int ncbi = cb + 1, ntp = tp, nslot = slot;
+            if (ncbi == ncb) {
+                ncbi = 0; ++ntp;
+                if (++nslot == tap_group) nslot = 0;
+            }
+            if (kb + 1 < nkb) {
+                if (ntp != tp && nslot == 0) {              // the next k-block starts a new tap group: recompute the table
+                    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");   // everyone is done with the old one
+                    geometry(ntp);
+                    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+                }
+                prefetch(nslot, ncbi);
+            }
+            mbar_wait(&empty_bar[st], eph);
             unsigned char *sa = tiles + (size_t)st * stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = sw128(r0 + 32 * i, c4);
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t off = sw128(r0 + 64 * i, c4);
                 if (SPLIT) {
                     float4 hi, lo;
                     hi.x = tf32_hi(v[i].x); lo.x = v[i].x - hi.x;
@@ -188,15 +230,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[st]);   // one arrival per producer warp
+            if (++st == stages) { st = 0; eph ^= 1u; }
+            cb = ncbi; tp = ntp; slot = nslot;
         }
 
         // ================= epilogue: TMEM -> registers -> NCHW =================
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-        const int lg = warp & 3, chalf = warp >> 2;          // TMEM lane group of this warp, column half
+        const int lg = warp & 3, cq = warp >> 2;             // TMEM lane group of this warp, column quarter
         const bool affine = s.flags & SIDE_DCN_FUSE_AFFINE, relu = s.flags & SIDE_DCN_FUSE_RELU;
-        float *yp = a.y + (size_t)b * s.Cout * s.P + p;
-        const int cbeg = chalf * (N / 2), cend = cbeg + N / 2;
+        int b, ho, wo;
+        const bool pix_ok = pixel_of(lg * 32 + lane, b, ho, wo);
+        float *yp = a.y + (pix_ok ? (size_t)b * s.Cout * s.P + (size_t)ho * s.Wo + wo : 0);
+        const int cbeg = cq * (N / 4), cend = cbeg + N / 4;
         for (int c = cbeg; c < cend; c += 8) {
             float acc[8];
             tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, acc);
@@ -215,12 +261,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 if (pix_ok) yp[(size_t)n * s.P] = o;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // ================= MMA issuer =================
         if (lane == 0) {
+            int st = 0;
+            uint32_t fph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % stages, it = kb / stages;
-                mbar_wait(&full_bar[st], (uint32_t)(it & 1));
+                mbar_wait(&full_bar[st], fph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
                 const uint32_t sb = sa + a_bytes;
@@ -239,6 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                     }
                 }
                 tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
+                if (++st == stages) { st = 0; fph ^= 1u; }
             }
             tc_commit(&tmem_full_bar);         // accumulator complete
         }
@@ -246,11 +294,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     } else {
         // ================= weight loader (TMA bulk copies) =================
         if (lane == 0) {
+            int st = 0;
+            uint32_t eph = 1;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % stages, it = kb / stages;
-                if (it > 0) mbar_wait(&empty_bar[st], (uint32_t)((it - 1) & 1));
+                mbar_wait(&empty_bar[st], eph);
                 mbar_expect_tx(&full_bar[st], b_bytes);
                 bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)kb * (b_bytes / 4), b_bytes, &full_bar[st]);
+                if (++st == stages) { st = 0; eph ^= 1u; }
             }
         }
         __syncwarp();
@@ -258,7 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
     }
 }
@@ -300,8 +350,8 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
         set_error("side_dcn_fwd: workspace too small for the tcgen05 weight tiles + NHWC copy");
         return SIDE_ERR_WORKSPACE;
     }
-    if ((long long)s.B * s.H * s.W * s.Cin >= (1ll << 31)) {
-        set_error("side_dcn_fwd: input too large for 32-bit gather offsets");
+    if ((long long)s.B * s.H * s.W * s.Cin * 4 >= (1ll << 32)) {
+        set_error("side_dcn_fwd: input too large for 32-bit gather byte offsets");
         return SIDE_ERR_UNSUPPORTED;
     }
     float *wp = reinterpret_cast<float *>(ws);
@@ -311,20 +361,34 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     if ((rc = launch_tc_weight_prep(w, wp, s.Cout, s.Cin, s.KK, split ? 1 : 0, st))) return rc;
 
     const uint32_t stage_bytes = (split ? 2u : 1u) * (kATileBytes + (uint32_t)s.Cout * 128u);
-    int stages = (int)((200u * 1024u) / stage_bytes);
-    stages = std::max(2, std::min(stages, kTcMaxStages));
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    // operand stages: the gather, not the MMA, bounds this kernel, so 2-3 stages are enough; what is left of the 228 KB
+    // stays L1 for the 36 corner reads per pixel.  The tap table holds all taps when it fits next to the stages.
+    int stages = std::max(2, std::min((int)((100u * 1024u) / stage_bytes), 3));
+    int tap_group = std::min(s.KK, kTcMaxTapGroup);
+    while (tap_group > 1 && (size_t)stages * stage_bytes + (size_t)tap_group * kTcBM * sizeof(TapRec) + 1024 > 220 * 1024) --tap_group;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)tap_group * kTcBM * sizeof(TapRec) + 1024;
+    if (smem > 226 * 1024) {
+        set_error("side_dcn_fwd: tcgen05 path does not fit shared memory for Cout=%d", s.Cout);
+        return SIDE_ERR_UNSUPPORTED;
+    }
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < (split ? 2 : 1) * s.Cout) tmem_cols <<= 1;
-    // instruction descriptor: D = fp32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = tc_idesc_tf32(kTcBM, s.Cout);
-    const unsigned grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
+    TcTiling tl;
+    unsigned grid;
+    if (s.Ho % 8 == 0 && s.Wo % 16 == 0) {
+        tl.th = 8; tl.tw = 16; tl.tiles_x = s.Wo / 16; tl.tiles_y = s.Ho / 8;
+        grid = (unsigned)((long long)s.B * tl.tiles_x * tl.tiles_y);
+    } else {
+        tl.th = 1; tl.tw = 128; tl.tiles_x = tl.tiles_y = 0;
+        grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
+    }
     if (split) {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;
-        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols);
+        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group);
     } else {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false>, smem))) return rc;
-        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols);
+        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group);
     }
     SIDE_LAUNCH_CHECK("dcn_fwd_tc_kernel");
     return SIDE_OK;
