@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per GPU per step (config #4: batch 32)")
     ap.add_argument("--micro-batch", type=int, default=4)
-    ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "fp32"), choices=["fp32", "3xtf32", "tf32"])
+    ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
+                    help="3xtf32 (default): tcgen05 with the exact hi/lo split, fp32-class accuracy (<= 1e-4 rel); fp32: SIMT")
+    ap.add_argument("--cudnn-only", action="store_true",
+                    help="keep the heads and the 3-D aggregation network on cuDNN fp32 (as the reference runs them)")
     ap.add_argument("--allow-tf32", action="store_true", help="let cuDNN use TF32 for the out-of-scope convolutions")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline microbenchmarks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -122,6 +125,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads this box has (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(ncpu, 1))
     model = build_model()
     cores = torch.get_num_threads()
     val, times = cpu_reference_pairs_per_s(model, args.steps, args.warmup)
@@ -250,11 +259,18 @@ def main():
     cpu_model = build_model()
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
+        except AttributeError:
+            pass
         v, times = cpu_reference_pairs_per_s(cpu_model, args.cpu_pairs, 1)
         cpu_base = {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": "%d pairs (batch 1, 384x1280, K=100 RoIs) after 1 warm-up; reference-style torch CPU ops "
                               "(torchvision deform_conv2d / roi_align loop, torch.topk decode)" % args.cpu_pairs}
     model = cpu_model.to(dev)
+    if args.cudnn_only:
+        model.heads_tensor_core = False
+        model.depth_estimator.tensor_core = False
     det = StereoDetector(model, grid_size=28, K=100)
 
     P, mb = args.pairs, args.micro_batch
@@ -361,6 +377,8 @@ def main():
                                    "random-init weights with calibrated BatchNorm" % (P, mb),
                        "pairs_per_gpu_per_step": P, "micro_batch": mb, "parallelism": "pair-sharded x%d, all_gather(detections)" % world,
                        "dcn_precision": args.dcn_precision, "cudnn_tf32": bool(args.allow_tf32),
+                       "tensor_core_convs": "cuDNN fp32 only" if args.cudnn_only else
+                       "heads + 3-D aggregation network on tcgen05 3xTF32 (fp32-class accuracy); DLA-34 base cuDNN fp32",
                        "l2": "inputs larger than L2 (%.0f MB of images per step)" % (2 * P * 3 * H_IN * W_IN * 4 / 1e6)},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * H_IN * W_IN * 4,
                     "d2h_bytes_per_step": P * 100 * 22 * 4, "ms_per_step": ms_e2e / args.steps},

@@ -161,3 +161,28 @@ def gwc_volume(L, R, D, G):
     vol = np.empty((B, G, D, H, W), np.float32)
     _chk(lib().orc_gwc_volume(pL, pR, vol.ctypes.data_as(C.POINTER(C.c_float)), B, Cc, H, W, D, G), "orc_gwc_volume")
     return vol
+
+
+def conv3d_bn_relu(x, w, scale=None, shift=None, relu=False, residual=None):
+    """x [N,Cin,D,H,W], w [Cout,Cin,3,3,3] -> [N,Cout,D,H,W]; folded eval-mode BatchNorm, ReLU, residual."""
+    x, px = _f(x); w, pw = _f(w)
+    N, Cin, D, H, W = x.shape
+    Cout = w.shape[0]
+    Pf = C.POINTER(C.c_float)
+    ps = pt = pr = None
+    if scale is not None:
+        scale, ps = _f(scale); shift, pt = _f(shift)
+    if residual is not None:
+        residual, pr = _f(residual)
+    y = np.empty((N, Cout, D, H, W), np.float32)
+    _chk(lib().orc_conv3d_bn_relu(px, pw, ps, pt, pr, y.ctypes.data_as(Pf), N, Cin, D, H, W, Cout, 1 if relu else 0),
+         "orc_conv3d_bn_relu")
+    return y
+
+
+def maxpool_hw2(x):
+    x, px = _f(x)
+    N, Cc, D, H, W = x.shape
+    y = np.empty((N, Cc, D, H // 2, W // 2), np.float32)
+    _chk(lib().orc_maxpool_hw2(px, y.ctypes.data_as(C.POINTER(C.c_float)), N * Cc, D, H, W), "orc_maxpool_hw2")
+    return y

@@ -629,3 +629,65 @@ ORC_API int orc_gwc_volume(const float *L, const float *R, float *vol, int B, in
                 }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Aggregation network layer: the arithmetic behind
+ * cost_volume.dres0/dres1/dres2/classify (stereo_network_old.py:139-171, convbn_3d :29-32):
+ *   y = relu?( conv3d(x, w; 3x3x3, stride 1, padding 1, no bias) * scale[o] + shift[o] ) (+ residual)
+ * where scale/shift are the eval-mode BatchNorm3d folded (gamma / sqrt(var + eps), beta - mean * scale).
+ * nn.Conv3d itself is a third-party (ATen / cuDNN) op: this restatement is pinned against torch's CPU conv3d in
+ * tests/test_oracle_golden.py.  NCDHW layout, double accumulation.
+ * --------------------------------------------------------------------------------------------- */
+ORC_API int orc_conv3d_bn_relu(const float *x, const float *w, const float *scale, const float *shift,
+                               const float *residual, float *y, int N, int Cin, int D, int H, int W, int Cout, int relu)
+{
+    const size_t S = (size_t)D * H * W;
+    for (int n = 0; n < N; ++n)
+        for (int o = 0; o < Cout; ++o)
+            for (int d = 0; d < D; ++d)
+                for (int h = 0; h < H; ++h)
+                    for (int xw = 0; xw < W; ++xw) {
+                        double acc = 0;
+                        for (int c = 0; c < Cin; ++c) {
+                            const float *xp = x + ((size_t)n * Cin + c) * S;
+                            const float *wp = w + ((size_t)o * Cin + c) * 27;
+                            for (int kd = 0; kd < 3; ++kd) {
+                                const int dd = d + kd - 1;
+                                if (dd < 0 || dd >= D) continue;
+                                for (int kh = 0; kh < 3; ++kh) {
+                                    const int hh = h + kh - 1;
+                                    if (hh < 0 || hh >= H) continue;
+                                    for (int kw = 0; kw < 3; ++kw) {
+                                        const int ww = xw + kw - 1;
+                                        if (ww < 0 || ww >= W) continue;
+                                        acc += (double)xp[((size_t)dd * H + hh) * W + ww] * wp[(kd * 3 + kh) * 3 + kw];
+                                    }
+                                }
+                            }
+                        }
+                        float v = (float)acc;
+                        if (scale) v = v * scale[o] + shift[o];
+                        if (relu && v < 0.f) v = 0.f;
+                        const size_t idx = ((size_t)n * Cout + o) * S + ((size_t)d * H + h) * W + xw;
+                        if (residual) v += residual[idx];
+                        y[idx] = v;
+                    }
+    return 0;
+}
+
+/* MaxPool3d((1,2,2)) (stereo_network_old.py:156,165), NCDHW */
+ORC_API int orc_maxpool_hw2(const float *x, float *y, int NC, int D, int H, int W)
+{
+    const int Ho = H / 2, Wo = W / 2;
+    for (int i = 0; i < NC * D; ++i)
+        for (int h = 0; h < Ho; ++h)
+            for (int w = 0; w < Wo; ++w) {
+                const float *p = x + ((size_t)i * H + 2 * h) * W + 2 * w;
+                float m = p[0];
+                if (p[1] > m) m = p[1];
+                if (p[W] > m) m = p[W];
+                if (p[W + 1] > m) m = p[W + 1];
+                y[((size_t)i * Ho + h) * Wo + w] = m;
+            }
+    return 0;
+}

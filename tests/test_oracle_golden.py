@@ -109,3 +109,26 @@ def test_volume_builders_against_torch_restatement():
     assert np.array_equal(v[:, :8, 0], L) and np.array_equal(v[:, 8:, 0], R)     # D=1 slice == torch.cat((L,R),1) (:348)
     w = co.gwc_volume(L, R, 6, 4)
     assert rel_err(w, tp.gwc_volume(torch.from_numpy(L), torch.from_numpy(R), 6, 4).numpy()) < 1e-6
+
+
+def test_conv3d_layer_restatement_vs_torch():
+    """The aggregation-network layer of the oracle (conv3d 3x3x3 pad 1 + folded BatchNorm3d + ReLU + residual, MaxPool3d(1,2,2))
+    against the ops the reference module calls (nn.Conv3d / BatchNorm3d / MaxPool3d, stereo_network_old.py:139-171)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import c_oracle as co
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 6, 4, 5, 7, generator=g)
+    w = torch.randn(8, 6, 3, 3, 3, generator=g) * 0.2
+    bn = torch.nn.BatchNorm3d(8).eval()
+    bn.running_mean.normal_(0, 0.2, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    bn.weight.data.uniform_(0.8, 1.2, generator=g); bn.bias.data.normal_(0, 0.1, generator=g)
+    res = torch.randn(2, 8, 4, 5, 7, generator=g)
+    with torch.no_grad():
+        ref = F.relu(bn(F.conv3d(x, w, padding=1))) + res
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach()
+    shift = (bn.bias - bn.running_mean * scale).detach()
+    out = co.conv3d_bn_relu(x.numpy(), w.numpy(), scale.numpy(), shift.numpy(), relu=True, residual=res.numpy())
+    assert rel_err(out, ref.numpy()) < 1e-5
+    y = torch.randn(1, 3, 2, 6, 8, generator=g)
+    assert np.array_equal(co.maxpool_hw2(y.numpy()), F.max_pool3d(y, (1, 2, 2)).numpy())
