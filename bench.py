@@ -33,6 +33,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: BASELINE config #5 (training step)")
+    ap.add_argument("--train-batch", type=int, default=2, help="pairs per GPU per training step (config #5: 16 pairs / 8 GPUs)")
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per GPU per step (config #4: batch 32)")
     ap.add_argument("--micro-batch", type=int, default=4)
     ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
@@ -188,6 +190,13 @@ def kernel_rooflines(pk, precision):
     for name, fn in variants.items():
         ms = time_op(fn, flush=flush)
         out[name] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    # config #2 backward (gradient of the volume w.r.t. both feature maps; reads the 604 MB gradient once, atomics into 15.7 MB)
+    fLg, fRg = fL.clone().requires_grad_(True), fR.clone().requires_grad_(True)
+    cost, _ = ops.inst_costvol(fLg, fRg, left, right, fb, 48, 16, 319.0)
+    gcost = torch.randn_like(cost)
+    ms = time_op(lambda: torch.autograd.grad(cost, (fLg, fRg), gcost, retain_graph=True), flush=flush, iters=5)
+    out["inst_costvol_bwd"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    del cost, gcost, fLg, fRg
     # reference-shaped volume: 100 RoIs x 16 x 32 ch
     l2, r2, _ = make_boxes(1, 100, seed=1)
     f32L, f32R = fL[:, :32].contiguous(), fR[:, :32].contiguous()
@@ -224,16 +233,101 @@ def kernel_rooflines(pk, precision):
             dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = {"error": str(e)[:80]}
             continue
         fl = 2.0 * B * Cout * Cin * 9 * H * W
-        dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = {"ms": ms, "TFLOPs": fl / ms / 1e9, "frac_tensor": fl / ms / 1e9 / pk["tf_burst"]}
+        rec = {"ms": ms, "TFLOPs": fl / ms / 1e9, "frac_tensor": fl / ms / 1e9 / pk["tf_burst"]}
+        # the same op through torchvision's CUDA deform_conv2d on this GPU (BASELINE config #3), forward and forward+backward
+        try:
+            import torchvision
+            rec["torchvision_fwd_ms"] = time_op(lambda: torchvision.ops.deform_conv2d(x, off, w, b, padding=1, mask=mask), flush=flush, iters=5)
+            xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+
+            def tv_fb():
+                y = torchvision.ops.deform_conv2d(xg, off, wg, b, padding=1, mask=mask)
+                torch.autograd.grad(y, (xg, wg), torch.ones_like(y))
+
+            def our_fb():
+                y = ops.dcn_v2_conv(xg, off, mask, wg, b, 1, 1, 1, 1)
+                torch.autograd.grad(y, (xg, wg), torch.ones_like(y))
+
+            rec["torchvision_fwd_bwd_ms"] = time_op(tv_fb, flush=flush, iters=3)
+            rec["fwd_bwd_ms"] = time_op(our_fb, flush=flush, iters=3)
+        except Exception as e:   # torchvision missing on the box: report ours only
+            rec["torchvision"] = "unavailable: %s" % str(e)[:60]
+        dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = rec
     out["dcn_fwd_" + precision] = dcn
     return out
 
 
 # ----------------------------------------------------------------------------------------------------
+# BASELINE config #5: data-parallel training step (2 synthetic pairs per GPU by default, NCCL gradient all-reduce)
+# ----------------------------------------------------------------------------------------------------
+def run_train(args):
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from side_b200 import _lib, ops
+    from side_b200.engine import allreduce_gradients
+    from side_b200.utils.synthetic import make_batch, make_boxes
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(args.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.allow_tf32)
+    ops.set_dcn_precision(args.dcn_precision)
+    model = build_model().to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1.25e-4)
+    B = args.train_batch
+    batch = {k: v.to(dev) for k, v in make_batch(B, H_IN, W_IN, seed=50 + rank).items()}
+    left, right, shape = make_boxes(B, 8, seed=60 + rank)          # 8 ground-truth objects per pair (SURVEY config #5)
+    target = (left.to(dev), right.to(dev), shape)
+    gt_depth = torch.rand((B, int(shape[1]), 1), device=dev) * 55 + 5
+
+    def step():
+        z = model(batch, True, target, 1.0)[0]
+        loss = torch.nn.functional.l1_loss(z['depth'], gt_depth) + sum(z[k].pow(2).mean() for k in ("hm", "wh", "reg", "dim", "orien"))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_gradients(model.parameters())
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        print(json.dumps({"metric": "stereo training pairs/sec (384x1280, DLA-34)", "value": world * B * args.steps / (ms / 1000.0),
+                          "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": "SIDE DLA-34 stereo training step (config #5): %d pairs/GPU, 8 GT RoIs/pair, forward + "
+                                                 "L1 depth / head losses + backward + NCCL gradient all-reduce + Adam" % B,
+                                     "pairs_per_gpu_per_step": B, "parallelism": "data-parallel x%d, bucketed all_reduce" % world,
+                                     "dcn_precision": args.dcn_precision},
+                          "gpu_launches": _lib.launch_count(), "loss": float(loss)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -219,11 +219,15 @@ int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *g
  *   side_conv_tc_prep_weights: w [Cout, Cin, taps] (= nn.Conv3d.weight viewed [Cout, Cin, 27]) -> wp, the per-k-block
  *       swizzled shared-memory image (hi and lo), side_conv_tc_weight_bytes(Cin, Cout, taps) bytes.  Once per layer.
  *   side_conv3d_tc_fwd: x_hi, x_lo [N, D, H, W, Cin] -> y [N, D, H, W, Cout] (fp32, may be NULL) and / or its split
- *       y_hi, y_lo (may be NULL); out = relu?(conv * scale[o] + shift[o]) + residual[.., o].
+ *       y_hi, y_lo (may be NULL); relu = 1: out = relu(conv * scale[o] + shift[o]) + residual (dres2(cost) + cost, :216);
+ *       relu = 2: out = relu(conv * scale[o] + shift[o] + residual) (DLA BasicBlock); relu = 0: no activation.
+ *       stride_hw = 2 (2-D kernels only): [N, D, H/2, W/2, Cout] outputs; the TMA box then traverses the input with
+ *       element strides, so a strided convolution costs no more than a dense one.
  *       Needs Cin % 32 == 0; Cout % 16 == 0 (<= 128) or Cout % 128 == 0 (<= 1536, processed as 128-wide n-tiles); a
  *       (D, H, W) that tiles into 128-voxel boxes (box w = largest power of two <= 128 dividing W, then rows, then
- *       slices: 16x16, 8x8 with even D, 4x4 with D % 8 == 0, 96x320 as 2 rows x 64 columns); kernel 3x3x3 or 1x3x3
- *       (2-D convolutions are D = 1, kd = 1: the head convolutions of stereo_network.forward, :343-348).
+ *       slices: 16x16, 8x8 with even D, 4x4 with D % 8 == 0, 96x320 as 2 rows x 64 columns); kernel 3x3x3, 1x3x3 or
+ *       1x1x1 (2-D convolutions are kd = 1 with the batch as D or D = 1: the head convolutions of
+ *       stereo_network.forward, :343-348, and the DLA-34 levels 2-5 of feature_extraction_dla34.py).
  * Helpers (one pass over HBM each):
  *   side_ncdhw_to_cl_split  x [N, C, S] (* scale[N, D], D | S, or NULL) -> hi, lo [N, S, C]   (volume from
  *                           side_inst_costvol_fwd; scale = xcross applies the gate deferred by SIDE_VOL_XCROSS)
@@ -236,7 +240,7 @@ size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps);
 int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int taps, void *stream);
 int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                        const float *residual, float *y, float *y_hi, float *y_lo, int N, int D, int H, int W, int Cin,
-                       int Cout, int kd, int kh, int kw, int relu, void *stream);
+                       int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream);
 int side_ncdhw_to_cl_split(const float *x, const float *scale, float *hi, float *lo, int N, int C, long long S, int D,
                            void *stream);
 int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);

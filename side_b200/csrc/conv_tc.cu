@@ -47,7 +47,8 @@ struct ConvTcParams {
     int D, H, W;                      // spatial extent of one sample
     int bw, bh, bd;                   // TMA box extent along w, h, d; bd*bh*bw == 128
     int wt, ht;                       // boxes per row (W / bw) and per column (H / bh)
-    int kd, kh, kw;                   // kernel extent (3,3,3) or (1,3,3)
+    int kd, kh, kw;                   // kernel extent (3,3,3), (1,3,3) or (1,1,1)
+    int sh, sw;                       // stride along h / w (1 or 2); D, H, W above are OUTPUT extents
     int stages;
 };
 
@@ -139,8 +140,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(&empty_bar[st], phs ^ 1u);
                     unsigned char *sa = tiles + (size_t)st * stage_bytes;
                     mbar_expect_tx(&full_bar[st], stage_bytes);
-                    tma_load_5d(sa, &tm_hi, cb * 32, w0 + kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
-                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, w0 + kwi - pw, h0 + khi - ph, d0 + kdi - pd, n, &full_bar[st]);
+                    const int cw = w0 * p.sw + kwi - pw, ch = h0 * p.sh + khi - ph;     // input coordinates of the box origin
+                    tma_load_5d(sa, &tm_hi, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
                     bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
                 }
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float o = fmaf(v[j] + vx[j], s_scale[cbase + c + j], s_shift[cbase + c + j]);
-                    if (p.relu) o = fmaxf(o, 0.f);
+                    if (p.relu == 1) o = fmaxf(o, 0.f);
                     v[j] = o;
                 }
                 if (p.residual) {
@@ -220,6 +222,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         const float4 rr = __ldg(rp + j);
                         v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
                     }
+                }
+                if (p.relu == 2) {                                   // BasicBlock: relu(bn(conv) + residual)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (p.y) {
                     float4 *yp = reinterpret_cast<float4 *>(p.y + row + c);
@@ -274,7 +280,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
 }
 
 // channels-last activation [Nn, D, H, W, C] fp32 -> box {32, bw, bh, bd, 1}, 128-byte swizzle, zero fill out of bounds
-static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw)
+static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw,
+                         int sh = 1, int sw = 1)
 {
     PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
     if (!enc) {
@@ -283,8 +290,10 @@ static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int 
     }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Nn};
     cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
-    cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    // strided convolution: the box spans bw*sw x bh*sh input pixels, traversed with element strides (sw, sh), i.e. it still
+    // delivers bw x bh pixels -- the ones a stride-s convolution reads for bw x bh outputs
+    cuuint32_t box[5] = {32, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh), (cuuint32_t)bd, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -329,21 +338,28 @@ extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, in
 
 extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale,
                                   const float *shift, const float *residual, float *y, float *y_hi, float *y_lo, int Nn,
-                                  int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int relu, void *stream)
+                                  int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int relu,
+                                  void *stream)
 {
     SIDE_REQUIRE(Nn >= 0 && D > 0 && H > 0 && W > 0, "side_conv3d_tc_fwd: bad shape");
     SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && (Cout <= 128 || Cout % 128 == 0),
                  "side_conv3d_tc_fwd: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (got %d -> %d)", Cin, Cout);
-    SIDE_REQUIRE((kd == 1 || kd == 3) && kh == 3 && kw == 3, "side_conv3d_tc_fwd: kernel must be 3x3x3 or 1x3x3");
+    SIDE_REQUIRE((kd == 3 && kh == 3 && kw == 3) || (kd == 1 && kh == 3 && kw == 3) || (kd == 1 && kh == 1 && kw == 1),
+                 "side_conv3d_tc_fwd: kernel must be 3x3x3, 1x3x3 or 1x1x1");
+    SIDE_REQUIRE(stride_hw == 1 || (stride_hw == 2 && kd == 1 && H % 2 == 0 && W % 2 == 0),
+                 "side_conv3d_tc_fwd: stride must be 1, or 2 for 2-D kernels on even maps");
+    SIDE_REQUIRE(relu >= 0 && relu <= 2, "side_conv3d_tc_fwd: relu must be 0 (none), 1 (before the residual) or 2 (after it)");
     if (Nn == 0) return SIDE_OK;
-    // 128-voxel box: bw = largest power of two <= 128 dividing W, then rows, then depth slices
+    const int Ho = H / stride_hw, Wo = W / stride_hw;          // "same" padding: ceil(H / s) with even H
+    // 128-voxel box of OUTPUT voxels: bw = largest power of two <= 128 dividing Wo, then rows, then depth slices
     int bw = 128;
-    while (bw > 1 && W % bw) bw >>= 1;
+    while (bw > 1 && Wo % bw) bw >>= 1;
     int bh = 128 / bw;
-    while (bh > 1 && H % bh) bh >>= 1;
+    while (bh > 1 && Ho % bh) bh >>= 1;
     const int bd = 128 / (bw * bh);
-    SIDE_REQUIRE(bd >= 1 && D % bd == 0, "side_conv3d_tc_fwd: %dx%dx%d does not tile into 128-voxel boxes (box %dx%dx%d)", D, H, W,
+    SIDE_REQUIRE(bd >= 1 && D % bd == 0, "side_conv3d_tc_fwd: %dx%dx%d does not tile into 128-voxel boxes (box %dx%dx%d)", D, Ho, Wo,
                  bd, bh, bw);
+    SIDE_REQUIRE(bw * stride_hw <= 256 && bh * stride_hw <= 256, "side_conv3d_tc_fwd: box too large for the stride");
     SIDE_REQUIRE((long long)Nn * D * H * W < (1ll << 31), "side_conv3d_tc_fwd: too many voxels");
     SIDE_REQUIRE(y || (y_hi && y_lo), "side_conv3d_tc_fwd: no output requested");
     SIDE_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "side_conv3d_tc_fwd: y_hi and y_lo go together");
@@ -353,18 +369,18 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
 
     CUtensorMap tm_hi, tm_lo;
     int rc;
-    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw))) return rc;
-    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw))) return rc;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw))) return rc;
 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
     p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N;
     p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
-    const long long mtiles = (long long)Nn * D * H * W / kCvBM;
+    const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
     p.ntiles = (int)(mtiles * p.n_ntiles);
-    p.D = D; p.H = H; p.W = W; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = W / bw; p.ht = H / bh;
-    p.kd = kd; p.kh = kh; p.kw = kw;
+    p.D = D; p.H = Ho; p.W = Wo; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = Wo / bw; p.ht = Ho / bh;
+    p.kd = kd; p.kh = kh; p.kw = kw; p.sh = stride_hw; p.sw = stride_hw;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;

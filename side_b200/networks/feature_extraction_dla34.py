@@ -120,9 +120,88 @@ class DLA(nn.Module):
         ys = []
         x = self.base_layer(x)
         for i in range(6):
+            if i == 2 and self._tc_ok(x):
+                return ys + self._levels_tc(x)
             x = getattr(self, "level%d" % i)(x)
             ys.append(x)
         return ys
+
+    # -- levels 2-5 (90 % of the base's FLOPs) on the tensor cores, inference only ---------------------------------
+    # Every convolution of the four Trees is a tcgen05 implicit GEMM (ops.conv3d_tc, 3xTF32, fp32-class accuracy) on
+    # channels-last activations with the batch as the box's depth axis: 3x3 and 1x1 kernels, stride-2 through TMA
+    # element strides, eval-mode BatchNorm folded into the epilogue together with ReLU and the BasicBlock residual.
+    tensor_core = True
+
+    @staticmethod
+    def _tiles(B, H, W):
+        bw = 128
+        while bw > 1 and W % bw:
+            bw >>= 1
+        bh = 128 // bw
+        while bh > 1 and H % bh:
+            bh >>= 1
+        bd = 128 // (bw * bh)
+        return B % bd == 0
+
+    def _tc_ok(self, x):
+        if not (self.tensor_core and x.is_cuda and not self.training and not torch.is_grad_enabled()):
+            return False
+        B, C, H, W = x.shape
+        if C % 32 or H % 16 or W % 16:
+            return False
+        return all(self._tiles(B, H >> k, W >> k) for k in (1, 2, 3, 4))
+
+    def _tc_fold(self, conv, bn):
+        st = self.__dict__.setdefault("_tc_cache", {})
+        key = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+               bn.running_var._version)
+        ent = st.get(id(conv))
+        if ent is None or ent[0] != key:
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+            shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+            ent = (key, ops.conv_tc_prepare(conv.weight.detach()), scale, shift)
+            st[id(conv)] = ent
+        return ent[1], ent[2], ent[3]
+
+    def _conv_tc(self, t, conv, bn, relu, residual=None):
+        """t = (full, hi, lo) channels-last [1, B, H, W, C] -> same triple after conv + folded BN (+ residual) (+ ReLU)."""
+        wp, scale, shift = self._tc_fold(conv, bn)
+        k = conv.kernel_size[0]
+        return ops.conv3d_tc(t[1], t[2], wp, conv.out_channels, ksize=(1, k, k), scale=scale, shift=shift, relu=relu,
+                             residual=residual, full=True, split=True, stride=conv.stride[0])
+
+    def _block_tc(self, t, residual, blk):
+        y = self._conv_tc(t, blk.conv1, blk.bn1, True)
+        return self._conv_tc(y, blk.conv2, blk.bn2, "after", residual=residual)
+
+    def _tree_tc(self, t, tree, children=None):
+        children = [] if children is None else children
+        bottom = ops.maxpool_hw2_cl(t[0], full=True, split=True) if tree.downsample is not None else t
+        residual = self._conv_tc(bottom, tree.project[0], tree.project[1], False)[0] if tree.project is not None else bottom[0]
+        if tree.level_root:
+            children.append(bottom)
+        if tree.levels == 1:
+            x1 = self._block_tc(t, residual, tree.tree1)
+            x2 = self._block_tc(x1, x1[0], tree.tree2)
+            xs = [x2, x1] + children
+            cat = (None, torch.cat([c[1] for c in xs], -1), torch.cat([c[2] for c in xs], -1))
+            y = self._conv_tc(cat, tree.root.conv, tree.root.bn, "after" if tree.root.residual else True,
+                              residual=xs[0][0] if tree.root.residual else None)
+            return y
+        x1 = self._tree_tc(t, tree.tree1)
+        children.append(x1)
+        return self._tree_tc(x1, tree.tree2, children=children)
+
+    def _levels_tc(self, x):
+        B, C, H, W = x.shape
+        full = x.permute(0, 2, 3, 1).contiguous().view(1, B, H, W, C)
+        t = (full,) + ops.tf32_split(full)
+        outs = []
+        for i in range(2, 6):
+            t = self._tree_tc(t, getattr(self, "level%d" % i))
+            f = t[0]
+            outs.append(f.view(B, f.shape[2], f.shape[3], f.shape[4]).permute(0, 3, 1, 2).contiguous())
+        return outs
 
     def load_pretrained_model(self, path):
         """Loads ImageNet DLA weights from a LOCAL file (the reference downloads them, Q4)."""

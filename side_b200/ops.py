@@ -519,20 +519,22 @@ def conv_tc_prepare(weight):
 
 
 def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, relu=False, residual=None, full=False,
-              split=True):
-    """x_hi, x_lo [N, D, H, W, Cin] -> (y, y_hi, y_lo) [N, D, H, W, Cout] (entries not requested are None)."""
+              split=True, stride=1):
+    """x_hi, x_lo [N, D, H, W, Cin] -> (y, y_hi, y_lo) [N, D, H/stride, W/stride, Cout] (entries not requested are None).
+    relu: False / True (before the residual) / "after" (after the residual, DLA BasicBlock)."""
     lib = _lib.load()
     x_hi, x_lo = _chk(x_hi, "x_hi"), _chk(x_lo, "x_lo")
     N, D, H, W, Cin = x_hi.shape
     dev = x_hi.device
-    y = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if full else None
-    y_hi = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if split else None
-    y_lo = torch.empty((N, D, H, W, Cout), device=dev, dtype=_F32) if split else None
+    oshape = (N, D, H // stride, W // stride, Cout)
+    y = torch.empty(oshape, device=dev, dtype=_F32) if full else None
+    y_hi = torch.empty(oshape, device=dev, dtype=_F32) if split else None
+    y_lo = torch.empty(oshape, device=dev, dtype=_F32) if split else None
     if residual is not None:
         residual = _chk(residual, "residual")
     _lib.check(lib.side_conv3d_tc_fwd(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
                                       _p(y), _p(y_hi), _p(y_lo), N, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2],
-                                      1 if relu else 0, _stream()), "side_conv3d_tc_fwd")
+                                      int(stride), 2 if relu == "after" else (1 if relu else 0), _stream()), "side_conv3d_tc_fwd")
     return y, y_hi, y_lo
 
 

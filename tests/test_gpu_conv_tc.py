@@ -156,3 +156,50 @@ def test_conv2d_tc_wide_n_tiles(lib):
     y, yh, yl = ops.conv3d_tc(hi, lo, ops.conv_tc_prepare(w.to(dev)), 256, ksize=(1, 3, 3), relu=True, full=True, split=True)
     assert rel_err(y.cpu().numpy()[:, 0], ref) < 1e-4
     assert torch.equal(yh + yl, y)
+
+
+def test_conv2d_tc_stride2_and_1x1(lib):
+    """Stride-2 3x3 (TMA element strides) and 1x1 kernels with the batch as the box's depth axis; ReLU after the residual."""
+    from side_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    dev = torch.device("cuda")
+    x = torch.randn(4, 32, 24, 80, generator=g)
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous().unsqueeze(0)        # [1, B, H, W, C]
+    hi, lo = ops.tf32_split(cl(x).to(dev))
+    w = torch.randn(64, 32, 3, 3, generator=g) * 0.1
+    ref = cl(F.conv2d(x.double(), w.double(), stride=2, padding=1)).numpy()
+    y, _, _ = ops.conv3d_tc(hi, lo, ops.conv_tc_prepare(w.to(dev)), 64, ksize=(1, 3, 3), full=True, split=False, stride=2)
+    assert tuple(y.shape) == (1, 4, 12, 40, 64)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4
+    w1 = torch.randn(48, 32, 1, 1, generator=g) * 0.2
+    res = torch.randn(4, 48, 24, 80, generator=g)
+    ref = cl((F.conv2d(x.double(), w1.double()) + res.double()).relu()).numpy()
+    y, _, _ = ops.conv3d_tc(hi, lo, ops.conv_tc_prepare(w1.to(dev)), 48, ksize=(1, 1, 1), relu="after", residual=cl(res).to(dev),
+                            full=True, split=False)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", [(4, 192, 640), (8, 64, 128)])
+def test_dla_levels_tc_match_cudnn(lib, B, H, W):
+    """DLA-34 levels 2-5 on tcgen05 vs the same modules on cuDNN fp32: every level output <= 1e-4 of its range."""
+    from side_b200.networks.feature_extraction_dla34 import dla34
+    torch.manual_seed(4)
+    m = dla34().eval()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    m = m.cuda()
+    x = torch.randn(B, 32, H, W, device="cuda")          # level-1 output
+    with torch.no_grad():
+        assert m._tc_ok(x)
+        assert not m._tc_ok(x[:2])                       # a 2-image batch does not fill the 12x40 level's boxes: cuDNN path
+        outs = m._levels_tc(x)
+        ref, t = [], x
+        for i in range(2, 6):
+            t = getattr(m, "level%d" % i)(t)
+            ref.append(t)
+    for i, (a, b) in enumerate(zip(outs, ref)):
+        assert a.shape == b.shape
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err < 1e-4, (i + 2, err)
