@@ -163,6 +163,61 @@ __global__ void __launch_bounds__(kVolBlock) gwc_volume_fwd_kernel(const float *
     }
 }
 
+// Register-tiled variant (W % 4 == 0, D % 4 == 0, compile-time channels per group): one thread produces a 4 (x) by 4 (d)
+// block.  The 16 products of a channel need only the 7 right-view values R[x0-d-3 .. x0+3-d], fetched as two aligned
+// 16-byte shared loads from a row that is zero-padded on the left by D + 4 columns (so x < d reads zeros and the mask
+// needs no branch); outputs leave as 16-byte evict-first stores.  1 shared load per output instead of 8.
+template <int CPG>
+__global__ void __launch_bounds__(kVolBlock) gwc_volume_fwd_tiled_kernel(const float *__restrict__ L, const float *__restrict__ R,
+                                                                        float *__restrict__ vol, int C, int H, int W, int D, int G)
+{
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const int y = blockIdx.x % H, bg = blockIdx.x / H;
+    const int b = bg / G, gi = bg - b * G;
+    const int pad = D + 4, RW = W + pad;                 // right-view row stride (floats), pad % 4 == 0
+    float *Ls = sm, *Rs = sm + CPG * W;
+    const size_t HW = (size_t)H * W;
+    const float *lsrc = L + ((size_t)b * C + gi * CPG) * HW + (size_t)y * W;
+    const float *rsrc = R + ((size_t)b * C + gi * CPG) * HW + (size_t)y * W;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar, 2u * (uint32_t)(CPG * W) * 4u);
+        for (int cc = 0; cc < CPG; ++cc) {
+            bulk_g2s(Ls + cc * W, lsrc + (size_t)cc * HW, (uint32_t)W * 4u, &bar);
+            bulk_g2s(Rs + cc * RW + pad, rsrc + (size_t)cc * HW, (uint32_t)W * 4u, &bar);
+        }
+    }
+    for (int i = threadIdx.x; i < CPG * pad; i += blockDim.x) Rs[(i / pad) * RW + (i % pad)] = 0.f;
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const float inv = 1.0f / (float)CPG;
+    float *out = vol + (((size_t)b * G + gi) * D) * HW + (size_t)y * W;
+    const int nxq = W >> 2, ndq = D >> 2;
+    for (int item = threadIdx.x; item < nxq * ndq; item += blockDim.x) {
+        const int dq = item / nxq, xq = item - dq * nxq;
+        const int x0 = 4 * xq, d0 = 4 * dq;
+        float acc[4][4] = {};                             // [dd][xx]
+#pragma unroll
+        for (int cc = 0; cc < CPG; ++cc) {
+            const float4 l = *reinterpret_cast<const float4 *>(Ls + cc * W + x0);
+            const float *rp = Rs + cc * RW + pad + x0 - d0 - 4;      // 16-byte aligned: pad, x0, d0 are multiples of 4
+            const float4 ra = *reinterpret_cast<const float4 *>(rp), rb = *reinterpret_cast<const float4 *>(rp + 4);
+            const float r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};   // r[k] = R[x0 - d0 - 4 + k]
+            const float lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                for (int xx = 0; xx < 4; ++xx) acc[dd][xx] = fmaf(lv[xx], r[4 + xx - dd], acc[dd][xx]);   // R[x0+xx-(d0+dd)]
+        }
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd)
+            st_cs(reinterpret_cast<float4 *>(out + (size_t)(d0 + dd) * HW + x0),
+                  make_float4(acc[dd][0] * inv, acc[dd][1] * inv, acc[dd][2] * inv, acc[dd][3] * inv));
+    }
+}
+
 // gL[c,y,x] = (1/cpg) sum_{d<=x} g[g(c),d,y,x] R[c,y,x-d];  gR[c,y,x] = (1/cpg) sum_{d: x+d<W} g[g(c),d,y,x+d] L[c,y,x+d]
 __global__ void __launch_bounds__(kVolBlock) gwc_volume_bwd_kernel(const float *__restrict__ L, const float *__restrict__ R,
                                                                   const float *__restrict__ g, float *__restrict__ gL,
@@ -244,6 +299,22 @@ extern "C" int side_gwc_volume_fwd(const float *L, const float *R, float *vol, i
     SIDE_REQUIRE(blocks < (1ll << 31), "side_gwc_volume_fwd: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (use_tma && (D & 3) == 0 && (cpg == 4 || cpg == 8 || cpg == 16)) {
+        const size_t smem_t = sizeof(float) * ((size_t)cpg * W + (size_t)cpg * (W + D + 4));
+        if (smem_t <= 200 * 1024) {
+#define GWC_TILED(CPGT)                                                                                         \
+    do {                                                                                                        \
+        if ((rc = set_smem_attr((const void *)gwc_volume_fwd_tiled_kernel<CPGT>, smem_t))) return rc;            \
+        gwc_volume_fwd_tiled_kernel<CPGT><<<(unsigned)blocks, kVolBlock, smem_t, st>>>(L, R, vol, C, H, W, D, G); \
+    } while (0)
+            if (cpg == 4) GWC_TILED(4);
+            else if (cpg == 8) GWC_TILED(8);
+            else GWC_TILED(16);
+#undef GWC_TILED
+            SIDE_LAUNCH_CHECK("gwc_volume_fwd_tiled_kernel");
+            return SIDE_OK;
+        }
+    }
 #define GWC_LAUNCH(CPGT)                                                                                         \
     do {                                                                                                         \
         if ((rc = set_smem_attr((const void *)gwc_volume_fwd_kernel<CPGT>, smem))) return rc;                    \
