@@ -249,6 +249,16 @@ int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo,
 int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream);
 int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * DLA-34 stem: Conv2d(k, stride, padding (k-1)/2, bias=False) + eval-mode BatchNorm2d
+ * (folded: scale, shift; NULL = identity) + ReLU as one direct fp32 convolution, NCHW in / out.  Built for the three
+ * stem layers of feature_extraction_dla34.py (DLA.base_layer 3->16 k7 s1, level0 16->16 k3 s1, level1 16->32 k3 s2);
+ * other shapes return SIDE_ERR_UNSUPPORTED (the caller keeps cuDNN).
+ *   x [B, Cin, H, W], w [Cout, Cin, k, k] -> y [B, Cout, Ho, Wo]
+ * --------------------------------------------------------------------------------------------- */
+int side_stem_conv_fwd(const float *x, const float *w, const float *scale, const float *shift, float *y, int B, int Cin, int H,
+                       int W, int Cout, int k, int stride, int relu, void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

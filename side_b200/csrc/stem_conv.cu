@@ -1,0 +1,119 @@
+// stem_conv.cu -- the DLA-34 stem: base_layer 7x7 (3 -> 16), level0 3x3 (16 -> 16) and
+// level1 3x3 stride 2 (16 -> 32) at full resolution, each followed by BatchNorm + ReLU (feature_extraction_dla34.py
+// :281-293 of the reference, `_make_conv_level`).  16-32 channels give the tensor cores nothing to chew on (an
+// M128 x N16 tf32 MMA is bound by its A-operand fetch), so these are direct fp32 SIMT convolutions: a CTA stages the input
+// halo of a 64 x 8 output tile and the whole filter bank in shared memory; a thread owns 2 adjacent output pixels and ALL
+// output channels, so every input value it loads feeds Cout FMAs and every (broadcast) 16-byte weight load feeds 8.
+// Eval-mode BatchNorm and ReLU are folded into the store.  cuDNN spends 3-4x longer on these three layers (its fp32
+// kernels are tuned for wide channels) plus separate BN / ReLU passes.
+#include "common.cuh"
+
+namespace side {
+
+constexpr int kStemTW = 64, kStemTH = 8;     // output tile; 256 threads, 2 pixels each
+
+template <int CIN, int COUT, int K, int S, int CCHUNK>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                        const float *__restrict__ scale, const float *__restrict__ shift,
+                                                        float *__restrict__ y, int H, int W, int Ho, int Wo, int relu)
+{
+    constexpr int P = (K - 1) / 2;
+    constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1;
+    constexpr int IWP = IW | 1;                                  // odd row pitch: stride-2 reads stay conflict-free
+    extern __shared__ __align__(16) float sm[];
+    float *ws = sm;                                              // [CIN * K * K][COUT]
+    float *in_s = sm + CIN * K * K * COUT;                       // [CCHUNK][IH][IWP]
+    const int b = blockIdx.z, oy0 = blockIdx.y * kStemTH, ox0 = blockIdx.x * kStemTW;
+    const int tid = threadIdx.x, tx = (tid & 31) * 2, ty = tid >> 5;
+    for (int i = tid; i < CIN * K * K * COUT; i += 256) {
+        const int o = i % COUT, ck = i / COUT;                   // ws[ck][o] = w[o][ck]   (w is [COUT][CIN][K][K])
+        ws[i] = __ldg(w + (size_t)o * CIN * K * K + ck);
+    }
+    float acc0[COUT], acc1[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc0[o] = acc1[o] = 0.f;
+    const float *xb = x + (size_t)b * CIN * H * W;
+    const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
+    for (int c0 = 0; c0 < CIN; c0 += CCHUNK) {
+        __syncthreads();
+        for (int i = tid; i < CCHUNK * IH * IW; i += 256) {
+            const int xx = i % IW, r = i / IW, yy = r % IH, c = r / IH;
+            const int gy = iy0 + yy, gx = ix0 + xx;
+            float v = 0.f;
+            if (c0 + c < CIN && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(xb + ((size_t)(c0 + c) * H + gy) * W + gx);
+            in_s[(c * IH + yy) * IWP + xx] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < CCHUNK && c0 + c < CIN; ++c) {
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const float *row = in_s + (c * IH + ty * S + ky) * IWP + tx * S;
+                const float *wr = ws + ((c0 + c) * K * K + ky * K) * COUT;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float v0 = row[kx], v1 = row[kx + S];
+#pragma unroll
+                    for (int o4 = 0; o4 < COUT / 4; ++o4) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(wr + kx * COUT + 4 * o4);
+                        acc0[4 * o4] = fmaf(v0, wv.x, acc0[4 * o4]);         acc1[4 * o4] = fmaf(v1, wv.x, acc1[4 * o4]);
+                        acc0[4 * o4 + 1] = fmaf(v0, wv.y, acc0[4 * o4 + 1]); acc1[4 * o4 + 1] = fmaf(v1, wv.y, acc1[4 * o4 + 1]);
+                        acc0[4 * o4 + 2] = fmaf(v0, wv.z, acc0[4 * o4 + 2]); acc1[4 * o4 + 2] = fmaf(v1, wv.z, acc1[4 * o4 + 2]);
+                        acc0[4 * o4 + 3] = fmaf(v0, wv.w, acc0[4 * o4 + 3]); acc1[4 * o4 + 3] = fmaf(v1, wv.w, acc1[4 * o4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy < Ho && ox < Wo) {
+        float *yp = y + ((size_t)b * COUT * Ho + oy) * Wo + ox;
+        const bool two = ox + 1 < Wo;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
+            float a = fmaf(acc0[o], sc, sh), c = fmaf(acc1[o], sc, sh);
+            if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            if (two && ((reinterpret_cast<uintptr_t>(yp + (size_t)o * Ho * Wo) & 7) == 0))
+                *reinterpret_cast<float2 *>(yp + (size_t)o * Ho * Wo) = make_float2(a, c);
+            else {
+                yp[(size_t)o * Ho * Wo] = a;
+                if (two) yp[(size_t)o * Ho * Wo + 1] = c;
+            }
+        }
+    }
+}
+
+template <int CIN, int COUT, int K, int S, int CCHUNK>
+static int launch_stem(const float *x, const float *w, const float *scale, const float *shift, float *y, int B, int H, int W,
+                       int relu, cudaStream_t st)
+{
+    constexpr int P = (K - 1) / 2;
+    const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
+    constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1, IWP = IW | 1;
+    const size_t smem = sizeof(float) * ((size_t)CIN * K * K * COUT + (size_t)CCHUNK * IH * IWP);
+    int rc = set_smem_attr((const void *)stem_conv_kernel<CIN, COUT, K, S, CCHUNK>, smem);
+    if (rc) return rc;
+    dim3 grid(ceil_div(Wo, kStemTW), ceil_div(Ho, kStemTH), B);
+    stem_conv_kernel<CIN, COUT, K, S, CCHUNK><<<grid, 256, smem, st>>>(x, w, scale, shift, y, H, W, Ho, Wo, relu);
+    SIDE_LAUNCH_CHECK("stem_conv_kernel");
+    return SIDE_OK;
+}
+
+}  // namespace side
+
+using namespace side;
+
+extern "C" int side_stem_conv_fwd(const float *x, const float *w, const float *scale, const float *shift, float *y, int B, int Cin,
+                                  int H, int W, int Cout, int k, int stride, int relu, void *stream)
+{
+    SIDE_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "side_stem_conv_fwd: bad shape");
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(y);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 3 && Cout == 16 && k == 7 && stride == 1) return launch_stem<3, 16, 7, 1, 3>(x, w, scale, shift, y, B, H, W, relu, st);
+    if (Cin == 16 && Cout == 16 && k == 3 && stride == 1) return launch_stem<16, 16, 3, 1, 16>(x, w, scale, shift, y, B, H, W, relu, st);
+    if (Cin == 16 && Cout == 32 && k == 3 && stride == 2) return launch_stem<16, 32, 3, 2, 8>(x, w, scale, shift, y, B, H, W, relu, st);
+    set_error("side_stem_conv_fwd: only the DLA-34 stem shapes are built (3->16 k7 s1, 16->16 k3 s1, 16->32 k3 s2), got %d->%d k%d s%d",
+              Cin, Cout, k, stride);
+    return SIDE_ERR_UNSUPPORTED;
+}

@@ -118,13 +118,38 @@ class DLA(nn.Module):
 
     def forward(self, x):
         ys = []
-        x = self.base_layer(x)
+        stem = self.direct_stem and x.is_cuda and not self.training and not torch.is_grad_enabled()
+        x = self._stem(self.base_layer)(x) if stem else self.base_layer(x)
         for i in range(6):
             if i == 2 and self._tc_ok(x):
                 return ys + self._levels_tc(x)
-            x = getattr(self, "level%d" % i)(x)
+            level = getattr(self, "level%d" % i)
+            x = self._stem(level)(x) if (stem and i < 2) else level(x)
             ys.append(x)
         return ys
+
+    # -- stem (base_layer, level0, level1) as direct fp32 convolutions with BatchNorm + ReLU folded in, inference only -----
+    direct_stem = True
+
+    def _stem(self, seq):
+        def run(x):
+            mods = list(seq)
+            for j in range(0, len(mods), 3):                      # (Conv2d, BatchNorm2d, ReLU) triples
+                conv, bn = mods[j], mods[j + 1]
+                shape = (conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0])
+                if shape not in ((3, 16, 7, 1), (16, 16, 3, 1), (16, 32, 3, 2)) or conv.dilation[0] != 1:
+                    x = mods[j + 2](bn(conv(x)))                  # not a DLA-34 stem shape: cuDNN
+                    continue
+                st = self.__dict__.setdefault("_stem_cache", {})
+                key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.data_ptr())
+                ent = st.get(id(bn))
+                if ent is None or ent[0] != key:
+                    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+                    ent = (key, scale, (bn.bias - bn.running_mean * scale).detach().float().contiguous())
+                    st[id(bn)] = ent
+                x = ops.stem_conv(x, conv.weight.detach(), ent[1], ent[2], stride=conv.stride[0], relu=True)
+            return x
+        return run
 
     # -- levels 2-5 (90 % of the base's FLOPs) on the tensor cores, inference only ---------------------------------
     # Every convolution of the four Trees is a tcgen05 implicit GEMM (ops.conv3d_tc, 3xTF32, fp32-class accuracy) on

@@ -604,3 +604,17 @@ def conv3d_c1_cl(x, w):
     out = torch.empty((N, D, H, W), device=x.device, dtype=_F32)
     _lib.check(lib.side_conv3d_c1_cl(x.data_ptr(), w.data_ptr(), out.data_ptr(), N, D, H, W, C, _stream()), "side_conv3d_c1_cl")
     return out
+
+
+def stem_conv(x, weight, scale=None, shift=None, stride=1, relu=True):
+    """Direct fp32 Conv2d(k, stride, pad (k-1)/2, no bias) + folded BatchNorm + ReLU for the DLA-34 stem shapes (NCHW)."""
+    lib = _lib.load()
+    x, weight = _chk(x, "x"), _chk(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = weight.shape
+    p = (k - 1) // 2
+    Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=_F32)
+    _lib.check(lib.side_stem_conv_fwd(x.data_ptr(), weight.data_ptr(), _p(scale), _p(shift), y.data_ptr(), B, Cin, H, W, Cout, k,
+                                      int(stride), 1 if relu else 0, _stream()), "side_stem_conv_fwd")
+    return y

@@ -203,3 +203,40 @@ def test_dla_levels_tc_match_cudnn(lib, B, H, W):
         assert a.shape == b.shape
         err = float((a - b).abs().max() / b.abs().max())
         assert err < 1e-4, (i + 2, err)
+
+
+@pytest.mark.parametrize("cfg", [(3, 16, 7, 1, 2, 70, 150), (16, 16, 3, 1, 2, 33, 129), (16, 32, 3, 2, 3, 64, 130), (16, 32, 3, 2, 1, 384, 1280)])
+def test_stem_conv_matches_fp64(lib, cfg):
+    """DLA-34 stem layers as direct fp32 convolutions with folded BatchNorm + ReLU (ragged tiles, odd widths, stride 2)."""
+    from side_b200 import ops
+    Cin, Cout, k, s, B, H, W = cfg
+    g = torch.Generator().manual_seed(Cin + k + W)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+    ref = (F.conv2d(x.double(), w.double(), stride=s, padding=(k - 1) // 2) * scale.double().view(1, -1, 1, 1)
+           + shift.double().view(1, -1, 1, 1)).relu()
+    y = ops.stem_conv(x.cuda(), w.cuda(), scale.cuda(), shift.cuda(), stride=s, relu=True)
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_dla_base_fast_paths_match_cudnn(lib):
+    """Whole DLA-34 base: direct stem + tcgen05 levels 2-5 vs the plain module on cuDNN fp32."""
+    from side_b200.networks.feature_extraction_dla34 import dla34
+    torch.manual_seed(6)
+    m = dla34().eval()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2); mod.bias.data.normal_(0, 0.1)
+    m = m.cuda()
+    x = torch.randn(4, 3, 128, 256, device="cuda")
+    with torch.no_grad():
+        fast = m(x)
+        m.direct_stem = m.tensor_core = False
+        ref = m(x)
+    assert len(fast) == len(ref) == 6
+    for i, (a, b) in enumerate(zip(fast, ref)):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-4, i
