@@ -248,6 +248,8 @@ int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo,
                         void *stream);
 int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream);
 int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream);
+/* channels-last [B, HW, C] -> NCHW [B, C, HW]: hands a tensor-core convolution output back to NCHW consumers */
+int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DLA-34 stem: Conv2d(k, stride, padding (k-1)/2, bias=False) + eval-mode BatchNorm2d

@@ -219,13 +219,14 @@ class DLA(nn.Module):
 
     def _levels_tc(self, x):
         B, C, H, W = x.shape
-        full = x.permute(0, 2, 3, 1).contiguous().view(1, B, H, W, C)
-        t = (full,) + ops.tf32_split(full)
+        hi, lo = ops.ncdhw_to_cl_split(x.unsqueeze(2))               # [B, 1, H, W, C] channels-last halves
+        hi, lo = hi.view(1, B, H, W, C), lo.view(1, B, H, W, C)
+        t = (hi + lo, hi, lo)                                        # hi + lo == x exactly
         outs = []
         for i in range(2, 6):
             t = self._tree_tc(t, getattr(self, "level%d" % i))
             f = t[0]
-            outs.append(f.view(B, f.shape[2], f.shape[3], f.shape[4]).permute(0, 3, 1, 2).contiguous())
+            outs.append(ops.cl_to_nchw(f, B, f.shape[4], (f.shape[2], f.shape[3])))
         return outs
 
     def load_pretrained_model(self, path):

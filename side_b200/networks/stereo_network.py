@@ -250,10 +250,11 @@ class stereo_network(nn.Module):
             wp, cout = S["stereo_w"]
             y, _, _ = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=True, split=False)
             blk, bias, widths = S["stereo_out"]
-            o = torch.addmm(bias, y.view(-1, cout), blk).view(B, H, W, -1).permute(0, 3, 1, 2)
+            # [n_out, hidden] @ [hidden, H*W] per image: the transposed operand is a view, the result is NCHW
+            o = torch.baddbmm(bias.view(1, -1, 1), blk.t().unsqueeze(0).expand(B, -1, -1), y.view(B, H * W, cout).transpose(1, 2))
             c0 = 0
             for h, wdt in zip(S["stereo"], widths):
-                z[h] = o[:, c0:c0 + wdt].contiguous()
+                z[h] = o[:, c0:c0 + wdt].reshape(B, wdt, H, W).contiguous()
                 c0 += wdt
         for h, (chain, last) in S["mono"].items():
             hi, lo = ops.ncdhw_to_cl_split(fl.unsqueeze(2))                                        # [B, 1, H, W, C]
@@ -261,8 +262,9 @@ class stereo_network(nn.Module):
             for i, (wp, cout) in enumerate(chain):
                 final = i == len(chain) - 1
                 y, hi, lo = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=final, split=not final)
-            o = torch.addmm(last.bias.detach(), y.view(-1, y.shape[-1]), last.weight.detach().view(last.out_channels, -1).t())
-            z[h] = o.view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+            wl = last.weight.detach().view(1, last.out_channels, -1).expand(B, -1, -1)
+            o = torch.baddbmm(last.bias.detach().view(1, -1, 1), wl, y.view(B, H * W, y.shape[-1]).transpose(1, 2))
+            z[h] = o.view(B, last.out_channels, H, W)
         return {h: z[h] for h in self.heads}
 
     fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream

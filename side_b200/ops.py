@@ -618,3 +618,15 @@ def stem_conv(x, weight, scale=None, shift=None, stride=1, relu=True):
     _lib.check(lib.side_stem_conv_fwd(x.data_ptr(), weight.data_ptr(), _p(scale), _p(shift), y.data_ptr(), B, Cin, H, W, Cout, k,
                                       int(stride), 1 if relu else 0, _stream()), "side_stem_conv_fwd")
     return y
+
+
+def cl_to_nchw(x, B, C, spatial):
+    """channels-last buffer [B, *spatial, C] -> NCHW [B, C, *spatial]."""
+    lib = _lib.load()
+    x = _chk(x, "x")
+    HW = 1
+    for v in spatial:
+        HW *= v
+    y = torch.empty((B, C) + tuple(spatial), device=x.device, dtype=_F32)
+    _lib.check(lib.side_cl_to_nchw(x.data_ptr(), y.data_ptr(), B, C, HW, _stream()), "side_cl_to_nchw")
+    return y
