@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: BASELINE config #5 (training step)")
     ap.add_argument("--train-batch", type=int, default=2, help="pairs per GPU per training step (config #5: 16 pairs / 8 GPUs)")
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per GPU per step (config #4: batch 32)")
-    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
                     help="3xtf32 (default): tcgen05 with the exact hi/lo split, fp32-class accuracy (<= 1e-4 rel); fp32: SIMT")
     ap.add_argument("--cudnn-only", action="store_true",
