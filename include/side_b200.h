@@ -99,6 +99,14 @@ int side_dcn_fwd(const float *x, const float *offset, const float *mask, const f
                  int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg, long long offset_bs,
                  long long mask_bs, int flags, void *ws, size_t ws_bytes, void *stream);
 
+/* Channels-last front end of the tcgen05 path (inference): x_nhwc [B, H, W, Cin] is already channels-last and
+ * om_cl [B, Ho, Wo, om_ld] is the channels-last output of DCN.conv_offset_mask (dcn_v2.py:105-123; channels 0..2*kh*kw-1 =
+ * interleaved (dy, dx), then kh*kw mask logits), e.g. computed by side_conv3d_tc_fwd with Cout padded to 32.  y is NCHW.
+ * Only SIDE_DCN_PREC_3XTF32 / _TF32; flags may add FUSE_AFFINE / FUSE_RELU (MASK_IS_LOGIT is implied). */
+int side_dcn_fwd_cl(const float *x_nhwc, const float *om_cl, int om_ld, const float *w, const float *bias, const float *scale,
+                    const float *shift, float *y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
+                    int pw, int dh, int dw, int flags, void *ws, size_t ws_bytes, void *stream);
+
 /* Replaces _ext.dcn_v2_backward (dcn_v2.h:41-73 -> dcn_v2_cuda_backward, dcn_v2_cuda.cu:207-336 and the
  * col2im / col2im_coord kernels, dcn_v2_im2col_cuda.cu:197-327).  All five gradients are OVERWRITTEN
  * (the reference zero-initialises them, :252-256).  grad_mask is w.r.t. the post-sigmoid mask unless
@@ -241,8 +249,8 @@ int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int 
 int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                        const float *residual, float *y, float *y_hi, float *y_lo, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream);
-int side_ncdhw_to_cl_split(const float *x, const float *scale, float *hi, float *lo, int N, int C, long long S, int D,
-                           void *stream);
+int side_ncdhw_to_cl_split(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C, long long S,
+                           int D, void *stream);   /* full (may be NULL): the unsplit channels-last copy as well */
 int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);
 int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
                         void *stream);

@@ -21,6 +21,7 @@ SIGNATURES = {
     "side_launch_count": (_ll, [_i]),
     "side_dcn_fwd_ws_bytes": (_sz, [_i] * 8),
     "side_dcn_fwd": (_i, [_vp] * 8 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
+    "side_dcn_fwd_cl": (_i, [_vp, _vp, _i] + [_vp] * 5 + [_i] * 14 + [_vp, _sz, _vp]),
     "side_dcn_bwd_ws_bytes": (_sz, [_i] * 8),
     "side_dcn_bwd": (_i, [_vp] * 10 + [_i] * 14 + [_ll, _ll, _i, _vp, _sz, _vp]),
     "side_proposal_shift": (_i, [_vp] * 3 + [_i] * 3 + [_f] + [_vp] * 4),
@@ -44,7 +45,7 @@ SIGNATURES = {
     "side_conv_tc_weight_bytes": (_sz, [_i] * 3),
     "side_conv_tc_prep_weights": (_i, [_vp] * 2 + [_i] * 3 + [_vp]),
     "side_conv3d_tc_fwd": (_i, [_vp] * 9 + [_i] * 11 + [_vp]),
-    "side_ncdhw_to_cl_split": (_i, [_vp] * 4 + [_i] * 2 + [_ll, _i, _vp]),
+    "side_ncdhw_to_cl_split": (_i, [_vp] * 5 + [_i] * 2 + [_ll, _i, _vp]),
     "side_tf32_split": (_i, [_vp] * 3 + [_ll, _vp]),
     "side_gate_mul_split": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_maxpool_hw2_cl": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),

@@ -18,8 +18,8 @@ __device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
 }
 
 // in [N, C, S] -> hi, lo [N, S, C]; optional scale[n, p / per_d] (the cosine gate of the slice the voxel belongs to)
-__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ hi,
-                                         float *__restrict__ lo, int C, long long S, int D, int per_d)
+__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ full,
+                                         float *__restrict__ hi, float *__restrict__ lo, int C, long long S, int D, int per_d)
 {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -42,6 +42,7 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
             const size_t o = ((size_t)n * S + p) * C + c;
             hi[o] = h;
             lo[o] = v - h;
+            if (full) full[o] = v;
         }
     }
 }
@@ -140,8 +141,8 @@ using namespace side;
 
 static inline unsigned ew_grid(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148 * 16); }
 
-extern "C" int side_ncdhw_to_cl_split(const float *x, const float *scale, float *hi, float *lo, int N, int C, long long S,
-                                      int D, void *stream)
+extern "C" int side_ncdhw_to_cl_split(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C,
+                                      long long S, int D, void *stream)
 {
     SIDE_REQUIRE(N >= 0 && C > 0 && S > 0, "side_ncdhw_to_cl_split: bad shape");
     SIDE_REQUIRE(scale == nullptr || (D > 0 && S % D == 0), "side_ncdhw_to_cl_split: scale needs D | S");
@@ -150,7 +151,8 @@ extern "C" int side_ncdhw_to_cl_split(const float *x, const float *scale, float 
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
     dim3 g((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), b(32, 8);
     if (scale) SIDE_REQUIRE_DEV(scale);
-    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, scale, hi, lo, C, S, D, scale ? (int)(S / D) : 1);
+    if (full) SIDE_REQUIRE_DEV(full);
+    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, scale ? (int)(S / D) : 1);
     SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
     return SIDE_OK;
 }

@@ -10,6 +10,7 @@ struct DcnShape {
     int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg;
     int Ho, Wo, KK, P;          // KK = kh*kw, P = Ho*Wo
     long long offset_bs, mask_bs;  // batch strides in floats
+    int om_cs, om_ps;              // channel / pixel stride of offset and mask (NCHW: P, 1; channels-last rows of ld floats: 1, ld)
     int flags;
 };
 
@@ -34,9 +35,9 @@ __device__ __forceinline__ DcnTap dcn_tap(const DcnShape &s, const float *__rest
 {
     const int p = ho * s.Wo + wo;
     const int i = tap / s.kw, j = tap - i * s.kw;
-    const float *ob = offset + (size_t)b * s.offset_bs + ((size_t)g * 2 * s.KK + 2 * tap) * s.P + p;
-    const float oh = __ldg(ob), ow = __ldg(ob + s.P);
-    float m = __ldg(mask + (size_t)b * s.mask_bs + ((size_t)g * s.KK + tap) * s.P + p);
+    const float *ob = offset + (size_t)b * s.offset_bs + ((size_t)g * 2 * s.KK + 2 * tap) * s.om_cs + (size_t)p * s.om_ps;
+    const float oh = __ldg(ob), ow = __ldg(ob + s.om_cs);
+    float m = __ldg(mask + (size_t)b * s.mask_bs + ((size_t)g * s.KK + tap) * s.om_cs + (size_t)p * s.om_ps);
     if (s.flags & SIDE_DCN_MASK_IS_LOGIT) m = sigmoid_acc(m);
     const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + oh;
     const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + ow;
@@ -90,6 +91,7 @@ inline int dcn_fill_shape(DcnShape &s, int B, int Cin, int H, int W, int Cout, i
     s.P = s.Ho * s.Wo;
     s.offset_bs = offset_bs ? offset_bs : (long long)dg * 2 * s.KK * s.P;
     s.mask_bs = mask_bs ? mask_bs : (long long)dg * s.KK * s.P;
+    s.om_cs = s.P; s.om_ps = 1;
     SIDE_REQUIRE((long long)B * s.P < (1ll << 31) && (long long)Cin * H * W < (1ll << 31), "dcn: tensor too large");
     return SIDE_OK;
 }

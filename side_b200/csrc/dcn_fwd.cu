@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kDcnThreads, 3) dcn_fwd_simt_kernel(DcnFwdArgs
 }
 
 // dcn_fwd_tc.cu (tcgen05 / TMEM path)
-int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st);
+int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_nhwc = nullptr);
 size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int flags);
 bool dcn_fwd_tc_supported(int Cin, int Cout, int dg);
 
@@ -227,4 +227,35 @@ extern "C" int side_dcn_fwd(const float *x, const float *offset, const float *ma
     dcn_fwd_simt_kernel<<<grid, kDcnThreads, 0, st>>>(a);
     SIDE_LAUNCH_CHECK("dcn_fwd_simt_kernel");
     return SIDE_OK;
+}
+
+// Channels-last front end of the tcgen05 path: x is ALREADY [B, H, W, Cin] and the offset / mask-logit tensor is the
+// channels-last output [B, Ho, Wo, om_ld] of the offset convolution (channels 0 .. 2KK-1 = interleaved (dy, dx),
+// 2KK .. 3KK-1 = mask logits), e.g. produced by side_conv3d_tc_fwd.  Saves the NHWC staging copy and reads all 27
+// values of a pixel from one 128-byte row.
+extern "C" int side_dcn_fwd_cl(const float *x_nhwc, const float *om_cl, int om_ld, const float *w, const float *bias,
+                               const float *scale, const float *shift, float *y, int B, int Cin, int H, int W, int Cout, int kh,
+                               int kw, int sh, int sw, int ph, int pw, int dh, int dw, int flags, void *ws, size_t ws_bytes,
+                               void *stream)
+{
+    DcnFwdArgs a{};
+    flags |= SIDE_DCN_MASK_IS_LOGIT;
+    int rc = dcn_fill_shape(a.s, B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, 1, 1, 1, flags);
+    if (rc) return rc;
+    SIDE_REQUIRE(om_ld >= 3 * kh * kw, "side_dcn_fwd_cl: om_ld=%d < 3*kh*kw", om_ld);
+    SIDE_REQUIRE((flags & SIDE_DCN_PREC_MASK) != SIDE_DCN_PREC_FP32 && dcn_fwd_tc_supported(Cin, Cout, 1),
+                 "side_dcn_fwd_cl: only the tcgen05 precisions (3xTF32 / TF32) with Cin %% 32 == 0, Cout %% 16 == 0 are built");
+    SIDE_REQUIRE_DEV(x_nhwc); SIDE_REQUIRE_DEV(om_cl); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(y);
+    if (bias) SIDE_REQUIRE_DEV(bias);
+    if (flags & SIDE_DCN_FUSE_AFFINE) { SIDE_REQUIRE_DEV(scale); SIDE_REQUIRE_DEV(shift); }
+    const size_t need = side_dcn_fwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("side_dcn_fwd_cl: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+        return SIDE_ERR_WORKSPACE;
+    }
+    SIDE_REQUIRE_DEV(ws);
+    a.s.offset_bs = a.s.mask_bs = (long long)a.s.P * om_ld;
+    a.s.om_cs = 1; a.s.om_ps = om_ld;
+    a.x = x_nhwc; a.offset = om_cl; a.mask = om_cl + 2 * a.s.KK; a.bias = bias; a.scale = scale; a.shift = shift; a.y = y;
+    return dcn_fwd_tc(a, w, ws, ws_bytes, (cudaStream_t)stream, x_nhwc);
 }

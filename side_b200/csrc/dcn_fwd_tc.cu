@@ -338,7 +338,7 @@ size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int f
     return tc_weight_bytes(Cin, Cout, KK, flags) + sizeof(float) * (size_t)B * Cin * H * W;
 }
 
-int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st)
+int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_nhwc)
 {
     const DcnShape &s = a.s;
     const bool split = (s.flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
@@ -356,8 +356,9 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     }
     float *wp = reinterpret_cast<float *>(ws);
     float *xt = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws) + tc_weight_bytes(s.Cin, s.Cout, s.KK, s.flags));
-    int rc = launch_nchw_to_nhwc(a.x, xt, s.B, s.Cin, s.H * s.W, st);
-    if (rc) return rc;
+    int rc = SIDE_OK;
+    if (x_nhwc) xt = const_cast<float *>(x_nhwc);           // the caller already holds the channels-last copy
+    else if ((rc = launch_nchw_to_nhwc(a.x, xt, s.B, s.Cin, s.H * s.W, st))) return rc;
     if ((rc = launch_tc_weight_prep(w, wp, s.Cout, s.Cin, s.KK, split ? 1 : 0, st))) return rc;
 
     const uint32_t stage_bytes = (split ? 2u : 1u) * (kATileBytes + (uint32_t)s.Cout * 128u);

@@ -73,7 +73,56 @@ class DCN(DCNv2):
             self.conv_offset_mask.weight.zero_()
             self.conv_offset_mask.bias.zero_()
 
+    # -- inference fast path: offset conv on tcgen05 too, everything channels-last -----------------------------------
+    tensor_core_offsets = True
+
+    @staticmethod
+    def _tiles(B, H, W):
+        bw = 128
+        while bw > 1 and W % bw:
+            bw >>= 1
+        bh = 128 // bw
+        while bh > 1 and H % bh:
+            bh >>= 1
+        return B % (128 // (bw * bh)) == 0
+
+    def _cl_ok(self, x):
+        B, C, H, W = x.shape
+        return (self.tensor_core_offsets and x.is_cuda and not torch.is_grad_enabled() and self.deformable_groups == 1
+                and ops.get_dcn_precision() != "fp32" and self.kernel_size == (3, 3) and self.stride == (1, 1)
+                and self.padding == (1, 1) and self.dilation == (1, 1) and C % 32 == 0 and self.out_channels % 16 == 0
+                and self.out_channels <= 256 and self._tiles(B, H, W))
+
+    def _om_weights(self):
+        """conv_offset_mask as a 32-output-channel tcgen05 convolution (27 real channels, zero padding), bias in the epilogue."""
+        c = self.conv_offset_mask
+        key = (c.weight.data_ptr(), c.weight._version, c.bias._version)
+        st = self.__dict__.get("_om_cache")
+        if st is None or st[0] != key:
+            w = torch.zeros((32,) + tuple(c.weight.shape[1:]), device=c.weight.device, dtype=torch.float32)
+            w[:c.out_channels] = c.weight.detach()
+            b = torch.zeros((32,), device=c.weight.device, dtype=torch.float32)
+            b[:c.out_channels] = c.bias.detach()
+            st = (key, ops.conv_tc_prepare(w), b)
+            self.__dict__["_om_cache"] = st
+        return st[1], st[2]
+
+    def _forward_cl(self, input, bn, relu):
+        B, C, H, W = input.shape
+        full, hi, lo = ops.ncdhw_to_cl_split(input.unsqueeze(2), want_full=True)            # [B, 1, H, W, C]
+        wp, bias = self._om_weights()
+        om, _, _ = ops.conv3d_tc(hi.view(1, B, H, W, C), lo.view(1, B, H, W, C), wp, 32, ksize=(1, 3, 3), shift=bias,
+                                 full=True, split=False)                                       # [1, B, H, W, 32]
+        scale = shift = None
+        if bn is not None:
+            scale = (bn.weight * torch.rsqrt(bn.running_var + bn.eps)).contiguous()
+            shift = (bn.bias - bn.running_mean * scale).contiguous()
+        return ops.dcn_fwd_cl(full.view(B, H, W, C), om.view(B, H, W, 32), self.weight, self.bias, self.stride, self.padding,
+                              self.dilation, scale=scale, shift=shift, relu=relu)
+
     def forward(self, input, bn=None, relu=False):
+        if self._cl_ok(input) and (bn is None or not bn.training):
+            return self._forward_cl(input, bn, relu)
         om = self.conv_offset_mask(input)
         if self.deformable_groups != 1:
             # generic path, literally the reference's sequence

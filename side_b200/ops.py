@@ -538,8 +538,8 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     return y, y_hi, y_lo
 
 
-def ncdhw_to_cl_split(x, scale=None):
-    """x [N, C, D, H, W] (* scale [N, D] per depth slice) -> hi, lo [N, D, H, W, C]."""
+def ncdhw_to_cl_split(x, scale=None, want_full=False):
+    """x [N, C, D, H, W] (* scale [N, D] per depth slice) -> hi, lo [N, D, H, W, C] (and the unsplit copy first if want_full)."""
     lib = _lib.load()
     x = _chk(x, "x")
     N, C = x.shape[:2]
@@ -555,9 +555,10 @@ def ncdhw_to_cl_split(x, scale=None):
             raise RuntimeError("scale must be [N, D]")
     hi = torch.empty((N,) + sp + (C,), device=x.device, dtype=_F32)
     lo = torch.empty_like(hi)
-    _lib.check(lib.side_ncdhw_to_cl_split(x.data_ptr(), _p(scale), hi.data_ptr(), lo.data_ptr(), N, C, S, D, _stream()),
+    full = torch.empty_like(hi) if want_full else None
+    _lib.check(lib.side_ncdhw_to_cl_split(x.data_ptr(), _p(scale), _p(full), hi.data_ptr(), lo.data_ptr(), N, C, S, D, _stream()),
                "side_ncdhw_to_cl_split")
-    return hi, lo
+    return (full, hi, lo) if want_full else (hi, lo)
 
 
 def tf32_split(x):
@@ -629,4 +630,29 @@ def cl_to_nchw(x, B, C, spatial):
         HW *= v
     y = torch.empty((B, C) + tuple(spatial), device=x.device, dtype=_F32)
     _lib.check(lib.side_cl_to_nchw(x.data_ptr(), y.data_ptr(), B, C, HW, _stream()), "side_cl_to_nchw")
+    return y
+
+
+def dcn_fwd_cl(x_nhwc, om_cl, weight, bias, stride, padding, dilation, scale=None, shift=None, relu=False, precision=None):
+    """Inference DCN on channels-last inputs: x_nhwc [B, H, W, Cin], om_cl [B, Ho, Wo, ld] (offsets then mask logits per pixel)
+    -> y [B, Cout, Ho, Wo].  tcgen05 precisions only."""
+    lib = _lib.load()
+    x_nhwc, om_cl, weight = _chk(x_nhwc, "x_nhwc"), _chk(om_cl, "om_cl"), _chk(weight, "weight")
+    B, H, W, Cin = x_nhwc.shape
+    Cout, _, kh, kw = weight.shape
+    sh, sw = _pair(stride); ph, pw = _pair(padding); dh, dw = _pair(dilation)
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    prec = precision or _default_precision
+    flags = PRECISIONS["3xtf32" if prec == "fp32" else prec]
+    if scale is not None:
+        flags |= _lib.DCN_FUSE_AFFINE
+    if relu:
+        flags |= _lib.DCN_FUSE_RELU
+    y = torch.empty((B, Cout, Ho, Wo), device=x_nhwc.device, dtype=_F32)
+    nws = lib.side_dcn_fwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags)
+    ws = torch.empty((max(nws, 16),), device=x_nhwc.device, dtype=torch.uint8)
+    _lib.check(lib.side_dcn_fwd_cl(x_nhwc.data_ptr(), om_cl.data_ptr(), om_cl.shape[-1], weight.data_ptr(), _p(bias), _p(scale),
+                                   _p(shift), y.data_ptr(), B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, flags,
+                                   ws.data_ptr(), nws, _stream()), "side_dcn_fwd_cl")
     return y

@@ -192,3 +192,36 @@ def test_tensor_core_paths(lib, prec, tol):
                 pytest.skip("tcgen05 path not built yet")
             raise
         assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < tol, (prec, Cin, Cout, H, W)
+
+
+@pytest.mark.parametrize("cfg", [(8, 64, 64, 24, 80), (4, 128, 64, 48, 160), (4, 512, 256, 12, 40), (1, 64, 64, 96, 320)])
+def test_dcn_module_channels_last_fused_path(lib, cfg):
+    """Inference fast path of the DCN module: conv_offset_mask on tcgen05 (3xTF32, 27 -> 32 padded channels, channels-last) feeding
+    side_dcn_fwd_cl, with folded BatchNorm + ReLU -- against the same module on the fp32 SIMT path (cuDNN offset conv)."""
+    from side_b200 import ops
+    from side_b200.dcn_v2 import DCN
+    B, Cin, Cout, H, W = cfg
+    torch.manual_seed(Cin + H)
+    m = DCN(Cin, Cout, (3, 3), 1, 1).cuda().eval()
+    with torch.no_grad():
+        m.conv_offset_mask.weight.normal_(0, 1.0 / (9 * Cin) ** 0.5)      # non-trivial offsets (std ~ 1 px) and masks
+        m.conv_offset_mask.bias.normal_(0, 0.3)
+        m.bias.normal_(0, 0.1)
+    bn = torch.nn.BatchNorm2d(Cout).cuda().eval()
+    bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.uniform_(0.8, 1.2); bn.bias.data.normal_(0, 0.1)
+    x = torch.randn(B, Cin, H, W, device="cuda")
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ops.set_dcn_precision("fp32")
+            assert not m._cl_ok(x)
+            ref = m(x, bn=bn, relu=True)
+            ops.set_dcn_precision("3xtf32")
+            assert m._cl_ok(x)
+            out = m(x, bn=bn, relu=True)
+            assert float((out - ref).abs().max() / ref.abs().max()) < 1e-4
+            assert float((m(x) - (ops.set_dcn_precision("fp32") or m(x))).abs().max() / ref.abs().max()) < 1e-4
+    finally:
+        ops.set_dcn_precision("fp32")
+        torch.backends.cudnn.allow_tf32 = old_tf32
