@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
                     help="3xtf32 (default): tcgen05 with the exact hi/lo split, fp32-class accuracy (<= 1e-4 rel); fp32: SIMT")
+    ap.add_argument("--conv-mode", type=int, default=0, help="side_conv_tc_set_mode bit mask: 0 default, 1 halo reuse in the voxel-major kernel, 32 no role-swapped kernel")
     ap.add_argument("--cudnn-only", action="store_true",
                     help="keep the heads and the 3-D aggregation network on cuDNN fp32 (as the reference runs them)")
     ap.add_argument("--allow-tf32", action="store_true", help="let cuDNN use TF32 for the out-of-scope convolutions")
@@ -348,6 +349,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = bool(args.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.allow_tf32)
     ops.set_dcn_precision(args.dcn_precision)
+    lib.side_conv_tc_set_mode(args.conv_mode)
     pk = peaks()
 
     cpu_model = build_model()

@@ -249,6 +249,9 @@ int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int 
 int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                        const float *residual, float *y, float *y_hi, float *y_lo, int N, int D, int H, int W, int Cin,
                        int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream);
+/* test / benchmark hook, bit mask: 0 = default; 1 = halo-box reuse in the voxel-major kernel; 32 = disable the role-swapped
+ * Cout = 64 kernel.  Results are identical up to fp32 summation order. */
+int side_conv_tc_set_mode(int mode);
 int side_ncdhw_to_cl_split(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C, long long S,
                            int D, void *stream);   /* full (may be NULL): the unsplit channels-last copy as well */
 int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);

@@ -50,6 +50,13 @@ struct ConvTcParams {
     int kd, kh, kw;                   // kernel extent (3,3,3), (1,3,3) or (1,1,1)
     int sh, sw;                       // stride along h / w (1 or 2); D, H, W above are OUTPUT extents
     int stages;
+    // "kh view" mode (3x3 / 3x3x3 kernels, stride 1, bd == 1, bw % 8 == 0): one TMA box with a one-row halo above and below
+    // ((bh + 2) x bw pixels) serves the three vertical taps -- tap kh reads the box from row kh on, a start address that
+    // is a multiple of 1024 bytes, so the 128-byte swizzle phase is unchanged.  A ring (a_slots) and B ring (b_slots)
+    // are then separate: A is loaded once per (kd, kw, channel block), B once per tap.
+    int khv, a_slots, b_slots;
+    int dbg;                          // timing experiments only (side_conv_tc_set_mode bits 1, 2): skip the B / A copies
+    uint32_t a_part;                  // bytes of one half (hi or lo) of an A slot
 };
 
 // m-tile -> first voxel coordinates of its box
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kCvMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kCvMaxStages];
+    __shared__ __align__(8) uint64_t fullA[2], emptyA[2];       // kh-view mode: A ring (full_bar / empty_bar are the B ring)
     __shared__ __align__(8) uint64_t tmem_full[2];
     __shared__ __align__(8) uint64_t tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -96,13 +104,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         s_shift[i] = p.shift ? p.shift[i] : 0.0f;
     }
     if (tid == 0) {
-        for (int i = 0; i < stages; ++i) {
+        for (int i = 0; i < kCvMaxStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 1);
         }
         mbar_fence_init();
     }
@@ -119,7 +129,6 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int khw = p.kh * p.kw;
     const int pd = (p.kd - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
 
     if (warp == 0) {
@@ -129,22 +138,60 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_lo) : "memory");
             int st = 0;
             uint32_t phs = 0;
+            if (p.khv) {
+                unsigned char *bring = tiles + (size_t)p.a_slots * 2 * p.a_part;
+                int sa_i = 0;
+                uint32_t pha = 0;
+                for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                    const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+                    int n, d0, h0, w0;
+                    conv_tile_origin(p, mt, n, d0, h0, w0);
+                    const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
+                    for (int kdi = 0; kdi < p.kd; ++kdi)
+                        for (int kwi = 0; kwi < 3; ++kwi)
+                            for (int cb = 0; cb < p.ncb; ++cb) {
+                                mbar_wait(&emptyA[sa_i], pha ^ 1u);
+                                unsigned char *sa = tiles + (size_t)sa_i * 2 * p.a_part;
+                                mbar_expect_tx(&fullA[sa_i], 2 * p.a_part);
+                                tma_load_5d(sa, &tm_hi, cb * 32, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                                tma_load_5d(sa + p.a_part, &tm_lo, cb * 32, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                                if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
+                                for (int khi = 0; khi < 3; ++khi) {
+                                    const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
+                                    mbar_wait(&empty_bar[st], phs ^ 1u);
+                                    mbar_expect_tx(&full_bar[st], 2 * b_part);
+                                    bulk_g2s(bring + (size_t)st * 2 * b_part, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
+                                    if (++st == p.b_slots) { st = 0; phs ^= 1u; }
+                                }
+                            }
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
                 int n, d0, h0, w0;
                 conv_tile_origin(p, mt, n, d0, h0, w0);
                 const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
+                // (kd, kh, kw, channel block) carried incrementally: this single thread's instruction latency is on the critical
+                // path of every k-block, integer divisions here cost more than the MMAs they feed
+                int kdi = 0, khi = 0, kwi = 0, cb = 0;
                 for (int kb = 0; kb < p.nkb; ++kb) {
-                    const int tap = kb / p.ncb, cb = kb - tap * p.ncb;
-                    const int kdi = tap / khw, r2 = tap - kdi * khw, khi = r2 / p.kw, kwi = r2 - khi * p.kw;
                     mbar_wait(&empty_bar[st], phs ^ 1u);
                     unsigned char *sa = tiles + (size_t)st * stage_bytes;
-                    mbar_expect_tx(&full_bar[st], stage_bytes);
+                    mbar_expect_tx(&full_bar[st], ((p.dbg & 4) ? 0u : 2 * kCvATile) + ((p.dbg & 2) ? 0u : 2 * b_part));
                     const int cw = w0 * p.sw + kwi - pw, ch = h0 * p.sh + khi - ph;     // input coordinates of the box origin
-                    tma_load_5d(sa, &tm_hi, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
-                    tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
-                    bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
+                    if (!(p.dbg & 4)) {
+                        tma_load_5d(sa, &tm_hi, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                        tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                    }
+                    if (!(p.dbg & 2)) bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
+                    if (++cb == p.ncb) {
+                        cb = 0;
+                        if (++kwi == p.kw) {
+                            kwi = 0;
+                            if (++khi == p.kh) { khi = 0; ++kdi; }
+                        }
+                    }
                 }
             }
         }
@@ -159,6 +206,43 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             const uint32_t idesc = tc_idesc_tf32(kCvBM, N), idesc2 = tc_idesc_tf32(kCvBM, 2 * N);
             int st = 0, acc = 0;
             uint32_t phs = 0, acc_ph = 0;
+            if (p.khv) {
+                const uint32_t bring = smem_u32(tiles + (size_t)p.a_slots * 2 * p.a_part);
+                const uint32_t view = (uint32_t)p.bw * 128u;          // bytes per halo row: tap kh starts kh rows further down
+                int sa_i = 0;
+                uint32_t pha = 0;
+                const int ngroups = p.kd * 3 * p.ncb;
+                for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                    mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
+                    const uint32_t tmem_x = tmem_d + (uint32_t)N;
+                    for (int g = 0; g < ngroups; ++g) {
+                        mbar_wait(&fullA[sa_i], pha);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + (size_t)sa_i * 2 * p.a_part);
+                        for (int khi = 0; khi < 3; ++khi) {
+                            mbar_wait(&full_bar[st], phs);
+                            tc_fence_after();
+                            const uint32_t sb = bring + (uint32_t)st * 2 * b_part;
+                            const uint32_t av = sa + (uint32_t)khi * view;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_hi = tc_smem_desc(av + k * 32), b_hi = tc_smem_desc(sb + k * 32);
+                                const uint64_t a_lo = tc_smem_desc(av + p.a_part + k * 32);
+                                tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (g | khi | k) != 0 ? 1u : 0u);
+                                tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, 1u);
+                            }
+                            tc_commit(&empty_bar[st]);
+                            if (++st == p.b_slots) { st = 0; phs ^= 1u; }
+                        }
+                        tc_commit(&emptyA[sa_i]);
+                        if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
+                    }
+                    tc_commit(&tmem_full[acc]);
+                    if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
                 tc_fence_after();
@@ -177,6 +261,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                         const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32);
+                        if (p.dbg & 16) continue;
                         tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);     // [hi*hi | hi*lo]
                         tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, 1u);                          // + lo*hi
                     }
@@ -205,7 +290,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             const size_t row = vox * p.Ntot + (size_t)nt * N;            // float offset of this row's first channel
             const int cbase = nt * N;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
-            for (int c = 0; c < N; c += 16) {
+            for (int c = 0; c < ((p.dbg & 8) ? 0 : N); c += 16) {
                 float v[16], vx[16];
                 tc_ld16(taddr + (uint32_t)c, v);
                 tc_ld16(taddr + (uint32_t)(N + c), vx);
@@ -281,7 +366,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
 
 // channels-last activation [Nn, D, H, W, C] fp32 -> box {32, bw, bh, bd, 1}, 128-byte swizzle, zero fill out of bounds
 static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw,
-                         int sh = 1, int sw = 1)
+                         int sh = 1, int sw = 1, int halo_h = 0)
 {
     PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
     if (!enc) {
@@ -292,7 +377,7 @@ static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int 
     cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
     // strided convolution: the box spans bw*sw x bh*sh input pixels, traversed with element strides (sw, sh), i.e. it still
     // delivers bw x bh pixels -- the ones a stride-s convolution reads for bw x bh outputs
-    cuuint32_t box[5] = {32, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh), (cuuint32_t)bd, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh + 2 * halo_h), (cuuint32_t)bd, 1};
     cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -304,7 +389,21 @@ static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int 
     return SIDE_OK;
 }
 
+// exported to conv_tct.cu
+int conv_make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw, int sh,
+                       int sw, int halo_h)
+{
+    return make_act_tmap(tm, base, Nn, D, H, W, C, bd, bh, bw, sh, sw, halo_h);
+}
+bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride);
+int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
+                    const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin, int kd,
+                    int relu, int sm_count, cudaStream_t st);
+
 static int g_sm_count = 0;
+static int g_disable_tct = 0;
+static int g_enable_khv = 0;      // test hook: side_conv_tc_set_mode
+static int g_dbg = 0;
 
 }  // namespace side
 
@@ -367,10 +466,28 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
     if (y) SIDE_REQUIRE_DEV(y);
     if (y_hi) { SIDE_REQUIRE_DEV(y_hi); SIDE_REQUIRE_DEV(y_lo); }
 
-    CUtensorMap tm_hi, tm_lo;
+    // kh-view mode when the geometry allows it and the two rings fit in shared memory
+    const uint32_t b_slot = 2 * (uint32_t)conv_ntile(Cout) * 128u;
+    const uint32_t a_part = (uint32_t)(bh + 2) * bw * 128u;
+    int khv = (kh == 3 && stride_hw == 1 && bd == 1 && (bw % 8) == 0 && g_enable_khv) ? 1 : 0;
+    int b_slots = 0;
+    if (khv) {
+        b_slots = std::min(4, (int)((196u * 1024u - 2u * 2u * a_part) / b_slot));
+        if (2u * 2u * a_part >= 196u * 1024u || b_slots < 2) khv = 0;
+    }
     int rc;
-    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw))) return rc;
-    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw))) return rc;
+    if (g_sm_count == 0) {
+        int dev = 0;
+        SIDE_CUDA(cudaGetDevice(&dev));
+        SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // Cout == 64 on 256-voxel slices: role-swapped kernel (weights on M, 256 voxels on N), see conv_tct.cu
+    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw))
+        return conv_tct_launch(x_hi, x_lo, wp, scale, shift, residual, y, y_hi, y_lo, Nn, D, H, W, Cin, kd, relu, g_sm_count,
+                               (cudaStream_t)stream);
+    CUtensorMap tm_hi, tm_lo;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv))) return rc;
 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
@@ -383,7 +500,8 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
     p.kd = kd; p.kh = kh; p.kw = kw; p.sh = stride_hw; p.sw = stride_hw;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
+    const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + 1024;
     if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
     if (g_sm_count == 0) {
         int dev = 0;
@@ -393,5 +511,17 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
     const unsigned grid = (unsigned)std::min(p.ntiles, g_sm_count);
     conv_tc_kernel<<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
     SIDE_LAUNCH_CHECK("conv_tc_kernel");
+    return SIDE_OK;
+}
+
+/* test / benchmark hook (bit mask).  0 = default.  1: the voxel-major kernel reuses one halo box for the three vertical taps
+ * (measured: no gain there -- that kernel is bound by the ~115-cycle floor of each tcgen05.mma, not by operand delivery);
+ * 32: disable the role-swapped Cout = 64 kernel (conv_tct.cu); 2 / 4 / 8 / 16: timing experiments that skip the B copies /
+ * A copies / epilogue / MMAs (results are garbage). */
+extern "C" int side_conv_tc_set_mode(int mode)
+{
+    g_enable_khv = (mode & 1) && !(mode & 30);
+    g_dbg = mode & 30;
+    g_disable_tct = (mode & 32) != 0;
     return SIDE_OK;
 }

@@ -36,8 +36,12 @@ def _cl(x):      # NCDHW -> NDHWC
     (1, 48, 16, 16, 32, 16, False, False, False),    # plain conv, D = 48
     (5, 2, 8, 8, 64, 32, False, True, False),        # odd sample count, persistent tail
 ])
-def test_conv3d_tc_matches_fp64(lib, cfg):
+@pytest.mark.parametrize("mode", [0, 1, 32])
+def test_conv3d_tc_matches_fp64(lib, cfg, mode):
+    """mode 0: default (role-swapped kernel for Cout = 64 on 16x16 maps); 1: halo-box reuse in the voxel-major kernel;
+    32: voxel-major kernel everywhere."""
     from side_b200 import ops
+    lib.side_conv_tc_set_mode(mode)
     N, D, H, W, Cin, Cout, relu, affine, res = cfg
     g = torch.Generator().manual_seed(N * 1000 + Cin + Cout)
     x = torch.randn(N, Cin, D, H, W, generator=g)
@@ -64,6 +68,7 @@ def test_conv3d_tc_matches_fp64(lib, cfg):
     assert rel_err(y.cpu().numpy(), ref) < 1e-4
     assert torch.equal(yh + yl, y)                                    # split outputs reassemble the fp32 result exactly
     assert torch.equal(yh, (y.view(torch.int32) & -8192).view(torch.float32))
+    lib.side_conv_tc_set_mode(0)
 
 
 def test_layout_and_pool_helpers(lib):

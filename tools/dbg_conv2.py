@@ -1,0 +1,21 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from side_b200 import ops, _lib
+lib = _lib.load()
+dev = torch.device("cuda")
+N, D, H, W, Cin = 200, 16, 16, 16, 64
+x = torch.randn(N, D, H, W, Cin, device=dev); hi, lo = ops.tf32_split(x)
+for Cout in (16, 32, 64, 128):
+    wp = ops.conv_tc_prepare(torch.randn(Cout, Cin, 3, 3, 3, device=dev) * 0.05)
+    for mode in (1, 15):
+        lib.side_conv_tc_set_mode(mode)
+        for _ in range(2): ops.conv3d_tc(hi, lo, wp, Cout, relu=True, full=False, split=True)
+        torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): ops.conv3d_tc(hi, lo, wp, Cout, relu=True, full=False, split=True)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        ksteps = N * D * H * W / 128 * 27 * (Cin // 32) * 4 / 148
+        print("Cout", Cout, "mode", mode, "%.3f ms   %.0f clk per k-step (2 MMAs) at 1.9 GHz" % (ms, ms * 1e-3 * 1.9e9 / ksteps))
+lib.side_conv_tc_set_mode(0)
