@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     } else if (warp == 16) {
         // ================= MMA issuer =================
         if (lane == 0) {
+            const uint32_t idesc2 = tc_idesc_tf32(kTcBM, 2 * N <= 256 ? 2 * N : N);
             int st = 0;
             uint32_t fph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -274,6 +275,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 #pragma unroll
                 for (int k = 0; k < kTcBK / 8; ++k) {
                     const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
+                    if (SPLIT && 2 * N <= 256) {
+                        // every tcgen05.mma costs ~115 cycles whatever N is (measured, conv_tct.cu): hi*hi and hi*lo go out as
+                        // ONE instruction of width 2N against the adjacent [B_hi | B_lo] tiles (main -> columns 0..N, cross ->
+                        // N..2N), lo*hi then accumulates onto the cross columns: 2 instructions per k-step instead of 3
+                        const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
+                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, 1u);
+                        continue;
+                    }
                     tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
                     if (SPLIT) {
                         // The two small cross terms go to a SECOND accumulator (columns N..2N): the tensor core adds
