@@ -298,10 +298,14 @@ def run_train(args):
     torch.cuda.synchronize()
     _lib.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -318,7 +322,7 @@ def run_train(args):
                                                  "L1 depth / head losses + backward + NCCL gradient all-reduce + Adam" % B,
                                      "pairs_per_gpu_per_step": B, "parallelism": "data-parallel x%d, bucketed all_reduce" % world,
                                      "dcn_precision": args.dcn_precision},
-                          "gpu_launches": _lib.launch_count(), "loss": float(loss)}))
+                          "gpu_launches": _lib.launch_count(), "loss": float(loss.detach())}))
     if world > 1:
         dist.destroy_process_group()
 
