@@ -48,7 +48,10 @@ enum {
     SIDE_DCN_PREC_FP32     = 0 << 4, /* SIMT fp32 FMA implicit GEMM (default; <=1e-5 rel vs the reference) */
     SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel) */
     SIDE_DCN_PREC_TF32     = 2 << 4, /* tcgen05 kind::tf32 single pass (~1e-3 rel, opt-in) */
-    SIDE_DCN_PREC_MASK     = 3 << 4
+    SIDE_DCN_PREC_MASK     = 3 << 4,
+    SIDE_DCN_BWD_SCALAR    = 1 << 8  /* side_dcn_bwd: force the scalar-atomic kernel that keeps the reference's thread mapping
+                                        (one thread per (pixel, tap), serial over channels); default is the channels-last
+                                        path with 16-byte vector reductions whenever dg == 1, Cin % 64 == 0, P % 4 == 0 */
 };
 
 /* flags for side_inst_costvol_fwd / _bwd */

@@ -20,6 +20,7 @@ inline int cuda_fail(cudaError_t e, const char *what)
 
 // NCHW -> NHWC staging copy (layout.cu)
 int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaStream_t st);
+int launch_nhwc_to_nchw(const float *in, float *out, int B, int C, int HW, cudaStream_t st);
 
 // true when p is device (or managed) memory of the current context; NULL is handled by callers
 bool is_device_ptr(const void *p);

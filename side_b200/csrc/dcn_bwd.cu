@@ -169,16 +169,26 @@ __global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float *__restr
     }
 }
 
+// channels-last path (dcn_bwd_cl.cu)
+bool dcn_bwd_cl_supported(const DcnShape &s);
+size_t dcn_bwd_cl_fixed_floats(const DcnShape &s);
+int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const float *mask, const float *w, const float *gy,
+                   float *gx, float *goffset, float *gmask, float *gw, float *gbias, float *ws, size_t ws_floats,
+                   cudaStream_t st);
+
 }  // namespace side
 
 using namespace side;
 
 extern "C" size_t side_dcn_bwd_ws_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw, int flags)
 {
-    (void)Cout; (void)flags;
+    (void)flags;
     if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0) return 0;
-    // preferred: columns for the whole batch (same-size output assumed as an upper bound for stride>=1)
-    return sizeof(float) * (size_t)B * Cin * kh * kw * (size_t)H * W;
+    // preferred: columns for the whole batch (same-size output assumed as an upper bound for stride>=1), plus the
+    // channels-last staging of the fast path: permuted weights and their gradient, input and grad_input copies
+    const size_t cols = (size_t)B * Cin * kh * kw * (size_t)H * W;
+    const size_t fixed = 2 * (size_t)std::max(Cout, 0) * Cin * kh * kw + 2 * (size_t)B * Cin * H * W;
+    return sizeof(float) * (cols + fixed);
 }
 
 extern "C" int side_dcn_bwd(const float *x, const float *offset, const float *mask, const float *w, const float *gy,
@@ -198,6 +208,10 @@ extern "C" int side_dcn_bwd(const float *x, const float *offset, const float *ma
     }
     SIDE_REQUIRE_DEV(ws);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & SIDE_DCN_BWD_SCALAR) && dcn_bwd_cl_supported(s) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+        ws_bytes / sizeof(float) >= dcn_bwd_cl_fixed_floats(s) + per_sample / sizeof(float))
+        return dcn_bwd_cl_run(s, x, offset, mask, w, gy, gx, goffset, gmask, gw, gbias, reinterpret_cast<float *>(ws),
+                              ws_bytes / sizeof(float), st);
     const int K = Cin * s.KK, P = s.P;
     const int chunk = (int)std::min<size_t>((size_t)B, ws_bytes / per_sample);
     a.x = x; a.offset = offset; a.mask = mask; a.gcol = reinterpret_cast<float *>(ws);

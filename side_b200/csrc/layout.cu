@@ -52,6 +52,15 @@ int launch_nchw_to_nhwc(const float *in, float *out, int B, int C, int HW, cudaS
     return SIDE_OK;
 }
 
+int launch_nhwc_to_nchw(const float *in, float *out, int B, int C, int HW, cudaStream_t st)
+{
+    dim3 tg(ceil_div(HW, 32), ceil_div(C, 32), B), tb(32, 8);
+    SIDE_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, "nhwc_to_nchw: grid too large");
+    nhwc_to_nchw_kernel<<<tg, tb, 0, st>>>(in, out, C, HW);
+    SIDE_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+    return SIDE_OK;
+}
+
 }  // namespace side
 
 extern "C" int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream)

@@ -82,7 +82,7 @@ def dcn_forward_raw(x, offset_t, mask_t, weight, bias, stride, padding, dilation
 
 def dcn_backward_raw(x, offset_t, mask_t, weight, gy, stride, padding, dilation, dg, *, offset_bs=0, mask_bs=0,
                      flags=0, offset_ptr=None, mask_ptr=None, goffset_ptr=None, gmask_ptr=None, goffset=None,
-                     gmask=None):
+                     gmask=None, ws_bytes=None):
     lib = _lib.load()
     x = _chk(x, "input")
     weight = _chk(weight, "weight")
@@ -101,9 +101,11 @@ def dcn_backward_raw(x, offset_t, mask_t, weight, gy, stride, padding, dilation,
         goffset_ptr, gmask_ptr = goffset.data_ptr(), gmask.data_ptr()
     P = gy.shape[2] * gy.shape[3]
     per_sample = 4 * Cin * kh * kw * P
-    free, _ = torch.cuda.mem_get_info(x.device)
-    nb = max(1, min(B, int(free * 0.5) // per_sample))
-    ws = torch.empty((per_sample * nb,), device=x.device, dtype=torch.uint8)
+    want = lib.side_dcn_bwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags)     # whole batch in one pass
+    if ws_bytes is None:
+        free, _ = torch.cuda.mem_get_info(x.device)
+        ws_bytes = min(want, max(per_sample, int(free * 0.5)))
+    ws = torch.empty((max(int(ws_bytes), per_sample),), device=x.device, dtype=torch.uint8)
     rc = lib.side_dcn_bwd(x.data_ptr(), offset_ptr or offset_t.data_ptr(), mask_ptr or mask_t.data_ptr(),
                           weight.data_ptr(), gy.data_ptr(), gx.data_ptr(), goffset_ptr, gmask_ptr, gw.data_ptr(),
                           gb.data_ptr(), B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, offset_bs, mask_bs, flags,

@@ -225,3 +225,82 @@ def test_dcn_module_channels_last_fused_path(lib, cfg):
     finally:
         ops.set_dcn_precision("fp32")
         torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+# ------------------------------------------------------------------------------------------------
+# channels-last backward (dcn_bwd_cl.cu): taken for dg == 1, Cin % 64 == 0, P % 4 == 0
+# ------------------------------------------------------------------------------------------------
+def test_backward_channels_last_vs_oracle(lib):
+    """Ragged tiles (H, W not multiples of the 8x16 pixel tile), stride / dilation, samples far outside the image,
+    Cin = 64 (two items per warp step) and Cin = 128 / 192 (one), against the C oracle."""
+    from side_b200 import _lib, ops
+    rng = np.random.default_rng(11)
+    for (B, Cin, H, W, Cout, k, s, p, d, spread) in [(2, 64, 10, 12, 8, 3, 1, 1, 1, 2.0), (1, 128, 9, 20, 12, 3, 1, 1, 1, 2.0),
+                                                      (2, 64, 13, 18, 20, 3, 2, 1, 1, 3.0), (1, 192, 6, 8, 4, 3, 1, 2, 2, 40.0),
+                                                      (3, 64, 4, 4, 64, 1, 1, 0, 1, 1.0)]:
+        Ho = (H + 2 * p - (d * (k - 1) + 1)) // s + 1
+        Wo = (W + 2 * p - (d * (k - 1) + 1)) // s + 1
+        if (Ho * Wo) % 4:
+            continue
+        x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+        off = (rng.standard_normal((B, 2 * k * k, Ho, Wo)) * spread).astype(np.float32)
+        mask = rng.random((B, k * k, Ho, Wo)).astype(np.float32)
+        w = (rng.standard_normal((Cout, Cin, k, k)) * 0.1).astype(np.float32)
+        gy = rng.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)
+        gref = co.dcn_backward(x, off, mask, w, gy, s, p, d, 1)
+        g = ops.dcn_backward_raw(dev(x), dev(off), dev(mask), dev(w), dev(gy), s, p, d, 1)
+        gs = ops.dcn_backward_raw(dev(x), dev(off), dev(mask), dev(w), dev(gy), s, p, d, 1, flags=_lib.DCN_BWD_SCALAR)
+        for mine, sc, r, n in zip(g, gs, gref, "gx goff gmask gw gb".split()):
+            assert rel_err(mine.cpu().numpy(), r) < 1e-4, (n, B, Cin, H, W, Cout, k, s, p, d)
+            assert rel_err(sc.cpu().numpy(), r) < 1e-4, ("scalar", n, B, Cin, H, W, Cout, k, s, p, d)
+
+
+@pytest.mark.parametrize("shape", DLA_SHAPES)
+def test_backward_dla_shapes_vs_torchvision(lib, shape):
+    """config #3 backward: all five gradients against torchvision's CUDA deform_conv2d autograd, B = 2."""
+    import torchvision.ops as tvo
+    from side_b200 import _lib, ops
+    Cin, Cout, H, W = shape
+    torch.manual_seed(Cin + Cout + W)
+    x = torch.randn(2, Cin, H, W, device="cuda", requires_grad=True)
+    off = (torch.randn(2, 18, H, W, device="cuda") * 2).requires_grad_(True)
+    mask = torch.sigmoid(torch.randn(2, 9, H, W, device="cuda")).requires_grad_(True)
+    w = ((torch.rand(Cout, Cin, 3, 3, device="cuda") * 2 - 1) / (9 * Cin) ** 0.5).requires_grad_(True)
+    b = torch.rand(Cout, device="cuda", requires_grad=True)
+    gy = torch.randn(2, Cout, H, W, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = tvo.deform_conv2d(x, off, w, b, padding=1, mask=mask)
+        gref = torch.autograd.grad(ref, (x, off, mask, w, b), gy)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    g = ops.dcn_backward_raw(x.detach(), off.detach(), mask.detach(), w.detach(), gy, 1, 1, 1, 1)
+    for mine, r, n in zip(g, gref, "gx goff gmask gw gb".split()):
+        assert rel_err(mine.cpu().numpy(), r.cpu().numpy()) < 1e-4, (n, shape)
+
+
+def test_backward_channels_last_fused_logits_and_chunked_workspace(lib):
+    """The fused module path (27-channel logits tensor, strided grads) and a workspace that only holds one sample of
+    columns must give the same gradients as the whole-batch pass."""
+    from side_b200 import _lib, ops
+    torch.manual_seed(21)
+    B, Cin, Cout, H, W = 3, 64, 32, 16, 24
+    x = torch.randn(B, Cin, H, W, device="cuda", requires_grad=True)
+    om = torch.randn(B, 27, H, W, device="cuda", requires_grad=True)
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.rand(Cout, device="cuda", requires_grad=True)
+    gy = torch.randn(B, Cout, H, W, device="cuda")
+    y = ops.dcn_fused(x, om, w, b, 1, 1, 1)
+    ga = torch.autograd.grad(y, (x, om, w, b), gy)
+    o1, o2, mk = torch.chunk(om, 3, dim=1)
+    offs, msk = torch.cat((o1, o2), 1).detach().contiguous(), torch.sigmoid(mk).detach().contiguous()
+    full = ops.dcn_backward_raw(x.detach(), offs, msk, w.detach(), gy, 1, 1, 1, 1, flags=_lib.DCN_BWD_SCALAR)
+    P, K = H * W, Cin * 9
+    fixed = 4 * (2 * Cout * K + 2 * B * Cin * H * W)
+    part = ops.dcn_backward_raw(x.detach(), offs, msk, w.detach(), gy, 1, 1, 1, 1, ws_bytes=fixed + 4 * K * P + 64)
+    for a, c, n in zip(part, full, "gx goff gmask gw gb".split()):
+        assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 1e-4, n
+    assert rel_err(ga[0].cpu().numpy(), full[0].cpu().numpy()) < 1e-4
+    assert rel_err(ga[2].cpu().numpy(), full[3].cpu().numpy()) < 1e-4
+    assert rel_err(ga[1][:, :18].cpu().numpy(), full[1].cpu().numpy()) < 1e-4
