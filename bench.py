@@ -197,6 +197,19 @@ def kernel_rooflines(pk, precision):
     gcost = torch.randn_like(cost)
     ms = time_op(lambda: torch.autograd.grad(cost, (fLg, fRg), gcost, retain_graph=True), flush=flush, iters=5)
     out["inst_costvol_bwd"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts}
+    from side_b200 import _lib as _sl
+    ops.VOL_BWD_FLAGS = _sl.VOL_BWD_SCALAR            # the scalar-atomic kernel (torchvision's thread mapping) for comparison
+    try:
+        ms = time_op(lambda: torch.autograd.grad(cost, (fLg, fRg), gcost, retain_graph=True), flush=flush, iters=3)
+    finally:
+        ops.VOL_BWD_FLAGS = 0
+    out["inst_costvol_bwd_scalar_atomics"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"],
+                                              "alg_bytes": byts}
+    del cost
+    cost, _ = ops.inst_costvol(fLg, fRg, left, right, fb, 48, 16, 319.0, gate=True)
+    ms = time_op(lambda: torch.autograd.grad(cost, (fLg, fRg), gcost, retain_graph=True), flush=flush, iters=5)
+    out["inst_costvol_bwd_gate"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts,
+                                    "note": "recompute raw volume + gate backward in place + gather backward"}
     del cost, gcost, fLg, fRg
     # reference-shaped volume: 100 RoIs x 16 x 32 ch
     l2, r2, _ = make_boxes(1, 100, seed=1)

@@ -65,8 +65,11 @@ enum {
                                from torchvision's operation order by a few ulp (<= 1e-5 relative);
                                channel placement and L-R stay exact.  Needs P == 16, C % 8 == 0, D <= 256 and
                                side_inst_costvol_fast_ws_bytes(...) bytes of workspace. */
-    SIDE_VOL_XCROSS = 1 << 3 /* with SEPARABLE and without GATE: also return the gate scalar xcross[N, D] computed in the
+    SIDE_VOL_XCROSS = 1 << 3, /* with SEPARABLE and without GATE: also return the gate scalar xcross[N, D] computed in the
                                same pass, WITHOUT applying it (the consumer, side_ncdhw_to_cl_split, multiplies) */
+    SIDE_VOL_BWD_SCALAR = 1 << 4 /* side_inst_costvol_bwd: force the scalar-atomic kernel (torchvision's roi_align backward
+                               thread mapping, 32 atomics per volume element); default for P == 16, C % 8 == 0 is the
+                               separable gather kernel that keeps the x-pass sums in registers */
 };
 
 /* decode flavour */
@@ -153,6 +156,16 @@ int side_inst_costvol_fwd(const float *featL, const float *featR, const float *l
 int side_inst_costvol_bwd(const float *featL, const float *featR, const float *left, const float *right,
                           const float *fb, const uint8_t *valid, const float *gcost, float *gfeatL, float *gfeatR,
                           int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *stream);
+
+/* Same gradients with a workspace: for SIDE_VOL_GATE the raw volume is recomputed by the separable forward, the gate's
+ * backward runs in place on it and the separable gather kernel (register sums, one atomic per window pixel) finishes --
+ * several times faster than the scalar kernel above.  Falls back to side_inst_costvol_bwd when P != 16 or C % 8 != 0.
+ * ws_bytes >= side_inst_costvol_bwd_fast_ws_bytes(...) (0 without the gate). */
+size_t side_inst_costvol_bwd_fast_ws_bytes(int B, int C, int H, int W, int N, int D, int flags);
+int side_inst_costvol_bwd_fast(const float *featL, const float *featR, const float *left, const float *right,
+                               const float *fb, const uint8_t *valid, const float *gcost, float *gfeatL, float *gfeatR,
+                               int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *ws,
+                               size_t ws_bytes, void *stream);
 
 /* Stand-alone cosine gate on an already built volume (drop-in cost_volume.forward(cost, ...) entry,
  * stereo_network_old.py:194-203).  out may alias cost.  bwd: gcost = d loss / d cost. */

@@ -29,6 +29,8 @@ SIGNATURES = {
     "side_inst_costvol_fast_ws_bytes": (_sz, [_i] * 6),
     "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
     "side_inst_costvol_bwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
+    "side_inst_costvol_bwd_fast_ws_bytes": (_sz, [_i] * 7),
+    "side_inst_costvol_bwd_fast": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
     "side_xcross_gate_fwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "side_xcross_gate_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "side_softargmin_fwd": (_i, [_vp] * 4 + [_i] * 3 + [_vp]),
@@ -67,6 +69,7 @@ VOL_GATE = 1 << 0
 VOL_FMA = 1 << 1
 VOL_SEPARABLE = 1 << 2
 VOL_XCROSS = 1 << 3
+VOL_BWD_SCALAR = 1 << 4
 DECODE_HEAT_IS_LOGIT = 1 << 0
 
 _lib = None

@@ -895,6 +895,223 @@ __global__ void __launch_bounds__(kVolThreads) inst_costvol_bwd_kernel(VolParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Separable backward, GATHER form (ungated volume; the gate's backward is side_xcross_gate_bwd).
+//
+// The scalar kernel above mirrors torchvision's roi_align backward: 32 fp32 atomics per volume element, 1.6 G atomics for
+// config #2.  The forward is separable (y interpolation shared by all D candidates, see inst_costvol_sep_kernel), so its
+// adjoint is too:
+//     gU[side][ph][x][c] = sum_d sum_j 0.25 * tri(clamp(s_dj, 0, W-1) - x) * G[side][d][ph][j >> 1][c]      (x pass)
+//     gfeat[y][x][c]    += sum_s  wy_s(y) * gU[ph = s >> 1][x][c]                                             (y pass)
+// where s_dj are the 32 x-sample positions of slice d (an arithmetic progression, so the samples touching one column are
+// a contiguous, computable range), tri(t) = max(0, 1 - |t|) is the bilinear weight and G = (g_L + g_{L-R}, g_R - g_{L-R}).
+// A CTA owns (RoI, 8 channels): 4 producer warps stream the three gradient planes of one slice after another into an
+// 8-deep shared-memory ring (already combined per side, scaled by 1/4 and laid out [pw][ph][c]), 12 consumer warps own
+// (column, 4 bin rows) x 8 channels each with the sums in REGISTERS -- no atomics in the x pass at all.  The y pass runs
+// once per CTA from shared memory and issues one atomic per (row, column, channel) of the RoI's window, coalesced along
+// x: about 10 M atomics for config #2 instead of 1.6 G.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBgCC = 8;
+constexpr int kBgThreads = 512, kBgProd = 128, kBgCons = 384;
+constexpr int kBgStages = 8;
+constexpr int kBgPwF = 4 * 36;                  // floats per bin column pw: 4 row-quads x (4 rows x 8 channels + 4 pad)
+constexpr int kBgSideF = 16 * kBgPwF;           // floats per side
+constexpr int kBgStageF = 2 * kBgSideF;         // floats per ring slot (18 KB)
+constexpr int kBgKU = 2;                        // (column, row-quad) units per consumer thread
+constexpr int kBgCols = kBgCons * kBgKU / 4;    // window columns (both sides together) per pass: 192
+constexpr int kBgMaxRows = 512;
+
+__global__ void __launch_bounds__(kBgThreads, 1) inst_costvol_bwd_gather_kernel(VolParams p)
+{
+    extern __shared__ __align__(16) float ring[];         // kBgStages slots; reused as gU[ph][c][col] by the y pass
+    __shared__ float4 geo[kSepMaxD];                       // lx1, bin_w(left), rx1, bin_w(right) per slice
+    __shared__ float2 ginv[kSepMaxD];                      // 2 / bin_w per side
+    __shared__ AxisSample ytab[32];
+    __shared__ short2 yrange[kBgMaxRows];                  // first / last y sample touching each row of the window
+    __shared__ __align__(8) uint64_t full_bar[kBgStages], empty_bar[kBgStages];
+    __shared__ int s_win[4], s_rows[2];
+
+    const int n = blockIdx.y, c0 = blockIdx.x * kBgCC;
+    if (p.valid && !p.valid[n]) return;
+    const int C = p.C, D = p.D, W = p.W, H = p.H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *lb = p.left + (size_t)n * 5, *rb = p.right + (size_t)n * 5;
+    const int b = min(max((int)lb[0], 0), p.B - 1);
+    const float fb = p.fb[b];
+    if (tid == 0) { s_win[0] = W; s_win[1] = -1; s_win[2] = W; s_win[3] = -1; }
+    if (tid < kBgStages) { mbar_init(&full_bar[tid], kBgProd / 32); mbar_init(&empty_bar[tid], kBgCons / 32); }
+    mbar_fence_init();
+    __syncthreads();
+    for (int d = tid; d < D; d += kBgThreads) {
+        float dbin, lx1, lx2, rx1, rx2, y1, y2;
+        proposal_for(lb, rb, fb, d, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+        const float bl = __fmul_rn(fmaxf(__fsub_rn(lx2, lx1), 1.0f), 0.0625f), br = __fmul_rn(fmaxf(__fsub_rn(rx2, rx1), 1.0f), 0.0625f);
+        geo[d] = make_float4(lx1, bl, rx1, br);
+        ginv[d] = make_float2(2.0f / bl, 2.0f / br);
+        int a0, a1;
+        sep_cells(lx1, bl, 0, 31, W, a0, a1);
+        atomicMin(&s_win[0], a0); atomicMax(&s_win[1], a1);
+        sep_cells(rx1, br, 0, 31, W, a0, a1);
+        atomicMin(&s_win[2], a0); atomicMax(&s_win[3], a1);
+    }
+    if (tid < 32) {
+        float dbin, lx1, lx2, rx1, rx2, y1, y2;
+        proposal_for(lb, rb, fb, 0, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
+        const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
+        ytab[tid] = axis_sample(y1, __fmul_rn(rh, 0.0625f), tid >> 1, tid & 1, H);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int y0 = H, y1 = -1;
+        for (int s = 0; s < 32; ++s)
+            if (ytab[s].lo >= 0) { y0 = min(y0, ytab[s].lo); y1 = max(y1, ytab[s].hi); }
+        s_rows[0] = y0; s_rows[1] = y1;
+    }
+    __syncthreads();
+    const int ymin = s_rows[0], nrows = s_rows[1] - s_rows[0] + 1;
+    const int wl0 = s_win[0], wr0 = s_win[2];
+    const int wL = max(s_win[1] - s_win[0] + 1, 0), wR = max(s_win[3] - s_win[2] + 1, 0);
+    const int T = wL + wR;
+    if (nrows <= 0 || T <= 0) return;                       // no valid sample: zero gradient
+    for (int yy = tid; yy < nrows; yy += kBgThreads) {
+        int s0 = 32, s1 = -1;
+        for (int s = 0; s < 32; ++s)
+            if (ytab[s].lo >= 0 && (ytab[s].lo == ymin + yy || ytab[s].hi == ymin + yy)) { s0 = min(s0, s); s1 = max(s1, s); }
+        yrange[yy] = make_short2((short)s0, (short)s1);
+    }
+    const int npass = (T + kBgCols - 1) / kBgCols;
+    const size_t cs = (size_t)D * 256;
+    float *gfL = p.gfeatL + ((size_t)b * C + c0) * H * W, *gfR = p.gfeatR + ((size_t)b * C + c0) * H * W;
+    int it = 0;                                             // slices streamed so far (ring position), all passes
+
+    for (int pass = 0; pass < npass; ++pass) {
+        if (warp < kBgProd / 32) {
+            // ================= producers: lane = (bin row ph fastest, group of 4 bin columns), 4 channels each =================
+            const int ph = tid & 15, pwq = (tid >> 4) & 3, chalf = tid >> 6;
+            const float *g0 = p.gcost + ((size_t)n * 3 * C + c0 + chalf * 4) * cs + ph * 16 + pwq * 4;
+            const int soff = (ph >> 2) * 36 + (ph & 3) * 8 + chalf * 4 + pwq * 4 * kBgPwF;
+            for (int d = 0; d < D; ++d, ++it) {
+                const int stage = it % kBgStages;
+                float a[4][4], bq[4][4], cq[4][4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float *gp = g0 + (size_t)cc * cs + (size_t)d * 256;
+                    const float4 va = __ldcs(reinterpret_cast<const float4 *>(gp));
+                    const float4 vb = __ldcs(reinterpret_cast<const float4 *>(gp + (size_t)C * cs));
+                    const float4 vc = __ldcs(reinterpret_cast<const float4 *>(gp + (size_t)2 * C * cs));
+                    a[cc][0] = va.x; a[cc][1] = va.y; a[cc][2] = va.z; a[cc][3] = va.w;
+                    bq[cc][0] = vb.x; bq[cc][1] = vb.y; bq[cc][2] = vb.z; bq[cc][3] = vb.w;
+                    cq[cc][0] = vc.x; cq[cc][1] = vc.y; cq[cc][2] = vc.z; cq[cc][3] = vc.w;
+                }
+                mbar_wait(&empty_bar[stage], ((uint32_t)(it / kBgStages) & 1u) ^ 1u);
+                float *st = ring + (size_t)stage * kBgStageF + soff;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *reinterpret_cast<float4 *>(st + j * kBgPwF) =
+                        make_float4(0.25f * (a[0][j] + cq[0][j]), 0.25f * (a[1][j] + cq[1][j]), 0.25f * (a[2][j] + cq[2][j]),
+                                    0.25f * (a[3][j] + cq[3][j]));
+                    *reinterpret_cast<float4 *>(st + kBgSideF + j * kBgPwF) =
+                        make_float4(0.25f * (bq[0][j] - cq[0][j]), 0.25f * (bq[1][j] - cq[1][j]), 0.25f * (bq[2][j] - cq[2][j]),
+                                    0.25f * (bq[3][j] - cq[3][j]));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
+            __syncthreads();                                // (A) consumers done with the ring
+            __syncthreads();                                // (B) gU written
+        } else {
+            // ================= consumers: unit = (window column, 4 bin rows) x 8 channels, sums in registers =================
+            const int ct = tid - kBgProd;
+            float acc[kBgKU][4][8];
+            int ux[kBgKU], uside[kBgKU];
+#pragma unroll
+            for (int k = 0; k < kBgKU; ++k) {
+                const int col = pass * kBgCols + ((ct + k * kBgCons) >> 2);
+                uside[k] = col >= T ? -1 : (col >= wL ? 1 : 0);
+                ux[k] = uside[k] == 1 ? wr0 + col - wL : wl0 + col;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[k][i][c] = 0.f;
+            }
+            const int phq = ct & 3;
+            const float wmax = (float)(W - 1), wlim = (float)W;
+            for (int d = 0; d < D; ++d, ++it) {
+                const int stage = it % kBgStages;
+                const float4 g4 = geo[d];
+                const float2 gi = ginv[d];
+                mbar_wait(&full_bar[stage], (uint32_t)(it / kBgStages) & 1u);
+                const float *slot = ring + (size_t)stage * kBgStageF + phq * 36;
+#pragma unroll
+                for (int k = 0; k < kBgKU; ++k) {
+                    if (uside[k] < 0) continue;
+                    const float start = uside[k] ? g4.z : g4.x, bin = uside[k] ? g4.w : g4.y, inv_h = uside[k] ? gi.y : gi.x;
+                    const float xf = (float)ux[k];
+                    const float r0 = (xf - 1.f - start) * inv_h - 0.5f, r1 = (xf + 1.f - start) * inv_h - 0.5f;
+                    const int jlo = max(0, (int)floorf(fminf(fmaxf(r0, -4.f), 64.f)));
+                    const int jhi = min(31, (int)ceilf(fminf(fmaxf(r1, -4.f), 64.f)));
+                    const float *sb = slot + (uside[k] ? kBgSideF : 0);
+                    for (int pw = jlo >> 1; pw <= (jhi >> 1); ++pw) {
+                        float w = 0.f;
+#pragma unroll
+                        for (int ix = 0; ix < 2; ++ix) {
+                            const float s = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pw, bin)),
+                                                      __fmul_rn(__fmul_rn((float)ix + 0.5f, bin), 0.5f));
+                            const float sc = fminf(fmaxf(s, 0.f), wmax);
+                            const float t = 1.f - fabsf(sc - xf);
+                            if (s >= -1.f && s <= wlim && t > 0.f) w += t;
+                        }
+                        if (!(w > 0.f)) continue;
+                        const float *q = sb + pw * kBgPwF;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 v0 = *reinterpret_cast<const float4 *>(q + i * 8);
+                            const float4 v1 = *reinterpret_cast<const float4 *>(q + i * 8 + 4);
+                            acc[k][i][0] = fmaf(w, v0.x, acc[k][i][0]); acc[k][i][1] = fmaf(w, v0.y, acc[k][i][1]);
+                            acc[k][i][2] = fmaf(w, v0.z, acc[k][i][2]); acc[k][i][3] = fmaf(w, v0.w, acc[k][i][3]);
+                            acc[k][i][4] = fmaf(w, v1.x, acc[k][i][4]); acc[k][i][5] = fmaf(w, v1.y, acc[k][i][5]);
+                            acc[k][i][6] = fmaf(w, v1.z, acc[k][i][6]); acc[k][i][7] = fmaf(w, v1.w, acc[k][i][7]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            }
+            __syncthreads();                                // (A)
+#pragma unroll
+            for (int k = 0; k < kBgKU; ++k) {
+                const int colL = (ct + k * kBgCons) >> 2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ring[((phq * 4 + i) * kBgCC + c) * kBgCols + colL] = acc[k][i][c];
+            }
+            __syncthreads();                                // (B)
+        }
+        // ================= y pass: all threads, lanes along the window columns =================
+        const int ncols = min(kBgCols, T - pass * kBgCols);
+        const int total = kBgCC * nrows * ncols;
+        for (int o = tid; o < total; o += kBgThreads) {
+            const int colL = o % ncols, r = o / ncols, yy = r % nrows, c = r / nrows;
+            const short2 yr = yrange[yy];
+            const int y = ymin + yy;
+            float v = 0.f;
+            for (int s = yr.x; s <= yr.y; ++s) {
+                const AxisSample ys = ytab[s];
+                const float wy = (ys.lo == y ? ys.h : 0.f) + (ys.hi == y ? ys.l : 0.f);
+                v = fmaf(wy, ring[((s >> 1) * kBgCC + c) * kBgCols + colL], v);
+            }
+            if (v != 0.f) {
+                const int col = pass * kBgCols + colL;
+                const bool right = col >= wL;
+                const int x = right ? wr0 + col - wL : wl0 + col;
+                atomicAdd((right ? gfR : gfL) + ((size_t)c * H + y) * W + x, v);
+            }
+        }
+        __syncthreads();                                    // (C) ring free for the next pass
+    }
+}
+
 __global__ void proposal_shift_kernel(const float *__restrict__ left, const float *__restrict__ right,
                                       const float *__restrict__ fb, int N, int B, int D, float x_clamp,
                                       float *__restrict__ pro_left, float *__restrict__ pro_right,
@@ -1121,6 +1338,15 @@ extern "C" int side_inst_costvol_bwd(const float *featL, const float *featR, con
     SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right);
     SIDE_REQUIRE_DEV(fb); SIDE_REQUIRE_DEV(gcost); SIDE_REQUIRE_DEV(gfeatL); SIDE_REQUIRE_DEV(gfeatR);
     const bool gate = flags & SIDE_VOL_GATE;
+    cudaStream_t st0 = (cudaStream_t)stream;
+    // ungated volume on the fused geometry: register-accumulating gather kernel (no atomics in the x pass)
+    if (!gate && !(flags & SIDE_VOL_BWD_SCALAR) && P == 16 && C % kBgCC == 0 && D <= kSepMaxD && H <= kBgMaxRows && N <= 65535) {
+        const size_t smem = sizeof(float) * (size_t)kBgStages * kBgStageF;
+        if ((rc = set_smem_attr((const void *)inst_costvol_bwd_gather_kernel, smem))) return rc;
+        inst_costvol_bwd_gather_kernel<<<dim3((unsigned)(C / kBgCC), (unsigned)N), kBgThreads, smem, st0>>>(p);
+        SIDE_LAUNCH_CHECK("inst_costvol_bwd_gather_kernel");
+        return SIDE_OK;
+    }
     const bool stage = gate && vol_smem_bytes(C, P, true) <= 200 * 1024;
     const size_t smem = vol_smem_bytes(C, P, stage);
     const dim3 grid((unsigned)((long long)N * D));
@@ -1159,4 +1385,42 @@ extern "C" int side_xcross_gate_bwd(const float *cost, const float *gout, float 
                                                                                            nullptr, C, D, P * P);
     SIDE_LAUNCH_CHECK("xcross_gate_kernel<bwd>");
     return SIDE_OK;
+}
+
+// ---- backward with workspace: the gated volume's backward as  recompute raw volume (separable forward) -> gate backward
+//      in place -> separable gather backward; without the gate it is the gather kernel alone ----
+extern "C" size_t side_inst_costvol_bwd_fast_ws_bytes(int B, int C, int H, int W, int N, int D, int flags)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0 || D <= 0 || !(flags & SIDE_VOL_GATE)) return 0;
+    const size_t fwd = (side_inst_costvol_fast_ws_bytes(B, C, H, W, N, D) + 255) / 256 * 256;
+    return fwd + sizeof(float) * ((size_t)N * 3 * C * D * 256 + (size_t)N * D);
+}
+
+extern "C" int side_inst_costvol_bwd_fast(const float *featL, const float *featR, const float *left, const float *right,
+                                          const float *fb, const uint8_t *valid, const float *gcost, float *gfeatL,
+                                          float *gfeatR, int N, int B, int C, int H, int W, int D, int P, float x_clamp,
+                                          int flags, void *ws, size_t ws_bytes, void *stream)
+{
+    const bool fast_ok = P == 16 && C % kBgCC == 0 && C % kSepCC == 0 && D <= kSepMaxD && H <= kBgMaxRows && N <= 65535 && N > 0 &&
+                         !(flags & SIDE_VOL_BWD_SCALAR);
+    if (!(flags & SIDE_VOL_GATE) || !fast_ok)
+        return side_inst_costvol_bwd(featL, featR, left, right, fb, valid, gcost, gfeatL, gfeatR, N, B, C, H, W, D, P, x_clamp,
+                                     flags, stream);
+    const size_t need = side_inst_costvol_bwd_fast_ws_bytes(B, C, H, W, N, D, flags);
+    if (ws == nullptr || ws_bytes < need || !is_device_ptr(ws)) {
+        set_error("side_inst_costvol_bwd_fast: needs side_inst_costvol_bwd_fast_ws_bytes(...) = %zu bytes of device workspace", need);
+        return SIDE_ERR_WORKSPACE;
+    }
+    SIDE_REQUIRE_DEV(gcost);
+    const size_t fwd = (side_inst_costvol_fast_ws_bytes(B, C, H, W, N, D) + 255) / 256 * 256;
+    float *raw = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws) + fwd);
+    float *dbin = raw + (size_t)N * 3 * C * D * 256;
+    int rc = side_inst_costvol_fwd(featL, featR, left, right, fb, valid, raw, dbin, nullptr, N, B, C, H, W, D, P, x_clamp,
+                                   SIDE_VOL_SEPARABLE, ws, fwd, stream);
+    if (rc) return rc;
+    // gradient w.r.t. the raw volume, in place over the recomputed volume (each element is read before it is overwritten)
+    xcross_gate_kernel<true><<<(unsigned)((long long)N * D), 256, 0, (cudaStream_t)stream>>>(raw, gcost, raw, nullptr, C, D, 256);
+    SIDE_LAUNCH_CHECK("xcross_gate_kernel<bwd>");
+    return side_inst_costvol_bwd(featL, featR, left, right, fb, valid, raw, gfeatL, gfeatR, N, B, C, H, W, D, P, x_clamp,
+                                 flags & ~SIDE_VOL_GATE, stream);
 }

@@ -210,6 +210,9 @@ def proposal_shift(left, right, fb, D, x_clamp):
 USE_NHWC_GATHER = True   # False selects the NCHW gather kernel (same results, slower; kept for odd shapes / tests)
 
 
+VOL_BWD_FLAGS = 0   # tests / benchmarks: _lib.VOL_BWD_SCALAR forces the scalar-atomic backward kernel
+
+
 class _InstCostVol(torch.autograd.Function):
     @staticmethod
     def forward(ctx, featL, featR, left, right, fb, valid, D, P, x_clamp, gate, fma=False, separable=False):
@@ -251,9 +254,13 @@ class _InstCostVol(torch.autograd.Function):
         gcost = _chk(gcost, "grad_cost")
         gL = torch.zeros_like(featL)
         gR = torch.zeros_like(featR)
-        _lib.check(lib.side_inst_costvol_bwd(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
-                                             fb.data_ptr(), _p(valid), gcost.data_ptr(), gL.data_ptr(), gR.data_ptr(),
-                                             N, B, C, H, W, D, P, x_clamp, flags, _stream()), "side_inst_costvol_bwd")
+        flags |= VOL_BWD_FLAGS
+        nws = lib.side_inst_costvol_bwd_fast_ws_bytes(B, C, H, W, N, D, flags) if P == 16 and C % 8 == 0 else 0
+        ws = torch.empty((nws,), device=featL.device, dtype=torch.uint8) if nws else None
+        _lib.check(lib.side_inst_costvol_bwd_fast(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(),
+                                                  fb.data_ptr(), _p(valid), gcost.data_ptr(), gL.data_ptr(), gR.data_ptr(),
+                                                  N, B, C, H, W, D, P, x_clamp, flags, _p(ws), nws, _stream()),
+                   "side_inst_costvol_bwd_fast")
         return gL, gR, None, None, None, None, None, None, None, None, None, None
 
 

@@ -243,3 +243,74 @@ def test_separable_path_valid_mask_and_absurd_boxes(lib):
     assert rel_err(c[valid == 1], gref[valid == 1]) < 1e-4
     raw, _, xc = ops.inst_costvol_ungated(*args, valid=dev(valid))
     assert np.all(raw.cpu().numpy()[valid == 0] == 0) and np.all(xc.cpu().numpy()[valid == 0] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# separable gather backward (inst_costvol_bwd_gather_kernel): P == 16, C % 8 == 0
+# ------------------------------------------------------------------------------------------------
+def _grads(ops, args, gc, gate, valid=None):
+    tg = [a.clone().requires_grad_(True) for a in args[:2]]
+    cost, _ = ops.inst_costvol(tg[0], tg[1], *args[2:], gate=gate, valid=valid)
+    return torch.autograd.grad(cost, tg, gc)
+
+
+@pytest.mark.parametrize("gate", [False, True])
+@pytest.mark.parametrize("cfg", [(2, 8, 14, 44, 5, 5), (1, 16, 24, 80, 6, 48), (1, 8, 96, 320, 7, 16)])
+def test_gather_backward_vs_scalar_kernel_and_port(lib, cfg, gate):
+    """The register-accumulating gather backward against the scalar-atomic kernel (itself checked against autograd of
+    the reference-style RoIAlign loop), on boxes at both borders, a sub-pixel box, a box wider than one 192-column
+    pass, an invalid RoI -- and directly against the CPU autograd of the port for the small case."""
+    from side_b200 import _lib, ops
+    B, C, H, W, N, D = cfg
+    rng = np.random.default_rng(C + D + W)
+    fL, fR, left, right, fb = _random_case(rng, B, C, H, W, N)
+    if W == 320:
+        left[:4, 1:] = [[300., 5., 318., 40.], [2., 10., 30., 20.], [100.2, 50.1, 100.6, 50.4], [40., 3., 290., 90.]]
+        right[:4, 1:] = [[290., 5., 309., 41.], [-6., 10., 22., 20.], [97.2, 50.1, 97.7, 50.4], [20., 3., 270., 90.]]
+    valid = np.ones(N, np.uint8)
+    valid[N - 1] = 0
+    args = (dev(fL), dev(fR), dev(left), dev(right), dev(fb), D, 16, W - 1.0)
+    gc = torch.from_numpy(rng.standard_normal((N, 3 * C, D, 16, 16)).astype(np.float32)).cuda()
+    g = _grads(ops, args, gc, gate, dev(valid))
+    ops.VOL_BWD_FLAGS = _lib.VOL_BWD_SCALAR
+    try:
+        gs = _grads(ops, args, gc, gate, dev(valid))
+    finally:
+        ops.VOL_BWD_FLAGS = 0
+    for mine, r, n in zip(g, gs, ("gfeatL", "gfeatR")):
+        assert rel_err(mine.cpu().numpy(), r.cpu().numpy()) < 1e-4, (n, cfg, gate)
+    if W == 44:
+        tl = [torch.from_numpy(a).requires_grad_(True) for a in (fL, fR)]
+        keep = valid.astype(bool)
+        cref, _ = tp.inst_costvol(tl[0], tl[1], torch.from_numpy(left[keep]), torch.from_numpy(right[keep]), torch.from_numpy(fb),
+                                  D, 16, W - 1.0, gate=gate)
+        gref = torch.autograd.grad(cref, tl, gc.cpu()[torch.from_numpy(keep)])
+        for mine, r, n in zip(g, gref, ("gfeatL", "gfeatR")):
+            assert rel_err(mine.cpu().numpy(), r.numpy()) < 1e-4, ("port", n, gate)
+
+
+def test_gather_backward_config2_linearity(lib):
+    """config #2 size (64 RoIs x 48 candidates x 64 channels): <g, J v> == <J^T g, v> -- the backward is the exact
+    adjoint of the (linear, ungated) forward -- and the scalar kernel agrees."""
+    from side_b200 import _lib, ops
+    from side_b200.utils.synthetic import make_boxes
+    torch.manual_seed(1)
+    fL, fR = torch.randn(1, 64, 96, 320, device="cuda"), torch.randn(1, 64, 96, 320, device="cuda")
+    left, right, _ = make_boxes(1, 64, seed=0)
+    fb = torch.tensor([384.38], device="cuda")
+    args = (fL, fR, left.cuda(), right.cuda(), fb, 48, 16, 319.0)
+    cost, _ = ops.inst_costvol(*args)
+    gc = torch.randn_like(cost)
+    lhs = (cost.double() * gc.double()).sum().item()
+    scale = (cost.double().norm() * gc.double().norm()).item()
+    del cost
+    g = _grads(ops, args, gc, False)
+    rhs = ((g[0].double() * fL.double()).sum() + (g[1].double() * fR.double()).sum()).item()
+    assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
+    ops.VOL_BWD_FLAGS = _lib.VOL_BWD_SCALAR
+    try:
+        gs = _grads(ops, args, gc, False)
+    finally:
+        ops.VOL_BWD_FLAGS = 0
+    for a, b2 in zip(g, gs):
+        assert rel_err(a.cpu().numpy(), b2.cpu().numpy()) < 1e-4
