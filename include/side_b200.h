@@ -49,6 +49,8 @@ enum {
     SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel) */
     SIDE_DCN_PREC_TF32     = 2 << 4, /* tcgen05 kind::tf32 single pass (~1e-3 rel, opt-in) */
     SIDE_DCN_PREC_MASK     = 3 << 4,
+    SIDE_DCN_BWD_SIMT_GEMM = 1 << 9, /* side_dcn_bwd: keep the column GEMM of the channels-last path on the fp32 SIMT kernel
+                                        (default: tcgen05 3xTF32 when Cout % 32 == 0 and the pixel count tiles by 128) */
     SIDE_DCN_BWD_SCALAR    = 1 << 8  /* side_dcn_bwd: force the scalar-atomic kernel that keeps the reference's thread mapping
                                         (one thread per (pixel, tap), serial over channels); default is the channels-last
                                         path with 16-byte vector reductions whenever dg == 1, Cin % 64 == 0, P % 4 == 0 */

@@ -65,6 +65,7 @@ DCN_PREC_FP32 = 0 << 4
 DCN_PREC_3XTF32 = 1 << 4
 DCN_PREC_TF32 = 2 << 4
 DCN_BWD_SCALAR = 1 << 8
+DCN_BWD_SIMT_GEMM = 1 << 9
 VOL_GATE = 1 << 0
 VOL_FMA = 1 << 1
 VOL_SEPARABLE = 1 << 2

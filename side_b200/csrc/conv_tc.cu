@@ -44,6 +44,7 @@ struct ConvTcParams {
     int relu;
     int N, ncb, nkb, ntiles;          // N = output channels of ONE n-tile (<= 128); ntiles = m-tiles * n_ntiles
     int Ntot, n_ntiles;               // all output channels, number of n-tiles (Ntot = n_ntiles * N)
+    long long ldy;                    // row stride of the outputs in floats (Ntot unless a column block of a wider matrix is written)
     int D, H, W;                      // spatial extent of one sample
     int bw, bh, bd;                   // TMA box extent along w, h, d; bd*bh*bw == 128
     int wt, ht;                       // boxes per row (W / bw) and per column (H / bh)
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             conv_tile_origin(p, mt, n, d0, h0, w0);
             const int ww = m % p.bw, r1 = m / p.bw, hh = r1 % p.bh, dd = r1 / p.bh;
             const size_t vox = (((size_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
-            const size_t row = vox * p.Ntot + (size_t)nt * N;            // float offset of this row's first channel
+            const size_t row = vox * (size_t)p.ldy + (size_t)nt * N;     // float offset of this row's first channel
             const int cbase = nt * N;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
             for (int c = 0; c < ((p.dbg & 8) ? 0 : N); c += 16) {
@@ -491,7 +492,7 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
-    p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N;
+    p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N; p.ldy = Cout;
     p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
     const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
@@ -513,6 +514,45 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
     SIDE_LAUNCH_CHECK("conv_tc_kernel");
     return SIDE_OK;
 }
+
+// Plain GEMM on the same kernel (1x1x1 "convolution" over rows/128 x 128 "voxels"): y[r][n] = sum_k x[r][k] w[n][k] for a
+// block of Ncols columns of a matrix with row stride ldy.  x is pre-split (hi, lo), wp holds Ncols/Nt swizzled n-tiles
+// ([n-tile][k-block][hi|lo][Nt x 32]).  Used by the DCN backward (dcn_bwd_cl.cu).
+namespace side {
+int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, float *y, long long ldy, long long rows, int K,
+                      int Ncols, int Nt, cudaStream_t st)
+{
+    SIDE_REQUIRE(rows > 0 && rows % kCvBM == 0 && rows / kCvBM < (1ll << 31) && K > 0 && K % 32 == 0,
+                 "conv_tc_rows_gemm: rows %% 128 == 0 and K %% 32 == 0 required");
+    SIDE_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 128 && Ncols % Nt == 0 && Ncols <= kCvMaxCout, "conv_tc_rows_gemm: bad column tiling");
+    int rc;
+    const int Hr = (int)(rows / kCvBM);
+    CUtensorMap tm_hi, tm_lo;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, 1, 1, Hr, kCvBM, K, 1, 1, kCvBM))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, 1, 1, Hr, kCvBM, K, 1, 1, kCvBM))) return rc;
+    ConvTcParams p;
+    p.wp = wp; p.y = y; p.y_hi = nullptr; p.y_lo = nullptr; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr;
+    p.relu = 0; p.N = Nt; p.Ntot = Ncols; p.n_ntiles = Ncols / Nt; p.ldy = ldy;
+    p.ncb = K / 32; p.nkb = p.ncb;
+    SIDE_REQUIRE((long long)Hr * p.n_ntiles < (1ll << 31), "conv_tc_rows_gemm: too many tiles");
+    p.ntiles = Hr * p.n_ntiles;
+    p.D = 1; p.H = Hr; p.W = kCvBM; p.bw = kCvBM; p.bh = 1; p.bd = 1; p.wt = 1; p.ht = Hr;
+    p.kd = 1; p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1;
+    const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
+    p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
+    p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
+    if (g_sm_count == 0) {
+        int dev = 0;
+        SIDE_CUDA(cudaGetDevice(&dev));
+        SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    conv_tc_kernel<<<(unsigned)std::min(p.ntiles, g_sm_count), kCvThreads, smem, st>>>(tm_hi, tm_lo, p);
+    SIDE_LAUNCH_CHECK("conv_tc_kernel");
+    return SIDE_OK;
+}
+}  // namespace side
 
 /* test / benchmark hook (bit mask).  0 = default.  1: the voxel-major kernel reuses one halo box for the three vertical taps
  * (measured: no gain there -- that kernel is bound by the ~115-cycle floor of each tcgen05.mma, not by operand delivery);

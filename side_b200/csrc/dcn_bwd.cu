@@ -187,7 +187,8 @@ extern "C" size_t side_dcn_bwd_ws_bytes(int B, int Cin, int H, int W, int Cout, 
     // preferred: columns for the whole batch (same-size output assumed as an upper bound for stride>=1), plus the
     // channels-last staging of the fast path: permuted weights and their gradient, input and grad_input copies
     const size_t cols = (size_t)B * Cin * kh * kw * (size_t)H * W;
-    const size_t fixed = 2 * (size_t)std::max(Cout, 0) * Cin * kh * kw + 2 * (size_t)B * Cin * H * W;
+    const size_t fixed = 4 * (size_t)std::max(Cout, 0) * Cin * kh * kw + 2 * (size_t)B * Cin * H * W +
+                         2 * (size_t)B * std::max(Cout, 0) * H * W;   // incl. the tensor-core GEMM operands
     return sizeof(float) * (cols + fixed);
 }
 

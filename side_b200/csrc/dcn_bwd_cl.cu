@@ -8,7 +8,9 @@
 // 96x320 layer of two images.
 //
 // Here the column buffer is PIXEL-major, gcol[b*P + p][tap*Cin + c], and the input / its gradient are channels-last:
-//   1. Wp[o][tap*Cin + c] = w[o][c][tap]; gcol = gy^T Wp      (tiled fp32 SGEMM, 64x128x16 tiles)
+//   1. gcol = gy^T Wp with Wp[o][tap*Cin + c] = w[o][c][tap]: the tcgen05 3xTF32 kernel of conv_tc.cu run as a plain GEMM
+//      (gy re-laid channels-last and split hi/lo, weights permuted + swizzled by one small kernel) when Cout % 32 == 0 and
+//      B*P % 128 == 0, else a tiled fp32 SGEMM (64x128x16 tiles)
 //   2. scatter kernel: a warp owns 32 pixels x one tap at a time; the sampling geometry of the 32 items goes through a
 //      per-warp shared table, then the lanes of the warp spread over CHANNEL QUADS of one (Cin >= 128) or two (Cin == 64)
 //      items: every corner read is one 16-byte load, the column is rewritten in place with the forward value, and
@@ -20,6 +22,7 @@
 // Accumulation order is not deterministic -- as in the reference (DCNv2/README.md:47-62).
 #include <algorithm>
 #include "dcn_common.cuh"
+#include "tc_common.cuh"
 
 namespace side {
 
@@ -132,6 +135,29 @@ __global__ void __launch_bounds__(256) dcn_weight_perm_kernel(const float *__res
     if (TO_PERM) dst[i] = __ldg(src + j);
     else dst[j] = __ldg(src + i);
 }
+
+// Weights of the column GEMM for conv_tc_rows_gemm: n = tap*Cin + c (output column), k = o; n-tiles of Nt columns, each
+// [k-block][hi|lo][Nt x 32] in the 128-byte-swizzled shared-memory image (see dcn_tc_weight_prep_kernel).
+__global__ void __launch_bounds__(256) dcn_bwd_wprep_tc_kernel(const float *__restrict__ w, float *__restrict__ wp, int Cout,
+                                                              int Cin, int KK, int Nt)
+{
+    const long long total = (long long)Cout * Cin * KK;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over (n, k), k fastest
+    if (i >= total) return;
+    const int k = (int)(i % Cout);
+    const int n = (int)(i / Cout);
+    const int tap = n / Cin, c = n - tap * Cin;
+    const float v = __ldg(w + ((size_t)k * Cin + c) * KK + tap);
+    const int nt = n / Nt, nl = n - nt * Nt, kb = k >> 5, kk = k & 31;
+    const size_t tile = (size_t)nt * 2 * Nt * Cout + (size_t)kb * 2 * Nt * 32;
+    const uint32_t off = (sw128(nl, kk >> 2) >> 2) + (kk & 3);
+    const float hi = tf32_hi(v);
+    wp[tile + off] = hi;
+    wp[tile + (size_t)Nt * 32 + off] = v - hi;
+}
+
+int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, float *y, long long ldy, long long rows, int K,
+                      int Ncols, int Nt, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // scatter kernel
@@ -306,6 +332,11 @@ size_t dcn_bwd_cl_fixed_floats(const DcnShape &s)
 {
     return 2 * (size_t)s.Cout * s.Cin * s.KK + 2 * (size_t)s.B * s.H * s.W * s.Cin;
 }
+// extra floats of the tensor-core column GEMM: swizzled hi/lo weights + channels-last hi/lo copy of gy
+size_t dcn_bwd_cl_tc_floats(const DcnShape &s)
+{
+    return 2 * (size_t)s.Cout * s.Cin * s.KK + 2 * (size_t)s.B * s.P * s.Cout;
+}
 
 int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const float *mask, const float *w, const float *gy,
                    float *gx, float *goffset, float *gmask, float *gw, float *gbias, float *ws, size_t ws_floats,
@@ -316,14 +347,34 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
     float *Wp = ws, *gWp = Wp + wsz, *x_cl = gWp + wsz, *gx_cl = x_cl + xsz, *gcol = gx_cl + xsz;
     const size_t fixed = 2 * wsz + 2 * xsz;
     SIDE_REQUIRE(ws_floats >= fixed + per_sample, "side_dcn_bwd: workspace too small for the channels-last path");
-    const int chunk = (int)std::min<size_t>((size_t)B, (ws_floats - fixed) / per_sample);
     int rc;
+    // tensor-core column GEMM when the shapes tile and the workspace has room for its operands next to >= 1 sample of columns
+    const size_t tcf = dcn_bwd_cl_tc_floats(s);
+    const bool use_tc = !(s.flags & SIDE_DCN_BWD_SIMT_GEMM) && Cout % 32 == 0 && Cin % 16 == 0 && ws_floats >= fixed + tcf + per_sample;
+    float *wtc = gcol, *gy_hi = wtc + 2 * wsz, *gy_lo = gy_hi + (size_t)B * P * Cout;
+    size_t avail = ws_floats - fixed;
+    if (use_tc) { gcol = gy_lo + (size_t)B * P * Cout; avail -= tcf; }
+    int chunk = (int)std::min<size_t>((size_t)B, avail / per_sample);
+    if (use_tc && ((size_t)chunk * P) % 128 != 0) {
+        // chunks must cover whole 128-row tiles: shrink to the largest chunk that does, or give up the tensor-core GEMM
+        while (chunk > 1 && (((size_t)chunk * P) % 128 != 0 || B % chunk != 0)) --chunk;
+    }
+    const bool tc = use_tc && ((size_t)chunk * P) % 128 == 0 && B % chunk == 0;
+    if (use_tc && !tc) { gcol = wtc; avail = ws_floats - fixed; chunk = (int)std::min<size_t>((size_t)B, avail / per_sample); }
+    const int Nt = Cin >= 128 ? 128 : Cin;
+    if (tc) {
+        dcn_bwd_wprep_tc_kernel<<<ceil_div((long long)wsz, 256), 256, 0, st>>>(w, wtc, Cout, Cin, KK, Nt);
+        SIDE_LAUNCH_CHECK("dcn_bwd_wprep_tc_kernel");
+        if ((rc = side_ncdhw_to_cl_split(gy, nullptr, nullptr, gy_hi, gy_lo, B, Cout, P, 1, st))) return rc;
+    }
     if ((rc = launch_nchw_to_nhwc(x, x_cl, B, Cin, s.H * s.W, st))) return rc;
     if (gx) SIDE_CUDA(cudaMemsetAsync(gx_cl, 0, sizeof(float) * xsz, st));
     if (gw) SIDE_CUDA(cudaMemsetAsync(gWp, 0, sizeof(float) * wsz, st));
-    dcn_weight_perm_kernel<true><<<ceil_div((long long)wsz, 256), 256, 0, st>>>(w, Wp, Cout, Cin, KK);
-    SIDE_LAUNCH_CHECK("dcn_weight_perm_kernel");
 
+    if (!tc) {
+        dcn_weight_perm_kernel<true><<<ceil_div((long long)wsz, 256), 256, 0, st>>>(w, Wp, Cout, Cin, KK);
+        SIDE_LAUNCH_CHECK("dcn_weight_perm_kernel");
+    }
     DcnBwdClArgs a{};
     a.x_cl = x_cl; a.offset = offset; a.mask = mask; a.gcol = gcol; a.gx_cl = gx ? gx_cl : nullptr;
     a.goffset = goffset; a.gmask = gmask; a.s = s;
@@ -333,7 +384,14 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
         a.b0 = b0; a.nb = nb;
         const float *gyb = gy + (size_t)b0 * Cout * P;
         // 1. gcol[bl][p][k'] = sum_o gy[b][o][p] Wp[o][k']
-        {
+        if (tc) {
+            for (int col0 = 0; col0 < Kp; col0 += 1536) {
+                const int ncols = std::min(1536, Kp - col0);
+                if ((rc = conv_tc_rows_gemm(gy_hi + (size_t)b0 * P * Cout, gy_lo + (size_t)b0 * P * Cout, wtc + (size_t)col0 * 2 * Cout,
+                                            gcol + col0, Kp, (long long)nb * P, Cout, ncols, Nt, st)))
+                    return rc;
+            }
+        } else {
             dim3 grid(ceil_div(Kp, kSgN), ceil_div(P, kSgM), nb);
             sgemm_tile_kernel<true, false><<<grid, 256, 0, st>>>(gyb, Wp, gcol, P, Kp, Cout, P, Kp, Kp, (long long)Cout * P, 0,
                                                                (long long)P * Kp, 1, Cout);

@@ -103,8 +103,10 @@ def dcn_backward_raw(x, offset_t, mask_t, weight, gy, stride, padding, dilation,
     per_sample = 4 * Cin * kh * kw * P
     want = lib.side_dcn_bwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags)     # whole batch in one pass
     if ws_bytes is None:
-        free, _ = torch.cuda.mem_get_info(x.device)
-        ws_bytes = min(want, max(per_sample, int(free * 0.5)))
+        ws_bytes = want
+        if want > (1 << 30):      # only large requests are checked against the free memory (the query costs a driver call)
+            free, _ = torch.cuda.mem_get_info(x.device)
+            ws_bytes = min(want, max(per_sample, int(free * 0.5)))
     ws = torch.empty((max(int(ws_bytes), per_sample),), device=x.device, dtype=torch.uint8)
     rc = lib.side_dcn_bwd(x.data_ptr(), offset_ptr or offset_t.data_ptr(), mask_ptr or mask_t.data_ptr(),
                           weight.data_ptr(), gy.data_ptr(), gx.data_ptr(), goffset_ptr, gmask_ptr, gw.data_ptr(),

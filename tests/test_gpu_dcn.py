@@ -237,7 +237,8 @@ def test_backward_channels_last_vs_oracle(lib):
     rng = np.random.default_rng(11)
     for (B, Cin, H, W, Cout, k, s, p, d, spread) in [(2, 64, 10, 12, 8, 3, 1, 1, 1, 2.0), (1, 128, 9, 20, 12, 3, 1, 1, 1, 2.0),
                                                       (2, 64, 13, 18, 20, 3, 2, 1, 1, 3.0), (1, 192, 6, 8, 4, 3, 1, 2, 2, 40.0),
-                                                      (3, 64, 4, 4, 64, 1, 1, 0, 1, 1.0)]:
+                                                      (3, 64, 4, 4, 64, 1, 1, 0, 1, 1.0), (1, 64, 8, 16, 32, 3, 1, 1, 1, 2.0),
+                                                      (2, 128, 16, 16, 96, 3, 1, 1, 1, 1.5)]:   # last two: tcgen05 column GEMM
         Ho = (H + 2 * p - (d * (k - 1) + 1)) // s + 1
         Wo = (W + 2 * p - (d * (k - 1) + 1)) // s + 1
         if (Ho * Wo) % 4:

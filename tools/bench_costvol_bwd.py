@@ -12,7 +12,7 @@ def timeit(fn, iters=10):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(3_000_000)
+    torch.cuda._sleep(30_000_000)
     e0.record()
     for _ in range(iters):
         fn()
