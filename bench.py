@@ -453,7 +453,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 5)):      # cuDNN autotuning and the caching allocator settle over the first few steps
+    for _ in range(max(args.warmup, 3)):
         step_resident()
     step_e2e()
     barrier()
