@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(kVolThreads) inst_costvol_bwd_kernel(VolParams
 // a contiguous, computable range), tri(t) = max(0, 1 - |t|) is the bilinear weight and G = (g_L + g_{L-R}, g_R - g_{L-R}).
 // A CTA owns (RoI, 8 channels): 4 producer warps stream the three gradient planes of one slice after another into an
 // 8-deep shared-memory ring (already combined per side, scaled by 1/4 and laid out [pw][ph][c]), 12 consumer warps own
-// (column, 4 bin rows) x 8 channels each with the sums in REGISTERS -- no atomics in the x pass at all.  The y pass runs
+// (column, 8 bin rows) x 8 channels each with the sums in REGISTERS -- no atomics in the x pass at all.  The y pass runs
 // once per CTA from shared memory and issues one atomic per (row, column, channel) of the RoI's window, coalesced along
 // x: about 10 M atomics for config #2 instead of 1.6 G.
 // ------------------------------------------------------------------------------------------------
@@ -917,8 +917,7 @@ constexpr int kBgStages = 8;
 constexpr int kBgPwF = 4 * 36;                  // floats per bin column pw: 4 row-quads x (4 rows x 8 channels + 4 pad)
 constexpr int kBgSideF = 16 * kBgPwF;           // floats per side
 constexpr int kBgStageF = 2 * kBgSideF;         // floats per ring slot (18 KB)
-constexpr int kBgKU = 2;                        // (column, row-quad) units per consumer thread
-constexpr int kBgCols = kBgCons * kBgKU / 4;    // window columns (both sides together) per pass: 192
+constexpr int kBgCols = kBgCons / 2;            // window columns (both sides together) per pass: 192 (a consumer thread owns 8 bin rows of one)
 constexpr int kBgMaxRows = 512;
 
 __global__ void __launch_bounds__(kBgThreads, 1) inst_costvol_bwd_gather_kernel(VolParams p)
@@ -1020,37 +1019,31 @@ __global__ void __launch_bounds__(kBgThreads, 1) inst_costvol_bwd_gather_kernel(
             __syncthreads();                                // (A) consumers done with the ring
             __syncthreads();                                // (B) gU written
         } else {
-            // ================= consumers: unit = (window column, 4 bin rows) x 8 channels, sums in registers =================
+            // ================= consumers: unit = (window column, 8 bin rows) x 8 channels, sums in registers =================
             const int ct = tid - kBgProd;
-            float acc[kBgKU][4][8];
-            int ux[kBgKU], uside[kBgKU];
+            const int phh = ct & 1;
+            const int col = pass * kBgCols + (ct >> 1);
+            const int uside = col >= T ? -1 : (col >= wL ? 1 : 0);
+            const int ux = uside == 1 ? wr0 + col - wL : wl0 + col;
+            float acc[8][8];
 #pragma unroll
-            for (int k = 0; k < kBgKU; ++k) {
-                const int col = pass * kBgCols + ((ct + k * kBgCons) >> 2);
-                uside[k] = col >= T ? -1 : (col >= wL ? 1 : 0);
-                ux[k] = uside[k] == 1 ? wr0 + col - wL : wl0 + col;
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[k][i][c] = 0.f;
-            }
-            const int phq = ct & 3;
-            const float wmax = (float)(W - 1), wlim = (float)W;
+                for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+            const float wmax = (float)(W - 1), wlim = (float)W, xf = (float)ux;
             for (int d = 0; d < D; ++d, ++it) {
                 const int stage = it % kBgStages;
                 const float4 g4 = geo[d];
                 const float2 gi = ginv[d];
                 mbar_wait(&full_bar[stage], (uint32_t)(it / kBgStages) & 1u);
-                const float *slot = ring + (size_t)stage * kBgStageF + phq * 36;
-#pragma unroll
-                for (int k = 0; k < kBgKU; ++k) {
-                    if (uside[k] < 0) continue;
-                    const float start = uside[k] ? g4.z : g4.x, bin = uside[k] ? g4.w : g4.y, inv_h = uside[k] ? gi.y : gi.x;
-                    const float xf = (float)ux[k];
+                if (uside >= 0) {
+                    const float start = uside ? g4.z : g4.x, bin = uside ? g4.w : g4.y, inv_h = uside ? gi.y : gi.x;
+                    // samples s_j = start + (j + 0.5) * bin / 2 that can touch column x lie in (x - 1, x + 1): one candidate of
+                    // slack on each side, the weights below decide
                     const float r0 = (xf - 1.f - start) * inv_h - 0.5f, r1 = (xf + 1.f - start) * inv_h - 0.5f;
                     const int jlo = max(0, (int)floorf(fminf(fmaxf(r0, -4.f), 64.f)));
                     const int jhi = min(31, (int)ceilf(fminf(fmaxf(r1, -4.f), 64.f)));
-                    const float *sb = slot + (uside[k] ? kBgSideF : 0);
+                    const float *sb = ring + (size_t)stage * kBgStageF + (uside ? kBgSideF : 0) + phh * 72;
                     for (int pw = jlo >> 1; pw <= (jhi >> 1); ++pw) {
                         float w = 0.f;
 #pragma unroll
@@ -1064,13 +1057,13 @@ __global__ void __launch_bounds__(kBgThreads, 1) inst_costvol_bwd_gather_kernel(
                         if (!(w > 0.f)) continue;
                         const float *q = sb + pw * kBgPwF;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 v0 = *reinterpret_cast<const float4 *>(q + i * 8);
-                            const float4 v1 = *reinterpret_cast<const float4 *>(q + i * 8 + 4);
-                            acc[k][i][0] = fmaf(w, v0.x, acc[k][i][0]); acc[k][i][1] = fmaf(w, v0.y, acc[k][i][1]);
-                            acc[k][i][2] = fmaf(w, v0.z, acc[k][i][2]); acc[k][i][3] = fmaf(w, v0.w, acc[k][i][3]);
-                            acc[k][i][4] = fmaf(w, v1.x, acc[k][i][4]); acc[k][i][5] = fmaf(w, v1.y, acc[k][i][5]);
-                            acc[k][i][6] = fmaf(w, v1.z, acc[k][i][6]); acc[k][i][7] = fmaf(w, v1.w, acc[k][i][7]);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 v0 = *reinterpret_cast<const float4 *>(q + (i >> 2) * 36 + (i & 3) * 8);
+                            const float4 v1 = *reinterpret_cast<const float4 *>(q + (i >> 2) * 36 + (i & 3) * 8 + 4);
+                            acc[i][0] = fmaf(w, v0.x, acc[i][0]); acc[i][1] = fmaf(w, v0.y, acc[i][1]);
+                            acc[i][2] = fmaf(w, v0.z, acc[i][2]); acc[i][3] = fmaf(w, v0.w, acc[i][3]);
+                            acc[i][4] = fmaf(w, v1.x, acc[i][4]); acc[i][5] = fmaf(w, v1.y, acc[i][5]);
+                            acc[i][6] = fmaf(w, v1.z, acc[i][6]); acc[i][7] = fmaf(w, v1.w, acc[i][7]);
                         }
                     }
                 }
@@ -1079,33 +1072,29 @@ __global__ void __launch_bounds__(kBgThreads, 1) inst_costvol_bwd_gather_kernel(
             }
             __syncthreads();                                // (A)
 #pragma unroll
-            for (int k = 0; k < kBgKU; ++k) {
-                const int colL = (ct + k * kBgCons) >> 2;
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) ring[((phq * 4 + i) * kBgCC + c) * kBgCols + colL] = acc[k][i][c];
-            }
+                for (int c = 0; c < 8; ++c) ring[((phh * 8 + i) * kBgCC + c) * kBgCols + (ct >> 1)] = acc[i][c];
             __syncthreads();                                // (B)
         }
-        // ================= y pass: all threads, lanes along the window columns =================
+        // ================= y pass: a warp per (channel, row) of the window, lanes along the columns =================
         const int ncols = min(kBgCols, T - pass * kBgCols);
-        const int total = kBgCC * nrows * ncols;
-        for (int o = tid; o < total; o += kBgThreads) {
-            const int colL = o % ncols, r = o / ncols, yy = r % nrows, c = r / nrows;
+        for (int r = warp; r < kBgCC * nrows; r += kBgThreads / 32) {
+            const int c = r / nrows, yy = r - c * nrows, y = ymin + yy;
             const short2 yr = yrange[yy];
-            const int y = ymin + yy;
-            float v = 0.f;
-            for (int s = yr.x; s <= yr.y; ++s) {
-                const AxisSample ys = ytab[s];
-                const float wy = (ys.lo == y ? ys.h : 0.f) + (ys.hi == y ? ys.l : 0.f);
-                v = fmaf(wy, ring[((s >> 1) * kBgCC + c) * kBgCols + colL], v);
-            }
-            if (v != 0.f) {
-                const int col = pass * kBgCols + colL;
-                const bool right = col >= wL;
-                const int x = right ? wr0 + col - wL : wl0 + col;
-                atomicAdd((right ? gfR : gfL) + ((size_t)c * H + y) * W + x, v);
+            float *rowL = gfL + ((size_t)c * H + y) * W, *rowR = gfR + ((size_t)c * H + y) * W;
+            for (int colL = lane; colL < ncols; colL += 32) {
+                float v = 0.f;
+                for (int s = yr.x; s <= yr.y; ++s) {
+                    const AxisSample ys = ytab[s];
+                    const float wy = (ys.lo == y ? ys.h : 0.f) + (ys.hi == y ? ys.l : 0.f);
+                    v = fmaf(wy, ring[((s >> 1) * kBgCC + c) * kBgCols + colL], v);
+                }
+                if (v != 0.f) {
+                    const int col = pass * kBgCols + colL;
+                    if (col >= wL) atomicAdd(rowR + wr0 + col - wL, v);
+                    else atomicAdd(rowL + wl0 + col, v);
+                }
             }
         }
         __syncthreads();                                    // (C) ring free for the next pass
