@@ -276,6 +276,21 @@ int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *str
 int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
                         void *stream);
 int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream);
+
+/* "3xFP16" variants of the five entries above: the operand pairs are fp16 arrays (hi = fp16(x), lo = fp16((x - hi) * 2^11)) and
+ * the MMAs are kind::f16 -- the same 22 significand bits per operand as the tf32 pair, fp32 accumulation, hi*hi in the main
+ * accumulator and the two cross terms in a second one that the epilogue scales by 2^-11; twice the tensor rate of 3xTF32 and
+ * half the operand bytes.  Needs Cin % 64 == 0 and |x| < 65504 (saturating conversions; activations behind a BatchNorm).
+ * Weight tiles take side_conv_tc_weight_bytes(...) / 2 bytes.  y, residual, scale, shift stay fp32. */
+int side_conv_tc_prep_weights_f16(const float *w, void *wp, int Cout, int Cin, int taps, void *stream);
+int side_conv3d_tc_fwd_f16(const void *x_hi, const void *x_lo, const void *wp, const float *scale, const float *shift,
+                           const float *residual, float *y, void *y_hi, void *y_lo, int N, int D, int H, int W, int Cin, int Cout,
+                           int kd, int kh, int kw, int stride_hw, int relu, void *stream);
+int side_ncdhw_to_cl_split_f16(const float *x, const float *scale, float *full, void *hi, void *lo, int N, int C, long long S,
+                               int D, int Cpad /* channels per output voxel >= C, the extra ones zero (k-blocks are 64 wide) */,
+                               void *stream);
+int side_gate_mul_split_f16(const float *y, const float *gate, void *hi, void *lo, int N, int D, int H, int W, int C, void *stream);
+int side_maxpool_hw2_cl_f16(const float *x, float *y, void *hi, void *lo, int N, int D, int H, int W, int C, void *stream);
 int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream);
 /* channels-last [B, HW, C] -> NCHW [B, C, HW]: hands a tensor-core convolution output back to NCHW consumers */
 int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream);

@@ -17,10 +17,31 @@ __device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
     h.w = tf32_hi(v.w); l.w = v.w - h.w;
 }
 
-// in [N, C, S] -> hi, lo [N, S, C]; optional scale[n, p / per_d] (the cosine gate of the slice the voxel belongs to)
-__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ full,
-                                         float *__restrict__ hi, float *__restrict__ lo, int C, long long S, int D, int per_d)
+// store the split of 4 consecutive channels at float4-index i: tf32 pairs (fp32 arrays) or fp16 pairs (half arrays)
+template <bool F16>
+__device__ __forceinline__ void store_split4(float4 *__restrict__ hi, float4 *__restrict__ lo, long long i, const float4 v)
 {
+    if (F16) {
+        uint32_t h0, l0, h1, l1;
+        f16_split2(v.x, v.y, h0, l0);
+        f16_split2(v.z, v.w, h1, l1);
+        reinterpret_cast<uint2 *>(hi)[i] = make_uint2(h0, h1);
+        reinterpret_cast<uint2 *>(lo)[i] = make_uint2(l0, l1);
+    } else {
+        float4 h, l;
+        split4(v, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// in [N, C, S] -> hi, lo [N, S, C]; optional scale[n, p / per_d] (the cosine gate of the slice the voxel belongs to)
+template <bool F16>
+__global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ full,
+                                         float *__restrict__ hi, float *__restrict__ lo, int C, long long S, int D, int per_d,
+                                         int Cpad)
+{
+    // outputs have Cpad >= C channels per voxel, the extra ones zero (fp16 k-blocks are 64 channels wide)
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -35,13 +56,20 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const long long p = p0 + i;
         const int c = c0 + threadIdx.x;
-        if (p < S && c < C) {
-            float v = tile[threadIdx.x][i];
+        if (p < S && c < Cpad) {
+            float v = c < C ? tile[threadIdx.x][i] : 0.f;
             if (scale) v = __fmul_rn(v, __ldg(scale + (size_t)n * D + (int)(p / per_d)));
-            const float h = tf32_hi(v);
-            const size_t o = ((size_t)n * S + p) * C + c;
-            hi[o] = h;
-            lo[o] = v - h;
+            const size_t o = ((size_t)n * S + p) * Cpad + c;
+            if (F16) {
+                __half h, l;
+                f16_split(v, h, l);
+                reinterpret_cast<__half *>(hi)[o] = h;
+                reinterpret_cast<__half *>(lo)[o] = l;
+            } else {
+                const float h = tf32_hi(v);
+                hi[o] = h;
+                lo[o] = v - h;
+            }
             if (full) full[o] = v;
         }
     }
@@ -58,6 +86,7 @@ __global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restri
 }
 
 // y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo
+template <bool F16>
 __global__ void gate_mul_split_kernel(const float4 *__restrict__ y, const float4 *__restrict__ gate, float4 *__restrict__ hi,
                                       float4 *__restrict__ lo, long long n4, int H, int WC4)
 {
@@ -66,14 +95,12 @@ __global__ void gate_mul_split_kernel(const float4 *__restrict__ y, const float4
         const int wc = (int)(i - row * WC4);
         const long long nd = row / H;
         const float4 v = __ldg(y + i), g = __ldg(gate + nd * WC4 + wc);
-        float4 h, l;
-        split4(make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w), h, l);
-        hi[i] = h;
-        lo[i] = l;
+        store_split4<F16>(hi, lo, i, make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w));
     }
 }
 
 // x [ND, H, W, C] -> max over 2x2 (h, w) windows -> [ND, H/2, W/2, C]; y and/or (hi, lo)
+template <bool F16>
 __global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, float4 *__restrict__ hi,
                                       float4 *__restrict__ lo, long long n4out, int H, int W, int C4)
 {
@@ -93,12 +120,7 @@ __global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__re
         m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(cc.z, d.z));
         m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(cc.w, d.w));
         if (y) y[i] = m;
-        if (hi) {
-            float4 h, l;
-            split4(m, h, l);
-            hi[i] = h;
-            lo[i] = l;
-        }
+        if (hi) store_split4<F16>(hi, lo, i, m);
     }
 }
 
@@ -141,18 +163,36 @@ using namespace side;
 
 static inline unsigned ew_grid(long long n, int block) { return (unsigned)std::min<long long>((n + block - 1) / block, 148 * 16); }
 
+static int ncdhw_to_cl_split_impl(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C,
+                                  long long S, int D, void *stream, bool f16, int Cpad);
 extern "C" int side_ncdhw_to_cl_split(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C,
                                       long long S, int D, void *stream)
 {
+    return ncdhw_to_cl_split_impl(x, scale, full, hi, lo, N, C, S, D, stream, false, C);
+}
+/* the _f16 variants write the fp16 operand pairs of side_conv3d_tc_fwd_f16 (hi, lo: half arrays of the same element count) */
+extern "C" int side_ncdhw_to_cl_split_f16(const float *x, const float *scale, float *full, void *hi, void *lo, int N, int C,
+                                          long long S, int D, int Cpad, void *stream)
+{
+    return ncdhw_to_cl_split_impl(x, scale, full, reinterpret_cast<float *>(hi), reinterpret_cast<float *>(lo), N, C, S, D, stream,
+                                  true, Cpad);
+}
+static int ncdhw_to_cl_split_impl(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C,
+                                  long long S, int D, void *stream, bool f16, int Cpad)
+{
+    if (Cpad <= 0) Cpad = C;
+    SIDE_REQUIRE(Cpad >= C, "side_ncdhw_to_cl_split: Cpad < C");
     SIDE_REQUIRE(N >= 0 && C > 0 && S > 0, "side_ncdhw_to_cl_split: bad shape");
     SIDE_REQUIRE(scale == nullptr || (D > 0 && S % D == 0), "side_ncdhw_to_cl_split: scale needs D | S");
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "side_ncdhw_to_cl_split: grid too large");
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
-    dim3 g((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), b(32, 8);
+    dim3 g((unsigned)((S + 31) / 32), (unsigned)((Cpad + 31) / 32), (unsigned)N), b(32, 8);
     if (scale) SIDE_REQUIRE_DEV(scale);
     if (full) SIDE_REQUIRE_DEV(full);
-    ncdhw_to_cl_split_kernel<<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, scale ? (int)(S / D) : 1);
+    const int per_d = scale ? (int)(S / D) : 1;
+    if (f16) ncdhw_to_cl_split_kernel<true><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
+    else ncdhw_to_cl_split_kernel<false><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
     SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
     return SIDE_OK;
 }
@@ -168,22 +208,51 @@ extern "C" int side_tf32_split(const float *x, float *hi, float *lo, long long n
     return SIDE_OK;
 }
 
+static int gate_mul_split_impl(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
+                               void *stream, bool f16);
 extern "C" int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
                                    void *stream)
+{
+    return gate_mul_split_impl(y, gate, hi, lo, N, D, H, W, C, stream, false);
+}
+extern "C" int side_gate_mul_split_f16(const float *y, const float *gate, void *hi, void *lo, int N, int D, int H, int W, int C,
+                                       void *stream)
+{
+    return gate_mul_split_impl(y, gate, reinterpret_cast<float *>(hi), reinterpret_cast<float *>(lo), N, D, H, W, C, stream, true);
+}
+static int gate_mul_split_impl(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
+                               void *stream, bool f16)
 {
     SIDE_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "side_gate_mul_split: bad shape (C %% 4 == 0)");
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE_DEV(y); SIDE_REQUIRE_DEV(gate); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
     const long long n4 = (long long)N * D * H * W * C / 4;
-    gate_mul_split_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
-        reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
+    if (f16)
+        gate_mul_split_kernel<true><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
+            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
+    else
+        gate_mul_split_kernel<false><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
+            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
     SIDE_LAUNCH_CHECK("gate_mul_split_kernel");
     return SIDE_OK;
 }
 
+static int maxpool_hw2_cl_impl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream,
+                               bool f16);
 extern "C" int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C,
                                    void *stream)
+{
+    return maxpool_hw2_cl_impl(x, y, hi, lo, N, D, H, W, C, stream, false);
+}
+extern "C" int side_maxpool_hw2_cl_f16(const float *x, float *y, void *hi, void *lo, int N, int D, int H, int W, int C,
+                                       void *stream)
+{
+    return maxpool_hw2_cl_impl(x, y, reinterpret_cast<float *>(hi), reinterpret_cast<float *>(lo), N, D, H, W, C, stream, true);
+}
+static int maxpool_hw2_cl_impl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream,
+                               bool f16)
 {
     SIDE_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0,
                  "side_maxpool_hw2_cl: bad shape (even H, W; C %% 4 == 0)");
@@ -193,9 +262,14 @@ extern "C" int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *l
     if (y) SIDE_REQUIRE_DEV(y);
     if (hi) { SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo); }
     const long long n4 = (long long)N * D * (H / 2) * (W / 2) * C / 4;
-    maxpool_hw2_cl_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
-        reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
+    if (f16)
+        maxpool_hw2_cl_kernel<true><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
+            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
+    else
+        maxpool_hw2_cl_kernel<false><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
+            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
     SIDE_LAUNCH_CHECK("maxpool_hw2_cl_kernel");
     return SIDE_OK;
 }

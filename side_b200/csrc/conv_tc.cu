@@ -81,6 +81,7 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *tm, in
         : "memory");
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                                 const __grid_constant__ CUtensorMap tm_lo, ConvTcParams p)
 {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_scale[kCvMaxCout], s_shift[kCvMaxCout];
 
+    constexpr int kKel = F16 ? 64 : 32;      // channels per 128-byte k-block row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
     const uint32_t b_part = (uint32_t)N * 128u;
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                                 mbar_wait(&emptyA[sa_i], pha ^ 1u);
                                 unsigned char *sa = tiles + (size_t)sa_i * 2 * p.a_part;
                                 mbar_expect_tx(&fullA[sa_i], 2 * p.a_part);
-                                tma_load_5d(sa, &tm_hi, cb * 32, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
-                                tma_load_5d(sa + p.a_part, &tm_lo, cb * 32, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                                tma_load_5d(sa, &tm_hi, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                                tma_load_5d(sa + p.a_part, &tm_lo, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
                                 if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
                                 for (int khi = 0; khi < 3; ++khi) {
                                     const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     mbar_expect_tx(&full_bar[st], ((p.dbg & 4) ? 0u : 2 * kCvATile) + ((p.dbg & 2) ? 0u : 2 * b_part));
                     const int cw = w0 * p.sw + kwi - pw, ch = h0 * p.sh + khi - ph;     // input coordinates of the box origin
                     if (!(p.dbg & 4)) {
-                        tma_load_5d(sa, &tm_hi, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
-                        tma_load_5d(sa + kCvATile, &tm_lo, cb * 32, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                        tma_load_5d(sa, &tm_hi, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                        tma_load_5d(sa + kCvATile, &tm_lo, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
                     }
                     if (!(p.dbg & 2)) bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             // main (columns 0..N) and the first cross term (N..2N) at once; lo*hi then accumulates onto N..2N.  The A tile
             // is fetched from shared memory twice per k-step instead of three times (the kernel is smem-bandwidth bound:
             // tf32 operands are 4 bytes, a 128 x N x 8 MMA reads (128 + N) * 32 bytes in 128 * N / 256 cycles).
-            const uint32_t idesc = tc_idesc_tf32(kCvBM, N), idesc2 = tc_idesc_tf32(kCvBM, 2 * N);
+            const uint32_t idesc = tc_idesc<F16>(kCvBM, N), idesc2 = tc_idesc<F16>(kCvBM, 2 * N);
             int st = 0, acc = 0;
             uint32_t phs = 0, acc_ph = 0;
             if (p.khv) {
@@ -231,8 +233,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t a_hi = tc_smem_desc(av + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                                 const uint64_t a_lo = tc_smem_desc(av + p.a_part + k * 32);
-                                tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (g | khi | k) != 0 ? 1u : 0u);
-                                tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, 1u);
+                                tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (g | khi | k) != 0 ? 1u : 0u);
+                                tc_mma<F16>(tmem_x, a_lo, b_hi, idesc, 1u);
                             }
                             tc_commit(&empty_bar[st]);
                             if (++st == p.b_slots) { st = 0; phs ^= 1u; }
@@ -263,8 +265,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                         const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32);
                         if (p.dbg & 16) continue;
-                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);     // [hi*hi | hi*lo]
-                        tc_mma_tf32(tmem_x, a_lo, b_hi, idesc, 1u);                          // + lo*hi
+                        tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);     // [hi*hi | hi*lo]
+                        tc_mma<F16>(tmem_x, a_lo, b_hi, idesc, 1u);                          // + lo*hi
                     }
                     tc_commit(&empty_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
@@ -297,7 +299,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 tc_ld16(taddr + (uint32_t)(N + c), vx);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float o = fmaf(v[j] + vx[j], s_scale[cbase + c + j], s_shift[cbase + c + j]);
+                    const float sum = F16 ? fmaf(vx[j], kF16LoInv, v[j]) : v[j] + vx[j];
+                    float o = fmaf(sum, s_scale[cbase + c + j], s_shift[cbase + c + j]);
                     if (p.relu == 1) o = fmaxf(o, 0.f);
                     v[j] = o;
                 }
@@ -318,7 +321,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                if (p.y_hi) {
+                if (F16 && p.y_hi) {
+                    uint32_t hh[8], ll[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f16_split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
+                    uint4 *hp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_hi) + row + c);
+                    uint4 *lp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_lo) + row + c);
+                    hp[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); hp[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+                    lp[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); lp[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+                } else if (p.y_hi) {
                     float4 *hp = reinterpret_cast<float4 *>(p.y_hi + row + c);
                     float4 *lp = reinterpret_cast<float4 *>(p.y_lo + row + c);
 #pragma unroll
@@ -367,7 +378,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
 
 // channels-last activation [Nn, D, H, W, C] fp32 -> box {32, bw, bh, bd, 1}, 128-byte swizzle, zero fill out of bounds
 static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw,
-                         int sh = 1, int sw = 1, int halo_h = 0)
+                         int sh = 1, int sw = 1, int halo_h = 0, bool f16 = false)
 {
     PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
     if (!enc) {
@@ -375,12 +386,14 @@ static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int 
         return SIDE_ERR_CUDA;
     }
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Nn};
-    cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+    const cuuint64_t es_b = f16 ? 2 : 4;       // fp16 activations: 64 channels per 128-byte box row instead of 32
+    cuuint64_t strides[4] = {(cuuint64_t)C * es_b, (cuuint64_t)W * C * es_b, (cuuint64_t)H * W * C * es_b,
+                             (cuuint64_t)D * H * W * C * es_b};
     // strided convolution: the box spans bw*sw x bh*sh input pixels, traversed with element strides (sw, sh), i.e. it still
     // delivers bw x bh pixels -- the ones a stride-s convolution reads for bw x bh outputs
-    cuuint32_t box[5] = {32, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh + 2 * halo_h), (cuuint32_t)bd, 1};
+    cuuint32_t box[5] = {f16 ? 64u : 32u, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh + 2 * halo_h), (cuuint32_t)bd, 1};
     cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims, strides, box, es,
+    CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -392,14 +405,35 @@ static int make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int 
 
 // exported to conv_tct.cu
 int conv_make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw, int sh,
-                       int sw, int halo_h)
+                       int sw, int halo_h, bool f16)
 {
-    return make_act_tmap(tm, base, Nn, D, H, W, C, bd, bh, bw, sh, sw, halo_h);
+    return make_act_tmap(tm, base, Nn, D, H, W, C, bd, bh, bw, sh, sw, halo_h, f16);
 }
-bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride);
+bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride, bool f16);
 int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                     const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin, int kd,
-                    int relu, int sm_count, cudaStream_t st);
+                    int relu, int sm_count, cudaStream_t st, bool f16);
+
+// fp16 weight tiles: w [Nt rows of this n-tile][Cin][taps] -> [k-block of 64 channels][hi|lo'][Nt x 64 halves], swizzled
+__global__ void __launch_bounds__(256) conv_tc_weight_prep_f16_kernel(const float *__restrict__ w, __half *__restrict__ wp, int Nt,
+                                                                     int Cin, int taps)
+{
+    const long long total = (long long)taps * Cin * Nt;
+    const int ncb = Cin / 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % 64);
+        const int n = (int)((i / 64) % Nt);
+        const int kb = (int)(i / ((long long)64 * Nt));
+        const int tap = kb / ncb, cb = kb - tap * ncb;
+        const float v = __ldg(w + ((size_t)n * Cin + cb * 64 + kk) * taps + tap);
+        const size_t tile = (size_t)kb * 2 * Nt * 64;
+        const uint32_t off = (sw128(n, kk >> 3) >> 1) + (kk & 7);
+        __half h, l;
+        f16_split(v, h, l);
+        wp[tile + off] = h;
+        wp[tile + (size_t)Nt * 64 + off] = l;
+    }
+}
 
 static int g_sm_count = 0;
 static int g_disable_tct = 0;
@@ -419,8 +453,19 @@ extern "C" size_t side_conv_tc_weight_bytes(int Cin, int Cout, int taps)
     return sizeof(float) * 2 * (size_t)Cin * Cout * taps;
 }
 
+static int conv_tc_prep_weights_impl(const float *w, float *wp, int Cout, int Cin, int taps, void *stream, bool f16);
 extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, int Cin, int taps, void *stream)
 {
+    return conv_tc_prep_weights_impl(w, wp, Cout, Cin, taps, stream, false);
+}
+/* fp16 "3xFP16" tiles (half the bytes of the tf32 ones: side_conv_tc_weight_bytes(...) / 2); needs Cin % 64 == 0 */
+extern "C" int side_conv_tc_prep_weights_f16(const float *w, void *wp, int Cout, int Cin, int taps, void *stream)
+{
+    return conv_tc_prep_weights_impl(w, reinterpret_cast<float *>(wp), Cout, Cin, taps, stream, true);
+}
+static int conv_tc_prep_weights_impl(const float *w, float *wp, int Cout, int Cin, int taps, void *stream, bool f16)
+{
+    SIDE_REQUIRE(!f16 || Cin % 64 == 0, "side_conv_tc_prep_weights_f16: needs Cin %% 64 == 0");
     SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && taps > 0 &&
                      (Cout <= 128 || Cout % 128 == 0),
                  "side_conv_tc_prep_weights: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (<= %d)",
@@ -428,6 +473,16 @@ extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, in
     SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(wp);
     // one swizzled tile set per n-tile: [n_tile][k-block][hi|lo][Nt x 32]
     const int Nt = conv_ntile(Cout);
+    if (f16) {
+        __half *wh = reinterpret_cast<__half *>(wp);
+        for (int nt = 0; nt < Cout / Nt; ++nt) {
+            const long long total = (long long)Nt * Cin * taps;
+            conv_tc_weight_prep_f16_kernel<<<(unsigned)std::min<long long>(1184, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                w + (size_t)nt * Nt * Cin * taps, wh + (size_t)nt * 2 * Nt * Cin * taps, Nt, Cin, taps);
+            SIDE_LAUNCH_CHECK("conv_tc_weight_prep_f16_kernel");
+        }
+        return SIDE_OK;
+    }
     for (int nt = 0; nt < Cout / Nt; ++nt) {
         int rc = launch_tc_weight_prep(w + (size_t)nt * Nt * Cin * taps, wp + (size_t)nt * 2 * Nt * Cin * taps, Nt, Cin, taps, 1,
                                        (cudaStream_t)stream);
@@ -436,11 +491,33 @@ extern "C" int side_conv_tc_prep_weights(const float *w, float *wp, int Cout, in
     return SIDE_OK;
 }
 
+static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
+                              const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin,
+                              int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream, bool f16);
 extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const float *wp, const float *scale,
                                   const float *shift, const float *residual, float *y, float *y_hi, float *y_lo, int Nn,
                                   int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int relu,
                                   void *stream)
 {
+    return conv3d_tc_fwd_impl(x_hi, x_lo, wp, scale, shift, residual, y, y_hi, y_lo, Nn, D, H, W, Cin, Cout, kd, kh, kw, stride_hw,
+                              relu, stream, false);
+}
+/* Same convolution on kind::f16 MMAs ("3xFP16": x = hi + lo' * 2^-11, fp16 pairs; twice the tensor rate of 3xTF32, half the
+ * operand bytes).  x_hi / x_lo / y_hi / y_lo are fp16 arrays, wp comes from side_conv_tc_prep_weights_f16; y, residual, scale
+ * and shift stay fp32.  Needs Cin % 64 == 0. */
+extern "C" int side_conv3d_tc_fwd_f16(const void *x_hi, const void *x_lo, const void *wp, const float *scale, const float *shift,
+                                      const float *residual, float *y, void *y_hi, void *y_lo, int Nn, int D, int H, int W,
+                                      int Cin, int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream)
+{
+    return conv3d_tc_fwd_impl(reinterpret_cast<const float *>(x_hi), reinterpret_cast<const float *>(x_lo),
+                              reinterpret_cast<const float *>(wp), scale, shift, residual, y, reinterpret_cast<float *>(y_hi),
+                              reinterpret_cast<float *>(y_lo), Nn, D, H, W, Cin, Cout, kd, kh, kw, stride_hw, relu, stream, true);
+}
+static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
+                              const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin,
+                              int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream, bool f16)
+{
+    SIDE_REQUIRE(!f16 || Cin % 64 == 0, "side_conv3d_tc_fwd_f16: needs Cin %% 64 == 0");
     SIDE_REQUIRE(Nn >= 0 && D > 0 && H > 0 && W > 0, "side_conv3d_tc_fwd: bad shape");
     SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && (Cout <= 128 || Cout % 128 == 0),
                  "side_conv3d_tc_fwd: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (got %d -> %d)", Cin, Cout);
@@ -483,17 +560,17 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
         SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     // Cout == 64 on 256-voxel slices: role-swapped kernel (weights on M, 256 voxels on N), see conv_tct.cu
-    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw))
+    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw, f16))
         return conv_tct_launch(x_hi, x_lo, wp, scale, shift, residual, y, y_hi, y_lo, Nn, D, H, W, Cin, kd, relu, g_sm_count,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, f16);
     CUtensorMap tm_hi, tm_lo;
-    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv))) return rc;
-    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv))) return rc;
+    if ((rc = make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv, f16))) return rc;
+    if ((rc = make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, bd, bh, bw, stride_hw, stride_hw, khv, f16))) return rc;
 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
     p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N; p.ldy = Cout;
-    p.ncb = Cin / 32; p.nkb = kd * kh * kw * p.ncb;
+    p.ncb = Cin / (f16 ? 64 : 32); p.nkb = kd * kh * kw * p.ncb;
     const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
     p.ntiles = (int)(mtiles * p.n_ntiles);
@@ -503,14 +580,15 @@ extern "C" int side_conv3d_tc_fwd(const float *x_hi, const float *x_lo, const fl
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
     const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + 1024;
-    if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
+    if ((rc = set_smem_attr(f16 ? (const void *)conv_tc_kernel<true> : (const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {
         int dev = 0;
         SIDE_CUDA(cudaGetDevice(&dev));
         SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const unsigned grid = (unsigned)std::min(p.ntiles, g_sm_count);
-    conv_tc_kernel<<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+    if (f16) conv_tc_kernel<true><<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+    else conv_tc_kernel<false><<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
     SIDE_LAUNCH_CHECK("conv_tc_kernel");
     return SIDE_OK;
 }
@@ -542,13 +620,13 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-    if ((rc = set_smem_attr((const void *)conv_tc_kernel, smem))) return rc;
+    if ((rc = set_smem_attr((const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {
         int dev = 0;
         SIDE_CUDA(cudaGetDevice(&dev));
         SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    conv_tc_kernel<<<(unsigned)std::min(p.ntiles, g_sm_count), kCvThreads, smem, st>>>(tm_hi, tm_lo, p);
+    conv_tc_kernel<false><<<(unsigned)std::min(p.ntiles, g_sm_count), kCvThreads, smem, st>>>(tm_hi, tm_lo, p);
     SIDE_LAUNCH_CHECK("conv_tc_kernel");
     return SIDE_OK;
 }

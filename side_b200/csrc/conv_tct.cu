@@ -68,6 +68,7 @@ __device__ __forceinline__ void tt_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                                  const __grid_constant__ CUtensorMap tm_lo, ConvTtParams p)
 {
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                             mbar_wait(&emptyX[sx], phx ^ 1u);
                             unsigned char *xs = xring + (size_t)sx * 2 * p.x_part;
                             mbar_expect_tx(&fullX[sx], 2 * p.x_part);
-                            tt_tma_load_5d(xs, &tm_hi, cb * 32, kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
-                            tt_tma_load_5d(xs + p.x_part, &tm_lo, cb * 32, kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
+                            tt_tma_load_5d(xs, &tm_hi, cb * (F16 ? 64 : 32), kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
+                            tt_tma_load_5d(xs + p.x_part, &tm_lo, cb * (F16 ? 64 : 32), kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
                             if (++sx == kTtXSlots) { sx = 0; phx ^= 1u; }
                             for (int khi = 0; khi < 3; ++khi) {
                                 const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = tc_idesc_tf32(128, kTtVox);
+            const uint32_t idesc = tc_idesc<F16>(128, kTtVox);
             const uint32_t view = (uint32_t)p.bw * 128u;              // bytes per halo row
             const int ngroups = p.kd * 3 * p.ncb;
             int sx = 0, sw = 0, acc = 0;
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                             const uint64_t a_hl = tc_smem_desc(ws + kTtWPart + k * 32);        // [W_hi ; W_lo]
                             const uint64_t a_zh = tc_smem_desc(ws + k * 32);                   // [0 ; W_hi]
                             const uint64_t b_hi = tc_smem_desc(xv + k * 32), b_lo = tc_smem_desc(xv + p.x_part + k * 32);
-                            tc_mma_tf32(tmem_d, a_hl, b_hi, idesc, (g | khi | k) != 0 ? 1u : 0u);
-                            tc_mma_tf32(tmem_d, a_zh, b_lo, idesc, 1u);
+                            tc_mma<F16>(tmem_d, a_hl, b_hi, idesc, (g | khi | k) != 0 ? 1u : 0u);
+                            tc_mma<F16>(tmem_d, a_zh, b_lo, idesc, 1u);
                         }
                         tc_commit(&emptyW[sw]);
                         if (++sw == kTtWSlots) { sw = 0; phw ^= 1u; }
@@ -200,6 +201,10 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
             for (int c = 0; c < 8; ++c) {
                 float v[32];
                 tt_ld32(taddr + (uint32_t)(c * 32), v);
+                if (F16 && !is_main) {                                // cross terms carry the 2^11 of the scaled lo operands
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= kF16LoInv;
+                }
                 float *eb = ex + (c & 1) * 1024;
                 const bool store_role = is_main == ((c & 1) == 0);    // even chunks: the main warp finishes, odd: the cross warp
                 if (!store_role) {
@@ -217,7 +222,12 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                         if (p.residual) o += __ldg(p.residual + o0 + (size_t)j * kTtCout);
                         if (p.relu == 2) o = fmaxf(o, 0.f);
                         if (p.y) p.y[o0 + (size_t)j * kTtCout] = o;
-                        if (p.y_hi) {
+                        if (F16 && p.y_hi) {
+                            __half h, l;
+                            f16_split(o, h, l);
+                            reinterpret_cast<__half *>(p.y_hi)[o0 + (size_t)j * kTtCout] = h;
+                            reinterpret_cast<__half *>(p.y_lo)[o0 + (size_t)j * kTtCout] = l;
+                        } else if (p.y_hi) {
                             const float h = tf32_hi(o);
                             p.y_hi[o0 + (size_t)j * kTtCout] = h;
                             p.y_lo[o0 + (size_t)j * kTtCout] = o - h;
@@ -241,11 +251,11 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
 
 // shared with conv_tc.cu
 int conv_make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H, int W, int C, int bd, int bh, int bw, int sh,
-                       int sw, int halo_h);
+                       int sw, int halo_h, bool f16);
 
-bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride)
+bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride, bool f16)
 {
-    if (Cout != kTtCout || Cin % 32 || stride != 1 || kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
+    if (Cout != kTtCout || Cin % (f16 ? 64 : 32) || stride != 1 || kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
     if (H * W != kTtVox || (W % 8) || W > 64) return false;          // one tile = one full depth slice
     const size_t smem = (size_t)kTtXSlots * 2 * (size_t)(H + 2) * W * 128 + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
     return smem <= 212 * 1024;
@@ -253,20 +263,21 @@ bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, 
 
 int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const float *scale, const float *shift,
                     const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin, int kd,
-                    int relu, int sm_count, cudaStream_t st)
+                    int relu, int sm_count, cudaStream_t st, bool f16)
 {
     CUtensorMap tm_hi, tm_lo;
     int rc;
-    if ((rc = conv_make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, 1, H, W, 1, 1, 1))) return rc;
-    if ((rc = conv_make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, 1, H, W, 1, 1, 1))) return rc;
+    if ((rc = conv_make_act_tmap(&tm_hi, x_hi, Nn, D, H, W, Cin, 1, H, W, 1, 1, 1, f16))) return rc;
+    if ((rc = conv_make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, 1, H, W, 1, 1, 1, f16))) return rc;
     ConvTtParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual; p.relu = relu;
-    p.ncb = Cin / 32; p.kd = kd; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
+    p.ncb = Cin / (f16 ? 64 : 32); p.kd = kd; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
     p.x_part = (uint32_t)(H + 2) * W * 128u;
     const size_t smem = (size_t)kTtXSlots * 2 * p.x_part + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
-    if ((rc = set_smem_attr((const void *)conv_tct_kernel, smem))) return rc;
+    if ((rc = set_smem_attr(f16 ? (const void *)conv_tct_kernel<true> : (const void *)conv_tct_kernel<false>, smem))) return rc;
     const unsigned grid = (unsigned)std::min(p.ntiles, sm_count);
-    conv_tct_kernel<<<grid, kTtThreads, smem, st>>>(tm_hi, tm_lo, p);
+    if (f16) conv_tct_kernel<true><<<grid, kTtThreads, smem, st>>>(tm_hi, tm_lo, p);
+    else conv_tct_kernel<false><<<grid, kTtThreads, smem, st>>>(tm_hi, tm_lo, p);
     SIDE_LAUNCH_CHECK("conv_tct_kernel");
     return SIDE_OK;
 }

@@ -1,5 +1,7 @@
 // tc_common.cuh -- tcgen05 / TMEM helpers shared by the tensor-core kernels (dcn_fwd_tc.cu, conv_tc.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "dcn_common.cuh"
 
 namespace side {
@@ -30,6 +32,51 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
+}
+
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction = the same 32 bytes per row as kind::tf32's K = 8,
+// so tiles, swizzle and descriptor stepping are identical; it runs at twice the tf32 rate.
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    if (F16) tc_mma_f16(tmem_d, adesc, bdesc, idesc, accum);
+    else tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accum);
+}
+
+// "3xFP16" operand split, the fp16 counterpart of the tf32 hi/lo split: x = hi + lo' * 2^-11 with hi = fp16(x) and
+// lo' = fp16((x - hi) * 2^11) -- 11 + 11 significand bits like two tf32 values; the 2^11 keeps lo' out of the fp16
+// subnormals.  hi*hi goes to the main accumulator, hi*lo' + lo'*hi to the cross accumulator, which the epilogue scales by
+// 2^-11.  Saturating conversions: |x| must stay below 65504 (activations behind a BatchNorm do).
+constexpr float kF16LoScale = 2048.0f, kF16LoInv = 1.0f / 2048.0f;
+__device__ __forceinline__ __half f16_sat(float v)
+{
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_half(r);
+}
+__device__ __forceinline__ void f16_split(float v, __half &h, __half &l)
+{
+    h = f16_sat(v);
+    l = f16_sat((v - __half2float(h)) * kF16LoScale);
+}
+
+// split two values and pack the halves pairwise (little endian: a in the low 16 bits)
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    __half ha, la, hb, lb;
+    f16_split(a, ha, la);
+    f16_split(b, hb, lb);
+    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
@@ -69,6 +116,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
 __host__ __device__ __forceinline__ uint32_t tc_idesc_tf32(int M, int N)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16: A = B = fp16 (format 0), D = fp32
+__host__ __device__ __forceinline__ uint32_t tc_idesc_f16(int M, int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ __forceinline__ uint32_t tc_idesc(int M, int N)
+{
+    return F16 ? tc_idesc_f16(M, N) : tc_idesc_tf32(M, N);
 }
 
 // w [Cout, Cin, KK] -> per-K-block tiles wp[kb][part][Cout x 32] in the swizzled shared-memory image (dcn_fwd_tc.cu)

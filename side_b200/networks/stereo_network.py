@@ -83,21 +83,22 @@ class cost_volume(nn.Module):
 
     # -- tensor-core path (inference): every Conv3d is side_conv3d_tc_fwd, activations stay channels-last ----------
     tensor_core = True     # False keeps the cuDNN convolutions (training always does)
+    tc_format = "tf32"     # "f16": kind::f16 MMAs on fp16 operand pairs (3xFP16, same 22-bit operands, twice the tensor rate)
 
     def _tc_state(self):
         """Swizzled tf32 hi/lo weight tiles and folded eval-mode BatchNorm per conv, rebuilt when a parameter changes."""
         convs = [(self.dres0[0], self.dres0[1]), (self.dres0[3], self.dres0[4]), (self.dres1[0], self.dres1[1]),
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
-        key = tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version, b.running_mean._version,
-                     b.running_var._version) for c, b in convs)
+        key = (self.tc_format,) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
+                                         b.running_mean._version, b.running_var._version) for c, b in convs)
         st = getattr(self, "_tc_cache", None)
         if st is None or st[0] != key:
             layers = []
             for c, b in convs:
                 scale = (b.weight / torch.sqrt(b.running_var + b.eps)).float().contiguous()
                 shift = (b.bias - b.running_mean * scale).float().contiguous()
-                layers.append((ops.conv_tc_prepare(c.weight.detach()), c.out_channels, scale, shift))
+                layers.append((ops.conv_tc_prepare(c.weight.detach(), fmt=self.tc_format), c.out_channels, scale, shift))
             st = (key, layers)
             self._tc_cache = st
         return st[1]
@@ -105,25 +106,27 @@ class cost_volume(nn.Module):
     def _tc_ok(self, cost):
         N, C3, D, P, P2 = cost.shape
         return (self.tensor_core and not self.training and not torch.is_grad_enabled() and cost.is_cuda and P == 16 and
-                P2 == 16 and D % 8 == 0 and C3 % 32 == 0 and C3 == self.dres0[0].in_channels)
+                P2 == 16 and D % 8 == 0 and C3 % 32 == 0 and C3 == self.dres0[0].in_channels and
+                self.tc_format in ("tf32", "f16"))
 
     def aggregate_tc(self, cost, xcross=None):
         """Same function as ``aggregate`` on tcgen05 (3xTF32): [N,3C,D,16,16] -> logits [N,D,4,4].
         ``xcross`` [N,D]: cosine gate still to be applied to ``cost`` (folded into the layout change)."""
         L = self._tc_state()
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
-        hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross)                     # [N, D, 16, 16, 3C]
+        fmt = self.tc_format
+        hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross, fmt=fmt)            # [N, D, 16, 16, 3C]
         _, hi, lo = conv(0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
         isp = self.strAM_2D(y.mean(dim=2).permute(0, 3, 1, 2))                 # mean over H -> [N, 64, D, W]
         gate = torch.sigmoid(isp).permute(0, 2, 3, 1).contiguous()             # [N, D, W, 64]
-        hi, lo = ops.gate_mul_split(y, gate)
+        hi, lo = ops.gate_mul_split(y, gate, fmt=fmt)
         _, hi, lo = conv(2, hi, lo)
         y, _, _ = conv(3, hi, lo, full=True, split=False)                      # dres1 out, 128 ch
-        p1, hi, lo = ops.maxpool_hw2_cl(y, full=True, split=True)              # [N, D, 8, 8, 128]
+        p1, hi, lo = ops.maxpool_hw2_cl(y, full=True, split=True, fmt=fmt)            # [N, D, 8, 8, 128]
         _, hi, lo = conv(4, hi, lo)
         y, _, _ = conv(5, hi, lo, full=True, split=False, residual=p1)         # dres2(cost) + cost
-        _, hi, lo = ops.maxpool_hw2_cl(y, full=False, split=True)              # [N, D, 4, 4, 128]
+        _, hi, lo = ops.maxpool_hw2_cl(y, full=False, split=True, fmt=fmt)            # [N, D, 4, 4, 128]
         y, _, _ = conv(6, hi, lo, full=True, split=False)                      # classify.0-2, 64 ch
         return ops.conv3d_c1_cl(y, self.classify[3].weight.detach())           # [N, D, 4, 4]
 

@@ -516,13 +516,24 @@ def dw_deconv(x, w, stride, pad):
 # ----------------------------------------------------------------------------------------------
 # aggregation network on the tensor cores (channels-last activations, tf32 hi/lo split)
 # ----------------------------------------------------------------------------------------------
-def conv_tc_prepare(weight):
-    """nn.Conv3d / nn.Conv2d weight [Cout, Cin, *k] -> swizzled per-k-block tiles (hi, lo) for side_conv3d_tc_fwd."""
+def conv_tc_prepare(weight, fmt="tf32"):
+    """nn.Conv3d / nn.Conv2d weight [Cout, Cin, *k] -> swizzled per-k-block tiles (hi, lo) for side_conv3d_tc_fwd.
+    fmt="f16": fp16 pairs for the kind::f16 ("3xFP16") variant, returned as a float16 tensor."""
     lib = _lib.load()
     weight = _chk(weight, "weight")
     Cout, Cin = weight.shape[:2]
     taps = weight[0, 0].numel()
     nbytes = lib.side_conv_tc_weight_bytes(Cin, Cout, taps)
+    if fmt == "f16":
+        if Cin % 64:                                  # zero input channels up to the 64-wide k-block (matches ncdhw_to_cl_split)
+            pad = 64 - Cin % 64
+            weight = torch.cat((weight, weight.new_zeros((Cout, pad) + tuple(weight.shape[2:]))), 1).contiguous()
+            Cin += pad
+            nbytes = lib.side_conv_tc_weight_bytes(Cin, Cout, taps)
+        wp = torch.empty((nbytes // 4,), device=weight.device, dtype=torch.float16)       # half the bytes of the tf32 tiles
+        _lib.check(lib.side_conv_tc_prep_weights_f16(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
+                   "side_conv_tc_prep_weights_f16")
+        return wp
     wp = torch.empty((nbytes // 4,), device=weight.device, dtype=_F32)
     _lib.check(lib.side_conv_tc_prep_weights(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
                "side_conv_tc_prep_weights")
@@ -534,22 +545,27 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     """x_hi, x_lo [N, D, H, W, Cin] -> (y, y_hi, y_lo) [N, D, H/stride, W/stride, Cout] (entries not requested are None).
     relu: False / True (before the residual) / "after" (after the residual, DLA BasicBlock)."""
     lib = _lib.load()
-    x_hi, x_lo = _chk(x_hi, "x_hi"), _chk(x_lo, "x_lo")
+    f16 = x_hi.dtype == torch.float16          # operand format follows the activations: fp16 pairs -> kind::f16 kernel
+    odt = torch.float16 if f16 else _F32
+    x_hi, x_lo = _chk(x_hi, "x_hi", odt), _chk(x_lo, "x_lo", odt)
+    if wp.dtype != odt:
+        raise RuntimeError("conv3d_tc: weight tiles (%s) and activations (%s) use different operand formats" % (wp.dtype, odt))
     N, D, H, W, Cin = x_hi.shape
     dev = x_hi.device
     oshape = (N, D, H // stride, W // stride, Cout)
     y = torch.empty(oshape, device=dev, dtype=_F32) if full else None
-    y_hi = torch.empty(oshape, device=dev, dtype=_F32) if split else None
-    y_lo = torch.empty(oshape, device=dev, dtype=_F32) if split else None
+    y_hi = torch.empty(oshape, device=dev, dtype=odt) if split else None
+    y_lo = torch.empty(oshape, device=dev, dtype=odt) if split else None
     if residual is not None:
         residual = _chk(residual, "residual")
-    _lib.check(lib.side_conv3d_tc_fwd(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
+    fn = lib.side_conv3d_tc_fwd_f16 if f16 else lib.side_conv3d_tc_fwd
+    _lib.check(fn(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
                                       _p(y), _p(y_hi), _p(y_lo), N, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2],
                                       int(stride), 2 if relu == "after" else (1 if relu else 0), _stream()), "side_conv3d_tc_fwd")
     return y, y_hi, y_lo
 
 
-def ncdhw_to_cl_split(x, scale=None, want_full=False):
+def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt="tf32"):
     """x [N, C, D, H, W] (* scale [N, D] per depth slice) -> hi, lo [N, D, H, W, C] (and the unsplit copy first if want_full)."""
     lib = _lib.load()
     x = _chk(x, "x")
@@ -564,6 +580,14 @@ def ncdhw_to_cl_split(x, scale=None, want_full=False):
         D = sp[0]
         if tuple(scale.shape) != (N, D):
             raise RuntimeError("scale must be [N, D]")
+    if fmt == "f16":
+        Cp = (C + 63) // 64 * 64                     # fp16 k-blocks are 64 channels: zero-padded channels-last rows
+        hi = torch.empty((N,) + sp + (Cp,), device=x.device, dtype=torch.float16)
+        lo = torch.empty_like(hi)
+        full = torch.empty((N,) + sp + (Cp,), device=x.device, dtype=_F32) if want_full else None
+        _lib.check(lib.side_ncdhw_to_cl_split_f16(x.data_ptr(), _p(scale), _p(full), hi.data_ptr(), lo.data_ptr(), N, C, S, D, Cp,
+                                                  _stream()), "side_ncdhw_to_cl_split_f16")
+        return (full, hi, lo) if want_full else (hi, lo)
     hi = torch.empty((N,) + sp + (C,), device=x.device, dtype=_F32)
     lo = torch.empty_like(hi)
     full = torch.empty_like(hi) if want_full else None
@@ -580,29 +604,33 @@ def tf32_split(x):
     return hi, lo
 
 
-def gate_mul_split(y, gate):
+def gate_mul_split(y, gate, fmt="tf32"):
     """y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo."""
     lib = _lib.load()
     y, gate = _chk(y, "y"), _chk(gate, "gate")
     N, D, H, W, C = y.shape
     if tuple(gate.shape) != (N, D, W, C):
         raise RuntimeError("gate must be [N, D, W, C]")
-    hi, lo = torch.empty_like(y), torch.empty_like(y)
-    _lib.check(lib.side_gate_mul_split(y.data_ptr(), gate.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, D, H, W, C, _stream()),
+    odt = torch.float16 if fmt == "f16" else _F32
+    hi, lo = torch.empty_like(y, dtype=odt), torch.empty_like(y, dtype=odt)
+    fn = lib.side_gate_mul_split_f16 if fmt == "f16" else lib.side_gate_mul_split
+    _lib.check(fn(y.data_ptr(), gate.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, D, H, W, C, _stream()),
                "side_gate_mul_split")
     return hi, lo
 
 
-def maxpool_hw2_cl(x, full=False, split=True):
+def maxpool_hw2_cl(x, full=False, split=True, fmt="tf32"):
     """MaxPool3d((1,2,2)) on channels-last x [N, D, H, W, C] -> (y, hi, lo) [N, D, H/2, W/2, C]."""
     lib = _lib.load()
     x = _chk(x, "x")
     N, D, H, W, C = x.shape
     shp = (N, D, H // 2, W // 2, C)
     y = torch.empty(shp, device=x.device, dtype=_F32) if full else None
-    hi = torch.empty(shp, device=x.device, dtype=_F32) if split else None
-    lo = torch.empty(shp, device=x.device, dtype=_F32) if split else None
-    _lib.check(lib.side_maxpool_hw2_cl(x.data_ptr(), _p(y), _p(hi), _p(lo), N, D, H, W, C, _stream()), "side_maxpool_hw2_cl")
+    odt = torch.float16 if fmt == "f16" else _F32
+    hi = torch.empty(shp, device=x.device, dtype=odt) if split else None
+    lo = torch.empty(shp, device=x.device, dtype=odt) if split else None
+    fn = lib.side_maxpool_hw2_cl_f16 if fmt == "f16" else lib.side_maxpool_hw2_cl
+    _lib.check(fn(x.data_ptr(), _p(y), _p(hi), _p(lo), N, D, H, W, C, _stream()), "side_maxpool_hw2_cl")
     return y, hi, lo
 
 

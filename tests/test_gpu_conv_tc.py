@@ -245,3 +245,105 @@ def test_dla_base_fast_paths_match_cudnn(lib):
     for i, (a, b) in enumerate(zip(fast, ref)):
         assert a.shape == b.shape
         assert float((a - b).abs().max() / b.abs().max()) < 1e-4, i
+
+
+# ------------------------------------------------------------------------------------------------
+# "3xFP16" operand format: kind::f16 MMAs on fp16 pairs (hi, lo * 2^11), same 22 significand bits as the tf32 pair
+# ------------------------------------------------------------------------------------------------
+def _f16_split(x):
+    hi = x.half()
+    lo = ((x - hi.float()) * 2048.0).half()
+    return hi, lo
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, D, H, W, Cin, Cout, relu, affine, residual
+    (2, 16, 16, 16, 64, 64, True, True, False),      # dres0.3 / dres1.0: role-swapped kernel
+    (1, 8, 16, 16, 192, 64, True, True, False),      # three k-blocks per tap, role-swapped kernel
+    (1, 8, 16, 16, 64, 128, True, True, False),      # dres1.3
+    (3, 16, 8, 8, 128, 128, True, True, True),       # dres2.3 + residual
+    (2, 16, 4, 4, 128, 64, True, True, False),       # classify.0
+    (5, 2, 8, 8, 64, 32, False, False, False),       # odd sample count, no affine
+])
+@pytest.mark.parametrize("mode", [0, 32])
+def test_conv3d_tc_f16_matches_fp64(lib, cfg, mode):
+    from side_b200 import ops
+    lib.side_conv_tc_set_mode(mode)
+    N, D, H, W, Cin, Cout, relu, affine, res = cfg
+    g = torch.Generator().manual_seed(N * 1000 + Cin + Cout + 7)
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (2.0 / (27 * Cout)) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5 if affine else None
+    shift = torch.randn(Cout, generator=g) * 0.1 if affine else None
+    r = torch.randn(N, Cout, D, H, W, generator=g) if res else None
+    ref = F.conv3d(x.double(), w.double(), padding=1)
+    if affine:
+        ref = ref * scale.double().view(1, -1, 1, 1, 1) + shift.double().view(1, -1, 1, 1, 1)
+    if relu:
+        ref = ref.relu()
+    if res:
+        ref = ref + r.double()
+    ref = _cl(ref).numpy()
+    dev = torch.device("cuda")
+    wp = ops.conv_tc_prepare(w.to(dev), fmt="f16")
+    hi, lo = _f16_split(_cl(x).to(dev))
+    y, yh, yl = ops.conv3d_tc(hi, lo, wp, Cout, scale=None if scale is None else scale.to(dev),
+                              shift=None if shift is None else shift.to(dev), relu=relu,
+                              residual=None if r is None else _cl(r).to(dev), full=True, split=True)
+    lib.side_conv_tc_set_mode(0)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4
+    assert yh.dtype == torch.float16 and torch.equal(yh, y.half())
+    rec = yh.float() + yl.float() / 2048.0                           # the pair carries the fp32 result to ~2^-21
+    assert float((rec - y).abs().max()) <= 2e-6 * float(y.abs().max())
+
+
+def test_f16_layout_and_pool_helpers(lib):
+    from side_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    dev = torch.device("cuda")
+    x = torch.randn(3, 40, 4, 6, 10, generator=g)                    # 40 channels -> padded to 64
+    sc = torch.rand(3, 4, generator=g) + 0.5
+    hi, lo = ops.ncdhw_to_cl_split(x.to(dev), scale=sc.to(dev), fmt="f16")
+    assert tuple(hi.shape) == (3, 4, 6, 10, 64) and hi.dtype == torch.float16
+    want = _cl(x * sc[:, None, :, None, None])
+    rec = (hi.float() + lo.float() / 2048.0).cpu()
+    assert float((rec[..., :40] - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    assert float(rec[..., 40:].abs().max()) == 0.0
+    y = torch.randn(2, 5, 6, 8, 12, generator=g)
+    gate = torch.rand(2, 5, 8, 12, generator=g)
+    hi, lo = ops.gate_mul_split(y.to(dev), gate.to(dev), fmt="f16")
+    want = y * gate.unsqueeze(2)
+    assert float(((hi.float() + lo.float() / 2048.0).cpu() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    full, hi, lo = ops.maxpool_hw2_cl(y.to(dev), full=True, split=True, fmt="f16")
+    ref = F.max_pool3d(y.permute(0, 4, 1, 2, 3), (1, 2, 2)).permute(0, 2, 3, 4, 1)
+    assert torch.equal(full.cpu(), ref)
+    assert float(((hi.float() + lo.float() / 2048.0).cpu() - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("N,D", [(3, 16), (2, 48)])
+def test_aggregate_tc_f16_matches_module_fp64(lib, N, D):
+    """The aggregation network with tc_format = "f16" against the float64 layer sequence: same bars as the tf32 path."""
+    from side_b200 import ops
+    from side_b200.networks.stereo_network import cost_volume
+    torch.manual_seed(11)
+    m = cost_volume(64).eval()
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2)
+            mod.bias.data.normal_(0, 0.1)
+    cost = torch.randn(N, 96, D, 16, 16)
+    xc = torch.rand(N, D) * 0.8 + 0.1
+    with torch.no_grad():
+        ref = m.double().aggregate((cost * xc[:, None, :, None, None]).double()).float()
+    m = m.float().cuda()
+    m.tc_format = "f16"
+    with torch.no_grad():
+        out = m.aggregate_tc(cost.cuda(), xcross=xc.cuda())
+        scale = float(ref.abs().max())
+        assert float((out.cpu() - ref).abs().max()) < 1e-4 * scale
+        db = torch.linspace(87, 5, D).repeat(N, 1)
+        d_tc = ops.softargmin(out.contiguous(), db.cuda()).cpu()
+        d_ref = ops.softargmin(ref.cuda().contiguous(), db.cuda()).cpu()
+        assert float(((d_tc - d_ref).abs() / d_ref.abs()).max()) < 1e-4
