@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
                     help="3xtf32 (default): tcgen05 with the exact hi/lo split, fp32-class accuracy (<= 1e-4 rel); fp32: SIMT")
+    ap.add_argument("--tc-format", default="f16", choices=["tf32", "f16"],
+                    help="operand format of the tensor-core convolutions: 3xTF32 or 3xFP16 (kind::f16 MMAs "
+                         "on fp16 hi/lo pairs, the same 22-bit operands at twice the tensor rate)")
     ap.add_argument("--conv-mode", type=int, default=0, help="side_conv_tc_set_mode bit mask: 0 default, 1 halo reuse in the voxel-major kernel, 32 no role-swapped kernel")
     ap.add_argument("--cudnn-only", action="store_true",
                     help="keep the heads and the 3-D aggregation network on cuDNN fp32 (as the reference runs them)")
@@ -384,6 +387,7 @@ def main():
     if args.cudnn_only:
         model.heads_tensor_core = False
         model.depth_estimator.tensor_core = False
+    ops.set_tc_format(args.tc_format)
     det = StereoDetector(model, grid_size=28, K=100)
 
     P, mb = args.pairs, args.micro_batch
@@ -467,20 +471,24 @@ def main():
         return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
 
     def conv_work(out, x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), **k):
-        return 2.0 * (x_hi.numel() // x_hi.shape[-1]) * Cout * x_hi.shape[-1] * ksize[0] * ksize[1] * ksize[2]
+        cin = getattr(wp, "cin_alg", x_hi.shape[-1])          # zero-padded input channels (96 -> 128 for fp16) do not count
+        return 2.0 * (x_hi.numel() // x_hi.shape[-1]) * Cout * cin * ksize[0] * ksize[1] * ksize[2]
+
+    def conv_fmt(x_hi, *a, **k):
+        return "f16" if x_hi.dtype == torch.float16 else "tf32"
 
     if args.profiler_range:
         torch.cuda.profiler.start()
     def dcn_cl_work(out, x_nhwc, om_cl, weight, *a, **k):
         return 2.0 * out.numel() * weight.shape[1] * weight.shape[2] * weight.shape[3]
 
-    with OpTimer("dcn_forward_raw", dcn_work) as tm, OpTimer("dcn_fwd_cl", dcn_cl_work) as tm2, OpTimer("conv3d_tc", conv_work) as tmc:
+    with OpTimer("dcn_forward_raw", dcn_work) as tm, OpTimer("dcn_fwd_cl", dcn_cl_work) as tm2, OpTimer("conv3d_tc", conv_work, conv_fmt) as tmc:
         ms_res = timed(step_resident, args.steps)
     if args.profiler_range:
         torch.cuda.profiler.stop()
     dcn, dcn2 = tm.summary(), tm2.summary()
     dcn = {k: dcn[k] + dcn2[k] for k in ("calls", "ms", "work")}       # NCHW entry + channels-last entry of the same kernel
-    cv = tmc.summary()
+    cv, cv16 = tmc.summary("tf32"), tmc.summary("f16")
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop()
@@ -493,17 +501,22 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
 
-    def roof(name, label, summ):
+    def roof(name, label, summ, f16=False):
         tf = summ["work"] / (summ["ms"] / 1000.0) / 1e12 if summ["ms"] > 0 else 0.0
+        note = ("3xFP16: fp16 MMAs run at the bf16 rate and every product takes 3 of them, so 1/3 = 0.333 is the ceiling of this "
+                "fraction" if f16 else
+                "3xTF32: tf32 rate is half of bf16 and every product takes 3 MMAs, so 1/6 = 0.167 is the ceiling of this fraction")
         return {"kernel": "%s, %d launches in the timed region" % (label, summ["calls"]), "bound": "tensor", "achieved": tf,
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": traffic.get(name),
-                "peak_source": pk["src"] + " bf16 sustained (cuBLAS); this kernel is 3xTF32: tf32 rate is half of bf16 and every "
-                               "product takes 3 MMAs, so 1/6 = 0.167 is the ceiling of this fraction",
+                "peak_source": pk["src"] + " bf16 sustained (cuBLAS); this kernel is " + note,
                 "share_of_step": summ["ms"] / ms_res, "algorithmic_flop_per_step": summ["work"] / max(args.steps, 1)}
 
     r_dcn = roof("dcn_fwd_tc_kernel", "dcn_fwd (%s)" % args.dcn_precision, dcn)
-    r_cv = roof("conv_tc_kernel", "conv3d_tc (aggregation network + heads + DLA levels 2-5 + DCN offset convs, 3xtf32)", cv)
-    dominant, other = (r_cv, r_dcn) if cv["ms"] >= dcn["ms"] else (r_dcn, r_cv)
+    label = "conv3d_tc %s (aggregation network + heads + DLA levels 2-5 + DCN offset convs: conv_tct_kernel / conv_tc_kernel)"
+    r_cv = roof("conv_tc_kernel", label % "3xtf32", cv)
+    r_cv16 = roof("conv_tc_kernel_f16", label % "3xfp16, kind::f16", cv16, f16=True)
+    ranked = sorted([r_cv, r_cv16, r_dcn], key=lambda r: -r["share_of_step"])
+    dominant, other, third = ranked
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -514,8 +527,9 @@ def main():
                        "pairs_per_gpu_per_step": P, "micro_batch": mb, "parallelism": "pair-sharded x%d, all_gather(detections)" % world,
                        "dcn_precision": args.dcn_precision, "cudnn_tf32": bool(args.allow_tf32),
                        "tensor_core_convs": "cuDNN fp32 only" if args.cudnn_only else
-                       "3-D aggregation network, heads, DLA-34 levels 2-5 and the DCN offset convolutions on tcgen05 3xTF32 "
-                       "(fp32-class accuracy, <= 1e-4 rel.); DLA stem as direct fp32 SIMT convolutions; strAM conv2d cuDNN fp32",
+                       "3-D aggregation network, heads, DLA-34 levels 2-5 and the DCN offset convolutions on tcgen05 %s "
+                       "(fp32-class accuracy: 22-bit operands, fp32 accumulation, <= 1e-4 rel.); DLA stem as direct fp32 SIMT "
+                       "convolutions; strAM conv2d cuDNN fp32" % ("3xFP16 (kind::f16)" if args.tc_format == "f16" else "3xTF32"),
                        "l2": "inputs larger than L2 (%.0f MB of images per step)" % (2 * P * 3 * H_IN * W_IN * 4 / 1e6)},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * H_IN * W_IN * 4,
                     "d2h_bytes_per_step": P * 100 * 22 * 4, "ms_per_step": ms_e2e / args.steps},
@@ -523,6 +537,7 @@ def main():
             "clocks": clk,
             "roofline": dominant,
             "roofline_second": other,
+            "roofline_third": third,
             "cpu_baseline": cpu_base,
         }
         if not args.no_kernels and world == 1:

@@ -96,7 +96,7 @@ class DCN(DCNv2):
     def _om_weights(self):
         """conv_offset_mask as a 32-output-channel tcgen05 convolution (27 real channels, zero padding), bias in the epilogue."""
         c = self.conv_offset_mask
-        key = (c.weight.data_ptr(), c.weight._version, c.bias._version)
+        key = (ops.get_tc_format(), c.weight.data_ptr(), c.weight._version, c.bias._version)
         st = self.__dict__.get("_om_cache")
         if st is None or st[0] != key:
             w = torch.zeros((32,) + tuple(c.weight.shape[1:]), device=c.weight.device, dtype=torch.float32)

@@ -124,14 +124,14 @@ class OpTimer:
     Wraps ``ops.dcn_forward_raw`` (or any named attribute of ``side_b200.ops``): an event pair is recorded on the
     current stream around every call, nothing synchronises until ``summary()``."""
 
-    def __init__(self, name, work_fn):
-        self.name, self.work_fn = name, work_fn
+    def __init__(self, name, work_fn, key_fn=None):
+        self.name, self.work_fn, self.key_fn = name, work_fn, key_fn
         self.records = []
         self._orig = None
 
     def __enter__(self):
         self._orig = getattr(ops, self.name)
-        orig, recs, work_fn = self._orig, self.records, self.work_fn
+        orig, recs, work_fn, key_fn = self._orig, self.records, self.work_fn, self.key_fn
 
         def timed(*a, **k):
             e0 = torch.cuda.Event(enable_timing=True)
@@ -139,7 +139,7 @@ class OpTimer:
             e0.record()
             out = orig(*a, **k)
             e1.record()
-            recs.append((e0, e1, work_fn(out, *a, **k)))
+            recs.append((e0, e1, work_fn(out, *a, **k), key_fn(*a, **k) if key_fn else None))
             return out
 
         setattr(ops, self.name, timed)
@@ -148,8 +148,10 @@ class OpTimer:
     def __exit__(self, *exc):
         setattr(ops, self.name, self._orig)
 
-    def summary(self):
+    def summary(self, key=None):
+        """Totals over all recorded calls, or over those whose ``key_fn`` value equals ``key``."""
         torch.cuda.synchronize()
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.records)
-        work = sum(w for _, _, w in self.records)
-        return dict(calls=len(self.records), ms=ms, work=work)
+        recs = [r for r in self.records if key is None or r[3] == key]
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
+        work = sum(w for _, _, w, _ in recs)
+        return dict(calls=len(recs), ms=ms, work=work)

@@ -178,8 +178,8 @@ class DLA(nn.Module):
 
     def _tc_fold(self, conv, bn):
         st = self.__dict__.setdefault("_tc_cache", {})
-        key = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
-               bn.running_var._version)
+        key = (ops.get_tc_format(), conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
+               bn.running_mean._version, bn.running_var._version)
         ent = st.get(id(conv))
         if ent is None or ent[0] != key:
             scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
@@ -219,9 +219,15 @@ class DLA(nn.Module):
 
     def _levels_tc(self, x):
         B, C, H, W = x.shape
-        hi, lo = ops.ncdhw_to_cl_split(x.unsqueeze(2))               # [B, 1, H, W, C] channels-last halves
-        hi, lo = hi.view(1, B, H, W, C), lo.view(1, B, H, W, C)
-        t = (hi + lo, hi, lo)                                        # hi + lo == x exactly
+        if ops.get_tc_format() == "f16":
+            # fp16 pairs; the 32 input channels of level 2 are zero-padded to the 64-channel k-block (weights likewise)
+            full, hi, lo = ops.ncdhw_to_cl_split(x.unsqueeze(2), want_full=True)
+            Cp = hi.shape[-1]
+            t = (full.view(1, B, H, W, Cp), hi.view(1, B, H, W, Cp), lo.view(1, B, H, W, Cp))
+        else:
+            hi, lo = ops.ncdhw_to_cl_split(x.unsqueeze(2))           # [B, 1, H, W, C] channels-last halves
+            hi, lo = hi.view(1, B, H, W, C), lo.view(1, B, H, W, C)
+            t = (hi + lo, hi, lo)                                    # hi + lo == x exactly
         outs = []
         for i in range(2, 6):
             t = self._tree_tc(t, getattr(self, "level%d" % i))

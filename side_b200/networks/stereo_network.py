@@ -83,14 +83,15 @@ class cost_volume(nn.Module):
 
     # -- tensor-core path (inference): every Conv3d is side_conv3d_tc_fwd, activations stay channels-last ----------
     tensor_core = True     # False keeps the cuDNN convolutions (training always does)
-    tc_format = "tf32"     # "f16": kind::f16 MMAs on fp16 operand pairs (3xFP16, same 22-bit operands, twice the tensor rate)
+    tc_format = None       # None: ops.get_tc_format(); "tf32" / "f16" pins the operand format of this module
 
     def _tc_state(self):
         """Swizzled tf32 hi/lo weight tiles and folded eval-mode BatchNorm per conv, rebuilt when a parameter changes."""
         convs = [(self.dres0[0], self.dres0[1]), (self.dres0[3], self.dres0[4]), (self.dres1[0], self.dres1[1]),
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
-        key = (self.tc_format,) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
+        fmt = self.tc_format or ops.get_tc_format()
+        key = (fmt,) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
                                          b.running_mean._version, b.running_var._version) for c, b in convs)
         st = getattr(self, "_tc_cache", None)
         if st is None or st[0] != key:
@@ -98,7 +99,7 @@ class cost_volume(nn.Module):
             for c, b in convs:
                 scale = (b.weight / torch.sqrt(b.running_var + b.eps)).float().contiguous()
                 shift = (b.bias - b.running_mean * scale).float().contiguous()
-                layers.append((ops.conv_tc_prepare(c.weight.detach(), fmt=self.tc_format), c.out_channels, scale, shift))
+                layers.append((ops.conv_tc_prepare(c.weight.detach(), fmt=fmt), c.out_channels, scale, shift))
             st = (key, layers)
             self._tc_cache = st
         return st[1]
@@ -107,14 +108,14 @@ class cost_volume(nn.Module):
         N, C3, D, P, P2 = cost.shape
         return (self.tensor_core and not self.training and not torch.is_grad_enabled() and cost.is_cuda and P == 16 and
                 P2 == 16 and D % 8 == 0 and C3 % 32 == 0 and C3 == self.dres0[0].in_channels and
-                self.tc_format in ("tf32", "f16"))
+                self.tc_format in (None, "tf32", "f16"))
 
     def aggregate_tc(self, cost, xcross=None):
         """Same function as ``aggregate`` on tcgen05 (3xTF32): [N,3C,D,16,16] -> logits [N,D,4,4].
         ``xcross`` [N,D]: cosine gate still to be applied to ``cost`` (folded into the layout change)."""
         L = self._tc_state()
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
-        fmt = self.tc_format
+        fmt = self.tc_format or ops.get_tc_format()
         hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross, fmt=fmt)            # [N, D, 16, 16, 3C]
         _, hi, lo = conv(0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
@@ -220,7 +221,7 @@ class stereo_network(nn.Module):
         stereo = [h for h in self.heads if h not in self.left_only]
         mono = [h for h in self.heads if h in self.left_only]
         params = [p for h in self.heads for p in self.__getattr__(h).parameters()]
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (ops.get_tc_format(),) + tuple((p.data_ptr(), p._version) for p in params)
         st = getattr(self, "_heads_cache", None)
         if st is None or st[0] != key:
             d = {"stereo": stereo, "mono": {}}

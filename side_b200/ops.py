@@ -212,6 +212,22 @@ def proposal_shift(left, right, fb, D, x_clamp):
 USE_NHWC_GATHER = True   # False selects the NCHW gather kernel (same results, slower; kept for odd shapes / tests)
 
 
+_tc_format = "tf32"
+
+
+def set_tc_format(fmt):
+    """Operand format of the tensor-core convolutions: "tf32" (3xTF32) or "f16" (3xFP16: kind::f16 MMAs on fp16 (hi, lo * 2^11)
+    pairs -- the same 22-bit operands and fp32 accumulation at twice the tensor rate; |activations| must stay below 65504)."""
+    global _tc_format
+    if fmt not in ("tf32", "f16"):
+        raise ValueError("tc format must be 'tf32' or 'f16'")
+    _tc_format = fmt
+
+
+def get_tc_format():
+    return _tc_format
+
+
 VOL_BWD_FLAGS = 0   # tests / benchmarks: _lib.VOL_BWD_SCALAR forces the scalar-atomic backward kernel
 
 
@@ -516,12 +532,14 @@ def dw_deconv(x, w, stride, pad):
 # ----------------------------------------------------------------------------------------------
 # aggregation network on the tensor cores (channels-last activations, tf32 hi/lo split)
 # ----------------------------------------------------------------------------------------------
-def conv_tc_prepare(weight, fmt="tf32"):
+def conv_tc_prepare(weight, fmt=None):
     """nn.Conv3d / nn.Conv2d weight [Cout, Cin, *k] -> swizzled per-k-block tiles (hi, lo) for side_conv3d_tc_fwd.
     fmt="f16": fp16 pairs for the kind::f16 ("3xFP16") variant, returned as a float16 tensor."""
     lib = _lib.load()
+    fmt = fmt or _tc_format
     weight = _chk(weight, "weight")
     Cout, Cin = weight.shape[:2]
+    cin_alg = Cin                                    # unpadded input channels (algorithmic FLOP accounting in bench.py)
     taps = weight[0, 0].numel()
     nbytes = lib.side_conv_tc_weight_bytes(Cin, Cout, taps)
     if fmt == "f16":
@@ -533,6 +551,7 @@ def conv_tc_prepare(weight, fmt="tf32"):
         wp = torch.empty((nbytes // 4,), device=weight.device, dtype=torch.float16)       # half the bytes of the tf32 tiles
         _lib.check(lib.side_conv_tc_prep_weights_f16(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
                    "side_conv_tc_prep_weights_f16")
+        wp.cin_alg = cin_alg
         return wp
     wp = torch.empty((nbytes // 4,), device=weight.device, dtype=_F32)
     _lib.check(lib.side_conv_tc_prep_weights(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
@@ -565,9 +584,10 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     return y, y_hi, y_lo
 
 
-def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt="tf32"):
+def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt=None):
     """x [N, C, D, H, W] (* scale [N, D] per depth slice) -> hi, lo [N, D, H, W, C] (and the unsplit copy first if want_full)."""
     lib = _lib.load()
+    fmt = fmt or _tc_format
     x = _chk(x, "x")
     N, C = x.shape[:2]
     sp = tuple(x.shape[2:])
@@ -604,9 +624,10 @@ def tf32_split(x):
     return hi, lo
 
 
-def gate_mul_split(y, gate, fmt="tf32"):
+def gate_mul_split(y, gate, fmt=None):
     """y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo."""
     lib = _lib.load()
+    fmt = fmt or _tc_format
     y, gate = _chk(y, "y"), _chk(gate, "gate")
     N, D, H, W, C = y.shape
     if tuple(gate.shape) != (N, D, W, C):
@@ -619,9 +640,10 @@ def gate_mul_split(y, gate, fmt="tf32"):
     return hi, lo
 
 
-def maxpool_hw2_cl(x, full=False, split=True, fmt="tf32"):
+def maxpool_hw2_cl(x, full=False, split=True, fmt=None):
     """MaxPool3d((1,2,2)) on channels-last x [N, D, H, W, C] -> (y, hi, lo) [N, D, H/2, W/2, C]."""
     lib = _lib.load()
+    fmt = fmt or _tc_format
     x = _chk(x, "x")
     N, D, H, W, C = x.shape
     shp = (N, D, H // 2, W // 2, C)

@@ -23,6 +23,15 @@ def strict_fp32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+@pytest.fixture(params=["tf32", "f16"])
+def tc_fmt(request):
+    """Run the test under both operand formats of the tensor-core convolutions (3xTF32 / 3xFP16)."""
+    from side_b200 import ops
+    ops.set_tc_format(request.param)
+    yield request.param
+    ops.set_tc_format("tf32")
+
+
 def _cl(x):      # NCDHW -> NDHWC
     return x.permute(0, 2, 3, 4, 1).contiguous()
 
@@ -129,7 +138,7 @@ def test_aggregate_tc_matches_module_fp64(lib, N, D):
 
 
 @pytest.mark.parametrize("shape", [(2, 96, 320), (1, 16, 320), (3, 8, 64)])
-def test_heads_tc_match_cudnn_heads(lib, shape):
+def test_heads_tc_match_cudnn_heads(lib, shape, tc_fmt):
     """stereo_network heads (:343-348) on tcgen05 (stacked first convolutions, n-tiles of 128, 2 x 64 pixel boxes) vs the
     module's own cuDNN fp32 path on the same weights: <= 1e-4 of each head's range."""
     from side_b200.networks import get_pose_net
@@ -185,7 +194,7 @@ def test_conv2d_tc_stride2_and_1x1(lib):
 
 
 @pytest.mark.parametrize("B,H,W", [(4, 192, 640), (8, 64, 128)])
-def test_dla_levels_tc_match_cudnn(lib, B, H, W):
+def test_dla_levels_tc_match_cudnn(lib, B, H, W, tc_fmt):
     """DLA-34 levels 2-5 on tcgen05 vs the same modules on cuDNN fp32: every level output <= 1e-4 of its range."""
     from side_b200.networks.feature_extraction_dla34 import dla34
     torch.manual_seed(4)
@@ -226,7 +235,7 @@ def test_stem_conv_matches_fp64(lib, cfg):
     assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-5
 
 
-def test_dla_base_fast_paths_match_cudnn(lib):
+def test_dla_base_fast_paths_match_cudnn(lib, tc_fmt):
     """Whole DLA-34 base: direct stem + tcgen05 levels 2-5 vs the plain module on cuDNN fp32."""
     from side_b200.networks.feature_extraction_dla34 import dla34
     torch.manual_seed(6)

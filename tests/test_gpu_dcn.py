@@ -10,6 +10,15 @@ pytestmark = pytest.mark.gpu
 from oracle import c_oracle as co  # noqa: E402
 
 
+@pytest.fixture(params=["tf32", "f16"])
+def tc_fmt(request):
+    """Run the test under both operand formats of the tensor-core convolutions (3xTF32 / 3xFP16)."""
+    from side_b200 import ops
+    ops.set_tc_format(request.param)
+    yield request.param
+    ops.set_tc_format("tf32")
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -195,7 +204,7 @@ def test_tensor_core_paths(lib, prec, tol):
 
 
 @pytest.mark.parametrize("cfg", [(8, 64, 64, 24, 80), (4, 128, 64, 48, 160), (4, 512, 256, 12, 40), (1, 64, 64, 96, 320)])
-def test_dcn_module_channels_last_fused_path(lib, cfg):
+def test_dcn_module_channels_last_fused_path(lib, cfg, tc_fmt):
     """Inference fast path of the DCN module: conv_offset_mask on tcgen05 (3xTF32, 27 -> 32 padded channels, channels-last) feeding
     side_dcn_fwd_cl, with folded BatchNorm + ReLU -- against the same module on the fp32 SIMT path (cuDNN offset conv)."""
     from side_b200 import ops
