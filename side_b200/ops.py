@@ -212,7 +212,7 @@ def proposal_shift(left, right, fb, D, x_clamp):
 USE_NHWC_GATHER = True   # False selects the NCHW gather kernel (same results, slower; kept for odd shapes / tests)
 
 
-_tc_format = "tf32"
+_tc_format = "f16"
 
 
 def set_tc_format(fmt):

@@ -16,10 +16,14 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def strict_fp32():
     """The strAM Conv2d stays cuDNN: keep it in true fp32 (torch lets cuDNN use TF32 by default)."""
+    from side_b200 import ops
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    old_fmt = ops.get_tc_format()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    ops.set_tc_format("tf32")          # the tests of this file name the operand format they exercise (tc_fmt fixture / fmt=...)
     yield
+    ops.set_tc_format(old_fmt)
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
@@ -29,7 +33,6 @@ def tc_fmt(request):
     from side_b200 import ops
     ops.set_tc_format(request.param)
     yield request.param
-    ops.set_tc_format("tf32")
 
 
 def _cl(x):      # NCDHW -> NDHWC

@@ -14,9 +14,10 @@ from oracle import c_oracle as co  # noqa: E402
 def tc_fmt(request):
     """Run the test under both operand formats of the tensor-core convolutions (3xTF32 / 3xFP16)."""
     from side_b200 import ops
+    old = ops.get_tc_format()
     ops.set_tc_format(request.param)
     yield request.param
-    ops.set_tc_format("tf32")
+    ops.set_tc_format(old)
 
 
 def dev(a):

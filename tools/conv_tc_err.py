@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
 from side_b200 import ops
+ops.set_tc_format("tf32")      # this tool feeds tf32 pairs (ops.tf32_split)
 from side_b200.networks.stereo_network import cost_volume
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -2,6 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from side_b200 import ops, _lib
+ops.set_tc_format("tf32")      # this tool feeds tf32 pairs (ops.tf32_split)
 lib = _lib.load()
 dev = torch.device("cuda")
 for (N, D, H, W, Cin, Cout) in [(400, 16, 16, 16, 64, 64), (400, 16, 16, 16, 64, 128)]:

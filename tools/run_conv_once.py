@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from side_b200 import ops
+ops.set_tc_format("tf32")      # this tool feeds tf32 pairs (ops.tf32_split)
 N, D, H, W, Cin, Cout = (int(v) for v in sys.argv[1:7])
 dev = torch.device("cuda")
 torch.manual_seed(0)

@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from side_b200 import ops
+ops.set_tc_format("tf32")      # this tool feeds tf32 pairs (ops.tf32_split)
 from side_b200.utils.synthetic import make_boxes
 dev = torch.device("cuda")
 torch.manual_seed(0)
