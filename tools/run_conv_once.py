@@ -1,14 +1,19 @@
-"""A few launches of the tcgen05 conv3d at the aggregation network's layer shapes (for ncu).  argv: N D H W Cin Cout"""
+"""A few launches of the tcgen05 conv3d at the aggregation network's layer shapes (for ncu).  argv: N D H W Cin Cout [tf32|f16]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from side_b200 import ops
-ops.set_tc_format("tf32")      # this tool feeds tf32 pairs (ops.tf32_split)
 N, D, H, W, Cin, Cout = (int(v) for v in sys.argv[1:7])
+fmt = sys.argv[7] if len(sys.argv) > 7 else "tf32"
+ops.set_tc_format(fmt)
 dev = torch.device("cuda")
 torch.manual_seed(0)
 x = torch.randn(N, D, H, W, Cin, device=dev)
-hi, lo = ops.tf32_split(x)
+if fmt == "f16":
+    hi = x.half()
+    lo = ((x - hi.float()) * 2048.0).half()
+else:
+    hi, lo = ops.tf32_split(x)
 w = torch.randn(Cout, Cin, 3, 3, 3, device=dev) * 0.05
 wp = ops.conv_tc_prepare(w)
 sc, sh = torch.rand(Cout, device=dev) + 0.5, torch.randn(Cout, device=dev)
