@@ -75,6 +75,44 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
     }
 }
 
+// fp16 variant with 64-channel tiles: a lane owns two adjacent channels, so every warp store is 128 contiguous bytes of
+// one voxel's channels-last row (the generic kernel above would issue 2-byte stores)
+__global__ void __launch_bounds__(256) ncdhw_to_cl_split_f16_kernel(const float *__restrict__ in, const float *__restrict__ scale,
+                                                                   float *__restrict__ full, uint32_t *__restrict__ hi,
+                                                                   uint32_t *__restrict__ lo, int C, long long S, int D, int per_d,
+                                                                   int Cpad)
+{
+    __shared__ float tile[64][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64;
+    const float *ip = in + (size_t)n * C * S;
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < S) ? __ldg(ip + (size_t)c * S + p) : 0.f;
+    }
+    __syncthreads();
+    const int c = c0 + 2 * threadIdx.x;
+    if (c >= Cpad) return;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long p = p0 + i;
+        if (p >= S) continue;
+        float a = tile[2 * threadIdx.x][i], b = tile[2 * threadIdx.x + 1][i];
+        if (scale) {
+            const float g = __ldg(scale + (size_t)n * D + (int)(p / per_d));
+            a = __fmul_rn(a, g);
+            b = __fmul_rn(b, g);
+        }
+        const size_t o = (((size_t)n * S + p) * Cpad + c) >> 1;      // index of the channel PAIR
+        uint32_t h, l;
+        f16_split2(a, b, h, l);
+        hi[o] = h;
+        lo[o] = l;
+        if (full) reinterpret_cast<float2 *>(full)[o] = make_float2(a, b);
+    }
+}
+
 __global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo, long long n4)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -191,7 +229,11 @@ static int ncdhw_to_cl_split_impl(const float *x, const float *scale, float *ful
     if (scale) SIDE_REQUIRE_DEV(scale);
     if (full) SIDE_REQUIRE_DEV(full);
     const int per_d = scale ? (int)(S / D) : 1;
-    if (f16) ncdhw_to_cl_split_kernel<true><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
+    if (f16 && Cpad % 2 == 0) {
+        dim3 g2((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)N);
+        ncdhw_to_cl_split_f16_kernel<<<g2, b, 0, (cudaStream_t)stream>>>(x, scale, full, reinterpret_cast<uint32_t *>(hi),
+                                                                         reinterpret_cast<uint32_t *>(lo), C, S, D, per_d, Cpad);
+    } else if (f16) ncdhw_to_cl_split_kernel<true><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
     else ncdhw_to_cl_split_kernel<false><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
     SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
     return SIDE_OK;
