@@ -2,8 +2,10 @@
 // level1 3x3 stride 2 (16 -> 32) at full resolution, each followed by BatchNorm + ReLU (feature_extraction_dla34.py
 // :281-293 of the reference, `_make_conv_level`).  16-32 channels give the tensor cores nothing to chew on (an
 // M128 x N16 tf32 MMA is bound by its A-operand fetch), so these are direct fp32 SIMT convolutions: a CTA stages the input
-// halo of a 64 x 8 output tile and the whole filter bank in shared memory; a thread owns 2 adjacent output pixels and ALL
-// output channels, so every input value it loads feeds Cout FMAs and every (broadcast) 16-byte weight load feeds 8.
+// halo of a 64 x 8 output tile and the whole filter bank in shared memory; a thread owns 2 output pixels (columns lane and
+// lane + 32 of one row) and ALL output channels, so every input value it loads feeds Cout FMAs and every (broadcast) 16-byte
+// weight load feeds 8.  Shared-memory reads are conflict-free: lanes read consecutive words (stride-2 layers stage the even
+// and the odd input columns in separate half rows).
 // Eval-mode BatchNorm and ReLU are folded into the store.  cuDNN spends 3-4x longer on these three layers (its fp32
 // kernels are tuned for wide channels) plus separate BN / ReLU passes.
 #include "common.cuh"
@@ -19,12 +21,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
 {
     constexpr int P = (K - 1) / 2;
     constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1;
-    constexpr int IWP = IW | 1;                                  // odd row pitch: stride-2 reads stay conflict-free
+    constexpr int HALF = (IW + 1) / 2;                           // S == 2: even columns at [0, HALF), odd ones at [HALF, 2 HALF)
+    constexpr int IWP = (S == 2 ? 2 * HALF : IW) | 1;            // odd row pitch
     extern __shared__ __align__(16) float sm[];
     float *ws = sm;                                              // [CIN * K * K][COUT]
     float *in_s = sm + CIN * K * K * COUT;                       // [CCHUNK][IH][IWP]
     const int b = blockIdx.z, oy0 = blockIdx.y * kStemTH, ox0 = blockIdx.x * kStemTW;
-    const int tid = threadIdx.x, tx = (tid & 31) * 2, ty = tid >> 5;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;   // output columns tx and tx + 32 of tile row ty
     for (int i = tid; i < CIN * K * K * COUT; i += 256) {
         const int o = i % COUT, ck = i / COUT;                   // ws[ck][o] = w[o][ck]   (w is [COUT][CIN][K][K])
         ws[i] = __ldg(w + (size_t)o * CIN * K * K + ck);
@@ -41,18 +44,20 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
             const int gy = iy0 + yy, gx = ix0 + xx;
             float v = 0.f;
             if (c0 + c < CIN && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(xb + ((size_t)(c0 + c) * H + gy) * W + gx);
-            in_s[(c * IH + yy) * IWP + xx] = v;
+            in_s[(c * IH + yy) * IWP + (S == 2 ? (xx & 1) * HALF + (xx >> 1) : xx)] = v;
         }
         __syncthreads();
 #pragma unroll 1
         for (int c = 0; c < CCHUNK && c0 + c < CIN; ++c) {
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                const float *row = in_s + (c * IH + ty * S + ky) * IWP + tx * S;
+                const float *row = in_s + (c * IH + ty * S + ky) * IWP + tx;
                 const float *wr = ws + ((c0 + c) * K * K + ky * K) * COUT;
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const float v0 = row[kx], v1 = row[kx + S];
+                    // input column tx * S + kx (and 32 * S further right for the second pixel)
+                    const int ci = S == 2 ? (kx & 1) * HALF + (kx >> 1) : kx;
+                    const float v0 = row[ci], v1 = row[ci + 32];
 #pragma unroll
                     for (int o4 = 0; o4 < COUT / 4; ++o4) {
                         const float4 wv = *reinterpret_cast<const float4 *>(wr + kx * COUT + 4 * o4);
@@ -68,18 +73,14 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
     const int oy = oy0 + ty, ox = ox0 + tx;
     if (oy < Ho && ox < Wo) {
         float *yp = y + ((size_t)b * COUT * Ho + oy) * Wo + ox;
-        const bool two = ox + 1 < Wo;
+        const bool two = ox + 32 < Wo;
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
             const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
             float a = fmaf(acc0[o], sc, sh), c = fmaf(acc1[o], sc, sh);
             if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            if (two && ((reinterpret_cast<uintptr_t>(yp + (size_t)o * Ho * Wo) & 7) == 0))
-                *reinterpret_cast<float2 *>(yp + (size_t)o * Ho * Wo) = make_float2(a, c);
-            else {
-                yp[(size_t)o * Ho * Wo] = a;
-                if (two) yp[(size_t)o * Ho * Wo + 1] = c;
-            }
+            yp[(size_t)o * Ho * Wo] = a;                         // a warp writes 128 contiguous bytes per channel and half tile
+            if (two) yp[(size_t)o * Ho * Wo + 32] = c;
         }
     }
 }
@@ -90,7 +91,7 @@ static int launch_stem(const float *x, const float *w, const float *scale, const
 {
     constexpr int P = (K - 1) / 2;
     const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
-    constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1, IWP = IW | 1;
+    constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1, IWP = (S == 2 ? 2 * ((IW + 1) / 2) : IW) | 1;
     const size_t smem = sizeof(float) * ((size_t)CIN * K * K * COUT + (size_t)CCHUNK * IH * IWP);
     int rc = set_smem_attr((const void *)stem_conv_kernel<CIN, COUT, K, S, CCHUNK>, smem);
     if (rc) return rc;
