@@ -280,7 +280,9 @@ int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, i
 /* "3xFP16" variants of the five entries above: the operand pairs are fp16 arrays (hi = fp16(x), lo = fp16((x - hi) * 2^11)) and
  * the MMAs are kind::f16 -- the same 22 significand bits per operand as the tf32 pair, fp32 accumulation, hi*hi in the main
  * accumulator and the two cross terms in a second one that the epilogue scales by 2^-11; twice the tensor rate of 3xTF32 and
- * half the operand bytes.  Needs Cin % 64 == 0 and |x| < 65504 (saturating conversions; activations behind a BatchNorm).
+ * half the operand bytes.  Needs Cin % 32 == 0 (k-blocks are 64 channels: prepare the weights with Cin zero-padded to a
+ * multiple of 64; a half-full last block is zero-filled by TMA and its empty MMAs are skipped) and |x| < 65504
+ * (saturating conversions; activations behind a BatchNorm).
  * Weight tiles take side_conv_tc_weight_bytes(...) / 2 bytes.  y, residual, scale, shift stay fp32. */
 int side_conv_tc_prep_weights_f16(const float *w, void *wp, int Cout, int Cin, int taps, void *stream);
 int side_conv3d_tc_fwd_f16(const void *x_hi, const void *x_lo, const void *wp, const float *scale, const float *shift,

@@ -43,6 +43,7 @@ struct ConvTcParams {
     const float *residual;            // [M, Cout] added after the ReLU (dres2(cost) + cost), NULL = none
     int relu;
     int N, ncb, nkb, ntiles;          // N = output channels of ONE n-tile (<= 128); ntiles = m-tiles * n_ntiles
+    int klast;                        // MMA K-steps (of 32 bytes) that carry data in the LAST channel block (4, or 2 when Cin % 64 == 32 on fp16)
     int Ntot, n_ntiles;               // all output channels, number of n-tiles (Ntot = n_ntiles * N)
     long long ldy;                    // row stride of the outputs in floats (Ntot unless a column block of a wider matrix is written)
     int D, H, W;                      // spatial extent of one sample
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         mbar_wait(&fullA[sa_i], pha);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(tiles + (size_t)sa_i * 2 * p.a_part);
+                        const int ksteps = (g % p.ncb == p.ncb - 1) ? p.klast : 4;    // zero-padded tail of the last channel block
                         for (int khi = 0; khi < 3; ++khi) {
                             mbar_wait(&full_bar[st], phs);
                             tc_fence_after();
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                             const uint32_t av = sa + (uint32_t)khi * view;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
+                                if (k >= ksteps) break;
                                 const uint64_t a_hi = tc_smem_desc(av + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                                 const uint64_t a_lo = tc_smem_desc(av + p.a_part + k * 32);
                                 tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (g | khi | k) != 0 ? 1u : 0u);
@@ -255,13 +258,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 // accumulator cuts that bias 3x (the cross accumulator is ~2^-10 of the main one, its ulp is negligible).
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
                 const uint32_t tmem_x = tmem_d + (uint32_t)N;
+                int cbm = 0;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&full_bar[st], phs);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
                     const uint32_t sb = sa + 2 * kCvATile;
+                    const int ksteps = (cbm == p.ncb - 1) ? p.klast : 4;
+                    if (++cbm == p.ncb) cbm = 0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (k >= ksteps) break;
                         const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
                         const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32);
                         if (p.dbg & 16) continue;
@@ -517,7 +524,8 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
                               const float *residual, float *y, float *y_hi, float *y_lo, int Nn, int D, int H, int W, int Cin,
                               int Cout, int kd, int kh, int kw, int stride_hw, int relu, void *stream, bool f16)
 {
-    SIDE_REQUIRE(!f16 || Cin % 64 == 0, "side_conv3d_tc_fwd_f16: needs Cin %% 64 == 0");
+    // fp16: the last 64-channel block may be half full (Cin % 64 == 32): the TMA box reads past the channel extent (zero fill),
+    // the weight tiles are zero-padded by side_conv_tc_prep_weights_f16's caller, and the MMAs of the empty half are skipped
     SIDE_REQUIRE(Nn >= 0 && D > 0 && H > 0 && W > 0, "side_conv3d_tc_fwd: bad shape");
     SIDE_REQUIRE(Cin > 0 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= kCvMaxCout && (Cout <= 128 || Cout % 128 == 0),
                  "side_conv3d_tc_fwd: needs Cin %% 32 == 0 and Cout %% 16 == 0 (<= 128) or Cout %% 128 == 0 (got %d -> %d)", Cin, Cout);
@@ -560,7 +568,7 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
         SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     // Cout == 64 on 256-voxel slices: role-swapped kernel (weights on M, 256 voxels on N), see conv_tct.cu
-    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw, f16))
+    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw, f16))   // (takes Cin % 32 == 0)
         return conv_tct_launch(x_hi, x_lo, wp, scale, shift, residual, y, y_hi, y_lo, Nn, D, H, W, Cin, kd, relu, g_sm_count,
                                (cudaStream_t)stream, f16);
     CUtensorMap tm_hi, tm_lo;
@@ -570,7 +578,8 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual;
     p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N; p.ldy = Cout;
-    p.ncb = Cin / (f16 ? 64 : 32); p.nkb = kd * kh * kw * p.ncb;
+    p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.nkb = kd * kh * kw * p.ncb;
+    p.klast = (f16 && Cin % 64 == 32) ? 2 : 4;
     const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
     p.ntiles = (int)(mtiles * p.n_ntiles);
@@ -611,7 +620,7 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = nullptr; p.y_lo = nullptr; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr;
     p.relu = 0; p.N = Nt; p.Ntot = Ncols; p.n_ntiles = Ncols / Nt; p.ldy = ldy;
-    p.ncb = K / 32; p.nkb = p.ncb;
+    p.ncb = K / 32; p.nkb = p.ncb; p.klast = 4;
     SIDE_REQUIRE((long long)Hr * p.n_ntiles < (1ll << 31), "conv_tc_rows_gemm: too many tiles");
     p.ntiles = Hr * p.n_ntiles;
     p.D = 1; p.H = Hr; p.W = kCvBM; p.bw = kCvBM; p.bh = 1; p.bd = 1; p.wt = 1; p.ht = Hr;

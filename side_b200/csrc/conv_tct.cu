@@ -39,6 +39,7 @@ struct ConvTtParams {
     const float *scale, *shift, *residual;
     int relu;
     int ncb, kd, ntiles, D, bw, bh;   // bw * bh == 256, one tile = one (sample, depth slice)
+    int klast;                        // K-steps with data in the last channel block (2 when Cin % 64 == 32 on fp16, else 4)
     uint32_t x_part;                  // bytes of one half (hi or lo) of an X slot: (bh + 2) * bw * 128
 };
 
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                     mbar_wait(&fullX[sx], phx);
                     tc_fence_after();
                     const uint32_t xs = smem_u32(xring + (size_t)sx * 2 * p.x_part);
+                    const int ksteps = (g % p.ncb == p.ncb - 1) ? p.klast : 4;
                     for (int khi = 0; khi < 3; ++khi) {
                         mbar_wait(&fullW[sw], phw);
                         tc_fence_after();
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                         const uint32_t xv = xs + (uint32_t)khi * view;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
+                            if (k >= ksteps) break;
                             const uint64_t a_hl = tc_smem_desc(ws + kTtWPart + k * 32);        // [W_hi ; W_lo]
                             const uint64_t a_zh = tc_smem_desc(ws + k * 32);                   // [0 ; W_hi]
                             const uint64_t b_hi = tc_smem_desc(xv + k * 32), b_lo = tc_smem_desc(xv + p.x_part + k * 32);
@@ -255,7 +258,7 @@ int conv_make_act_tmap(CUtensorMap *tm, const float *base, int Nn, int D, int H,
 
 bool conv_tct_supported(int D, int H, int W, int Cin, int Cout, int kd, int kh, int kw, int stride, bool f16)
 {
-    if (Cout != kTtCout || Cin % (f16 ? 64 : 32) || stride != 1 || kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
+    if (Cout != kTtCout || Cin % 32 || stride != 1 || kh != 3 || kw != 3 || (kd != 1 && kd != 3)) return false;
     if (H * W != kTtVox || (W % 8) || W > 64) return false;          // one tile = one full depth slice
     const size_t smem = (size_t)kTtXSlots * 2 * (size_t)(H + 2) * W * 128 + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
     return smem <= 212 * 1024;
@@ -271,7 +274,7 @@ int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const
     if ((rc = conv_make_act_tmap(&tm_lo, x_lo, Nn, D, H, W, Cin, 1, H, W, 1, 1, 1, f16))) return rc;
     ConvTtParams p;
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual; p.relu = relu;
-    p.ncb = Cin / (f16 ? 64 : 32); p.kd = kd; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
+    p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.kd = kd; p.klast = (f16 && Cin % 64 == 32) ? 2 : 4; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
     p.x_part = (uint32_t)(H + 2) * W * 128u;
     const size_t smem = (size_t)kTtXSlots * 2 * p.x_part + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tct_kernel<true> : (const void *)conv_tct_kernel<false>, smem))) return rc;

@@ -601,7 +601,7 @@ def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt=None):
         if tuple(scale.shape) != (N, D):
             raise RuntimeError("scale must be [N, D]")
     if fmt == "f16":
-        Cp = (C + 63) // 64 * 64                     # fp16 k-blocks are 64 channels: zero-padded channels-last rows
+        Cp = (C + 31) // 32 * 32                     # rows of 32-channel multiples (TMA zero-fills the tail of a 64-channel k-block)
         hi = torch.empty((N,) + sp + (Cp,), device=x.device, dtype=torch.float16)
         lo = torch.empty_like(hi)
         full = torch.empty((N,) + sp + (Cp,), device=x.device, dtype=_F32) if want_full else None

@@ -276,6 +276,9 @@ def _f16_split(x):
     (3, 16, 8, 8, 128, 128, True, True, True),       # dres2.3 + residual
     (2, 16, 4, 4, 128, 64, True, True, False),       # classify.0
     (5, 2, 8, 8, 64, 32, False, False, False),       # odd sample count, no affine
+    (1, 8, 16, 16, 96, 64, True, True, False),       # dres0.0: half-full last channel block (TMA zero fill, MMAs skipped)
+    (2, 4, 8, 8, 32, 32, False, True, False),        # single half-full block
+    (1, 8, 16, 16, 160, 128, True, False, False),    # 2.5 blocks, voxel-major kernel
 ])
 @pytest.mark.parametrize("mode", [0, 32])
 def test_conv3d_tc_f16_matches_fp64(lib, cfg, mode):
