@@ -152,7 +152,7 @@ class DLA(nn.Module):
         return run
 
     # -- levels 2-5 (90 % of the base's FLOPs) on the tensor cores, inference only ---------------------------------
-    # Every convolution of the four Trees is a tcgen05 implicit GEMM (ops.conv3d_tc, 3xTF32, fp32-class accuracy) on
+    # Every convolution of the four Trees is a tcgen05 implicit GEMM (ops.conv3d_tc, 3xFP16 / 3xTF32 operand pairs, fp32-class accuracy) on
     # channels-last activations with the batch as the box's depth axis: 3x3 and 1x1 kernels, stride-2 through TMA
     # element strides, eval-mode BatchNorm folded into the epilogue together with ReLU and the BasicBlock residual.
     tensor_core = True

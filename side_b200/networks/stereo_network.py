@@ -86,7 +86,8 @@ class cost_volume(nn.Module):
     tc_format = None       # None: ops.get_tc_format(); "tf32" / "f16" pins the operand format of this module
 
     def _tc_state(self):
-        """Swizzled tf32 hi/lo weight tiles and folded eval-mode BatchNorm per conv, rebuilt when a parameter changes."""
+        """Swizzled hi/lo weight tiles (in the current operand format) and folded eval-mode BatchNorm per conv, rebuilt when a
+        parameter or the format changes."""
         convs = [(self.dres0[0], self.dres0[1]), (self.dres0[3], self.dres0[4]), (self.dres1[0], self.dres1[1]),
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
@@ -111,7 +112,7 @@ class cost_volume(nn.Module):
                 self.tc_format in (None, "tf32", "f16"))
 
     def aggregate_tc(self, cost, xcross=None):
-        """Same function as ``aggregate`` on tcgen05 (3xTF32): [N,3C,D,16,16] -> logits [N,D,4,4].
+        """Same function as ``aggregate`` on tcgen05 (3xFP16 or 3xTF32 operand pairs): [N,3C,D,16,16] -> logits [N,D,4,4].
         ``xcross`` [N,D]: cosine gate still to be applied to ``cost`` (folded into the layout change)."""
         L = self._tc_state()
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
@@ -216,7 +217,7 @@ class stereo_network(nn.Module):
         return True
 
     def _heads_state(self):
-        """Swizzled tf32 weight tiles of the 3x3 head convolutions.  The first convolutions of all stereo heads (same
+        """Swizzled weight tiles of the 3x3 head convolutions.  The first convolutions of all stereo heads (same
         input cat(left, right)) are stacked into ONE convolution; their 1x1 outputs become one block-diagonal matmul."""
         stereo = [h for h in self.heads if h not in self.left_only]
         mono = [h for h in self.heads if h in self.left_only]
