@@ -162,36 +162,49 @@ __global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__re
     }
 }
 
-// x [N, D, H, W, C], w [1, C, 3, 3, 3] -> out [N, D, H, W]   (Conv3d(C -> 1, 3, padding 1, bias=False)); one warp per voxel
+// x [N, D, H, W, C], w [1, C, 3, 3, 3] -> out [N, D, H, W]   (Conv3d(C -> 1, 3, padding 1, bias=False)).
+// C / 4 lanes per voxel (16 for C = 64, two voxels per warp): one 16-byte activation load and one 16-byte shared weight load
+// per tap and lane, all 27 taps unrolled so the loads of a voxel are in flight together, then a butterfly over the lanes.
+template <int LPV>
 __global__ void __launch_bounds__(256) conv3d_c1_cl_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                            float *__restrict__ out, long long nvox, int D, int H, int W, int C)
 {
-    extern __shared__ float ws[];   // [27][C]
+    extern __shared__ __align__(16) float ws[];   // [27][C]
     for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) {
         const int tap = i / C, c = i - tap * C;
         ws[i] = __ldg(w + (size_t)c * 27 + tap);
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long v = warp0; v < nvox; v += nwarps) {
-        const int wq = (int)(v % W);
-        long long r = v / W;
+    constexpr int VPW = 32 / LPV;                            // voxels per warp
+    const int lane = threadIdx.x & 31, sub = lane % LPV;     // channel quad(s) of this lane: sub, sub + LPV, ...
+    const long long w0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * VPW;
+    const long long wstride = (((long long)gridDim.x * blockDim.x) >> 5) * VPW;
+    const int C4 = C / 4;
+    for (long long vw = w0; vw < nvox; vw += wstride) {      // warp-uniform loop: every lane reaches the shuffles
+        const long long v = vw + lane / LPV;
+        const bool live = v < nvox;
+        const long long vv = live ? v : nvox - 1;
+        const int wq = (int)(vv % W);
+        long long r = vv / W;
         const int hq = (int)(r % H);
         r /= H;
         const int dq = (int)(r % D);
         const long long n = r / D;
         float acc = 0.f;
+#pragma unroll
         for (int tap = 0; tap < 27; ++tap) {
             const int dd = dq + tap / 9 - 1, hh = hq + (tap / 3) % 3 - 1, ww = wq + tap % 3 - 1;
             if (dd < 0 || dd >= D || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            const float *xp = x + ((((size_t)n * D + dd) * H + hh) * W + ww) * C;
-            const float *wp = ws + tap * C;
-            for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(xp + c), wp[c], acc);
+            const float4 *xp = reinterpret_cast<const float4 *>(x + ((((size_t)n * D + dd) * H + hh) * W + ww) * C);
+            const float4 *wp = reinterpret_cast<const float4 *>(ws + tap * C);
+            for (int c = sub; c < C4; c += LPV) {
+                const float4 a = __ldg(xp + c), b = wp[c];
+                acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[v] = acc;
+#pragma unroll
+        for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && live) out[v] = acc;
     }
 }
 
@@ -322,8 +335,10 @@ extern "C" int side_conv3d_c1_cl(const float *x, const float *w, float *out, int
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(out);
     const long long nvox = (long long)N * D * H * W;
-    conv3d_c1_cl_kernel<<<ew_grid(nvox * 32, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W,
-                                                                                                      C);
+    SIDE_REQUIRE(C % 4 == 0, "side_conv3d_c1_cl: C %% 4 == 0");
+    if (C >= 128) conv3d_c1_cl_kernel<32><<<ew_grid(nvox * 32, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
+    else if (C >= 64) conv3d_c1_cl_kernel<16><<<ew_grid(nvox * 16, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
+    else conv3d_c1_cl_kernel<4><<<ew_grid(nvox * 4, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
     SIDE_LAUNCH_CHECK("conv3d_c1_cl_kernel");
     return SIDE_OK;
 }
