@@ -247,6 +247,9 @@ int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *g
  *   side_conv3d_tc_fwd: x_hi, x_lo [N, D, H, W, Cin] -> y [N, D, H, W, Cout] (fp32, may be NULL) and / or its split
  *       y_hi, y_lo (may be NULL); relu = 1: out = relu(conv * scale[o] + shift[o]) + residual (dres2(cost) + cost, :216);
  *       relu = 2: out = relu(conv * scale[o] + shift[o] + residual) (DLA BasicBlock); relu = 0: no activation.
+ *       relu | 4: MaxPool3d((1,2,2)) (cost_volume.max_pool1 / max_pool2, :213, :218) of that result fused into the epilogue;
+ *       all outputs are then [N, D, H/2, W/2, Cout] (residual stays at the convolution's resolution).  Stride 1, boxes of
+ *       2..16 columns x an even number of rows (16x16 and 8x8 maps).
  *       stride_hw = 2 (2-D kernels only): [N, D, H/2, W/2, Cout] outputs; the TMA box then traverses the input with
  *       element strides, so a strided convolution costs no more than a dense one.
  *       Needs Cin % 32 == 0; Cout % 16 == 0 (<= 128) or Cout % 128 == 0 (<= 1536, processed as 128-wide n-tiles); a

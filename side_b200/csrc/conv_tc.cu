@@ -43,6 +43,7 @@ struct ConvTcParams {
     const float *residual;            // [M, Cout] added after the ReLU (dres2(cost) + cost), NULL = none
     int relu;
     int N, ncb, nkb, ntiles;          // N = output channels of ONE n-tile (<= 128); ntiles = m-tiles * n_ntiles
+    int pool;                         // 1: MaxPool3d((1,2,2)) fused into the epilogue, outputs are [N, D, H/2, W/2, Cout]
     int klast;                        // MMA K-steps (of 32 bytes) that carry data in the LAST channel block (4, or 2 when Cin % 64 == 32 on fp16)
     int Ntot, n_ntiles;               // all output channels, number of n-tiles (Ntot = n_ntiles * N)
     long long ldy;                    // row stride of the outputs in floats (Ntot unless a column block of a wider matrix is written)
@@ -298,6 +299,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             const int ww = m % p.bw, r1 = m / p.bw, hh = r1 % p.bh, dd = r1 / p.bh;
             const size_t vox = (((size_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
             const size_t row = vox * (size_t)p.ldy + (size_t)nt * N;     // float offset of this row's first channel
+            const size_t orow = !p.pool ? row
+                                        : ((((size_t)n * p.D + d0 + dd) * (p.H >> 1) + ((h0 + hh) >> 1)) * (p.W >> 1) + ((w0 + ww) >> 1)) *
+                                                  (size_t)p.ldy + (size_t)nt * N;       // pooled output voxel
             const int cbase = nt * N;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
             for (int c = 0; c < ((p.dbg & 8) ? 0 : N); c += 16) {
@@ -323,22 +327,32 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (p.y) {
-                    float4 *yp = reinterpret_cast<float4 *>(p.y + row + c);
+                if (p.pool) {
+                    // 2x2 window over (h, w): the four voxels are lanes l, l^1 (next column) and l^bw, l^bw^1 (next row) of this
+                    // warp (bw <= 16, even tile rows); the even-column / even-row lane stores the maximum
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.bw));
+                    }
+                }
+                const bool writer = !p.pool || !((ww | hh) & 1);
+                if (writer && p.y) {
+                    float4 *yp = reinterpret_cast<float4 *>(p.y + orow + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                if (F16 && p.y_hi) {
+                if (F16 && writer && p.y_hi) {
                     uint32_t hh[8], ll[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f16_split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
-                    uint4 *hp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_hi) + row + c);
-                    uint4 *lp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_lo) + row + c);
+                    uint4 *hp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_hi) + orow + c);
+                    uint4 *lp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_lo) + orow + c);
                     hp[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); hp[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
                     lp[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); lp[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
-                } else if (p.y_hi) {
-                    float4 *hp = reinterpret_cast<float4 *>(p.y_hi + row + c);
-                    float4 *lp = reinterpret_cast<float4 *>(p.y_lo + row + c);
+                } else if (writer && p.y_hi) {
+                    float4 *hp = reinterpret_cast<float4 *>(p.y_hi + orow + c);
+                    float4 *lp = reinterpret_cast<float4 *>(p.y_lo + orow + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4 h, l;
@@ -533,6 +547,8 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
                  "side_conv3d_tc_fwd: kernel must be 3x3x3, 1x3x3 or 1x1x1");
     SIDE_REQUIRE(stride_hw == 1 || (stride_hw == 2 && kd == 1 && H % 2 == 0 && W % 2 == 0),
                  "side_conv3d_tc_fwd: stride must be 1, or 2 for 2-D kernels on even maps");
+    const int pool = (relu >> 2) & 1;              // bit 2: fused MaxPool3d((1,2,2))
+    relu &= 3;
     SIDE_REQUIRE(relu >= 0 && relu <= 2, "side_conv3d_tc_fwd: relu must be 0 (none), 1 (before the residual) or 2 (after it)");
     if (Nn == 0) return SIDE_OK;
     const int Ho = H / stride_hw, Wo = W / stride_hw;          // "same" padding: ceil(H / s) with even H
@@ -568,7 +584,9 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
         SIDE_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     // Cout == 64 on 256-voxel slices: role-swapped kernel (weights on M, 256 voxels on N), see conv_tct.cu
-    if (!g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw, f16))   // (takes Cin % 32 == 0)
+    SIDE_REQUIRE(!pool || (stride_hw == 1 && bw >= 2 && bw <= 16 && bh % 2 == 0 && H % 2 == 0 && W % 2 == 0),
+                 "side_conv3d_tc_fwd: the fused 2x2 max-pool needs stride 1, even H and W and boxes of 2..16 columns x an even number of rows");
+    if (!pool && !g_disable_tct && !g_dbg && conv_tct_supported(D, H, W, Cin, Cout, kd, kh, kw, stride_hw, f16))   // (takes Cin % 32 == 0)
         return conv_tct_launch(x_hi, x_lo, wp, scale, shift, residual, y, y_hi, y_lo, Nn, D, H, W, Cin, kd, relu, g_sm_count,
                                (cudaStream_t)stream, f16);
     CUtensorMap tm_hi, tm_lo;
@@ -580,6 +598,7 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     p.relu = relu; p.N = conv_ntile(Cout); p.Ntot = Cout; p.n_ntiles = Cout / p.N; p.ldy = Cout;
     p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.nkb = kd * kh * kw * p.ncb;
     p.klast = (f16 && Cin % 64 == 32) ? 2 : 4;
+    p.pool = pool;
     const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
     p.ntiles = (int)(mtiles * p.n_ntiles);
@@ -620,7 +639,7 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     ConvTcParams p;
     p.wp = wp; p.y = y; p.y_hi = nullptr; p.y_lo = nullptr; p.scale = nullptr; p.shift = nullptr; p.residual = nullptr;
     p.relu = 0; p.N = Nt; p.Ntot = Ncols; p.n_ntiles = Ncols / Nt; p.ldy = ldy;
-    p.ncb = K / 32; p.nkb = p.ncb; p.klast = 4;
+    p.ncb = K / 32; p.nkb = p.ncb; p.klast = 4; p.pool = 0;
     SIDE_REQUIRE((long long)Hr * p.n_ntiles < (1ll << 31), "conv_tc_rows_gemm: too many tiles");
     p.ntiles = Hr * p.n_ntiles;
     p.D = 1; p.H = Hr; p.W = kCvBM; p.bw = kCvBM; p.bh = 1; p.bd = 1; p.wt = 1; p.ht = Hr;

@@ -124,11 +124,9 @@ class cost_volume(nn.Module):
         gate = torch.sigmoid(isp).permute(0, 2, 3, 1).contiguous()             # [N, D, W, 64]
         hi, lo = ops.gate_mul_split(y, gate, fmt=fmt)
         _, hi, lo = conv(2, hi, lo)
-        y, _, _ = conv(3, hi, lo, full=True, split=False)                      # dres1 out, 128 ch
-        p1, hi, lo = ops.maxpool_hw2_cl(y, full=True, split=True, fmt=fmt)            # [N, D, 8, 8, 128]
+        p1, hi, lo = conv(3, hi, lo, full=True, split=True, pool=True)         # dres1 out + max_pool1 -> [N, D, 8, 8, 128]
         _, hi, lo = conv(4, hi, lo)
-        y, _, _ = conv(5, hi, lo, full=True, split=False, residual=p1)         # dres2(cost) + cost
-        _, hi, lo = ops.maxpool_hw2_cl(y, full=False, split=True, fmt=fmt)            # [N, D, 4, 4, 128]
+        _, hi, lo = conv(5, hi, lo, residual=p1, pool=True)                    # dres2(cost) + cost, max_pool2 -> [N, D, 4, 4, 128]
         y, _, _ = conv(6, hi, lo, full=True, split=False)                      # classify.0-2, 64 ch
         return ops.conv3d_c1_cl(y, self.classify[3].weight.detach())           # [N, D, 4, 4]
 

@@ -560,9 +560,10 @@ def conv_tc_prepare(weight, fmt=None):
 
 
 def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, relu=False, residual=None, full=False,
-              split=True, stride=1):
+              split=True, stride=1, pool=False):
     """x_hi, x_lo [N, D, H, W, Cin] -> (y, y_hi, y_lo) [N, D, H/stride, W/stride, Cout] (entries not requested are None).
-    relu: False / True (before the residual) / "after" (after the residual, DLA BasicBlock)."""
+    relu: False / True (before the residual) / "after" (after the residual, DLA BasicBlock).
+    pool=True: MaxPool3d((1,2,2)) of the result fused into the epilogue (outputs [N, D, H/2, W/2, Cout])."""
     lib = _lib.load()
     f16 = x_hi.dtype == torch.float16          # operand format follows the activations: fp16 pairs -> kind::f16 kernel
     odt = torch.float16 if f16 else _F32
@@ -571,7 +572,7 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
         raise RuntimeError("conv3d_tc: weight tiles (%s) and activations (%s) use different operand formats" % (wp.dtype, odt))
     N, D, H, W, Cin = x_hi.shape
     dev = x_hi.device
-    oshape = (N, D, H // stride, W // stride, Cout)
+    oshape = (N, D, H // stride // (2 if pool else 1), W // stride // (2 if pool else 1), Cout)
     y = torch.empty(oshape, device=dev, dtype=_F32) if full else None
     y_hi = torch.empty(oshape, device=dev, dtype=odt) if split else None
     y_lo = torch.empty(oshape, device=dev, dtype=odt) if split else None
@@ -580,7 +581,8 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     fn = lib.side_conv3d_tc_fwd_f16 if f16 else lib.side_conv3d_tc_fwd
     _lib.check(fn(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
                                       _p(y), _p(y_hi), _p(y_lo), N, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2],
-                                      int(stride), 2 if relu == "after" else (1 if relu else 0), _stream()), "side_conv3d_tc_fwd")
+                                      int(stride), (2 if relu == "after" else (1 if relu else 0)) | (4 if pool else 0), _stream()),
+               "side_conv3d_tc_fwd")
     return y, y_hi, y_lo
 
 

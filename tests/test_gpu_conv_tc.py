@@ -362,3 +362,25 @@ def test_aggregate_tc_f16_matches_module_fp64(lib, N, D):
         d_tc = ops.softargmin(out.contiguous(), db.cuda()).cpu()
         d_ref = ops.softargmin(ref.cuda().contiguous(), db.cuda()).cpu()
         assert float(((d_tc - d_ref).abs() / d_ref.abs()).max()) < 1e-4
+
+
+@pytest.mark.parametrize("fmt", ["tf32", "f16"])
+@pytest.mark.parametrize("cfg", [(2, 16, 16, 16, 128, 128, False), (3, 8, 8, 8, 128, 128, True), (1, 4, 16, 16, 64, 128, False)])
+def test_conv3d_tc_fused_maxpool(lib, cfg, fmt):
+    """MaxPool3d((1,2,2)) fused into the epilogue (relu | 4) == the stand-alone pool of the unfused result, bit for bit,
+    for the fp32 output and for both halves of the operand pair."""
+    from side_b200 import ops
+    N, D, H, W, Cin, Cout, res = cfg
+    g = torch.Generator().manual_seed(Cin + H + N)
+    dev = torch.device("cuda")
+    x = torch.randn(N, Cin, D, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) * 0.05).to(dev)
+    sc, sh = (torch.rand(Cout, generator=g) + 0.5).to(dev), (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    r = torch.randn(N, D, H, W, Cout, generator=g).to(dev) if res else None
+    hi, lo = ops.ncdhw_to_cl_split(x, fmt=fmt)
+    wp = ops.conv_tc_prepare(w, fmt=fmt)
+    y, _, _ = ops.conv3d_tc(hi, lo, wp, Cout, scale=sc, shift=sh, relu=True, residual=r, full=True, split=False)
+    want, whi, wlo = ops.maxpool_hw2_cl(y, full=True, split=True, fmt=fmt)
+    got, ghi, glo = ops.conv3d_tc(hi, lo, wp, Cout, scale=sc, shift=sh, relu=True, residual=r, full=True, split=True, pool=True)
+    assert tuple(got.shape) == (N, D, H // 2, W // 2, Cout)
+    assert torch.equal(got, want) and torch.equal(ghi, whi) and torch.equal(glo, wlo)
