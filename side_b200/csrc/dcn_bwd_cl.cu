@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(256) dcn_bwd_wprep_tc_kernel(const float *__re
 
 int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, float *y, long long ldy, long long rows, int K,
                       int Ncols, int Nt, cudaStream_t st);
+// weight gradient on tcgen05 (dcn_gw_tc.cu)
+bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows);
+int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, cudaStream_t st);
+int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, float *gw, int B, int b0, int nb, int Cout, int Kp,
+                  int P, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // scatter kernel
@@ -166,6 +171,7 @@ struct DcnBwdClArgs {
     const float *x_cl;             // [B][H][W][Cin]
     const float *offset, *mask;    // as in the forward (batch strides / layout in s)
     float *gcol;                   // [nb*P][KK*Cin]  in: W^T gy, out: forward columns
+    void *col_hi, *col_lo;         // non-null: the forward columns go here as fp16 pairs [nb*P][KK*Cin] (tcgen05 weight GEMM)
     float *gx_cl;                  // [B][H][W][Cin] accumulator (zeroed) or null
     float *goffset, *gmask;        // NCHW planes (batch strides s.offset_bs / s.mask_bs) or null
     DcnShape s;
@@ -253,7 +259,16 @@ __global__ void __launch_bounds__(128) dcn_bwd_scatter_cl_kernel(DcnBwdClArgs a)
                     val.y = w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
                     val.z = w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
                     val.w = w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-                    *reinterpret_cast<float4 *>(gc + c0) = make_float4(val.x * m, val.y * m, val.z * m, val.w * m);
+                    if (a.col_hi) {
+                        uint32_t h0, l0, h1, l1;
+                        f16_split2(val.x * m, val.y * m, h0, l0);
+                        f16_split2(val.z * m, val.w * m, h1, l1);
+                        const size_t e4 = (((size_t)bl * s.P + pi) * Kp + (size_t)tap * Cin + c0) >> 2;
+                        reinterpret_cast<uint2 *>(a.col_hi)[e4] = make_uint2(h0, h1);
+                        reinterpret_cast<uint2 *>(a.col_lo)[e4] = make_uint2(l0, l1);
+                    } else {
+                        *reinterpret_cast<float4 *>(gc + c0) = make_float4(val.x * m, val.y * m, val.z * m, val.w * m);
+                    }
                     mv += g.x * val.x + g.y * val.y + g.z * val.z + g.w * val.w;
                     top.x = g.x * m; top.y = g.y * m; top.z = g.z * m; top.w = g.w * m;
                     vh += (a1 * v1.x + a2 * v2.x + a3 * v3.x + a4 * v4.x) * top.x + (a1 * v1.y + a2 * v2.y + a3 * v3.y + a4 * v4.y) * top.y +
@@ -337,6 +352,8 @@ size_t dcn_bwd_cl_tc_floats(const DcnShape &s)
 {
     return 2 * (size_t)s.Cout * s.Cin * s.KK + 2 * (size_t)s.B * s.P * s.Cout;
 }
+// extra floats of the tensor-core weight GEMM besides a second column buffer per sample: fp16 pairs of gy
+size_t dcn_bwd_cl_gw_floats(const DcnShape &s) { return (size_t)s.B * s.P * s.Cout; }
 
 int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const float *mask, const float *w, const float *gy,
                    float *gx, float *goffset, float *gmask, float *gw, float *gbias, float *ws, size_t ws_floats,
@@ -361,7 +378,25 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
     }
     const bool tc = use_tc && ((size_t)chunk * P) % 128 == 0 && B % chunk == 0;
     if (use_tc && !tc) { gcol = wtc; avail = ws_floats - fixed; chunk = (int)std::min<size_t>((size_t)B, avail / per_sample); }
+    // tensor-core weight GEMM: needs the columns as fp16 pairs (a second buffer of the same size per sample) and the gy pairs
+    bool gwtc = false;
+    float *gy_pairs = nullptr, *col_pairs = nullptr;
+    if (gw && tc && dcn_gw_tc_supported(Cout, Cin, KK, P, (long long)chunk * P)) {
+        const size_t gyf = dcn_bwd_cl_gw_floats(s);
+        if (avail >= gyf + 2 * per_sample) {
+            int c2 = (int)std::min<size_t>((size_t)B, (avail - gyf) / (2 * per_sample));
+            while (c2 > 1 && (((size_t)c2 * P) % 128 != 0 || B % c2 != 0)) --c2;
+            if (((size_t)c2 * P) % 128 == 0 && B % c2 == 0) {
+                gwtc = true;
+                chunk = c2;
+                gy_pairs = gcol;                                     // [gy pairs][gcol chunk][column pairs chunk]
+                gcol = gy_pairs + gyf;
+                col_pairs = gcol + (size_t)chunk * per_sample;
+            }
+        }
+    }
     const int Nt = Cin >= 128 ? 128 : Cin;
+    if (gwtc && (rc = dcn_gw_tc_split_gy(gy, gy_pairs, B, Cout, P, st))) return rc;
     if (tc) {
         dcn_bwd_wprep_tc_kernel<<<ceil_div((long long)wsz, 256), 256, 0, st>>>(w, wtc, Cout, Cin, KK, Nt);
         SIDE_LAUNCH_CHECK("dcn_bwd_wprep_tc_kernel");
@@ -404,12 +439,17 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
             if (KK == 9) a.tg = tiles >= 1184 ? 9 : tiles * 3 >= 1184 ? 3 : 1;
             const long long ctas = tiles * (KK / a.tg);
             SIDE_REQUIRE(ctas < (1ll << 31), "side_dcn_bwd: grid too large");
+            a.gcol = gcol;
+            a.col_hi = gwtc ? reinterpret_cast<void *>(col_pairs) : nullptr;
+            a.col_lo = gwtc ? reinterpret_cast<void *>(reinterpret_cast<__half *>(col_pairs) + (size_t)nb * P * Kp) : nullptr;
             if (Cin == 64) dcn_bwd_scatter_cl_kernel<16><<<(unsigned)ctas, 128, 0, st>>>(a);
             else dcn_bwd_scatter_cl_kernel<32><<<(unsigned)ctas, 128, 0, st>>>(a);
             SIDE_LAUNCH_CHECK("dcn_bwd_scatter_cl_kernel");
         }
         // 3. gWp[o][k'] += sum_p gy[b][o][p] col[bl][p][k']
-        if (gw) {
+        if (gw && gwtc) {
+            if ((rc = dcn_gw_tc_run(gy_pairs, a.col_hi, a.col_lo, gWp, B, b0, nb, Cout, Kp, P, st))) return rc;
+        } else if (gw) {
             const int tiles = ceil_div(Kp, kSgN) * ceil_div(Cout, kSgM) * nb;
             int splits = std::max(1, std::min(ceil_div(P, 256), ceil_div(592, tiles)));
             int kchunk = ceil_div(ceil_div(P, splits), kSgK) * kSgK;

@@ -1,0 +1,264 @@
+// dcn_gw_tc.cu -- weight gradient of the DCNv2 backward on tcgen05.
+//
+// Reference: the second Sgemm of dcn_v2_cuda_backward (DCNv2/src/cuda/dcn_v2_cuda.cu:306-316): grad_weight += grad_output_n *
+// columns^T, one sample at a time.  Here:  gW[o][k'] = sum over (sample, pixel) of gy[b][o][p] * col[b*P + p][k'],  k' = tap*Cin + c.
+//
+// The reduction runs over PIXELS.  gy is NCHW ([o][p], pixels contiguous), so it is a K-major A operand as it lies in memory.
+// The column buffer is pixel-major ([p][k'], k' contiguous, as the scatter kernel writes it): with the pixels as K that is an
+// MN-MAJOR B operand -- tcgen05 reads it in place (instruction-descriptor bit 16, canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16-byte units under the 128-byte swizzle: a TMA box of 64 k' x 64 pixels is 8 swizzle atoms stacked along K, SBO = 1024 B,
+// and the next 64 k' sit LBO = 8 KB further), so no transposed copy of the 283 MB buffer is needed.
+// Operands are 3xFP16 pairs (hi, lo * 2^11, see tc_common.cuh): the scatter kernel emits the column pairs, a small kernel
+// splits gy.  A CTA owns (128 output-channel rows, <= 256 columns, a range of 64-pixel k-blocks): one TMA warp, one MMA thread
+// (hi*hi into the main accumulator, hi*lo' + lo'*hi into the cross accumulator: 512 TMEM columns), four epilogue warps that add
+// the tile into the fp32 gradient with 16-byte reductions (split-K).  Cout = 64 uses the upper half of the tile as TMA zero fill.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace side {
+
+constexpr int kGwThreads = 192;
+constexpr int kGwStages = 2;
+constexpr uint32_t kGwAPart = 128 * 128;          // 16 KB: 128 rows (o) x 64 pixels fp16
+constexpr uint32_t kGwBChunk = 64 * 128;          // 8 KB: 64 pixels (K rows) x 64 k' fp16
+constexpr uint32_t kGwBPart = 4 * kGwBChunk;      // up to 256 columns
+constexpr uint32_t kGwStage = 2 * kGwAPart + 2 * kGwBPart;   // 96 KB
+
+struct GwParams {
+    float *gw;                 // [Cout][Kp] fp32, accumulated into
+    int Cout, Kp, P, nb;       // P % 64 == 0
+    int n_ntiles, n_mtiles, ksplits, kb_total;     // kb_total = nb * P / 64
+};
+
+__device__ __forceinline__ void gw_tma_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void gw_tma_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// MN-major, SWIZZLE_128B operand: 64 MN elements (128 bytes) per swizzle row, 8-row atoms along K every SBO = 1024 bytes,
+// the next 64 MN elements LBO bytes further
+__device__ __forceinline__ uint64_t gw_desc_mn(uint32_t saddr, uint32_t lbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_constant__ CUtensorMap tm_gy_hi,
+                                                                  const __grid_constant__ CUtensorMap tm_gy_lo,
+                                                                  const __grid_constant__ CUtensorMap tm_col_hi,
+                                                                  const __grid_constant__ CUtensorMap tm_col_lo, GwParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[kGwStages], empty_bar[kGwStages], tmem_full;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+
+    // work item of this CTA
+    int r = blockIdx.x;
+    const int ks = r % p.ksplits; r /= p.ksplits;
+    const int nt = r % p.n_ntiles;
+    const int mt = r / p.n_ntiles;
+    const int n0 = nt * 256, Nw = min(256, p.Kp - n0);              // multiple of 64
+    const int per = (p.kb_total + p.ksplits - 1) / p.ksplits;
+    const int kb0 = ks * per, kb1 = min(p.kb_total, kb0 + per);
+    const int nkb = kb1 - kb0;
+    const int kpi = p.P / 64;                                        // k-blocks per sample
+
+    if (tid == 0) {
+        for (int i = 0; i < kGwStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&tmem_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t bytes = 2 * kGwAPart + 2 * (uint32_t)(Nw / 64) * kGwBChunk;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int bl = kb / kpi, p0 = (kb - bl * kpi) * 64;
+                mbar_wait(&empty_bar[st], ph ^ 1u);
+                unsigned char *sa = tiles + (size_t)st * kGwStage;
+                mbar_expect_tx(&full_bar[st], bytes);
+                gw_tma_3d(sa, &tm_gy_hi, p0, mt * 128, bl, &full_bar[st]);                 // rows past Cout: zero fill
+                gw_tma_3d(sa + kGwAPart, &tm_gy_lo, p0, mt * 128, bl, &full_bar[st]);
+                unsigned char *sb = sa + 2 * kGwAPart;
+                for (int j = 0; j < Nw / 64; ++j) {
+                    gw_tma_2d(sb + (size_t)j * kGwBChunk, &tm_col_hi, n0 + 64 * j, bl * p.P + p0, &full_bar[st]);
+                    gw_tma_2d(sb + kGwBPart + (size_t)j * kGwBChunk, &tm_col_lo, n0 + 64 * j, bl * p.P + p0, &full_bar[st]);
+                }
+                if (++st == kGwStages) { st = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            // A: K-major (bit 15 = 0), B: MN-major (bit 16 = 1)
+            const uint32_t idesc = tc_idesc_f16(128, Nw) | (1u << 16);
+            const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + 256u;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&full_bar[st], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(tiles + (size_t)st * kGwStage);
+                const uint32_t sb = sa + 2 * kGwAPart;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                      // 16 pixels per instruction
+                    const uint64_t a_hi = tc_smem_desc(sa + k * 32), a_lo = tc_smem_desc(sa + kGwAPart + k * 32);
+                    const uint64_t b_hi = gw_desc_mn(sb + k * 2048, kGwBChunk), b_lo = gw_desc_mn(sb + kGwBPart + k * 2048, kGwBChunk);
+                    tc_mma_f16(tmem_d, a_hi, b_hi, idesc, (i | k) != 0 ? 1u : 0u);
+                    tc_mma_f16(tmem_x, a_hi, b_lo, idesc, (i | k) != 0 ? 1u : 0u);
+                    tc_mma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                }
+                tc_commit(&empty_bar[st]);
+                if (++st == kGwStages) { st = 0; ph ^= 1u; }
+            }
+            tc_commit(&tmem_full);
+        }
+        __syncwarp();
+    } else if (nkb > 0) {
+        // epilogue: TMEM lane = output channel row, column = k'
+        const int lg = warp & 3, o = mt * 128 + lg * 32 + lane;
+        mbar_wait(&tmem_full, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        float *gp = p.gw + (size_t)o * p.Kp + n0;
+        for (int c = 0; c < Nw; c += 16) {
+            float v[16], vx[16];
+            tc_ld16(taddr + (uint32_t)c, v);
+            tc_ld16(taddr + 256u + (uint32_t)c, vx);
+            if (o < p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + c + 4 * j),
+                                 "f"(fmaf(vx[4 * j], kF16LoInv, v[4 * j])), "f"(fmaf(vx[4 * j + 1], kF16LoInv, v[4 * j + 1])),
+                                 "f"(fmaf(vx[4 * j + 2], kF16LoInv, v[4 * j + 2])), "f"(fmaf(vx[4 * j + 3], kF16LoInv, v[4 * j + 3]))
+                                 : "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// gy [B][Cout][P] fp32 -> fp16 pairs of the same layout
+__global__ void __launch_bounds__(256) gw_split_gy_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo,
+                                                         long long n4)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        uint32_t h0, l0, h1, l1;
+        f16_split2(v.x, v.y, h0, l0);
+        f16_split2(v.z, v.w, h1, l1);
+        hi[i] = make_uint2(h0, h1);
+        lo[i] = make_uint2(l0, l1);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 gw_encode_fn()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows)
+{
+    return P % 64 == 0 && Cout % 8 == 0 && (Cin * KK) % 64 == 0 && rows < (1ll << 31) && gw_encode_fn() != nullptr;
+}
+
+// halves needed for the gy pairs (the column pairs are written by the scatter kernel into the caller's buffers)
+size_t dcn_gw_tc_gy_halves(int B, int Cout, int P) { return 2 * (size_t)B * Cout * P; }
+
+// gw [Cout][Kp] += gy[b0 .. b0+nb) col;  gy_pairs: [hi | lo] halves of the WHOLE batch's gy (split once by dcn_gw_tc_split_gy),
+// col_hi / col_lo: [nb*P][Kp] halves of this chunk
+int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, cudaStream_t st)
+{
+    const long long n4 = (long long)B * Cout * P / 4;
+    uint2 *hi = reinterpret_cast<uint2 *>(gy_pairs);
+    gw_split_gy_kernel<<<(unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(gy), hi, hi + n4, n4);
+    SIDE_LAUNCH_CHECK("gw_split_gy_kernel");
+    return SIDE_OK;
+}
+
+int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, float *gw, int B, int b0, int nb, int Cout, int Kp,
+                  int P, cudaStream_t st)
+{
+    PFN_cuTensorMapEncodeTiled_v12000 enc = gw_encode_fn();
+    SIDE_REQUIRE(enc != nullptr, "dcn_gw_tc: cuTensorMapEncodeTiled is not available from the driver");
+    const __half *gh = reinterpret_cast<const __half *>(gy_pairs), *gl = gh + (size_t)B * Cout * P;
+    CUtensorMap tm[4];
+    {   // gy pairs of samples b0 .. b0+nb: [p (inner), o, b], box {64, 128, 1}; rows past Cout are zero-filled
+        cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)Cout, (cuuint64_t)nb};
+        cuuint64_t strides[2] = {(cuuint64_t)P * 2, (cuuint64_t)Cout * P * 2};
+        cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            const __half *base = (i ? gl : gh) + (size_t)b0 * Cout * P;
+            CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half *>(base), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("dcn_gw_tc: cuTensorMapEncodeTiled(gy) failed (CUresult %d)", (int)r); return SIDE_ERR_CUDA; }
+        }
+    }
+    {   // column pairs: [k' (inner), pixel row], box {64 k', 64 pixels}
+        cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)nb * P};
+        cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+        cuuint32_t box[2] = {64, 64}, es[2] = {1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(&tm[2 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(i ? col_lo : col_hi), dims, strides, box,
+                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("dcn_gw_tc: cuTensorMapEncodeTiled(col) failed (CUresult %d)", (int)r); return SIDE_ERR_CUDA; }
+        }
+    }
+    GwParams p;
+    p.gw = gw; p.Cout = Cout; p.Kp = Kp; p.P = P; p.nb = nb;
+    p.n_ntiles = (Kp + 255) / 256; p.n_mtiles = (Cout + 127) / 128;
+    p.kb_total = nb * (P / 64);
+    const int tiles = p.n_ntiles * p.n_mtiles;
+    p.ksplits = std::max(1, std::min(p.kb_total, (296 + tiles - 1) / tiles));
+    const size_t smem = (size_t)kGwStages * kGwStage + 1024;
+    int rc;
+    if ((rc = set_smem_attr((const void *)dcn_gw_tc_kernel, smem))) return rc;
+    dcn_gw_tc_kernel<<<(unsigned)(tiles * p.ksplits), kGwThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    SIDE_LAUNCH_CHECK("dcn_gw_tc_kernel");
+    return SIDE_OK;
+}
+
+}  // namespace side
