@@ -17,7 +17,9 @@
 //      grad_input is accumulated with ONE 16-byte vector reduction (REDG.E.ADD.F32x4) per corner and channel quad --
 //      4x fewer atomic operations, 32 lanes of parallelism along the channels instead of a serial channel loop.
 //      grad_offset / grad_mask: lane-parallel partial sums, one butterfly per item, coalesced stores per tap.
-//   3. gWp = gy col  (split-K SGEMM, atomics on the small weight gradient), un-permuted into gw by a copy kernel
+//   3. gWp = gy col: split-K over the pixels on tcgen05 (dcn_gw_tc.cu: the scatter kernel emits the columns as fp16 pairs and the
+//      pixel-major buffer is read in place as an MN-major B operand), or the fp32 SIMT tile kernel below when the shapes do not
+//      tile (P % 64 != 0); 16-byte reductions on the small weight gradient, un-permuted into gw by a copy kernel
 //   4. gx: channels-last accumulator -> NCHW
 // Accumulation order is not deterministic -- as in the reference (DCNv2/README.md:47-62).
 #include <algorithm>
