@@ -45,8 +45,9 @@ enum {
     SIDE_DCN_FUSE_AFFINE   = 1 << 1, /* y = y*scale[o] + shift[o]  (eval-mode BatchNorm of DeformConv.actf,
                                         feature_extraction_dla34.py:348-351) */
     SIDE_DCN_FUSE_RELU     = 1 << 2, /* y = max(y, 0) after the affine */
-    SIDE_DCN_PREC_FP32     = 0 << 4, /* SIMT fp32 FMA implicit GEMM (default; <=1e-5 rel vs the reference) */
-    SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel) */
+    SIDE_DCN_PREC_FP32     = 0 << 4, /* SIMT fp32 FMA implicit GEMM (<=1e-5 rel vs the reference) */
+    SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel); falls back to
+                                        the SIMT kernel for shapes tcgen05 cannot tile.  What callers should pass. */
     SIDE_DCN_PREC_TF32     = 2 << 4, /* tcgen05 kind::tf32 single pass (~1e-3 rel, opt-in) */
     SIDE_DCN_PREC_MASK     = 3 << 4,
     SIDE_DCN_BWD_SIMT_GEMM = 1 << 9, /* side_dcn_bwd: keep the column GEMM of the channels-last path on the fp32 SIMT kernel
@@ -98,8 +99,9 @@ int side_device_ok(void);
  *   scale/shift [Cout] used only with SIDE_DCN_FUSE_AFFINE
  *   y      [B, Cout, Ho, Wo]
  *   ws     workspace of side_dcn_fwd_ws_bytes(...) bytes (re-laid-out weights); may be NULL when that is 0.
- * Supported: dg == 1, any kh/kw/stride/pad/dilation for the fp32 path; the tcgen05 paths additionally
- * need Cin % 32 == 0, Cout % 16 == 0, Cout <= 256.
+ * Supported: any kh/kw/stride/pad/dilation; deformable_groups dg > 1 when (Cin / dg) % 16 == 0 (fp32 SIMT kernel).  The tcgen05
+ * precisions need dg == 1, Cin % 32 == 0, Cout % 16 == 0, Cout <= 256; for other shapes they run the fp32 SIMT kernel, so
+ * SIDE_DCN_PREC_3XTF32 is safe to pass always (it is what side_b200.ops passes by default).
  * --------------------------------------------------------------------------------------------- */
 size_t side_dcn_fwd_ws_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw, int flags);
 int side_dcn_fwd(const float *x, const float *offset, const float *mask, const float *w, const float *bias,
@@ -297,6 +299,16 @@ int side_ncdhw_to_cl_split_f16(const float *x, const float *scale, float *full, 
 int side_gate_mul_split_f16(const float *y, const float *gate, void *hi, void *lo, int N, int D, int H, int W, int C, void *stream);
 int side_maxpool_hw2_cl_f16(const float *x, float *y, void *hi, void *lo, int N, int D, int H, int W, int C, void *stream);
 int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, int H, int W, int C, void *stream);
+/* Range guard of the 3xFP16 operand pairs.  fp16 covers 2^-24 .. 65504, the reference's fp32 far more.  Registers a ring of
+ * `nwords` zero-initialised uint32 slots in device memory for the CURRENT device (NULL unregisters).  From then on every entry that
+ * writes fp16 pairs (side_ncdhw_to_cl_split_f16, side_gate_mul_split_f16, side_maxpool_hw2_cl_f16, side_conv3d_tc_fwd_f16 with
+ * y_hi/y_lo, side_inst_costvol_fwd_cl) takes the next slot (round robin) and leaves there the float bit pattern of max |x| of
+ * the tensor it split (atomicMax: slots only grow).  The caller classifies the ring when it chooses -- a slot >= 0x477FE000
+ * (65504.0f): a saturating conversion happened, results invalid; a non-zero slot < 0x36800000 (2^-18): the 2^-36 absolute
+ * resolution of the pair no longer meets the 1e-4 parity bar -- zeroes it, and on either finding repeats the work with the
+ * 3xTF32 entries (8-bit exponent).  With more than `nwords` guarded launches between two readings slots are shared (maxima
+ * merge: saturation is still caught, an underflow may be masked). */
+int side_tc_range_guard(void *status_words, int nwords);
 /* channels-last [B, HW, C] -> NCHW [B, C, HW]: hands a tensor-core convolution output back to NCHW consumers */
 int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream);
 

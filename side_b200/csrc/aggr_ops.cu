@@ -39,8 +39,9 @@ __device__ __forceinline__ void store_split4(float4 *__restrict__ hi, float4 *__
 template <bool F16>
 __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const float *__restrict__ scale, float *__restrict__ full,
                                          float *__restrict__ hi, float *__restrict__ lo, int C, long long S, int D, int per_d,
-                                         int Cpad)
+                                         int Cpad, uint32_t *rs)
 {
+    float amax = 0.f;                    // fp16 range guard (tc_common.cuh)
     // outputs have Cpad >= C channels per voxel, the extra ones zero (fp16 k-blocks are 64 channels wide)
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -62,6 +63,7 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
             const size_t o = ((size_t)n * S + p) * Cpad + c;
             if (F16) {
                 __half h, l;
+                amax = fmaxf(amax, fabsf(v));
                 f16_split(v, h, l);
                 reinterpret_cast<__half *>(hi)[o] = h;
                 reinterpret_cast<__half *>(lo)[o] = l;
@@ -73,6 +75,7 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
             if (full) full[o] = v;
         }
     }
+    if (F16 && rs) range_commit(rs, amax);
 }
 
 // fp16 variant with 64-channel tiles: a lane owns two adjacent channels, so every warp store is 128 contiguous bytes of
@@ -80,7 +83,7 @@ __global__ void ncdhw_to_cl_split_kernel(const float *__restrict__ in, const flo
 __global__ void __launch_bounds__(256) ncdhw_to_cl_split_f16_kernel(const float *__restrict__ in, const float *__restrict__ scale,
                                                                    float *__restrict__ full, uint32_t *__restrict__ hi,
                                                                    uint32_t *__restrict__ lo, int C, long long S, int D, int per_d,
-                                                                   int Cpad)
+                                                                   int Cpad, uint32_t *rs)
 {
     __shared__ float tile[64][33];
     const int n = blockIdx.z;
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(256) ncdhw_to_cl_split_f16_kernel(const float 
     }
     __syncthreads();
     const int c = c0 + 2 * threadIdx.x;
-    if (c >= Cpad) return;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    float amax = 0.f;
+    for (int i = threadIdx.y; i < 32 && c < Cpad; i += blockDim.y) {
         const long long p = p0 + i;
         if (p >= S) continue;
         float a = tile[2 * threadIdx.x][i], b = tile[2 * threadIdx.x + 1][i];
@@ -106,11 +109,13 @@ __global__ void __launch_bounds__(256) ncdhw_to_cl_split_f16_kernel(const float 
         }
         const size_t o = (((size_t)n * S + p) * Cpad + c) >> 1;      // index of the channel PAIR
         uint32_t h, l;
+        amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
         f16_split2(a, b, h, l);
         hi[o] = h;
         lo[o] = l;
         if (full) reinterpret_cast<float2 *>(full)[o] = make_float2(a, b);
     }
+    if (rs) range_commit(rs, amax);
 }
 
 __global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo, long long n4)
@@ -126,23 +131,28 @@ __global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restri
 // y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo
 template <bool F16>
 __global__ void gate_mul_split_kernel(const float4 *__restrict__ y, const float4 *__restrict__ gate, float4 *__restrict__ hi,
-                                      float4 *__restrict__ lo, long long n4, int H, int WC4)
+                                      float4 *__restrict__ lo, long long n4, int H, int WC4, uint32_t *rs)
 {
+    float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / WC4;             // (n, d, h)
         const int wc = (int)(i - row * WC4);
         const long long nd = row / H;
         const float4 v = __ldg(y + i), g = __ldg(gate + nd * WC4 + wc);
-        store_split4<F16>(hi, lo, i, make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w));
+        const float4 o = make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w);
+        if (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        store_split4<F16>(hi, lo, i, o);
     }
+    if (F16 && rs) range_commit(rs, amax);
 }
 
 // x [ND, H, W, C] -> max over 2x2 (h, w) windows -> [ND, H/2, W/2, C]; y and/or (hi, lo)
 template <bool F16>
 __global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, float4 *__restrict__ hi,
-                                      float4 *__restrict__ lo, long long n4out, int H, int W, int C4)
+                                      float4 *__restrict__ lo, long long n4out, int H, int W, int C4, uint32_t *rs)
 {
     const int Ho = H / 2, Wo = W / 2;
+    float amax = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4out; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         long long r = i / C4;
@@ -158,8 +168,12 @@ __global__ void maxpool_hw2_cl_kernel(const float4 *__restrict__ x, float4 *__re
         m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(cc.z, d.z));
         m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(cc.w, d.w));
         if (y) y[i] = m;
-        if (hi) store_split4<F16>(hi, lo, i, m);
+        if (hi) {
+            if (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(m.x), fabsf(m.y))), fmaxf(fabsf(m.z), fabsf(m.w)));
+            store_split4<F16>(hi, lo, i, m);
+        }
     }
+    if (F16 && rs && hi) range_commit(rs, amax);
 }
 
 // x [N, D, H, W, C], w [1, C, 3, 3, 3] -> out [N, D, H, W]   (Conv3d(C -> 1, 3, padding 1, bias=False)).
@@ -245,9 +259,11 @@ static int ncdhw_to_cl_split_impl(const float *x, const float *scale, float *ful
     if (f16 && Cpad % 2 == 0) {
         dim3 g2((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)N);
         ncdhw_to_cl_split_f16_kernel<<<g2, b, 0, (cudaStream_t)stream>>>(x, scale, full, reinterpret_cast<uint32_t *>(hi),
-                                                                         reinterpret_cast<uint32_t *>(lo), C, S, D, per_d, Cpad);
-    } else if (f16) ncdhw_to_cl_split_kernel<true><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
-    else ncdhw_to_cl_split_kernel<false><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad);
+                                                                         reinterpret_cast<uint32_t *>(lo), C, S, D, per_d, Cpad,
+                                                                         range_slot_next());
+    } else if (f16) ncdhw_to_cl_split_kernel<true><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad,
+                                                                                      range_slot_next());
+    else ncdhw_to_cl_split_kernel<false><<<g, b, 0, (cudaStream_t)stream>>>(x, scale, full, hi, lo, C, S, D, per_d, Cpad, nullptr);
     SIDE_LAUNCH_CHECK("ncdhw_to_cl_split_kernel");
     return SIDE_OK;
 }
@@ -285,11 +301,11 @@ static int gate_mul_split_impl(const float *y, const float *gate, float *hi, flo
     if (f16)
         gate_mul_split_kernel<true><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
-            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
+            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4, range_slot_next());
     else
         gate_mul_split_kernel<false><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float4 *>(y), reinterpret_cast<const float4 *>(gate), reinterpret_cast<float4 *>(hi),
-            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4);
+            reinterpret_cast<float4 *>(lo), n4, H, W * C / 4, nullptr);
     SIDE_LAUNCH_CHECK("gate_mul_split_kernel");
     return SIDE_OK;
 }
@@ -320,11 +336,11 @@ static int maxpool_hw2_cl_impl(const float *x, float *y, float *hi, float *lo, i
     if (f16)
         maxpool_hw2_cl_kernel<true><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
-            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
+            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4, range_slot_next());
     else
         maxpool_hw2_cl_kernel<false><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), reinterpret_cast<float4 *>(hi),
-            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4);
+            reinterpret_cast<float4 *>(lo), n4, H, W, C / 4, nullptr);
     SIDE_LAUNCH_CHECK("maxpool_hw2_cl_kernel");
     return SIDE_OK;
 }

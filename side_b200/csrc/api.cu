@@ -30,6 +30,23 @@ bool is_device_ptr(const void *p)
 
 __global__ void probe_kernel(int *out) { *out = 100; }
 
+// fp16 range guard (tc_common.cuh): one registered ring of 32-bit slots per device, handed out round robin
+struct RangeRing {
+    std::atomic<uint32_t *> base{nullptr};
+    std::atomic<unsigned> n{0}, next{0};
+};
+static RangeRing g_range[64];
+uint32_t *range_slot_next()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    RangeRing &r = g_range[dev];
+    uint32_t *base = r.base.load(std::memory_order_acquire);
+    const unsigned n = r.n.load(std::memory_order_relaxed);
+    if (!base || !n) return nullptr;
+    return base + r.next.fetch_add(1, std::memory_order_relaxed) % n;
+}
+
 }  // namespace side
 
 extern "C" int side_abi_version(void) { return SIDE_ABI_VERSION; }
@@ -49,6 +66,26 @@ extern "C" int side_device_ok(void)
         return 0;  // no sm_100a image for this device
     }
     return 1;
+}
+
+extern "C" int side_tc_range_guard(void *status_words, int nwords)
+{
+    int dev = 0;
+    SIDE_CUDA(cudaGetDevice(&dev));
+    SIDE_REQUIRE(dev >= 0 && dev < 64, "side_tc_range_guard: device index out of range");
+    side::RangeRing &r = side::g_range[dev];
+    if (!status_words) {
+        r.base.store(nullptr, std::memory_order_release);
+        r.n.store(0);
+        return SIDE_OK;
+    }
+    SIDE_REQUIRE(nwords >= 1, "side_tc_range_guard: nwords must be >= 1");
+    SIDE_REQUIRE_DEV(status_words);
+    r.base.store(nullptr, std::memory_order_release);
+    r.n.store((unsigned)nwords);
+    r.next.store(0);
+    r.base.store(reinterpret_cast<uint32_t *>(status_words), std::memory_order_release);
+    return SIDE_OK;
 }
 
 extern "C" long long side_launch_count(int reset)

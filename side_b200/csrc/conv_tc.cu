@@ -58,6 +58,7 @@ struct ConvTcParams {
     // is a multiple of 1024 bytes, so the 128-byte swizzle phase is unchanged.  A ring (a_slots) and B ring (b_slots)
     // are then separate: A is loaded once per (kd, kw, channel block), B once per tap.
     int khv, a_slots, b_slots;
+    uint32_t *rs;                     // fp16 range-guard slot of this launch (tc_common.cuh) or NULL
     int dbg;                          // timing experiments only (side_conv_tc_set_mode bits 1, 2): skip the B / A copies
     uint32_t a_part;                  // bytes of one half (hi or lo) of an A slot
 };
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         const int m = lg * 32 + lane;
         int acc = 0;
         uint32_t acc_ph = 0;
+        float amax = 0.f;                        // max |x| of what this thread splits into fp16 pairs (range guard)
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
@@ -345,6 +347,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 if (F16 && writer && p.y_hi) {
                     uint32_t hh[8], ll[8];
 #pragma unroll
+                    for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#pragma unroll
                     for (int j = 0; j < 8; ++j) f16_split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
                     uint4 *hp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_hi) + orow + c);
                     uint4 *lp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(p.y_lo) + orow + c);
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
+        if (F16 && p.rs && p.y_hi) range_commit(p.rs, amax);
     }
 
     tc_fence_before();
@@ -607,6 +612,7 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
+    p.rs = f16 ? range_slot_next() : nullptr;
     const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tc_kernel<true> : (const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {
@@ -646,7 +652,7 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     p.kd = 1; p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
-    p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0;
+    p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0; p.rs = nullptr;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     if ((rc = set_smem_attr((const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {

@@ -41,6 +41,7 @@ struct ConvTtParams {
     int ncb, kd, ntiles, D, bw, bh;   // bw * bh == 256, one tile = one (sample, depth slice)
     int klast;                        // K-steps with data in the last channel block (2 when Cin % 64 == 32 on fp16, else 4)
     uint32_t x_part;                  // bytes of one half (hi or lo) of an X slot: (bh + 2) * bw * 128
+    uint32_t *rs;                     // fp16 range-guard slot of this launch (tc_common.cuh) or NULL
 };
 
 __device__ __forceinline__ void tt_tma_load_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4,
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
         const float sc = s_scale[ch], sh = s_shift[ch];
         int acc = 0;
         uint32_t acc_ph = 0;
+        float amax = 0.f;                        // range guard: max |x| of what this thread splits into fp16 pairs
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
                         if (p.y) p.y[o0 + (size_t)j * kTtCout] = o;
                         if (F16 && p.y_hi) {
                             __half h, l;
+                            amax = fmaxf(amax, fabsf(o));
                             f16_split(o, h, l);
                             reinterpret_cast<__half *>(p.y_hi)[o0 + (size_t)j * kTtCout] = h;
                             reinterpret_cast<__half *>(p.y_lo)[o0 + (size_t)j * kTtCout] = l;
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
+        if (F16 && p.rs && p.y_hi) range_commit(p.rs, amax);
     }
 
     tc_fence_before();
@@ -276,6 +280,7 @@ int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const
     p.wp = wp; p.y = y; p.y_hi = y_hi; p.y_lo = y_lo; p.scale = scale; p.shift = shift; p.residual = residual; p.relu = relu;
     p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.kd = kd; p.klast = (f16 && Cin % 64 == 32) ? 2 : 4; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
     p.x_part = (uint32_t)(H + 2) * W * 128u;
+    p.rs = f16 ? range_slot_next() : nullptr;
     const size_t smem = (size_t)kTtXSlots * 2 * p.x_part + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tct_kernel<true> : (const void *)conv_tct_kernel<false>, smem))) return rc;
     const unsigned grid = (unsigned)std::min(p.ntiles, sm_count);

@@ -189,7 +189,7 @@ extern "C" size_t side_dcn_bwd_ws_bytes(int B, int Cin, int H, int W, int Cout, 
     const size_t cols = (size_t)B * Cin * kh * kw * (size_t)H * W;
     const size_t fixed = 4 * (size_t)std::max(Cout, 0) * Cin * kh * kw + 2 * (size_t)B * Cin * H * W +
                          3 * (size_t)B * std::max(Cout, 0) * H * W;   // incl. the tensor-core GEMM operands (gy pairs twice)
-    return sizeof(float) * (2 * cols + fixed);                        // columns: fp32 (in) + fp16 pairs (out)
+    return sizeof(float) * (2 * cols + fixed + 64);                   // columns: fp32 (in) + fp16 pairs (out); + gy range scale
 }
 
 extern "C" int side_dcn_bwd(const float *x, const float *offset, const float *mask, const float *w, const float *gy,

@@ -355,7 +355,8 @@ size_t dcn_bwd_cl_tc_floats(const DcnShape &s)
     return 2 * (size_t)s.Cout * s.Cin * s.KK + 2 * (size_t)s.B * s.P * s.Cout;
 }
 // extra floats of the tensor-core weight GEMM besides a second column buffer per sample: fp16 pairs of gy
-size_t dcn_bwd_cl_gw_floats(const DcnShape &s) { return (size_t)s.B * s.P * s.Cout; }
+// (+ 64 floats: the power-of-two range scale of gy, see dcn_gw_tc.cu)
+size_t dcn_bwd_cl_gw_floats(const DcnShape &s) { return (size_t)s.B * s.P * s.Cout + 64; }
 
 int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const float *mask, const float *w, const float *gy,
                    float *gx, float *goffset, float *gmask, float *gw, float *gbias, float *ws, size_t ws_floats,
@@ -369,7 +370,10 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
     int rc;
     // tensor-core column GEMM when the shapes tile and the workspace has room for its operands next to >= 1 sample of columns
     const size_t tcf = dcn_bwd_cl_tc_floats(s);
-    const bool use_tc = !(s.flags & SIDE_DCN_BWD_SIMT_GEMM) && Cout % 32 == 0 && Cin % 16 == 0 && ws_floats >= fixed + tcf + per_sample;
+    // n-tile of the column GEMM: 128 columns when Kp tiles by 128, else 64 (Cin = 64 * odd: Kp = 9 * Cin is a multiple of 64 only);
+    // every 1536-column slice and the tail Kp % 1536 are then whole n-tiles and wtc (2 * wsz floats) holds exactly Kp / Nt of them
+    const int Nt = (Cin >= 128 && Kp % 128 == 0) ? 128 : 64;
+    const bool use_tc = !(s.flags & SIDE_DCN_BWD_SIMT_GEMM) && Cout % 32 == 0 && Kp % Nt == 0 && ws_floats >= fixed + tcf + per_sample;
     float *wtc = gcol, *gy_hi = wtc + 2 * wsz, *gy_lo = gy_hi + (size_t)B * P * Cout;
     size_t avail = ws_floats - fixed;
     if (use_tc) { gcol = gy_lo + (size_t)B * P * Cout; avail -= tcf; }
@@ -397,7 +401,6 @@ int dcn_bwd_cl_run(const DcnShape &s, const float *x, const float *offset, const
             }
         }
     }
-    const int Nt = Cin >= 128 ? 128 : Cin;
     if (gwtc && (rc = dcn_gw_tc_split_gy(gy, gy_pairs, B, Cout, P, st))) return rc;
     if (tc) {
         dcn_bwd_wprep_tc_kernel<<<ceil_div((long long)wsz, 256), 256, 0, st>>>(w, wtc, Cout, Cin, KK, Nt);

@@ -30,6 +30,7 @@ constexpr uint32_t kGwStage = 2 * kGwAPart + 2 * kGwBPart;   // 96 KB
 
 struct GwParams {
     float *gw;                 // [Cout][Kp] fp32, accumulated into
+    const uint32_t *gy_absmax; // bits of max |gy| over the whole batch (gw_absmax_kernel): fixes the power-of-two range scale
     int Cout, Kp, P, nb;       // P % 64 == 0
     int n_ntiles, n_mtiles, ksplits, kb_total;     // kb_total = nb * P / 64
 };
@@ -53,6 +54,30 @@ __device__ __forceinline__ uint64_t gw_desc_mn(uint32_t saddr, uint32_t lbo)
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
+}
+
+// gy is a back-propagated gradient: its magnitude is arbitrary (1e-10 for mean-reduced losses over 96x320 maps, 1e+6 for summed
+// ones), while fp16 pairs only resolve 2^-24 .. 65504.  The split therefore runs on gy * 2^s with s chosen from max |gy| so that
+// the largest element lands in [2^12, 2^13): exact (power of two), 26 binades of headroom below before `hi` goes subnormal, and
+// the weight-gradient epilogue multiplies the tile by 2^-s.  Both sides derive s from the same absmax word.
+__device__ __forceinline__ float gw_range_scale(uint32_t absmax_bits, bool inverse)
+{
+    int e = (int)(absmax_bits >> 23) - 127;                 // floor(log2(max |gy|)); zero / subnormal maxima -> no scaling
+    if (absmax_bits < 0x00800000u || absmax_bits >= 0x7F800000u) e = 12;
+    int s = 12 - e;                                         // scale = 2^s
+    s = max(-126, min(126, s));
+    return __uint_as_float((uint32_t)(127 + (inverse ? -s : s)) << 23);
+}
+
+__global__ void __launch_bounds__(256) gw_absmax_kernel(const float4 *__restrict__ x, uint32_t *__restrict__ out, long long n4)
+{
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));     // fmaxf drops NaNs
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));    // non-negative floats order like their bits
 }
 
 __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_constant__ CUtensorMap tm_gy_hi,
@@ -146,6 +171,7 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
         float *gp = p.gw + (size_t)o * p.Kp + n0;
+        const float inv = gw_range_scale(__ldg(p.gy_absmax), true), invx = inv * kF16LoInv;
         for (int c = 0; c < Nw; c += 16) {
             float v[16], vx[16];
             tc_ld16(taddr + (uint32_t)c, v);
@@ -154,8 +180,8 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp + c + 4 * j),
-                                 "f"(fmaf(vx[4 * j], kF16LoInv, v[4 * j])), "f"(fmaf(vx[4 * j + 1], kF16LoInv, v[4 * j + 1])),
-                                 "f"(fmaf(vx[4 * j + 2], kF16LoInv, v[4 * j + 2])), "f"(fmaf(vx[4 * j + 3], kF16LoInv, v[4 * j + 3]))
+                                 "f"(fmaf(vx[4 * j], invx, v[4 * j] * inv)), "f"(fmaf(vx[4 * j + 1], invx, v[4 * j + 1] * inv)),
+                                 "f"(fmaf(vx[4 * j + 2], invx, v[4 * j + 2] * inv)), "f"(fmaf(vx[4 * j + 3], invx, v[4 * j + 3] * inv))
                                  : "memory");
             }
         }
@@ -168,12 +194,14 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
     }
 }
 
-// gy [B][Cout][P] fp32 -> fp16 pairs of the same layout
+// gy [B][Cout][P] fp32 -> fp16 pairs of (gy * 2^s), same layout
 __global__ void __launch_bounds__(256) gw_split_gy_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo,
-                                                         long long n4)
+                                                         long long n4, const uint32_t *__restrict__ absmax)
 {
+    const float sc = gw_range_scale(__ldg(absmax), false);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(x + i);
+        float4 v = __ldg(x + i);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
         uint32_t h0, l0, h1, l1;
         f16_split2(v.x, v.y, h0, l0);
         f16_split2(v.z, v.w, h1, l1);
@@ -211,8 +239,12 @@ int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, 
 {
     const long long n4 = (long long)B * Cout * P / 4;
     uint2 *hi = reinterpret_cast<uint2 *>(gy_pairs);
-    gw_split_gy_kernel<<<(unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(gy), hi, hi + n4, n4);
+    uint32_t *absmax = reinterpret_cast<uint32_t *>(hi + 2 * n4);           // first word behind the pairs (dcn_bwd_cl_gw_floats)
+    SIDE_CUDA(cudaMemsetAsync(absmax, 0, sizeof(uint32_t), st));
+    const unsigned grid = (unsigned)std::min<long long>((n4 + 255) / 256, 148 * 16);
+    gw_absmax_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(gy), absmax, n4);
+    SIDE_LAUNCH_CHECK("gw_absmax_kernel");
+    gw_split_gy_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(gy), hi, hi + n4, n4, absmax);
     SIDE_LAUNCH_CHECK("gw_split_gy_kernel");
     return SIDE_OK;
 }
@@ -249,6 +281,7 @@ int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, 
     }
     GwParams p;
     p.gw = gw; p.Cout = Cout; p.Kp = Kp; p.P = P; p.nb = nb;
+    p.gy_absmax = reinterpret_cast<const uint32_t *>(gl + (size_t)B * Cout * P);
     p.n_ntiles = (Kp + 255) / 256; p.n_mtiles = (Cout + 127) / 128;
     p.kb_total = nb * (P / 64);
     const int tiles = p.n_ntiles * p.n_mtiles;

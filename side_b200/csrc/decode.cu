@@ -324,9 +324,13 @@ static int launch_decode(DecParams &p, bool ddd, void *ws, size_t ws_bytes, void
     regionA = (regionA + 15) & ~(size_t)15;
     p.regionA_bytes = regionA;
     const size_t smem = regionA + (size_t)p.Kpad * 8;
-    if (smem > 220 * 1024) {
-        set_error("decode: H*W=%d needs %zu bytes of shared memory (> 220 KB)", p.H * p.W, smem);
-        return SIDE_ERR_UNSUPPORTED;
+    {   // static (per-warp histograms, ~33 KB) + dynamic shared memory against the 227 KB opt-in limit of sm_100a
+        cudaFuncAttributes fa;
+        SIDE_CUDA(cudaFuncGetAttributes(&fa, ddd ? (const void *)nms_topk_decode_kernel<true> : (const void *)nms_topk_decode_kernel<false>));
+        if (smem + fa.sharedSizeBytes > 227 * 1024) {
+            set_error("decode: H*W=%d needs %zu + %zu bytes of shared memory (> 227 KB)", p.H * p.W, smem, (size_t)fa.sharedSizeBytes);
+            return SIDE_ERR_UNSUPPORTED;
+        }
     }
     p.ws_ticket = reinterpret_cast<unsigned int *>(ws);
     p.ws_comp = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(ws) + 256 * ((p.B * 4 + 255) / 256));

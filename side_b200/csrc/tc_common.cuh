@@ -69,6 +69,30 @@ __device__ __forceinline__ void f16_split(float v, __half &h, __half &l)
     l = f16_sat((v - __half2float(h)) * kF16LoScale);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Range guard of the fp16 pairs.  fp16 resolves 2^-24 .. 65504 where the reference's fp32 covers 2^-149 .. 3.4e38: a tensor
+// whose largest element reaches 65504 saturates, one whose largest element is below 2^-18 loses more than the 1e-4 parity bar
+// to the subnormal spacing of `lo'` (absolute error 2^-36).  Every kernel that WRITES fp16 pairs tracks max |x| of what it
+// splits and folds it into one 32-bit slot of a device status ring registered with side_tc_range_guard(): the host hands
+// each guarded launch the next slot (round robin), a warp only issues its atomicMax when its maximum beats what the slot
+// already holds (a handful of atomics per launch, no ordering between launches needed).  The host classifies the slots when
+// it wants to know (side_b200.ops.tc_range_status: any slot >= 65504 -> saturated, any non-zero slot < 2^-18 -> underflow),
+// zeroes them and, if a flag is up, repeats the work in 3xTF32.
+// ------------------------------------------------------------------------------------------------
+uint32_t *range_slot_next();                       // api.cu: next slot of the ring registered for the current device, or nullptr
+
+// all 32 lanes of a warp call this once at the end of the kernel with the maximum |x| they split
+__device__ __forceinline__ void range_commit(uint32_t *slot, float amax)
+{
+    amax = warp_max(amax);
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) {
+        const uint32_t b = __float_as_uint(amax);  // non-negative floats order like their bit patterns; +inf counts as saturation
+        uint32_t cur;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(slot) : "memory");
+        if (b > cur) atomicMax(slot, b);
+    }
+}
+
 // split two values and pack the halves pairwise (little endian: a in the low 16 bits)
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t &hi, uint32_t &lo)
 {

@@ -34,6 +34,9 @@ class StereoDetector:
         self.model.K = K
         self._graph = None
         self._static = None
+        self.keep_heads = False      # True: the head maps of the last step stay in .last_heads ('hm' after the sigmoid)
+        self.last_heads = None
+        self.range_fallbacks = 0     # steps process_checked() had to repeat in 3xTF32
 
     @torch.no_grad()
     def process(self, batch):
@@ -43,7 +46,28 @@ class StereoDetector:
                                             grid_size=self.grid, K=self.K)
         if self.use_cost_volume:
             info = torch.cat([info, out['depth']], dim=2)
+        if self.keep_heads:
+            self.last_heads = out
         return dets, dets_right, info
+
+    def process_checked(self, batch):
+        """``process`` + the range guard of the 3xFP16 operand pairs: the kernels that write fp16 pairs report saturation
+        (an activation reached 65504) / underflow (a tensor below 2^-18 everywhere) into a device status word; when it is set
+        the step is repeated with the 3xTF32 kernels (8-bit exponent, same accuracy class, half the tensor rate).  Costs one
+        4-byte device-to-host copy per step -- free in a serving loop that reads the detections anyway."""
+        dev = batch['input'].device
+        if not batch['input'].is_cuda or ops.get_tc_format() != "f16":
+            return self.process(batch)
+        ops.tc_range_status(dev)                         # clear what earlier work left behind
+        out = self.process(batch)
+        if ops.tc_range_status(dev):
+            self.range_fallbacks += 1
+            ops.set_tc_format("tf32")
+            try:
+                out = self.process(batch)
+            finally:
+                ops.set_tc_format("f16")
+        return out
 
     # -- CUDA graph path -----------------------------------------------------------------------
     def capture(self, example_batch, warmup=3):
@@ -87,35 +111,118 @@ def gather_detections(dets, dets_right, info, group=None):
             [out[r, :, :, b:] for r in range(world)])
 
 
+def _buckets(params, bucket_bytes):
+    """Rank-independent bucketing: over ALL parameters that require a gradient, in reverse registration order (roughly
+    the order backward produces them), never over `p.grad is not None` -- a rank whose batch skipped a branch (no boxes:
+    the depth branch of stereo_network.forward does not run) still takes part in every collective with zeros."""
+    out, cur, size = [], [], 0
+    for p in reversed([p for p in params if p.requires_grad]):
+        cur.append(p)
+        size += p.numel() * p.element_size()
+        if size >= bucket_bytes:
+            out.append(cur)
+            cur, size = [], 0
+    if cur:
+        out.append(cur)
+    return out
+
+
 def allreduce_gradients(params, group=None, bucket_bytes=25 << 20):
-    """Averages gradients over ranks with bucketed asynchronous all-reduces (replaces DataParallel's reduce-add to
-    GPU 0 + per-step parameter broadcast).  BatchNorm statistics stay per replica, as in the reference."""
+    """Averages gradients over ranks with bucketed asynchronous all-reduces AFTER backward (replaces DataParallel's
+    reduce-add to GPU 0 + per-step parameter broadcast, data_parallel.py:70-72).  Parameters without a gradient on this
+    rank contribute zeros and receive the average, so bucket shapes and the collective sequence are the same on every rank.
+    BatchNorm statistics stay per replica, as in the reference.  Returns the number of buckets."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
-    grads = [p.grad for p in params if p.grad is not None]
-    buckets, cur, size = [], [], 0
-    for g in grads:
-        cur.append(g)
-        size += g.numel() * g.element_size()
-        if size >= bucket_bytes:
-            buckets.append(cur)
-            cur, size = [], 0
-    if cur:
-        buckets.append(cur)
     pending = []
-    for bk in buckets:
-        flat = torch.cat([g.reshape(-1) for g in bk])
+    for bk in _buckets(list(params), bucket_bytes):
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bk])
         pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, bk))
     for work, flat, bk in pending:
         work.wait()
         flat.div_(world)
         off = 0
-        for g in bk:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
+        for p in bk:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = flat[off:off + n].view_as(p).clone()
+            else:
+                p.grad.copy_(flat[off:off + n].view_as(p))
             off += n
-    return len(buckets)
+    return len(pending)
+
+
+class GradientAllReducer:
+    """Bucketed gradient averaging OVERLAPPED with backward (BASELINE config #5).
+
+    Every bucket owns one flat buffer and the parameters' ``.grad`` are views into it (no gather / scatter copies).  A
+    post-accumulate hook per parameter counts the bucket down; a complete bucket is all-reduced asynchronously on NCCL's
+    stream while autograd keeps producing the earlier layers' gradients.  Buckets are launched strictly in index order and
+    ``finish()`` launches whatever backward did not complete (parameters that got no gradient this step keep their zeros), so
+    every rank issues the same sequence of equally sized collectives whatever its batch looked like.
+
+        red = GradientAllReducer(model.parameters())
+        red.zero_grad(); loss.backward(); red.finish(); opt.step()
+    """
+
+    def __init__(self, params, group=None, bucket_bytes=25 << 20):
+        self.group = group
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.enabled else 1
+        self.buckets = _buckets(list(params), bucket_bytes)
+        self.flat, self._bucket_of = [], {}
+        for bi, bk in enumerate(self.buckets):
+            flat = torch.zeros(sum(p.numel() for p in bk), device=bk[0].device, dtype=bk[0].dtype)
+            off = 0
+            for p in bk:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[p] = bi
+                if self.enabled:
+                    p.register_post_accumulate_grad_hook(self._hook)
+            self.flat.append(flat)
+        self.bytes_per_step = sum(f.numel() * f.element_size() for f in self.flat)
+        self._reset()
+
+    def _reset(self):
+        self._left = [len(bk) for bk in self.buckets]
+        self._next = 0
+        self._work = []
+
+    def zero_grad(self):
+        """Zeroes the flat buffers and re-points ``.grad`` at them (use instead of optimizer.zero_grad(set_to_none=True))."""
+        for bk, flat in zip(self.buckets, self.flat):
+            flat.zero_()
+            off = 0
+            for p in bk:
+                if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + off * flat.element_size():
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self._reset()
+
+    def _launch_ready(self, force=False):
+        while self._next < len(self.buckets) and (force or self._left[self._next] <= 0):
+            self._work.append(dist.all_reduce(self.flat[self._next], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._next += 1
+
+    def _hook(self, p):
+        self._left[self._bucket_of[p]] -= 1
+        self._launch_ready()
+
+    def finish(self):
+        """After backward: launch the buckets still waiting (in order), wait for all, divide by the world size.
+        Returns the number of buckets whose all-reduce was already in flight when backward returned."""
+        if not self.enabled:
+            return 0
+        early = self._next
+        self._launch_ready(force=True)
+        for w in self._work:
+            w.wait()
+        for flat in self.flat:
+            flat.div_(self.world)
+        self._reset()
+        return early
 
 
 class OpTimer:

@@ -317,7 +317,7 @@ class stereo_network(nn.Module):
                 disp = self._depth_from_boxes(feaL, feaR, o['bbox'].view(-1, 5), o['bbox_right'].view(-1, 5), fb,
                                               o['keep'], D)
                 keep = o['keep'].bool()
-                depth = torch.zeros((B, K + 1), device=dev, dtype=torch.float32)
+                depth = torch.zeros((B, K + 1), device=dev, dtype=disp.dtype)
                 slot = torch.where(keep.view(B, K), o['slot'].long(), torch.full_like(o['slot'], K, dtype=torch.long))
                 depth.scatter_(1, slot, disp.view(B, K))            # dropped rows land in the spare column K
                 depth = depth[:, :K].unsqueeze(2).contiguous()
@@ -334,6 +334,7 @@ class stereo_network(nn.Module):
                     order = torch.argsort(bl[:, 0], stable=True)   # group by image (reference :44-82)
                     bl, br = bl[order].contiguous(), br[order].contiguous()
                     disp = self._depth_from_boxes(feaL, feaR, bl, br, fb, None, D)
+                    depth = depth.to(disp.dtype)
                     bi = bl[:, 0].long()
                     onehot = bi.unsqueeze(1) == torch.arange(batch_size, device=dev).unsqueeze(0)
                     slot = (torch.cumsum(onehot, 0) - 1).gather(1, bi.clamp(0, batch_size - 1).unsqueeze(1)).squeeze(1)

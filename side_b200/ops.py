@@ -37,12 +37,13 @@ def _pair(v):
 # DCNv2
 # ----------------------------------------------------------------------------------------------
 PRECISIONS = {"fp32": _lib.DCN_PREC_FP32, "3xtf32": _lib.DCN_PREC_3XTF32, "tf32": _lib.DCN_PREC_TF32}
-_default_precision = "fp32"
+_default_precision = "3xtf32"
 
 
 def set_dcn_precision(name):
-    """Selects the arithmetic of the DCN contraction: 'fp32' (SIMT FMA), '3xtf32' (tcgen05, fp32-class
-    accuracy) or 'tf32' (tcgen05 single pass, ~1e-3 relative)."""
+    """Selects the arithmetic of the DCN contraction: '3xtf32' (default: tcgen05 with the exact hi/lo split, fp32-class
+    accuracy <= 1e-4 rel.; shapes the tensor-core kernel cannot tile -- Cin % 32, Cout % 16, Cout > 256, dg > 1 -- run the fp32
+    SIMT kernel), 'fp32' (always SIMT FMA) or 'tf32' (tcgen05 single pass, ~1e-3 relative, opt-in)."""
     global _default_precision
     if name not in PRECISIONS:
         raise ValueError("unknown DCN precision %r" % (name,))
@@ -226,6 +227,42 @@ def set_tc_format(fmt):
 
 def get_tc_format():
     return _tc_format
+
+
+# -- range guard of the fp16 operand pairs (include/side_b200.h: side_tc_range_guard) ---------------------------------------------
+_range_blocks = {}      # device index -> int32[_RANGE_SLOTS] ring registered with the library
+_RANGE_SLOTS = 1024
+_RANGE_SAT_BITS, _RANGE_TINY_BITS = 0x477FE000, 0x36800000      # 65504.0f, 2^-18 as float bit patterns
+TC_RANGE_SATURATED, TC_RANGE_UNDERFLOW = 1, 2
+
+
+def _range_guard(device):
+    """Registers (once per device) the ring of slots the kernels that write fp16 pairs leave max |x| of their tensor in."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    blk = _range_blocks.get(idx)
+    if blk is None:
+        blk = torch.zeros(_RANGE_SLOTS, device=torch.device("cuda", idx), dtype=torch.int32)
+        with torch.cuda.device(idx):
+            _lib.check(_lib.load().side_tc_range_guard(blk.data_ptr(), _RANGE_SLOTS), "side_tc_range_guard")
+        _range_blocks[idx] = blk
+    return blk
+
+
+def tc_range_status(device=None, reset=True):
+    """-> flags accumulated since the last reset: TC_RANGE_SATURATED (an activation tensor reached 65504: fp16 pairs invalid) |
+    TC_RANGE_UNDERFLOW (a non-zero tensor stayed below 2^-18: pairs lose the 1e-4 bar).  One small device-to-host copy (syncs)."""
+    idx = (torch.device(device).index if device is not None else None)
+    idx = torch.cuda.current_device() if idx is None else idx
+    blk = _range_blocks.get(idx)
+    if blk is None:
+        return 0
+    hi = blk.max()                                                   # float bit patterns of non-negative values order as ints
+    lo = torch.where(blk > 0, blk, torch.full_like(blk, 0x7FFFFFFF)).min()
+    hi, lo = int(hi.item()), int(lo.item())
+    flags = (TC_RANGE_SATURATED if hi >= _RANGE_SAT_BITS else 0) | (TC_RANGE_UNDERFLOW if lo < _RANGE_TINY_BITS else 0)
+    if reset and hi:
+        blk.zero_()
+    return flags
 
 
 VOL_BWD_FLAGS = 0   # tests / benchmarks: _lib.VOL_BWD_SCALAR forces the scalar-atomic backward kernel
@@ -543,6 +580,15 @@ def conv_tc_prepare(weight, fmt=None):
     taps = weight[0, 0].numel()
     nbytes = lib.side_conv_tc_weight_bytes(Cin, Cout, taps)
     if fmt == "f16":
+        # fp16 pairs resolve 2^-24 .. 65504: weights far from O(1) are normalised by an exact power of two that conv3d_tc folds
+        # back into the epilogue's per-channel scale (never taken by networks with sane initialisation: one host sync here)
+        amax = float(weight.abs().max())
+        inv_scale = 1.0
+        if amax > 0.0 and not (2.0 ** -8 <= amax <= 2.0 ** 8):
+            import math
+            e = math.floor(math.log2(amax))
+            weight = weight * (2.0 ** -e)
+            inv_scale = 2.0 ** e
         if Cin % 64:                                  # zero input channels up to the 64-wide k-block (matches ncdhw_to_cl_split)
             pad = 64 - Cin % 64
             weight = torch.cat((weight, weight.new_zeros((Cout, pad) + tuple(weight.shape[2:]))), 1).contiguous()
@@ -552,6 +598,7 @@ def conv_tc_prepare(weight, fmt=None):
         _lib.check(lib.side_conv_tc_prep_weights_f16(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
                    "side_conv_tc_prep_weights_f16")
         wp.cin_alg = cin_alg
+        wp.inv_scale = inv_scale
         return wp
     wp = torch.empty((nbytes // 4,), device=weight.device, dtype=_F32)
     _lib.check(lib.side_conv_tc_prep_weights(weight.data_ptr(), wp.data_ptr(), Cout, Cin, taps, _stream()),
@@ -578,6 +625,11 @@ def conv3d_tc(x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), scale=None, shift=None, rel
     y_lo = torch.empty(oshape, device=dev, dtype=odt) if split else None
     if residual is not None:
         residual = _chk(residual, "residual")
+    inv = getattr(wp, "inv_scale", 1.0)
+    if inv != 1.0:                                    # weights were normalised by a power of two (conv_tc_prepare)
+        scale = torch.full((Cout,), inv, device=dev, dtype=_F32) if scale is None else scale * inv
+    if f16 and split:
+        _range_guard(dev)
     fn = lib.side_conv3d_tc_fwd_f16 if f16 else lib.side_conv3d_tc_fwd
     _lib.check(fn(x_hi.data_ptr(), x_lo.data_ptr(), wp.data_ptr(), _p(scale), _p(shift), _p(residual),
                                       _p(y), _p(y_hi), _p(y_lo), N, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2],
@@ -603,6 +655,7 @@ def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt=None):
         if tuple(scale.shape) != (N, D):
             raise RuntimeError("scale must be [N, D]")
     if fmt == "f16":
+        _range_guard(x.device)
         Cp = (C + 31) // 32 * 32                     # rows of 32-channel multiples (TMA zero-fills the tail of a 64-channel k-block)
         hi = torch.empty((N,) + sp + (Cp,), device=x.device, dtype=torch.float16)
         lo = torch.empty_like(hi)
@@ -635,6 +688,8 @@ def gate_mul_split(y, gate, fmt=None):
     if tuple(gate.shape) != (N, D, W, C):
         raise RuntimeError("gate must be [N, D, W, C]")
     odt = torch.float16 if fmt == "f16" else _F32
+    if fmt == "f16":
+        _range_guard(y.device)
     hi, lo = torch.empty_like(y, dtype=odt), torch.empty_like(y, dtype=odt)
     fn = lib.side_gate_mul_split_f16 if fmt == "f16" else lib.side_gate_mul_split
     _lib.check(fn(y.data_ptr(), gate.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, D, H, W, C, _stream()),
@@ -651,6 +706,8 @@ def maxpool_hw2_cl(x, full=False, split=True, fmt=None):
     shp = (N, D, H // 2, W // 2, C)
     y = torch.empty(shp, device=x.device, dtype=_F32) if full else None
     odt = torch.float16 if fmt == "f16" else _F32
+    if fmt == "f16" and split:
+        _range_guard(x.device)
     hi = torch.empty(shp, device=x.device, dtype=odt) if split else None
     lo = torch.empty(shp, device=x.device, dtype=odt) if split else None
     fn = lib.side_maxpool_hw2_cl_f16 if fmt == "f16" else lib.side_maxpool_hw2_cl

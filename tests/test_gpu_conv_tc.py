@@ -384,3 +384,108 @@ def test_conv3d_tc_fused_maxpool(lib, cfg, fmt):
     got, ghi, glo = ops.conv3d_tc(hi, lo, wp, Cout, scale=sc, shift=sh, relu=True, residual=r, full=True, split=True, pool=True)
     assert tuple(got.shape) == (N, D, H // 2, W // 2, Cout)
     assert torch.equal(got, want) and torch.equal(ghi, whi) and torch.equal(glo, wlo)
+
+
+# ------------------------------------------------------------------------------------------------
+# range of the fp16 operand pairs: fp16 covers 2^-24 .. 65504, the reference's fp32 does not care
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("xs,ws", [(1e-6, 1.0), (1e-3, 1.0), (1e3, 1.0), (1.0, 1e-6), (1.0, 1e-3), (1.0, 1e3), (1.0, 1e5), (1e-3, 1e3)])
+def test_conv3d_tc_f16_scaled_operands(lib, xs, ws):
+    """Activations / weights scaled by 1e-6 .. 1e5 through the kind::f16 convolution: weights are normalised by an exact power
+    of two at preparation, activations down to ~1e-6 keep the 1e-4 bar, and no guard flag fires inside the supported range."""
+    from side_b200 import ops
+    N, D, H, W, Cin, Cout = 2, 8, 16, 16, 64, 64
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(N, Cin, D, H, W, generator=g) * xs
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (2.0 / (27 * Cout)) ** 0.5 * ws
+    ref = _cl(F.conv3d(x.double(), w.double(), padding=1).relu()).numpy()
+    dev = torch.device("cuda")
+    ops.tc_range_status(dev)
+    wp = ops.conv_tc_prepare(w.to(dev), fmt="f16")
+    hi, lo = ops.ncdhw_to_cl_split(x.to(dev), fmt="f16")
+    y, yh, yl = ops.conv3d_tc(hi, lo, wp, Cout, relu=True, full=True, split=True)
+    flags = ops.tc_range_status(dev)
+    amax = float(np.abs(ref).max())
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4, (xs, ws, flags)       # the fp32 output never depends on the OUTPUT pair's range
+    if amax >= 65504.0:
+        assert flags & ops.TC_RANGE_SATURATED, (flags, amax)              # ... but the pair handed to the next layer does
+    elif 1e-4 < amax < 3e4 and 1e-4 < xs * 4:
+        assert flags == 0, (flags, amax)
+    if not flags:
+        rec = yh.float() + yl.float() / 2048.0
+        assert float((rec - y).abs().max()) <= 4e-6 * float(y.abs().max())
+
+
+def test_f16_range_guard_flags(lib):
+    """Saturation (an activation >= 65504) and underflow (a non-zero tensor below 2^-18 everywhere) raise the sticky flags from
+    every producer of fp16 pairs; all-zero tensors and ordinary ones do not; reading resets."""
+    from side_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 4, 16, 16, generator=g).to(dev)
+    ops.tc_range_status(dev)
+    ops.ncdhw_to_cl_split(x, fmt="f16")
+    ops.ncdhw_to_cl_split(torch.zeros_like(x), fmt="f16")
+    assert ops.tc_range_status(dev) == 0
+    big = x.clone()
+    big[1, 3, 2, 5, 7] = 7.0e4
+    ops.ncdhw_to_cl_split(big, fmt="f16")
+    assert ops.tc_range_status(dev) == ops.TC_RANGE_SATURATED
+    assert ops.tc_range_status(dev) == 0                               # reading cleared it
+    ops.ncdhw_to_cl_split(x * 1e-7, fmt="f16")
+    assert ops.tc_range_status(dev) == ops.TC_RANGE_UNDERFLOW
+    y = torch.randn(2, 4, 16, 16, 64, generator=g).to(dev)
+    gate = torch.rand(2, 4, 16, 64, generator=g).to(dev)
+    ops.gate_mul_split(y * 1e6, gate, fmt="f16")
+    assert ops.tc_range_status(dev) == ops.TC_RANGE_SATURATED
+    ops.maxpool_hw2_cl(y * 1e6, full=False, split=True, fmt="f16")
+    assert ops.tc_range_status(dev) == ops.TC_RANGE_SATURATED
+    ops.gate_mul_split(y, gate, fmt="f16"); ops.maxpool_hw2_cl(y, full=False, split=True, fmt="f16")
+    assert ops.tc_range_status(dev) == 0
+    # convolution epilogues (voxel-major and role-swapped kernels): the OUTPUT pair saturates
+    for Cout in (64, 128):
+        w = torch.randn(Cout, 64, 3, 3, 3, generator=g).to(dev) * 0.05
+        wp = ops.conv_tc_prepare(w, fmt="f16")
+        hi, lo = ops.ncdhw_to_cl_split(x, fmt="f16")
+        ops.conv3d_tc(hi, lo, wp, Cout, relu=True, full=False, split=True)
+        assert ops.tc_range_status(dev) == 0
+        ops.conv3d_tc(hi, lo, wp, Cout, scale=torch.full((Cout,), 1e6, device=dev), relu=True, full=False, split=True)
+        assert ops.tc_range_status(dev) == ops.TC_RANGE_SATURATED, Cout
+    # the tf32 format has an 8-bit exponent and never reports
+    ops.ncdhw_to_cl_split(big, fmt="tf32")
+    assert ops.tc_range_status(dev) == 0
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1e-3, 1e3, 1e5])
+def test_aggregate_tc_f16_scaled_volume_with_fallback(lib, scale):
+    """Whole aggregation network on a volume scaled by 1e-6 .. 1e5: either the fp16 path meets the 1e-4 bar, or the guard fires
+    and the 3xTF32 rerun does (what StereoDetector.process_checked does for the full step)."""
+    from side_b200 import ops
+    from side_b200.networks.stereo_network import cost_volume
+    torch.manual_seed(13)
+    m = cost_volume(64).eval()
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2)
+            mod.bias.data.normal_(0, 0.1)
+    N, D = 2, 16
+    cost = torch.randn(N, 96, D, 16, 16) * scale
+    with torch.no_grad():
+        ref = m.double().aggregate(cost.double()).float()
+    m = m.float().cuda()
+    dev = torch.device("cuda")
+    rng = float(ref.abs().max())
+    with torch.no_grad():
+        m.tc_format = "f16"
+        ops.tc_range_status(dev)
+        out = m.aggregate_tc(cost.cuda())
+        flags = ops.tc_range_status(dev)
+        if flags:
+            m.tc_format = "tf32"
+            out = m.aggregate_tc(cost.cuda())
+        err = float((out.cpu() - ref).abs().max()) / rng
+    assert err < 1e-4, (scale, flags, err)
+    if scale >= 1e5:
+        assert flags & ops.TC_RANGE_SATURATED            # 1e5 * N(0,1) crosses 65504: the guard must have caught it

@@ -109,3 +109,16 @@ def test_small_map_in_a_fresh_process(lib):
             "torch.cuda.synchronize(); print(int(o['count'].sum()))") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_heat_map_too_large_for_shared_memory_is_refused(lib):
+    """static (~33 KB) + dynamic shared memory are checked together -- a 200x260 map (208 KB of keys) must come back
+    as SIDE_ERR_UNSUPPORTED with a message, not as an opaque launch failure."""
+    from side_b200 import ops
+    hm = torch.randn(1, 1, 200, 260, device="cuda")
+    wh = torch.rand(1, 3, 200, 260, device="cuda")
+    with pytest.raises(RuntimeError, match="shared memory"):
+        ops.bbox_decode_raw(hm, wh, wh, K=10)
+    torch.cuda.synchronize()                                  # the context is still healthy
+    o = ops.bbox_decode_raw(hm[:, :, :96, :].contiguous(), wh[:, :, :96, :].contiguous(), wh[:, :, :96, :].contiguous(), K=10)
+    assert o["score"].shape == (1, 10)

@@ -120,3 +120,34 @@ def test_cuda_graph_capture_matches_eager(lib, model):
     for a, b in zip(eager, out):
         assert torch.allclose(a, b, atol=1e-4, rtol=1e-4)
     assert det.launches_per_step > 30
+
+
+def test_bench_configuration_against_cpu_port(lib, model):
+    """the EXACT configuration bench.py times -- 384x1280, micro-batch 8, K = 100, DCN on tcgen05 3xTF32,
+    every tensor-core convolution on 3xFP16 pairs, separable volume, tensor-core DLA / heads / stem -- against the
+    reference-style port on this box's CPU with the same weights and inputs (2 of the 8 pairs: ~10 s of CPU)."""
+    from oracle import parity, torch_port
+    from side_b200 import ops
+    from side_b200.utils.synthetic import make_batch
+    n_ref = 2
+    batch = make_batch(8, 384, 1280, seed=1234)
+    cpu_model = model.cpu().eval()
+    with torch.no_grad(), torch_port.reference_ops():
+        zr = cpu_model({k: v[:n_ref] for k, v in batch.items()}, True, None, 1.0)[0]
+    m = model.cuda().eval()
+    old_fmt, old_prec = ops.get_tc_format(), ops.get_dcn_precision()
+    ops.set_tc_format("f16"); ops.set_dcn_precision("3xtf32")
+    try:
+        dev = torch.device("cuda")
+        ops.tc_range_status(dev)
+        with torch.no_grad():
+            z = m({k: v.cuda() for k, v in batch.items()}, True, None, 1.0)[0]
+        assert ops.tc_range_status(dev) == 0, "fp16 range guard fired on the bench configuration"
+    finally:
+        ops.set_tc_format(old_fmt); ops.set_dcn_precision(old_prec)
+    rep = parity.compare({k: v[:n_ref] for k, v in z.items()}, zr, K=100)
+    print("bench-configuration parity:", rep)
+    assert rep["heads_max_err"] < 1e-3, rep                      # per head, relative to the head's range (~130 layers deep)
+    assert rep["topk_agreement"] >= 0.98, rep                    # (class, peak index) keys found by both runs
+    assert rep["depth_median_rel"] < 1e-4, rep
+    assert rep["depth_frac_within_1e3"] >= 0.98, rep             # per matched detection |d - d_ref| / d_ref <= 1e-3
