@@ -9,6 +9,12 @@ A step = one pass of the hot path (DLA-34 + DCN neck, heads, decode, instance de
 `--pairs` synthetic stereo pairs per GPU in micro-batches of `--micro-batch`; ranks are sharded by pair
 (weak scaling: fixed pairs per GPU), the only collective is the all-gather of the fixed-shape detections.
   value : pairs/s with inputs resident in HBM       e2e : same through host buffers (H2D + D2H inside the timing)
+The same line also carries, measured in the same process right after the headline number:
+  strong      : BASELINE config #4 as written -- 32 pairs TOTAL, 32 / N per rank (strong scaling)
+  train       : BASELINE config #5 -- training step, 2 pairs per GPU, StereoLoss, NCCL gradient all-reduce overlapped with backward
+  tc_formats  : the headline throughput under both operand formats of the tensor-core convolutions (3xFP16 / strict 3xTF32)
+  parity      : agreement of the timed configuration with the CPU port on the pairs the CPU baseline processed
+  f16_range   : the fp16 range guard's verdict over the whole timed region
 """
 import argparse
 import json
@@ -48,6 +54,8 @@ def parse():
     ap.add_argument("--allow-tf32", action="store_true", help="let cuDNN use TF32 for the out-of-scope convolutions")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline microbenchmarks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the in-line training block (config #5)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the batch-1 latency block (config #1's GPU counterpart)")
     ap.add_argument("--cpu-pairs", type=int, default=2)
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the resident timed region (ncu --profile-from-start off)")
@@ -110,11 +118,14 @@ def build_model():
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference-style port on the host cores (oracle/torch_port.py)
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_pairs_per_s(model_cpu, n_pairs, warmup, seed=100):
+def cpu_reference_pairs_per_s(model_cpu, n_pairs, warmup, seed=100, keep=None):
+    """Times the reference-style port; ``keep`` (a list) receives (batch, head maps incl. depth) of every timed pair so the GPU
+    arm can be checked against them afterwards (oracle/parity.py)."""
     from oracle import torch_port
     from side_b200.engine import StereoDetector
     from side_b200.utils.synthetic import make_batch
     det = StereoDetector(model_cpu)
+    det.keep_heads = keep is not None
     times = []
     with torch_port.reference_ops():
         for i in range(warmup + n_pairs):
@@ -124,6 +135,8 @@ def cpu_reference_pairs_per_s(model_cpu, n_pairs, warmup, seed=100):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+                if keep is not None:
+                    keep.append((batch, det.last_heads))
     return len(times) / sum(times), times
 
 
@@ -277,68 +290,96 @@ def kernel_rooflines(pk, precision):
 # ----------------------------------------------------------------------------------------------------
 # BASELINE config #5: data-parallel training step (2 synthetic pairs per GPU by default, NCCL gradient all-reduce)
 # ----------------------------------------------------------------------------------------------------
+def train_setup(args, dev, rank, world):
+    """BASELINE config #5: ModelWithLoss-equivalent (GT RoIs built on the device, the reference's StereoLoss terms), Adam,
+    bucketed NCCL gradient all-reduce overlapped with backward.  -> (step function, reducer)"""
+    from side_b200.engine import GradientAllReducer
+    from side_b200.training import ModelWithLoss, StereoLoss
+    from side_b200.utils.synthetic import make_batch, make_targets
+    model = build_model().to(dev).train()
+    B = args.train_batch
+    batch = make_batch(B, H_IN, W_IN, seed=50 + rank)
+    batch.update(make_targets(B, 8, max_objs=50, seed=60 + rank))        # 8 ground-truth objects per pair (SURVEY config #5)
+    batch = {k: v.to(dev) for k, v in batch.items()}
+    mwl = ModelWithLoss(model, StereoLoss(grid=28), output_w=W_IN // 4)
+    opt = torch.optim.Adam(model.parameters(), lr=1.25e-4)
+    red = GradientAllReducer(model.parameters())
+    marks = []
+
+    def step():
+        red.zero_grad()
+        _, loss, _ = mwl(batch)
+        loss.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        early = red.finish()              # waits for the buckets still in flight: the time from here is EXPOSED communication
+        e1.record()
+        marks.append((e0, e1, early))
+        opt.step()
+        return loss
+
+    return step, red, marks
+
+
+def time_train(args, dev, rank, world, steps, profiler_range=False):
+    from side_b200 import _lib
+    step, red, marks = train_setup(args, dev, rank, world)
+    for _ in range(max(args.warmup, 5)):      # cuDNN autotuning and the caching allocator settle over the first few steps
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    del marks[:]
+    _lib.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if profiler_range:
+        torch.cuda.profiler.start()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if profiler_range:
+        torch.cuda.profiler.stop()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    exposed = sum(a.elapsed_time(b) for a, b, _ in marks) / max(len(marks), 1)
+    t = torch.tensor([e0.elapsed_time(e1), exposed], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, exposed = float(t[0].item()), float(t[1].item())
+    B = args.train_batch
+    return {"value": world * B * steps / (ms / 1000.0), "unit": "pairs/s", "ms_per_step": ms / steps, "steps": steps,
+            "pairs_per_gpu_per_step": B, "global_batch": world * B, "scaling": "weak",
+            "workload": "SIDE DLA-34 stereo training step (config #5): %d pairs/GPU, 8 GT RoIs/pair built on the device, forward + StereoLoss "
+                        "(focal + masked L1 + keypoint cross-entropies + L1 depth) + backward + NCCL gradient all-reduce + Adam" % B,
+            "allreduce_bytes_per_step": red.bytes_per_step if world > 1 else 0, "allreduce_buckets": len(red.buckets),
+            "buckets_in_flight_before_backward_ended": (sum(e for _, _, e in marks) / max(len(marks), 1)) if world > 1 else 0,
+            "exposed_allreduce_ms_per_step": exposed if world > 1 else 0.0,
+            "gpu_launches": _lib.launch_count(), "loss": float(loss.detach())}
+
+
 def run_train(args):
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    from side_b200 import _lib, ops
-    from side_b200.engine import allreduce_gradients
-    from side_b200.utils.synthetic import make_batch, make_boxes
+    from side_b200 import ops
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = bool(args.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.allow_tf32)
     ops.set_dcn_precision(args.dcn_precision)
-    model = build_model().to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1.25e-4)
-    B = args.train_batch
-    batch = {k: v.to(dev) for k, v in make_batch(B, H_IN, W_IN, seed=50 + rank).items()}
-    left, right, shape = make_boxes(B, 8, seed=60 + rank)          # 8 ground-truth objects per pair (SURVEY config #5)
-    target = (left.to(dev), right.to(dev), shape)
-    gt_depth = torch.rand((B, int(shape[1]), 1), device=dev) * 55 + 5
-
-    def step():
-        z = model(batch, True, target, 1.0)[0]
-        loss = torch.nn.functional.l1_loss(z['depth'], gt_depth) + sum(z[k].pow(2).mean() for k in ("hm", "wh", "reg", "dim", "orien"))
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_gradients(model.parameters())
-        opt.step()
-        return loss
-
-    for _ in range(max(args.warmup, 5)):      # cuDNN autotuning and the caching allocator settle over the first few steps
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    _lib.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if args.profiler_range:
-        torch.cuda.profiler.start()
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    if args.profiler_range:
-        torch.cuda.profiler.stop()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    tr = time_train(args, dev, rank, world, args.steps, args.profiler_range)
     if rank == 0:
-        print(json.dumps({"metric": "stereo training pairs/sec (384x1280, DLA-34)", "value": world * B * args.steps / (ms / 1000.0),
-                          "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 5),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "fp32", "data": "synthetic",
-                          "config": {"workload": "SIDE DLA-34 stereo training step (config #5): %d pairs/GPU, 8 GT RoIs/pair, forward + "
-                                                 "L1 depth / head losses + backward + NCCL gradient all-reduce + Adam" % B,
-                                     "pairs_per_gpu_per_step": B, "parallelism": "data-parallel x%d, bucketed all_reduce" % world,
-                                     "dcn_precision": args.dcn_precision},
-                          "gpu_launches": _lib.launch_count(), "loss": float(loss.detach())}))
+        line = {"metric": "stereo training pairs/sec (384x1280, DLA-34)", "value": tr["value"], "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 5), "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": tr["workload"], "pairs_per_gpu_per_step": args.train_batch,
+                           "parallelism": "data-parallel x%d, bucketed all_reduce overlapped with backward" % world,
+                           "dcn_precision": args.dcn_precision},
+                "gpu_launches": tr["gpu_launches"], "train": tr}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -373,13 +414,14 @@ def main():
     pk = peaks()
 
     cpu_model = build_model()
-    cpu_base = None
+    cpu_base, cpu_kept = None, []
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
         except AttributeError:
             pass
-        v, times = cpu_reference_pairs_per_s(cpu_model, args.cpu_pairs, 1)
+        cpu_kept = []
+        v, times = cpu_reference_pairs_per_s(cpu_model, args.cpu_pairs, 1, keep=cpu_kept)
         cpu_base = {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": "%d pairs (batch 1, 384x1280, K=100 RoIs) after 1 warm-up; reference-style torch CPU ops "
                               "(torchvision deform_conv2d / roi_align loop, torch.topk decode)" % args.cpu_pairs}
@@ -399,10 +441,11 @@ def main():
     fb = torch.full((mb,), KITTI_FB, device=dev)
     out_host = [torch.empty((P, 100, 6)).pin_memory(), torch.empty((P, 100, 6)).pin_memory(), torch.empty((P, 100, 10)).pin_memory()]
 
-    def step_resident():
+    def step_resident(pairs=None, micro=None):
+        pairs, micro = pairs or P, micro or mb
         outs = []
-        for i in range(0, P, mb):
-            outs.append(det.process({'input': dev_l[i:i + mb], 'input_right': dev_r[i:i + mb], 'fb': fb}))
+        for i in range(0, pairs, micro):
+            outs.append(det.process({'input': dev_l[i:i + micro], 'input_right': dev_r[i:i + micro], 'fb': fb[:micro]}))
         d, dr, info = (torch.cat([o[j] for o in outs], 0) for j in range(3))
         return gather_detections(d, dr, info)
 
@@ -482,24 +525,99 @@ def main():
     def dcn_cl_work(out, x_nhwc, om_cl, weight, *a, **k):
         return 2.0 * out.numel() * weight.shape[1] * weight.shape[2] * weight.shape[3]
 
-    with OpTimer("dcn_forward_raw", dcn_work) as tm, OpTimer("dcn_fwd_cl", dcn_cl_work) as tm2, OpTimer("conv3d_tc", conv_work, conv_fmt) as tmc:
+    def vol_work(out, featL, featR, left, right, fb_, D, P_, *a, **k):
+        # algorithmic bytes of the volume builder: the pairs written once (hi + lo fp16 = 4 B per element) + both feature maps read once
+        return float(out[0].numel() * 4 + 2 * featL.numel() * 4)
+
+    ops.tc_range_status(dev)                                  # clear: the flags below cover exactly the timed regions
+    with OpTimer("dcn_forward_raw", dcn_work) as tm, OpTimer("dcn_fwd_cl", dcn_cl_work) as tm2, \
+            OpTimer("conv3d_tc", conv_work, conv_fmt) as tmc, OpTimer("inst_costvol_cl", vol_work) as tmv:
         ms_res = timed(step_resident, args.steps)
     if args.profiler_range:
         torch.cuda.profiler.stop()
     dcn, dcn2 = tm.summary(), tm2.summary()
     dcn = {k: dcn[k] + dcn2[k] for k in ("calls", "ms", "work")}       # NCHW entry + channels-last entry of the same kernel
     cv, cv16 = tmc.summary("tf32"), tmc.summary("f16")
+    vol = tmv.summary()
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop()
+    range_flags = ops.tc_range_status(dev)
+
+    # ---- the same step under the other operand format (strict 3xTF32 next to 3xFP16), a short run ----
+    fmt_values = {args.tc_format: world * P * args.steps / (ms_res / 1000.0)}
+    if not args.cudnn_only:
+        other_fmt = "tf32" if args.tc_format == "f16" else "f16"
+        ops.set_tc_format(other_fmt)
+        step_resident()
+        n_o = max(1, min(args.steps, 2))
+        fmt_values[other_fmt] = world * P * n_o / (timed(step_resident, n_o) / 1000.0)
+        ops.set_tc_format(args.tc_format)
+        step_resident()
+
+    # ---- BASELINE config #4 as written: 32 pairs TOTAL over the ranks (strong scaling) ----
+    strong = None
+    if 32 % world == 0:
+        ps = 32 // world
+        ms_s = min(mb, ps)
+        if ps == P and ms_s == mb:
+            strong_ms = ms_res / args.steps
+        else:
+            step_resident(ps, ms_s)
+            strong_ms = timed(lambda: step_resident(ps, ms_s), args.steps) / args.steps
+        strong = {"value": 32 / (strong_ms / 1000.0), "unit": "pairs/s", "scaling": "strong", "pairs_total": 32, "pairs_per_rank": ps,
+                  "micro_batch": ms_s, "ms_per_step": strong_ms, "steps": args.steps,
+                  "workload": "SIDE DLA-34 stereo inference (config #4): 32 pairs in total, contiguous blocks of 32 / N per rank"}
+
+    # ---- BASELINE config #1's GPU counterpart: ONE stereo pair (the batch the real detector runs, stereoDetector.py:84-103) ----
+    latency = None
+    if world == 1 and not args.no_latency:
+        det1 = StereoDetector(model, grid_size=28, K=100)
+        b1 = {'input': dev_l[:1].clone(), 'input_right': dev_r[:1].clone(), 'fb': fb[:1].clone()}
+        for _ in range(3):
+            det1.process(b1)
+        n0 = _lib.launch_count()
+        eager_ms = timed(lambda: det1.process(b1), 10) / 10
+        per_step = (_lib.launch_count() - n0) // 10
+        det1.capture(b1)
+        graph_ms = timed(lambda: det1.replay(b1), 20) / 20
+        latency = {"pairs": 1, "eager_ms": eager_ms, "cuda_graph_ms": graph_ms, "library_launches_per_step": per_step,
+                   "note": "one 384x1280 pair, inputs resident: DLA levels, heads and DCN offset convolutions on tcgen05 at batch 1 "
+                           "(depth boxes of the 12x40 level hang over the 2-image batch), DCN forward split-K over the taps; whole "
+                           "detector step replayed as one CUDA graph"}
+
+    # ---- parity of the timed configuration against the CPU port on the pairs the CPU baseline just processed ----
+    par = None
+    if cpu_kept:
+        from oracle import parity
+        nref = min(len(cpu_kept), mb)
+        il, ir = dev_l[:mb].clone(), dev_r[:mb].clone()
+        for j in range(nref):
+            il[j].copy_(cpu_kept[j][0]['input'][0]); ir[j].copy_(cpu_kept[j][0]['input_right'][0])
+        det.keep_heads = True
+        det.process({'input': il, 'input_right': ir, 'fb': fb})
+        det.keep_heads = False
+        zg = {k: t[:nref].float().cpu() for k, t in det.last_heads.items()}
+        zc = {k: torch.cat([kept[1][k] for kept in cpu_kept[:nref]], 0) for k in cpu_kept[0][1]}
+        par = parity.compare(zg, zc, K=100, heat_is_logit=False)
+        par["note"] = ("GPU arm exactly as timed (micro-batch %d, %s convs, DCN %s) vs the CPU port on the same weights / inputs; "
+                       "heads: max|a-b| / max|b| per head map" % (mb, args.tc_format, args.dcn_precision))
+        det.last_heads = None
+
+    # ---- BASELINE config #5 in the same process ----
+    train = None
+    if not args.no_train:
+        torch.cuda.empty_cache()
+        train = time_train(args, dev, rank, world, max(3, min(args.steps, 10)))
 
     total_pairs = world * P * args.steps
     value = total_pairs / (ms_res / 1000.0)
     e2e = total_pairs / (ms_e2e / 1000.0)
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")      # dram bytes per launch from the committed ncu --set full captures
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
+    for name in ("r1_traffic.json", "r2_traffic.json"):            # dram bytes per launch from the committed ncu --set full captures
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            traffic.update(json.load(open(tpath)))
 
     def roof(name, label, summ, f16=False):
         tf = summ["work"] / (summ["ms"] / 1000.0) / 1e12 if summ["ms"] > 0 else 0.0
@@ -538,6 +656,20 @@ def main():
             "roofline": dominant,
             "roofline_second": other,
             "roofline_third": third,
+            "cost_volume": None if not vol["calls"] else {
+                "kernel": "inst_costvol_cl_kernel (gated channels-last fp16 pairs), %d launches in the timed region" % vol["calls"],
+                "bound": "hbm", "achieved": vol["work"] / (vol["ms"] / 1000.0) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": vol["work"] / (vol["ms"] / 1000.0) / 1e9 / pk["hbm"], "traffic": traffic.get("inst_costvol_cl_kernel"),
+                "ms_per_launch": vol["ms"] / vol["calls"], "algorithmic_bytes_per_launch": vol["work"] / vol["calls"],
+                "share_of_step": vol["ms"] / ms_res, "peak_source": pk["src"] + " copy bandwidth"},
+            "tc_formats": {("3xfp16" if k == "f16" else "3xtf32") + "_pairs_per_s": v for k, v in fmt_values.items()},
+            "f16_range": {"saturated": bool(range_flags & ops.TC_RANGE_SATURATED), "underflow": bool(range_flags & ops.TC_RANGE_UNDERFLOW),
+                          "note": "fp16 operand-pair range guard over the timed regions; a set flag means the step must rerun in 3xTF32 "
+                                  "(StereoDetector.process_checked)"},
+            "parity": par,
+            "latency": latency,
+            "strong": strong,
+            "train": train,
             "cpu_baseline": cpu_base,
         }
         if not args.no_kernels and world == 1:

@@ -171,6 +171,19 @@ int side_inst_costvol_bwd_fast(const float *featL, const float *featR, const flo
                                int N, int B, int C, int H, int W, int D, int P, float x_clamp, int flags, void *ws,
                                size_t ws_bytes, void *stream);
 
+/* The same volume emitted directly in the format its consumer (side_conv3d_tc_fwd_f16, cost_volume.dres0) reads: channels-last
+ * [N, D, P, P, 3C] and already split into fp16 operand pairs, with the cosine gate applied when SIDE_VOL_GATE is set -- one pass
+ * over HBM instead of volume write + re-read + re-write (stereo_network_old.py:366-376 and :197-203 in one kernel).
+ *   cost_hi, cost_lo  half [N, D, P, P, 3C]: hi = fp16(v), lo = fp16((v - hi) * 2^11), channels [L (C) | R (C) | L - R (C)]
+ *   depth_bin [N, D];  xcross [N, D] (may be NULL): the gate scalar of every slice, whether or not it was applied
+ * Built for C == 32 (the reference's reduced_channel), P == 16, 2 <= D <= 64; other shapes return SIDE_ERR_INVALID_ARG (callers use
+ * side_inst_costvol_fwd + side_ncdhw_to_cl_split_f16).  Values follow the separable evaluation order (<= 1e-5 relative to
+ * torchvision's RoIAlign; L - R from the kernel's own L and R).  ws: side_inst_costvol_cl_ws_bytes(...) bytes, 16-byte aligned. */
+size_t side_inst_costvol_cl_ws_bytes(int B, int C, int H, int W);
+int side_inst_costvol_fwd_cl(const float *featL, const float *featR, const float *left, const float *right, const float *fb,
+                             const uint8_t *valid, void *cost_hi, void *cost_lo, float *depth_bin, float *xcross, int N, int B,
+                             int C, int H, int W, int D, int P, float x_clamp, int flags, void *ws, size_t ws_bytes, void *stream);
+
 /* Stand-alone cosine gate on an already built volume (drop-in cost_volume.forward(cost, ...) entry,
  * stereo_network_old.py:194-203).  out may alias cost.  bwd: gcost = d loss / d cost. */
 int side_xcross_gate_fwd(const float *cost, float *out, float *xcross, int N, int C, int D, int P, void *stream);
@@ -256,7 +269,8 @@ int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *g
  *       element strides, so a strided convolution costs no more than a dense one.
  *       Needs Cin % 32 == 0; Cout % 16 == 0 (<= 128) or Cout % 128 == 0 (<= 1536, processed as 128-wide n-tiles); a
  *       (D, H, W) that tiles into 128-voxel boxes (box w = largest power of two <= 128 dividing W, then rows, then
- *       slices: 16x16, 8x8 with even D, 4x4 with D % 8 == 0, 96x320 as 2 rows x 64 columns); kernel 3x3x3, 1x3x3 or
+ *       slices: 16x16, 8x8 with even D, 4x4 with D % 8 == 0, 96x320 as 2 rows x 64 columns; for 2-D kernels, where D is the
+ *       batch, the last box may hang over the end of the batch: 2 images at the 12x40 DLA level use boxes of 4); kernel 3x3x3, 1x3x3 or
  *       1x1x1 (2-D convolutions are kd = 1 with the batch as D or D = 1: the head convolutions of
  *       stereo_network.forward, :343-348, and the DLA-34 levels 2-5 of feature_extraction_dla34.py).
  * Helpers (one pass over HBM each):

@@ -28,6 +28,8 @@ SIGNATURES = {
     "side_inst_costvol_ws_bytes": (_sz, [_i] * 4),
     "side_inst_costvol_fast_ws_bytes": (_sz, [_i] * 6),
     "side_inst_costvol_fwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
+    "side_inst_costvol_cl_ws_bytes": (_sz, [_i] * 4),
+    "side_inst_costvol_fwd_cl": (_i, [_vp] * 10 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),
     "side_inst_costvol_bwd": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp]),
     "side_inst_costvol_bwd_fast_ws_bytes": (_sz, [_i] * 7),
     "side_inst_costvol_bwd_fast": (_i, [_vp] * 9 + [_i] * 7 + [_f, _i, _vp, _sz, _vp]),

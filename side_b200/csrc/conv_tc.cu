@@ -49,7 +49,8 @@ struct ConvTcParams {
     long long ldy;                    // row stride of the outputs in floats (Ntot unless a column block of a wider matrix is written)
     int D, H, W;                      // spatial extent of one sample
     int bw, bh, bd;                   // TMA box extent along w, h, d; bd*bh*bw == 128
-    int wt, ht;                       // boxes per row (W / bw) and per column (H / bh)
+    int wt, ht, dt;                   // boxes per row (W / bw), per column (H / bh) and along depth (ceil(D / bd): the last box of a
+                                      // sample may hang over the end -- TMA zero-fills the loads, the epilogue skips those voxels)
     int kd, kh, kw;                   // kernel extent (3,3,3), (1,3,3) or (1,1,1)
     int sh, sw;                       // stride along h / w (1 or 2); D, H, W above are OUTPUT extents
     int stages;
@@ -59,6 +60,7 @@ struct ConvTcParams {
     // are then separate: A is loaded once per (kd, kw, channel block), B once per tap.
     int khv, a_slots, b_slots;
     uint32_t *rs;                     // fp16 range-guard slot of this launch (tc_common.cuh) or NULL
+    float acc_fix;                    // 1 + (MMA steps per accumulator) * 2^-26: undoes the accumulator's truncation bias
     int dbg;                          // timing experiments only (side_conv_tc_set_mode bits 1, 2): skip the B / A copies
     uint32_t a_part;                  // bytes of one half (hi or lo) of an A slot
 };
@@ -66,7 +68,7 @@ struct ConvTcParams {
 // m-tile -> first voxel coordinates of its box
 __device__ __forceinline__ void conv_tile_origin(const ConvTcParams &p, int mt, int &n, int &d0, int &h0, int &w0)
 {
-    const int tps = (p.D / p.bd) * p.ht * p.wt;        // tiles per sample
+    const int tps = p.dt * p.ht * p.wt;                // tiles per sample
     n = mt / tps;
     int r = mt - n * tps;
     const int wi = r % p.wt;
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             int n, d0, h0, w0;
             conv_tile_origin(p, mt, n, d0, h0, w0);
             const int ww = m % p.bw, r1 = m / p.bw, hh = r1 % p.bh, dd = r1 / p.bh;
+            const bool inb = d0 + dd < p.D;          // depth boxes may overhang the sample (2 images in boxes of 4 at the 12x40 level)
             const size_t vox = (((size_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
             const size_t row = vox * (size_t)p.ldy + (size_t)nt * N;     // float offset of this row's first channel
             const size_t orow = !p.pool ? row
@@ -312,12 +315,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 tc_ld16(taddr + (uint32_t)(N + c), vx);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float sum = F16 ? fmaf(vx[j], kF16LoInv, v[j]) : v[j] + vx[j];
+                    const float sum = F16 ? fmaf(vx[j], kF16LoInv, v[j] * p.acc_fix) : fmaf(v[j], p.acc_fix, vx[j]);
                     float o = fmaf(sum, s_scale[cbase + c + j], s_shift[cbase + c + j]);
                     if (p.relu == 1) o = fmaxf(o, 0.f);
                     v[j] = o;
                 }
-                if (p.residual) {
+                if (p.residual && inb) {
                     const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.bw));
                     }
                 }
-                const bool writer = !p.pool || !((ww | hh) & 1);
+                const bool writer = inb && (!p.pool || !((ww | hh) & 1));
                 if (writer && p.y) {
                     float4 *yp = reinterpret_cast<float4 *>(p.y + orow + c);
 #pragma unroll
@@ -563,8 +566,8 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     int bh = 128 / bw;
     while (bh > 1 && Ho % bh) bh >>= 1;
     const int bd = 128 / (bw * bh);
-    SIDE_REQUIRE(bd >= 1 && D % bd == 0, "side_conv3d_tc_fwd: %dx%dx%d does not tile into 128-voxel boxes (box %dx%dx%d)", D, Ho, Wo,
-                 bd, bh, bw);
+    SIDE_REQUIRE(bd >= 1 && (D % bd == 0 || kd == 1), "side_conv3d_tc_fwd: %dx%dx%d does not tile into 128-voxel boxes (box %dx%dx%d)", D, Ho, Wo,
+                 bd, bh, bw);       // 2-D kernels (D = batch): a last box hanging over the batch is zero-filled / skipped
     SIDE_REQUIRE(bw * stride_hw <= 256 && bh * stride_hw <= 256, "side_conv3d_tc_fwd: box too large for the stride");
     SIDE_REQUIRE((long long)Nn * D * H * W < (1ll << 31), "side_conv3d_tc_fwd: too many voxels");
     SIDE_REQUIRE(y || (y_hi && y_lo), "side_conv3d_tc_fwd: no output requested");
@@ -604,15 +607,17 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.nkb = kd * kh * kw * p.ncb;
     p.klast = (f16 && Cin % 64 == 32) ? 2 : 4;
     p.pool = pool;
-    const long long mtiles = (long long)Nn * D * Ho * Wo / kCvBM;
+    const int dt = (D + bd - 1) / bd;
+    const long long mtiles = (long long)Nn * dt * (Ho / bh) * (Wo / bw);
     SIDE_REQUIRE(mtiles * p.n_ntiles < (1ll << 31), "side_conv3d_tc_fwd: too many tiles");
     p.ntiles = (int)(mtiles * p.n_ntiles);
-    p.D = D; p.H = Ho; p.W = Wo; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = Wo / bw; p.ht = Ho / bh;
+    p.D = D; p.H = Ho; p.W = Wo; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = Wo / bw; p.ht = Ho / bh; p.dt = dt;
     p.kd = kd; p.kh = kh; p.kw = kw; p.sh = stride_hw; p.sw = stride_hw;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
     p.rs = f16 ? range_slot_next() : nullptr;
+    p.acc_fix = tc_acc_fix(kd * kh * kw * ((p.ncb - 1) * 4 + p.klast));
     const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tc_kernel<true> : (const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {
@@ -648,11 +653,12 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     p.ncb = K / 32; p.nkb = p.ncb; p.klast = 4; p.pool = 0;
     SIDE_REQUIRE((long long)Hr * p.n_ntiles < (1ll << 31), "conv_tc_rows_gemm: too many tiles");
     p.ntiles = Hr * p.n_ntiles;
-    p.D = 1; p.H = Hr; p.W = kCvBM; p.bw = kCvBM; p.bh = 1; p.bd = 1; p.wt = 1; p.ht = Hr;
+    p.D = 1; p.H = Hr; p.W = kCvBM; p.bw = kCvBM; p.bh = 1; p.bd = 1; p.wt = 1; p.ht = Hr; p.dt = 1;
     p.kd = 1; p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
     p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0; p.rs = nullptr;
+    p.acc_fix = tc_acc_fix(p.ncb * 4);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     if ((rc = set_smem_attr((const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {

@@ -42,6 +42,7 @@ struct ConvTtParams {
     int klast;                        // K-steps with data in the last channel block (2 when Cin % 64 == 32 on fp16, else 4)
     uint32_t x_part;                  // bytes of one half (hi or lo) of an X slot: (bh + 2) * bw * 128
     uint32_t *rs;                     // fp16 range-guard slot of this launch (tc_common.cuh) or NULL
+    float acc_fix;                    // 1 + (MMA steps per accumulator) * 2^-26 (tc_common.cuh: truncating accumulation)
 };
 
 __device__ __forceinline__ void tt_tma_load_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4,
@@ -206,7 +207,10 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
             for (int c = 0; c < 8; ++c) {
                 float v[32];
                 tt_ld32(taddr + (uint32_t)(c * 32), v);
-                if (F16 && !is_main) {                                // cross terms carry the 2^11 of the scaled lo operands
+                if (is_main) {                                        // undo the accumulator's truncation bias (main terms only)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= p.acc_fix;
+                } else if (F16) {                                     // cross terms carry the 2^11 of the scaled lo operands
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= kF16LoInv;
                 }
@@ -281,6 +285,7 @@ int conv_tct_launch(const float *x_hi, const float *x_lo, const float *wp, const
     p.ncb = f16 ? (Cin + 63) / 64 : Cin / 32; p.kd = kd; p.klast = (f16 && Cin % 64 == 32) ? 2 : 4; p.ntiles = Nn * D; p.D = D; p.bw = W; p.bh = H;
     p.x_part = (uint32_t)(H + 2) * W * 128u;
     p.rs = f16 ? range_slot_next() : nullptr;
+    p.acc_fix = tc_acc_fix(kd * 9 * ((p.ncb - 1) * 4 + p.klast));
     const size_t smem = (size_t)kTtXSlots * 2 * p.x_part + (size_t)kTtWSlots * kTtWSlot + 2 * 2 * 1024 * 4 + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tct_kernel<true> : (const void *)conv_tct_kernel<false>, smem))) return rc;
     const unsigned grid = (unsigned)std::min(p.ntiles, sm_count);

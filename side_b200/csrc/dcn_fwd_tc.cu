@@ -74,16 +74,26 @@ struct TcTiling {
     int tiles_x, tiles_y;
 };
 
+// Split-K over the taps for small maps (12x40 / 24x80 layers at small batch: 12 .. 90 pixel tiles on 148 SMs): ksplit CTAs
+// share a pixel tile, each contracts a contiguous range of taps and writes its raw sums to `partial`; the CTA that takes the
+// tile's last ticket adds the partials in split order (deterministic) and runs the bias / BatchNorm / ReLU epilogue.
+struct TcSplitK {
+    int ksplit;                // 1 = off
+    float *partial;            // [ksplit][B][Cout][P]
+    unsigned int *tickets;     // [tiles], zeroed before the launch
+};
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp,
                                                                   const float *__restrict__ xt, int stages, uint32_t idesc,
-                                                                  uint32_t tmem_cols, TcTiling tl, int tap_group)
+                                                                  uint32_t tmem_cols, TcTiling tl, int tap_group, TcSplitK sk)
 {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ unsigned int s_ticket;
 
     const DcnShape &s = a.s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,7 +107,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     TapRec *tapbuf = reinterpret_cast<TapRec *>(tiles + (size_t)stages * stage_bytes);      // [tap_group][128]
 
     const int ncb = s.Cin / kTcBK;
-    const int nkb = s.KK * ncb;
+    const int tile = (int)blockIdx.x / sk.ksplit, split = (int)blockIdx.x - tile * sk.ksplit;
+    const int tap_lo = split * s.KK / sk.ksplit, tap_hi = (split + 1) * s.KK / sk.ksplit;      // this CTA's taps
+    const int nkb = (tap_hi - tap_lo) * ncb;
 
     if (tid == 0) {
         for (int i = 0; i < stages; ++i) {
@@ -123,14 +135,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         int tile_b = 0, tile_y0 = 0, tile_x0 = 0;
         if (tl.th != 1) {
             const int per_img = tl.tiles_x * tl.tiles_y;
-            tile_b = blockIdx.x / per_img;
-            const int t = blockIdx.x - tile_b * per_img, ty = t / tl.tiles_x;
+            tile_b = tile / per_img;
+            const int t = tile - tile_b * per_img, ty = t / tl.tiles_x;
             tile_y0 = ty * 8; tile_x0 = (t - ty * tl.tiles_x) * 16;
         }
         // pixel of tile row m
         auto pixel_of = [&](int m, int &b, int &ho, int &wo) -> bool {
             if (tl.th == 1) {
-                const long long gp = (long long)blockIdx.x * kTcBM + m;
+                const long long gp = (long long)tile * kTcBM + m;
                 if (gp >= (long long)s.B * s.P) return false;
                 b = (int)(gp / s.P);
                 const int p = (int)(gp - (long long)b * s.P);
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         const int c4 = tid & 7, r0 = tid >> 3;
         float4 raw[8];
         auto geometry = [&](int tap0) {         // sample geometry of taps tap0 .. tap0 + tap_group - 1 for all 128 pixels
-            const int ntap = min(tap_group, s.KK - tap0);
+            const int ntap = min(tap_group, tap_hi - tap0);
             for (int i = tid; i < ntap * kTcBM; i += kTcProducerThreads) {
                 const int tt = i / kTcBM, m = i - tt * kTcBM;
                 int b, ho, wo;
@@ -178,11 +190,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 raw[4 * i + 3] = __ldg(reinterpret_cast<const float4 *>(xc + o.w));
             }
         };
-        geometry(0);
+        geometry(tap_lo);
         asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
         prefetch(0, 0);
         // all loop state is carried incrementally: no integer division in the k loop
-        int st = 0, tp = 0, cb = 0, slot = 0;
+        int st = 0, tp = tap_lo, cb = 0, slot = 0;
         uint32_t eph = 1;                        // parity to wait for on empty_bar[st] (first pass falls through)
         for (int kb = 0; kb < nkb; ++kb) {
             const TapRec *tb = tapbuf + slot * kTcBM;
@@ -243,9 +255,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         const bool pix_ok = pixel_of(lg * 32 + lane, b, ho, wo);
         float *yp = a.y + (pix_ok ? (size_t)b * s.Cout * s.P + (size_t)ho * s.Wo + wo : 0);
         const int cbeg = cq * (N / 4), cend = cbeg + N / 4;
+        const float acc_fix = tc_acc_fix(nkb * (kTcBK / 8));            // truncating accumulation, tc_common.cuh
+        const size_t pix_off = pix_ok ? (size_t)b * s.Cout * s.P + (size_t)ho * s.Wo + wo : 0;
+        float *pp = sk.ksplit > 1 ? sk.partial + (size_t)split * s.B * s.Cout * s.P + pix_off : nullptr;
         for (int c = cbeg; c < cend; c += 8) {
             float acc[8];
             tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, acc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= acc_fix;
             if (SPLIT) {                      // cross-term accumulator (see the MMA issuer)
                 float accx[8];
                 tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(N + c), accx);
@@ -255,10 +272,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int n = c + j;
+                if (pp) {                                      // split-K: raw partial sum, finished by the tile's last CTA
+                    if (pix_ok) __stcg(pp + (size_t)n * s.P, acc[j]);
+                    continue;
+                }
                 float o = acc[j] + (a.bias ? __ldg(a.bias + n) : 0.f);
                 if (affine) o = fmaf(o, __ldg(a.scale + n), __ldg(a.shift + n));
                 if (relu) o = fmaxf(o, 0.f);
                 if (pix_ok) yp[(size_t)n * s.P] = o;
+            }
+        }
+        if (sk.ksplit > 1) {
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+            if (tid == 0) s_ticket = atomicAdd(sk.tickets + tile, 1u);
+            asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
+            if (s_ticket == (unsigned)sk.ksplit - 1u) {
+                __threadfence();
+                const size_t split_stride = (size_t)s.B * s.Cout * s.P;
+                for (int n = cbeg; n < cend; ++n) {
+                    float o = 0.f;
+                    if (pix_ok)
+                        for (int k = 0; k < sk.ksplit; ++k) o += __ldcg(sk.partial + (size_t)k * split_stride + pix_off + (size_t)n * s.P);
+                    o += a.bias ? __ldg(a.bias + n) : 0.f;
+                    if (affine) o = fmaf(o, __ldg(a.scale + n), __ldg(a.shift + n));
+                    if (relu) o = fmaxf(o, 0.f);
+                    if (pix_ok) yp[(size_t)n * s.P] = o;
+                }
             }
         }
     } else if (warp == 16) {
@@ -309,7 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[st], eph);
                 mbar_expect_tx(&full_bar[st], b_bytes);
-                bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)kb * (b_bytes / 4), b_bytes, &full_bar[st]);
+                bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)(tap_lo * ncb + kb) * (b_bytes / 4), b_bytes, &full_bar[st]);
                 if (++st == stages) { st = 0; eph ^= 1u; }
             }
         }
@@ -342,10 +382,32 @@ static size_t tc_weight_bytes(int Cin, int Cout, int KK, int flags)
     return (sizeof(float) * (split ? 2 : 1) * (size_t)Cin * Cout * KK + 255) & ~(size_t)255;
 }
 
-// workspace = weight tiles + the channels-last copy of x
+// pixel tiles of a launch, and how many CTAs should share one (split-K over the taps) to fill the GPU
+static long long tc_tiles(int B, int Ho, int Wo)
+{
+    if (Ho % 8 == 0 && Wo % 16 == 0) return (long long)B * (Ho / 8) * (Wo / 16);
+    return ((long long)B * Ho * Wo + kTcBM - 1) / kTcBM;
+}
+static int tc_ksplit(long long tiles, int KK)
+{
+    if (tiles >= 100 || KK % 3 != 0) return 1;
+    if (tiles * 3 >= 100 || KK % 9 != 0) return 3;
+    return 9;
+}
+static size_t tc_split_bytes(int B, int Cout, int Ho, int Wo, int KK)
+{
+    const long long tiles = tc_tiles(B, Ho, Wo);
+    const int ks = tc_ksplit(tiles, KK);
+    if (ks == 1) return 0;
+    return sizeof(float) * (size_t)ks * B * Cout * Ho * Wo + ((sizeof(unsigned int) * (size_t)tiles + 255) & ~(size_t)255);
+}
+
+// workspace = weight tiles + the channels-last copy of x (+ split-K partial sums and tickets for small maps; sized for
+// same-size output, the upper bound for stride >= 1)
 size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int flags)
 {
-    return tc_weight_bytes(Cin, Cout, KK, flags) + sizeof(float) * (size_t)B * Cin * H * W;
+    return tc_weight_bytes(Cin, Cout, KK, flags) + ((sizeof(float) * (size_t)B * Cin * H * W + 255) & ~(size_t)255) +
+           tc_split_bytes(B, Cout, H, W, KK);
 }
 
 int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_nhwc)
@@ -356,7 +418,8 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
         set_error("side_dcn_fwd: tcgen05 path needs dg == 1, Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
         return SIDE_ERR_UNSUPPORTED;
     }
-    if (ws_bytes < dcn_fwd_tc_ws_bytes(s.B, s.Cin, s.H, s.W, s.Cout, s.KK, s.flags)) {
+    const size_t base_bytes = tc_weight_bytes(s.Cin, s.Cout, s.KK, s.flags) + ((sizeof(float) * (size_t)s.B * s.Cin * s.H * s.W + 255) & ~(size_t)255);
+    if (ws_bytes < base_bytes) {
         set_error("side_dcn_fwd: workspace too small for the tcgen05 weight tiles + NHWC copy");
         return SIDE_ERR_WORKSPACE;
     }
@@ -394,12 +457,27 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
         tl.th = 1; tl.tw = 128; tl.tiles_x = tl.tiles_y = 0;
         grid = (unsigned)ceil_div((long long)s.B * s.P, kTcBM);
     }
+    // split-K over the taps when the pixel tiles alone leave most SMs idle and the workspace has room for the partial sums
+    TcSplitK sk{1, nullptr, nullptr};
+    {
+        const int ks = tc_ksplit(grid, s.KK);
+        const size_t part_bytes = sizeof(float) * (size_t)ks * s.B * s.Cout * s.P;
+        const size_t tick_bytes = (sizeof(unsigned int) * (size_t)grid + 255) & ~(size_t)255;
+        if (ks > 1 && ws_bytes >= base_bytes + part_bytes + tick_bytes) {
+            unsigned char *pb = reinterpret_cast<unsigned char *>(ws) + base_bytes;
+            sk.ksplit = ks;
+            sk.partial = reinterpret_cast<float *>(pb);
+            sk.tickets = reinterpret_cast<unsigned int *>(pb + part_bytes);
+            SIDE_CUDA(cudaMemsetAsync(sk.tickets, 0, sizeof(unsigned int) * (size_t)grid, st));
+            grid *= (unsigned)ks;
+        }
+    }
     if (split) {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;
-        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group);
+        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk);
     } else {
         if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false>, smem))) return rc;
-        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group);
+        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk);
     }
     SIDE_LAUNCH_CHECK("dcn_fwd_tc_kernel");
     return SIDE_OK;

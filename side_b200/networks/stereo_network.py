@@ -85,13 +85,13 @@ class cost_volume(nn.Module):
     tensor_core = True     # False keeps the cuDNN convolutions (training always does)
     tc_format = None       # None: ops.get_tc_format(); "tf32" / "f16" pins the operand format of this module
 
-    def _tc_state(self):
+    def _tc_state(self, fmt=None):
         """Swizzled hi/lo weight tiles (in the current operand format) and folded eval-mode BatchNorm per conv, rebuilt when a
         parameter or the format changes."""
         convs = [(self.dres0[0], self.dres0[1]), (self.dres0[3], self.dres0[4]), (self.dres1[0], self.dres1[1]),
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
-        fmt = self.tc_format or ops.get_tc_format()
+        fmt = fmt or self.tc_format or ops.get_tc_format()
         key = (fmt,) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
                                          b.running_mean._version, b.running_var._version) for c, b in convs)
         st = getattr(self, "_tc_cache", None)
@@ -114,10 +114,16 @@ class cost_volume(nn.Module):
     def aggregate_tc(self, cost, xcross=None):
         """Same function as ``aggregate`` on tcgen05 (3xFP16 or 3xTF32 operand pairs): [N,3C,D,16,16] -> logits [N,D,4,4].
         ``xcross`` [N,D]: cosine gate still to be applied to ``cost`` (folded into the layout change)."""
-        L = self._tc_state()
-        conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
         fmt = self.tc_format or ops.get_tc_format()
         hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross, fmt=fmt)            # [N, D, 16, 16, 3C]
+        return self.aggregate_tc_pairs(hi, lo, fmt)
+
+    def aggregate_tc_pairs(self, hi, lo, fmt=None):
+        """``aggregate_tc`` from the gated volume already channels-last and split into operand pairs [N, D, 16, 16, 3C]
+        (what ops.inst_costvol_cl emits)."""
+        fmt = fmt or self.tc_format or ops.get_tc_format()
+        L = self._tc_state(fmt)
+        conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
         _, hi, lo = conv(0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
         isp = self.strAM_2D(y.mean(dim=2).permute(0, 3, 1, 2))                 # mean over H -> [N, 64, D, W]
@@ -270,6 +276,7 @@ class stereo_network(nn.Module):
             z[h] = o.view(B, last.out_channels, H, W)
         return {h: z[h] for h in self.heads}
 
+    fused_volume = True    # inference, fp16 pairs: volume builder writes the consumer format directly (ops.inst_costvol_cl)
     fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream
 
     def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D):
@@ -278,6 +285,11 @@ class stereo_network(nn.Module):
         if (self.fast_volume and est.tensor_core and featL.is_cuda and not self.training and not torch.is_grad_enabled() and self.roiSize == 16
                 and D % 8 == 0 and D <= 256 and C % 8 == 0 and (3 * C) % 32 == 0 and 3 * C == est.dres0[0].in_channels
                 and left.shape[0] <= 65535):
+            fmt = est.tc_format or ops.get_tc_format()
+            if self.fused_volume and fmt == "f16" and ops.inst_costvol_cl_ok(C, D, 16):
+                # the gated volume leaves the builder channels-last and split into the fp16 pairs dres0.0 reads: one HBM pass
+                hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid)
+                return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16"), depth_bin)
             # one pass over the volume: [L, R, L-R] written ungated with the gate scalars on the side; the gate is applied
             # while the volume is re-laid out channels-last for the tensor-core convolutions
             cost, depth_bin, xc = ops.inst_costvol_ungated(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid)
@@ -321,6 +333,17 @@ class stereo_network(nn.Module):
                 slot = torch.where(keep.view(B, K), o['slot'].long(), torch.full_like(o['slot'], K, dtype=torch.long))
                 depth.scatter_(1, slot, disp.view(B, K))            # dropped rows land in the spare column K
                 depth = depth[:, :K].unsqueeze(2).contiguous()
+            elif target is not None and len(target) == 4:
+                # fixed-shape ground-truth RoIs built on the device (side_b200.training.gt_rois): [B*M] image-major rows +
+                # validity mask, no compaction, no host synchronisation; kept rows land in their image's slots in order
+                bl, br, bboxShape, keep8 = target
+                Bt, Mt = int(bboxShape[0]), int(bboxShape[1])
+                disp = self._depth_from_boxes(feaL, feaR, bl.to(dev, torch.float32).contiguous(),
+                                              br.to(dev, torch.float32).contiguous(), fb, keep8.to(dev), D)
+                keep = keep8.to(dev).bool().view(Bt, Mt)
+                slot = torch.where(keep, torch.cumsum(keep, 1) - 1, torch.full((Bt, Mt), Mt, device=dev, dtype=torch.long))
+                depth = torch.zeros((Bt, Mt + 1), device=dev, dtype=disp.dtype).scatter(1, slot, disp.view(Bt, Mt))
+                depth = depth[:, :Mt].unsqueeze(2)
             else:
                 if target is not None:
                     bbox_keep, bbox_right_keep, bboxShape = target

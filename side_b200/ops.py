@@ -350,6 +350,36 @@ def inst_costvol_ungated(featL, featR, left, right, fb, D, P, x_clamp, valid=Non
     return cost, depth_bin, xc
 
 
+def inst_costvol_cl_ok(C, D, P):
+    """Shapes side_inst_costvol_fwd_cl is built for (the reference's: 32 reduced channels, 16x16 RoI bins)."""
+    return C == 32 and P == 16 and 2 <= D <= 64
+
+
+def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, gate=True):
+    """Inference-only: the (gated) volume straight in its consumer's format -> (hi, lo fp16 [N, D, P, P, 3C], depth_bin [N, D],
+    xcross [N, D]).  One pass over HBM; see include/side_b200.h side_inst_costvol_fwd_cl."""
+    lib = _lib.load()
+    featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
+    left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
+    if valid is not None:
+        valid = _chk(valid, "valid", torch.uint8)
+    B, C, H, W = featL.shape
+    N = left.shape[0]
+    dev = featL.device
+    _range_guard(dev)
+    hi = torch.empty((N, D, P, P, 3 * C), device=dev, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    depth_bin = torch.empty((N, D), device=dev, dtype=_F32)
+    xc = torch.empty((N, D), device=dev, dtype=_F32)
+    nws = lib.side_inst_costvol_cl_ws_bytes(B, C, H, W)
+    ws = torch.empty((nws,), device=dev, dtype=torch.uint8)
+    _lib.check(lib.side_inst_costvol_fwd_cl(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(), fb.data_ptr(),
+                                            _p(valid), hi.data_ptr(), lo.data_ptr(), depth_bin.data_ptr(), xc.data_ptr(), N, B, C, H,
+                                            W, D, P, float(x_clamp), _lib.VOL_GATE if gate else 0, ws.data_ptr(), nws, _stream()),
+               "side_inst_costvol_fwd_cl")
+    return hi, lo, depth_bin, xc
+
+
 class _XCrossGate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cost, C):

@@ -50,6 +50,43 @@ def make_boxes(B, n_per_image, seed=0, W4=320, H4=96):
     return left, right, torch.Size([B, n_per_image, 5])
 
 
+def make_targets(B, n_obj=8, max_objs=50, seed=0, W4=320, H4=96, grid=28):
+    """Synthetic ground truth of one training batch in the layout of stereoDataset.__getitem__ (modules/stereoDataset.py:272-285;
+    SURVEY.md config #5: 8 objects per pair, boxes as config #2): 'hm' [B,3,H4,W4] with a radius-2 gaussian per object,
+    'ind' / 'ind_float' [B,M] flat peak index, 'wh' [B,M,3] = (w_left, w_right, h), 'reg' [B,M,3] = (dx_left, dx_right, dy),
+    'dim', 'orien', 'depth', 'kept' [B,M,6], 'rot_mask' [B,M]; rows past n_obj are zero."""
+    g = torch.Generator().manual_seed(seed)
+    left, right, _ = make_boxes(B, n_obj, seed=seed, W4=W4, H4=H4)
+    left, right = left.view(B, n_obj, 5), right.view(B, n_obj, 5)
+    M = max_objs
+    t = {'hm': torch.zeros(B, 3, H4, W4), 'ind': torch.zeros(B, M, dtype=torch.long), 'ind_float': torch.zeros(B, M),
+         'wh': torch.zeros(B, M, 3), 'reg': torch.zeros(B, M, 3), 'dim': torch.zeros(B, M, 3), 'orien': torch.zeros(B, M, 2),
+         'depth': torch.zeros(B, M, 1), 'kept': torch.zeros(B, M, 6), 'rot_mask': torch.zeros(B, M)}
+    cxl, cxr = 0.5 * (left[..., 1] + left[..., 3]), 0.5 * (right[..., 1] + right[..., 3])
+    cy = 0.5 * (left[..., 2] + left[..., 4])
+    xi, yi = cxl.floor().clamp(0, W4 - 1), cy.floor().clamp(0, H4 - 1)
+    ind = (yi * W4 + xi).long()
+    t['ind'][:, :n_obj] = ind
+    t['ind_float'][:, :n_obj] = ind.float()
+    t['wh'][:, :n_obj] = torch.stack((left[..., 3] - left[..., 1], right[..., 3] - right[..., 1], left[..., 4] - left[..., 2]), 2)
+    t['reg'][:, :n_obj] = torch.stack((cxl - xi, cxr - xi, cy - yi), 2)
+    t['dim'][:, :n_obj] = torch.rand(B, n_obj, 3, generator=g) * 2 + 1
+    t['orien'][:, :n_obj] = torch.randn(B, n_obj, 2, generator=g)
+    t['depth'][:, :n_obj] = torch.rand(B, n_obj, 1, generator=g) * 55 + 5
+    t['kept'][:, :n_obj] = torch.rand(B, n_obj, 6, generator=g) * t['wh'][:, :n_obj, :1]
+    t['rot_mask'][:, :n_obj] = 1
+    cls = torch.randint(0, 3, (B, n_obj), generator=g)
+    yy, xx = torch.meshgrid(torch.arange(-2, 3), torch.arange(-2, 3), indexing="ij")
+    gauss = torch.exp(-(xx * xx + yy * yy).float() / (2 * (5 / 6.0) ** 2))
+    for b in range(B):
+        for o in range(n_obj):
+            x, y, c = int(xi[b, o]), int(yi[b, o]), int(cls[b, o])
+            x0, x1, y0, y1 = max(x - 2, 0), min(x + 3, W4), max(y - 2, 0), min(y + 3, H4)
+            patch = t['hm'][b, c, y0:y1, x0:x1]
+            torch.maximum(patch, gauss[y0 - y + 2:y1 - y + 2, x0 - x + 2:x1 - x + 2], out=patch)
+    return t
+
+
 def _calibrate_batchnorm(model, g):
     """Data-dependent BatchNorm statistics so that eval-mode activations stay O(1) (pure torch, CPU).
 

@@ -204,7 +204,8 @@ def test_tensor_core_paths(lib, prec, tol):
         assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < tol, (prec, Cin, Cout, H, W)
 
 
-@pytest.mark.parametrize("cfg", [(8, 64, 64, 24, 80), (4, 128, 64, 48, 160), (4, 512, 256, 12, 40), (1, 64, 64, 96, 320)])
+@pytest.mark.parametrize("cfg", [(8, 64, 64, 24, 80), (4, 128, 64, 48, 160), (4, 512, 256, 12, 40), (1, 64, 64, 96, 320),
+                                 (2, 512, 256, 12, 40), (2, 256, 128, 24, 80)])      # last two: one stereo pair, split-K over the taps
 def test_dcn_module_channels_last_fused_path(lib, cfg, tc_fmt):
     """Inference fast path of the DCN module: conv_offset_mask on tcgen05 (3xTF32, 27 -> 32 padded channels, channels-last) feeding
     side_dcn_fwd_cl, with folded BatchNorm + ReLU -- against the same module on the fp32 SIMT path (cuDNN offset conv)."""

@@ -66,3 +66,39 @@ def test_c_oracle_roi_align_bit_exact_vs_torchvision():
     for P in (16, 7):
         ref = tvo.roi_align(feat, rois, (P, P), 1.0, 2).numpy()
         assert np.array_equal(ref, co.roi_align(feat.numpy(), rois.numpy(), P))
+
+
+def test_training_glue_vs_reference_losses_and_gt_rois(R):
+    """side_b200.training against the reference's own loss classes (models/losses.py:114-198) and a literal restatement of
+    ModelWithLoss.forward's RoI construction (modules/stereoTrainer.py:41-63; that module itself needs `progress`, absent here)."""
+    import importlib
+    from side_b200 import training as T
+    from side_b200.utils.synthetic import make_targets
+    losses = importlib.import_module("models.losses")
+    t = make_targets(2, 8, seed=3)
+    torch.manual_seed(1)
+    out = {'hm': torch.randn(2, 3, 96, 320) - 2, 'wh': torch.rand(2, 3, 96, 320) * 20, 'reg': torch.rand(2, 3, 96, 320),
+           'dim': torch.randn(2, 3, 96, 320), 'orien': torch.randn(2, 2, 96, 320), 'kept_type': torch.randn(2, 168, 96, 320)}
+    hm = torch.clamp(torch.sigmoid(out['hm']), 1e-4, 1 - 1e-4)
+    assert torch.allclose(T.focal_loss(hm, t['hm']), losses.FocalLoss()(hm, t['hm']), rtol=1e-6)
+    assert torch.allclose(T.focal_loss(hm, torch.zeros_like(hm)), losses.FocalLoss()(hm, torch.zeros_like(hm)), rtol=1e-6)
+    assert torch.allclose(T.reg_l1(out['wh'], t['rot_mask'], t['ind'], t['wh']), losses.L1Loss()(out['wh'], t['rot_mask'], t['ind'], t['wh']), rtol=1e-6)
+    tgt = T.kept_label(t['kept'], t['wh'], 28)
+    assert torch.allclose(T.cross_loss(out['kept_type'][:, :112], t['ind'], tgt[:, :, 0]),
+                          losses.CrossLoss()(out['kept_type'][:, :112], t['rot_mask'], t['ind'], tgt[:, :, 0].unsqueeze(2)), rtol=1e-6)
+    # stereoTrainer.py:41-63, restated literally
+    xs, ys = t['ind_float'] % 320, t['ind_float'] // 320
+    wh, reg = t['wh'], t['reg']
+    xs_right = xs + reg[:, :, 1]
+    xs, ys = xs + reg[:, :, 0], ys + reg[:, :, 2]
+    center = torch.cat([xs.unsqueeze(2), ys.unsqueeze(2)], dim=2)
+    center_right = torch.cat([xs_right.unsqueeze(2), ys.unsqueeze(2)], dim=2)
+    bidx = torch.tensor([n for n in range(xs.shape[0])], dtype=torch.float32).unsqueeze(1).unsqueeze(2).repeat(1, xs.shape[1], 1)
+    bbox = torch.zeros((xs.shape[0], xs.shape[1], 5)); bbox_right = torch.zeros((xs.shape[0], xs.shape[1], 5))
+    bbox[:, :, 1:3] = center - 0.5 * wh[:, :, [0, 2]]; bbox[:, :, 3:5] = center + 0.5 * wh[:, :, [0, 2]]
+    bbox_right[:, :, 1:3] = center_right - 0.5 * wh[:, :, [1, 2]]; bbox_right[:, :, 3:5] = center_right + 0.5 * wh[:, :, [1, 2]]
+    bbox[:, :, 0:1], bbox_right[:, :, 0:1] = bidx, bidx
+    keep = torch.sum(bbox.view(-1, 5)[:, 1:5], dim=1) > 0
+    bl, br, shp, k8 = T.gt_rois(t, 320)
+    assert torch.equal(k8.bool(), keep) and tuple(shp) == tuple(bbox.shape)
+    assert torch.equal(bl[keep], bbox.view(-1, 5)[keep]) and torch.equal(br[keep], bbox_right.view(-1, 5)[keep])
