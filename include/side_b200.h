@@ -336,6 +336,39 @@ int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *
 int side_stem_conv_fwd(const float *x, const float *w, const float *scale, const float *shift, float *y, int B, int Cin, int H,
                        int W, int Cout, int k, int stride, int relu, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense photometric alignment of the post-process path.
+ * Replaces src/lib/dense_align/dense_align.py: the numpy normalisation + F.interpolate of align_parallel (:251-266),
+ * sample() with its Box3d ray casting (:14-70, box_3d.py:9-102) and enumeration_depth (:175-237).
+ * Images are PACKED texels: [H][W] float4 = (c0, c1, c2, 0), 16-byte aligned.
+ *   side_dense_align_prep_u8   img_hwc uint8 [H,W,3] -> ((x/255) - mean)/std -> 2x bilinear (align_corners=False) -> packed [2H][2W]
+ *                              mean3 / std3 are HOST pointers to 3 floats.
+ *   side_dense_align_up2_pack  planar float [3,H,W] -> 2x bilinear -> packed [2H][2W]
+ *   side_dense_align_pack / _unpack  planar [3,H,W] <-> packed [H][W]
+ *   side_dense_align_sample    box_left [rois,4], borders [rois,2] (both already in the scaled image), poses [rois,7]
+ *                              (x,y,z,w,h,l,theta), f / cx / cy of the scaled image, f_h x f_w its size ->
+ *                              uvz [rois,cap,3] (u, v, depth offset of the visible box surface; valid pixels first, in the
+ *                              reference's row-major order, zeros after), weight [rois,cap] (1 / 0), count [rois] (valid
+ *                              pixels found; > cap means the tail was dropped).
+ *   side_dense_align_enum      depth_enum [iters,rois], fb -> err_sum [iters,rois] = sum over pixels and channels of
+ *                              |grid_sample(L) - grid_sample(R shifted by the hypothesis' disparity)| * weight,
+ *                              best_depth [rois] = depth_enum[argmin (first minimum)], best_idx [rois] (may be NULL).
+ *                              pixels = second dimension of uvz / weight.  flags: SIDE_DA_ALIGN_CORNERS selects
+ *                              grid_sample(align_corners=True) (torch < 1.3 default, which the reference was written for);
+ *                              0 = align_corners=False (what the reference computes under the torch in this image).
+ * --------------------------------------------------------------------------------------------- */
+#define SIDE_DA_ALIGN_CORNERS (1 << 0)
+int side_dense_align_prep_u8(const unsigned char *img_hwc, float *out_packed, int H, int W, const float *mean3,
+                             const float *std3, void *stream);
+int side_dense_align_up2_pack(const float *img_chw, float *out_packed, int H, int W, void *stream);
+int side_dense_align_pack(const float *img_chw, float *out_packed, int H, int W, void *stream);
+int side_dense_align_unpack(const float *packed, float *img_chw, int H, int W, void *stream);
+int side_dense_align_sample(const float *box_left, const float *borders, const float *poses, int rois, float f, float cx,
+                            float cy, int f_h, int f_w, int cap, float *uvz, float *weight, int *count, void *stream);
+int side_dense_align_enum(const float *imL_packed, const float *imR_packed, const float *uvz, const float *weight,
+                          const float *depth_enum, float fb, int rois, int pixels, int iters, int H, int W, int flags,
+                          float *err_sum, float *best_depth, int *best_idx, void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

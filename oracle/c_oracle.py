@@ -186,3 +186,44 @@ def maxpool_hw2(x):
     y = np.empty((N, Cc, D, H // 2, W // 2), np.float32)
     _chk(lib().orc_maxpool_hw2(px, y.ctypes.data_as(C.POINTER(C.c_float)), N * Cc, D, H, W), "orc_maxpool_hw2")
     return y
+
+
+# ---- F2: dense photometric alignment (dense_align/dense_align.py) ----
+def da_prep_u8(img, mean, std):
+    """uint8 HWC image -> normalised, 2x bilinearly up-sampled planar [3, 2H, 2W] (align_parallel :251-266)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W, _ = img.shape
+    mean, pm = _f(mean); std, ps = _f(std)
+    out = np.empty((3, 2 * H, 2 * W), np.float32)
+    _chk(lib().orc_da_prep_u8(img.ctypes.data_as(C.POINTER(C.c_ubyte)), pm, ps, out.ctypes.data_as(C.POINTER(C.c_float)),
+                              H, W), "orc_da_prep_u8")
+    return out
+
+
+def da_sample(box_left, borders, poses, f, cx, cy, f_h, f_w, cap=8192):
+    """sample() (:14-70): returns (uvz [rois, max, 3], weight [rois, max], count [rois]) trimmed to the longest RoI."""
+    box_left, pb = _f(box_left); borders, pd = _f(borders); poses, pp = _f(poses)
+    rois = box_left.shape[0]
+    uvz = np.empty((rois, cap, 3), np.float32); wgt = np.empty((rois, cap), np.float32)
+    cnt = np.empty((rois,), np.int32)
+    P = C.POINTER(C.c_float)
+    _chk(lib().orc_da_sample(pb, pd, pp, rois, C.c_float(f), C.c_float(cx), C.c_float(cy), f_h, f_w, cap,
+                             uvz.ctypes.data_as(P), wgt.ctypes.data_as(P), cnt.ctypes.data_as(C.POINTER(C.c_int))),
+         "orc_da_sample")
+    assert cnt.max(initial=0) <= cap
+    m = int(cnt.max(initial=0))
+    return np.ascontiguousarray(uvz[:, :m]), np.ascontiguousarray(wgt[:, :m]), cnt
+
+
+def da_enum(imL, imR, uvz, weight, depth_enum, fb, align_corners=False):
+    """enumeration_depth (:175-237): returns (err_sum [iters, rois], best_depth [rois], best_idx [rois])."""
+    imL, pl = _f(imL); imR, pr = _f(imR); uvz, pu = _f(uvz); weight, pw = _f(weight); depth_enum, pd = _f(depth_enum)
+    H, W = imL.shape[-2:]
+    rois, pixels = weight.shape
+    iters = depth_enum.shape[0]
+    err = np.empty((iters, rois), np.float32); best = np.empty((rois,), np.float32); idx = np.empty((rois,), np.int32)
+    P = C.POINTER(C.c_float)
+    _chk(lib().orc_da_enum(pl, pr, pu, pw, pd, C.c_float(fb), rois, pixels, iters, H, W, 1 if align_corners else 0,
+                           err.ctypes.data_as(P), best.ctypes.data_as(P), idx.ctypes.data_as(C.POINTER(C.c_int))),
+         "orc_da_enum")
+    return err, best, idx

@@ -181,6 +181,81 @@ def gen_e2e(R):
          det=npy(det), det_right=npy(detr), info=npy(info))
 
 
+def dense_align_case():
+    """Seeded inputs of the dense-alignment fixture (shared with the tests): a 96 x 320 textured stereo pair whose right view
+    is the left one shifted by the disparity of ~20 m, KITTI-like calibration at 1/4 scale, 4 RoIs (one of them with no
+    valid pixel: its box lies beside the projected cuboid)."""
+    import types
+    rng = np.random.RandomState(5)
+    H, W = 96, 320
+    base = rng.rand(H // 4 + 2, W // 4 + 2, 3).astype(np.float32)
+    big = np.kron(base, np.ones((4, 4, 1), np.float32))[:H + 8, :W + 8]
+    k = np.ones(5, np.float32) / 5                                    # box blur -> smooth texture with gradients
+    for ax in (0, 1):
+        big = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), ax, big)
+    img_l = (np.clip(big[4:4 + H, 4:4 + W], 0, 1) * 255).astype(np.uint8)
+    img_r = np.ascontiguousarray(np.roll(img_l, -4, axis=1))
+    p2 = np.array([[721.54, 0, 609.56, 44.86], [0, 721.54, 172.85, 0.216], [0, 0, 1, 0.00275]], np.float32)
+    p2[:2] /= 4
+    p3 = p2.copy()
+    p3[0, 3] = -339.52 / 4
+    calib = types.SimpleNamespace(p2=p2, p3=p3)
+    opt = types.SimpleNamespace(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    box = np.array([[100., 30., 160., 70.], [200., 40., 230., 60.], [120., 20., 200., 80.], [20., 35., 70., 66.]], np.float32)
+    borders = np.array([[105., 150.], [202., 228.], [125., 190.], [24., 66.]], np.float32)
+    poses = np.array([[-1.5, 1.6, 20., 1.6, 1.5, 3.9, 0.3], [2.0, 1.7, 30., 1.6, 1.5, 3.9, -1.2],
+                      [0.2, 1.5, 8., 1.8, 1.6, 4.2, 1.3], [-9.5, 1.4, 18., 1.7, 1.5, 4.0, -0.4]], np.float32)
+    return img_l, img_r, calib, opt, box, borders, poses
+
+
+def gen_dense_align(R):
+    """F2: the reference's sample / enumeration_depth / align_parallel (dense_align/dense_align.py) executed unmodified."""
+    import importlib
+    import warnings
+    import torch.nn.functional as F
+    da = importlib.import_module("dense_align.dense_align")
+    img_l, img_r, calib, opt, box, borders, poses = dense_align_case()
+    box_t, borders_t, poses_t = torch.from_numpy(box), torch.from_numpy(borders), torch.from_numpy(poses)
+    H, W = img_l.shape[:2]
+    scale = 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        uvz, wgt = da.sample(calib, scale, 2 * H, 2 * W, box_t * scale, poses_t, borders_t * scale)
+        status, best_dis = da.align_parallel(calib, opt, img_l, img_r, box_t, borders_t, poses_t)
+        # the two images exactly as align_parallel prepares them (:251-266), and one enumeration with its error matrix
+        mean = np.array(opt.mean, dtype=np.float32).reshape(1, 1, 3)
+        std = np.array(opt.std, dtype=np.float32).reshape(1, 1, 3)
+
+        def prep(im):
+            im = (im.astype(np.float32) / 255.)
+            im = ((im - mean) / std).transpose(2, 0, 1)[np.newaxis, ...]
+            return F.interpolate(torch.from_numpy(im), scale_factor=2, mode='bilinear', align_corners=False)
+        im_l, im_r = prep(img_l), prep(img_r)
+        f = calib.p2[0, 0] * scale
+        bl = (calib.p2[0, 3] - calib.p3[0, 3]) * scale / f
+        dis_init = f * bl / poses_t[:, 2]
+        depth_enum = torch.zeros(50, box_t.size(0))
+        for i in range(50):
+            depth_enum[i] = dis_init.reciprocal() * f * bl - 50 * 0.5 / 2 + 0.5 * i
+        depth_enum[depth_enum < 1.5] = 1.5
+        seen = {}
+        tmin = torch.min
+
+        def spy(*a, **k):                       # enumeration_depth only returns the winner: keep the error matrix it minimises
+            seen["err"] = a[0].clone()
+            return tmin(*a, **k)
+        torch.min = spy
+        try:
+            best = da.enumeration_depth(im_l, im_r, uvz, wgt, depth_enum, f * bl)
+        finally:
+            torch.min = tmin
+    pos = np.random.RandomState(1).randint(0, 4 * H * W, 4096)
+    save("dense_align", img_l=img_l, img_r=img_r, uvz=npy(uvz), weight=npy(wgt), status=npy(status), best_dis=npy(best_dis),
+         depth_enum=npy(depth_enum), err_sum=npy(seen["err"]), best_depth=npy(best), fb=np.float32(f * bl),
+         im_l_sha256=np.array(sha(npy(im_l))), im_pos=pos, im_l_s=npy(im_l).reshape(3, -1)[:, pos],
+         im_r_s=npy(im_r).reshape(3, -1)[:, pos])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
@@ -188,6 +263,7 @@ def main():
     gen_proposals_and_volume(R)
     gen_decode(R)
     gen_e2e(R)
+    gen_dense_align(R)
 
 
 if __name__ == "__main__":

@@ -691,3 +691,187 @@ ORC_API int orc_maxpool_hw2(const float *x, float *y, int NC, int D, int H, int 
             }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * F2: dense photometric alignment (src/lib/dense_align/dense_align.py, box_3d.py).
+ * Pinned by tests/golden/dense_align.npz, generated by EXECUTING the reference's align_parallel /
+ * sample / enumeration_depth (oracle/gen_golden.py:gen_dense_align).  F.interpolate and F.grid_sample are
+ * ATen ops (torch 2.11 in the image: grid_sample defaults to align_corners=False); restated from
+ * ATen/native/UpSample.h (area_pixel_compute_source_index) and GridSampler.h (unnormalize + clip, bilinear).
+ * --------------------------------------------------------------------------------------------- */
+/* align_parallel's host preparation (dense_align.py:251-266): (img/255 - mean)/std, HWC->CHW, 2x bilinear up-sampling */
+static void orc_up2_src(int dst, int size, int *i0, int *ip, float *l0, float *l1)
+{
+    float src = 0.5f * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    *i0 = (int)src;
+    *ip = (*i0 < size - 1) ? 1 : 0;
+    *l1 = src - (float)*i0;
+    *l0 = 1.f - *l1;
+}
+ORC_API int orc_da_prep_u8(const unsigned char *img, const float *mean, const float *sd, float *out, int H, int W)
+{
+    const int H2 = 2 * H, W2 = 2 * W;
+    float *norm = (float *)malloc(sizeof(float) * 3 * (size_t)H * W);
+    if (!norm) return -1;
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < H * W; ++i) {
+            const float v = (float)img[(size_t)i * 3 + c] / 255.f;
+            norm[(size_t)c * H * W + i] = (v - mean[c]) / sd[c];
+        }
+    for (int c = 0; c < 3; ++c)
+        for (int y = 0; y < H2; ++y) {
+            int y0, yp; float h0, h1;
+            orc_up2_src(y, H, &y0, &yp, &h0, &h1);
+            for (int x = 0; x < W2; ++x) {
+                int x0, xp; float w0, w1;
+                orc_up2_src(x, W, &x0, &xp, &w0, &w1);
+                const float *p = norm + (size_t)c * H * W + (size_t)y0 * W + x0;
+                const float top = w0 * p[0] + w1 * p[xp];
+                const float bot = w0 * p[(size_t)yp * W] + w1 * p[(size_t)yp * W + xp];
+                out[((size_t)c * H2 + y) * W2 + x] = h0 * top + h1 * bot;
+            }
+        }
+    free(norm);
+    return 0;
+}
+
+static void orc_py_slice(int start, int stop, int len, int *s, int *e)
+{
+    if (start < 0) { start += len; if (start < 0) start = 0; } else if (start > len) start = len;
+    if (stop < 0) { stop += len; if (stop < 0) stop = 0; } else if (stop > len) stop = len;
+    *s = start; *e = stop;
+}
+static void orc_plane(const float *p1, const float *p2, const float *p3, float *pl)      /* box_3d.py:32-41 */
+{
+    const float a0 = p2[0] - p1[0], a1 = p2[1] - p1[1], a2 = p2[2] - p1[2];
+    const float b0 = p3[0] - p1[0], b1 = p3[1] - p1[1], b2 = p3[2] - p1[2];
+    const float n0 = a1 * b2 - a2 * b1, n1 = a2 * b0 - a0 * b2, n2 = a0 * b1 - a1 * b0;
+    pl[0] = n0; pl[1] = n1; pl[2] = n2;
+    pl[3] = -n0 * p1[0] - n1 * p1[1] - n2 * p1[2];
+}
+/* sample() (dense_align.py:14-70) for one RoI: writes up to cap valid (u, v, dz) triples in row-major order, returns the count */
+ORC_API int orc_da_sample(const float *box, const float *borders, const float *poses, int rois, float f, float cx, float cy,
+                          int f_h, int f_w, int cap, float *uvz, float *weight, int *count)
+{
+    static const int group[8][3] = {{0, 3, 4}, {2, 3, 4}, {1, 2, 4}, {0, 1, 4}, {0, 3, 5}, {2, 3, 5}, {1, 2, 5}, {0, 1, 5}};
+    memset(uvz, 0, sizeof(float) * 3 * (size_t)rois * cap);
+    memset(weight, 0, sizeof(float) * (size_t)rois * cap);
+    for (int i = 0; i < rois; ++i) {
+        const float *bx = box + 4 * i, *bd = borders + 2 * i, *ps = poses + 7 * i;
+        int width = (int)((bd[1] - bd[0]) / 56.f), height = (int)((bx[3] - bx[1]) / 56.f);
+        if (width < 1) width = 1;
+        if (height < 1) height = 1;
+        int r0, r1, c0, c1;
+        orc_py_slice((int)((bx[1] + bx[3]) / 2.f + 0.5f), (int)(bx[3] - (bx[3] - bx[1]) * 0.1f + 0.5f), f_h, &r0, &r1);
+        orc_py_slice((int)(bd[0] + 0.5f), (int)(bd[1] + 0.5f), f_w, &c0, &c1);
+        /* Box3d.__init__ (box_3d.py:10-56) */
+        const float cs = (float)cos((double)ps[6]), sn = (float)sin((double)ps[6]);
+        const float R[9] = {cs, 0.f, sn, 0.f, 1.f, 0.f, -sn, 0.f, cs};
+        const float hw = ps[3] / 2.f, hl = ps[5] / 2.f, hh = ps[4];
+        const float Po[8][3] = {{-hw, 0.f, -hl}, {-hw, 0.f, hl}, {hw, 0.f, hl}, {hw, 0.f, -hl},
+                                {-hw, -hh, -hl}, {-hw, -hh, hl}, {hw, -hh, hl}, {hw, -hh, -hl}};
+        float Pc[8][3], planes[6][4];
+        int nearest = 0;
+        float nd = 100000000.f;
+        for (int k = 0; k < 8; ++k) {
+            for (int r = 0; r < 3; ++r)
+                Pc[k][r] = ((R[3 * r] * Po[k][0] + R[3 * r + 1] * Po[k][1]) + R[3 * r + 2] * Po[k][2]) + ps[r];
+            const float nrm = sqrtf((Pc[k][0] * Pc[k][0] + Pc[k][1] * Pc[k][1]) + Pc[k][2] * Pc[k][2]);
+            if (nrm < nd) { nd = nrm; nearest = k; }
+        }
+        orc_plane(Pc[0], Pc[3], Pc[4], planes[0]);
+        orc_plane(Pc[2], Pc[3], Pc[6], planes[1]);
+        orc_plane(Pc[1], Pc[2], Pc[5], planes[2]);
+        orc_plane(Pc[0], Pc[1], Pc[4], planes[3]);
+        orc_plane(Pc[0], Pc[1], Pc[2], planes[4]);
+        orc_plane(Pc[4], Pc[5], Pc[6], planes[5]);
+        const float lo[3] = {-hw - 0.01f, -hh - 0.01f, -hl - 0.01f}, hi[3] = {hw + 0.01f, 0.f + 0.01f, hl + 0.01f};
+        int n = 0;
+        for (int r = r0; r < r1; r += height)
+            for (int c = c0; c < c1; c += width) {
+                const float u = (float)c, v = (float)r;
+                const float nu = (u - cx) / f, nv = (v - cy) / f;
+                int valid = 0;
+                float z = 0.f;
+                for (int k = 0; k < 3 && !valid; ++k) {                /* BoxRayInsec + mask_out_box (box_3d.py:58-102) */
+                    const float *pl = planes[group[nearest][k]];
+                    float t = (nu * pl[0] + nv * pl[1]) + 1.f * pl[2];
+                    t = -(1.f / t) * pl[3];
+                    const float i0 = nu * t - ps[0], i1 = nv * t - ps[1], i2 = 1.f * t - ps[2];
+                    const float o0 = (R[0] * i0 + R[3] * i1) + R[6] * i2;
+                    const float o1 = (R[1] * i0 + R[4] * i1) + R[7] * i2;
+                    const float o2 = (R[2] * i0 + R[5] * i1) + R[8] * i2;
+                    z = i2;
+                    valid = o0 >= lo[0] && o1 >= lo[1] && o2 >= lo[2] && o0 <= hi[0] && o1 <= hi[1] && o2 <= hi[2];
+                }
+                if (valid) {
+                    if (n < cap) {
+                        float *o = uvz + ((size_t)i * cap + n) * 3;
+                        o[0] = u; o[1] = v; o[2] = z;
+                        weight[(size_t)i * cap + n] = 1.f;
+                    }
+                    ++n;
+                }
+            }
+        count[i] = n;
+    }
+    return 0;
+}
+
+/* F.grid_sample(bilinear, padding_mode='border') of one position in a planar [3][H][W] image */
+static float orc_gs_unnorm(float g, int size, int align)
+{
+    float x = align ? ((g + 1.f) / 2.f) * (float)(size - 1) : ((g + 1.f) * (float)size - 1.f) / 2.f;
+    if (x < 0.f) x = 0.f;
+    if (x > (float)(size - 1)) x = (float)(size - 1);
+    return x;
+}
+static void orc_gs3(const float *im, int H, int W, float gx, float gy, int align, float *out)
+{
+    const float x = orc_gs_unnorm(gx, W, align), y = orc_gs_unnorm(gy, H, align);
+    const float xw = floorf(x), yn = floorf(y);
+    const float we = x - xw, ww = 1.f - we, wn = y - yn, ws = 1.f - wn;       /* GridSamplerKernel.cpp ApplyGridSample bilinear */
+    const int ix = (int)xw, iy = (int)yn;
+    const float nw = ws * ww, ne = ws * we, sw = wn * ww, se = wn * we;
+    for (int c = 0; c < 3; ++c) {
+        const float *p = im + (size_t)c * H * W;
+        float acc = p[(size_t)iy * W + ix] * nw;
+        if (ix + 1 < W) acc += p[(size_t)iy * W + ix + 1] * ne;
+        if (iy + 1 < H) acc += p[(size_t)(iy + 1) * W + ix] * sw;
+        if (ix + 1 < W && iy + 1 < H) acc += p[(size_t)(iy + 1) * W + ix + 1] * se;
+        out[c] = acc;
+    }
+}
+/* enumeration_depth (dense_align.py:175-237): err_sum [iters, rois], best_depth [rois], best_idx [rois] */
+ORC_API int orc_da_enum(const float *imL, const float *imR, const float *uvz, const float *weight, const float *depth_enum,
+                        float fb, int rois, int pixels, int iters, int H, int W, int align, float *err_sum, float *best_depth,
+                        int *best_idx)
+{
+    const float half_w = (float)(((double)W - 1.0) / 2.0), half_h = (float)(((double)H - 1.0) / 2.0);
+    for (int it = 0; it < iters; ++it)
+        for (int r = 0; r < rois; ++r) {
+            const float depth = depth_enum[(size_t)it * rois + r];
+            const float dis = (1.f / depth) * fb;
+            double s = 0;
+            for (int p = 0; p < pixels; ++p) {
+                const float *q = uvz + ((size_t)r * pixels + p) * 3;
+                const float wgt = weight[(size_t)r * pixels + p];
+                const float gy = (q[1] - half_h) / half_h;
+                const float dd = 1.f / (q[2] / fb + 1.f / dis);
+                float l[3], rr[3];
+                orc_gs3(imL, H, W, (q[0] - half_w) / half_w, gy, align, l);
+                orc_gs3(imR, H, W, ((q[0] - dd) - half_w) / half_w, gy, align, rr);
+                for (int c = 0; c < 3; ++c) s += fabsf((l[c] - rr[c]) * wgt);
+            }
+            err_sum[(size_t)it * rois + r] = (float)s;
+        }
+    for (int r = 0; r < rois; ++r) {
+        int bi = 0;
+        for (int it = 1; it < iters; ++it)
+            if (err_sum[(size_t)it * rois + r] < err_sum[(size_t)bi * rois + r]) bi = it;
+        best_depth[r] = depth_enum[(size_t)bi * rois + r];
+        best_idx[r] = bi;
+    }
+    return 0;
+}

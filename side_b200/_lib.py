@@ -63,6 +63,12 @@ SIGNATURES = {
     "side_conv_tc_set_mode": (_i, [_i]),
     "side_tc_range_guard": (_i, [_vp, _i]),
     "side_stem_conv_fwd": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "side_dense_align_prep_u8": (_i, [_vp] * 2 + [_i] * 2 + [C.POINTER(_f)] * 2 + [_vp]),
+    "side_dense_align_up2_pack": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
+    "side_dense_align_pack": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
+    "side_dense_align_unpack": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
+    "side_dense_align_sample": (_i, [_vp] * 3 + [_i] + [_f] * 3 + [_i] * 3 + [_vp] * 4),
+    "side_dense_align_enum": (_i, [_vp] * 5 + [_f] + [_i] * 6 + [_vp] * 4),
 }
 
 # flag values (include/side_b200.h)
@@ -80,6 +86,7 @@ VOL_SEPARABLE = 1 << 2
 VOL_XCROSS = 1 << 3
 VOL_BWD_SCALAR = 1 << 4
 DECODE_HEAT_IS_LOGIT = 1 << 0
+DA_ALIGN_CORNERS = 1 << 0
 
 _lib = None
 

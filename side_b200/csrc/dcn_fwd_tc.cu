@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int n = c + j;
+                if (n >= cend) break;                          // Cout = 16: a column quarter is 4 wide, the load 8
                 if (pp) {                                      // split-K: raw partial sum, finished by the tile's last CTA
                     if (pix_ok) __stcg(pp + (size_t)n * s.P, acc[j]);
                     continue;

@@ -21,7 +21,7 @@ def _pair(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
-class DCNv2(nn.Module):
+class DCNv2(ops.PreparedStateOwner, nn.Module):
     """Modulated deformable conv taking explicit offset / mask (reference dcn_v2.py:57-94)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, deformable_groups=1):
@@ -96,7 +96,7 @@ class DCN(DCNv2):
     def _om_weights(self):
         """conv_offset_mask as a 32-output-channel tcgen05 convolution (27 real channels, zero padding), bias in the epilogue."""
         c = self.conv_offset_mask
-        key = (ops.get_tc_format(), c.weight.data_ptr(), c.weight._version, c.bias._version)
+        key = (ops.prep_epoch(), ops.get_tc_format(), c.weight.data_ptr(), c.weight._version, c.bias._version)
         st = self.__dict__.get("_om_cache")
         if st is None or st[0] != key:
             w = torch.zeros((32,) + tuple(c.weight.shape[1:]), device=c.weight.device, dtype=torch.float32)

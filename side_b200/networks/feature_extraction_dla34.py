@@ -94,7 +94,7 @@ class Tree(nn.Module):
         return self.tree2(x1, children=children)
 
 
-class DLA(nn.Module):
+class DLA(ops.PreparedStateOwner, nn.Module):
     def __init__(self, levels, channels, block=BasicBlock, residual_root=False):
         super().__init__()
         self.channels = channels
@@ -141,7 +141,8 @@ class DLA(nn.Module):
                     x = mods[j + 2](bn(conv(x)))                  # not a DLA-34 stem shape: cuDNN
                     continue
                 st = self.__dict__.setdefault("_stem_cache", {})
-                key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.data_ptr())
+                key = (ops.prep_epoch(), bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+                       bn.weight.data_ptr())
                 ent = st.get(id(bn))
                 if ent is None or ent[0] != key:
                     scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
@@ -177,8 +178,8 @@ class DLA(nn.Module):
 
     def _tc_fold(self, conv, bn):
         st = self.__dict__.setdefault("_tc_cache", {})
-        key = (ops.get_tc_format(), conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version,
-               bn.running_mean._version, bn.running_var._version)
+        key = (ops.prep_epoch(), ops.get_tc_format(), conv.weight.data_ptr(), conv.weight._version, bn.weight._version,
+               bn.bias._version, bn.running_mean._version, bn.running_var._version)
         ent = st.get(id(conv))
         if ent is None or ent[0] != key:
             scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()

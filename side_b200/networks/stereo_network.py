@@ -42,7 +42,7 @@ def get_proposal_shift(left_boxes, right_boxes, depth_rate, fbs, trans_invs=None
                               input_w // 4 - 1.)
 
 
-class cost_volume(nn.Module):
+class cost_volume(ops.PreparedStateOwner, nn.Module):
     """3-D aggregation network + soft-argmin depth regression (reference :135-244)."""
 
     def __init__(self, inChannel, reduced_channel=32):
@@ -92,7 +92,7 @@ class cost_volume(nn.Module):
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
         fmt = fmt or self.tc_format or ops.get_tc_format()
-        key = (fmt,) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
+        key = (ops.prep_epoch(), fmt) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
                                          b.running_mean._version, b.running_var._version) for c, b in convs)
         st = getattr(self, "_tc_cache", None)
         if st is None or st[0] != key:
@@ -154,7 +154,7 @@ def fill_fc_weights(layers):
             nn.init.constant_(m.bias, 0)
 
 
-class stereo_network(nn.Module):
+class stereo_network(ops.PreparedStateOwner, nn.Module):
     def __init__(self, base_name, heads, pretrained, down_ratio, final_kernel, last_level, head_conv, out_channel=0):
         super().__init__()
         self.down_ratio = down_ratio
@@ -226,7 +226,7 @@ class stereo_network(nn.Module):
         stereo = [h for h in self.heads if h not in self.left_only]
         mono = [h for h in self.heads if h in self.left_only]
         params = [p for h in self.heads for p in self.__getattr__(h).parameters()]
-        key = (ops.get_tc_format(),) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (ops.prep_epoch(), ops.get_tc_format()) + tuple((p.data_ptr(), p._version) for p in params)
         st = getattr(self, "_heads_cache", None)
         if st is None or st[0] != key:
             d = {"stereo": stereo, "mono": {}}

@@ -11,6 +11,35 @@ from . import _lib
 _F32 = torch.float32
 
 
+# Prepared state (swizzled weight tiles, folded BatchNorm) is cached per module under keys built from parameter addresses and
+# version counters.  Two events change a module's numbers WITHOUT touching those: nn.Module._apply (.cpu() / .cuda() swap
+# `param.data`, and the allocator may hand the old address back) and a training-mode BatchNorm forward (torch.batch_norm updates
+# running_mean / running_var without bumping their version counters).  Modules that own a cache call invalidate_prepared()
+# from train() / _apply(); every cache key carries the epoch.
+_prep_epoch = 0
+
+
+def invalidate_prepared():
+    global _prep_epoch
+    _prep_epoch += 1
+
+
+def prep_epoch():
+    return _prep_epoch
+
+
+class PreparedStateOwner:
+    """Mixin for nn.Modules that cache prepared weights: drops the caches on train() / eval() / .to() / .cuda() / .cpu()."""
+
+    def train(self, mode=True):
+        invalidate_prepared()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate_prepared()
+        return super()._apply(fn, *args, **kwargs)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 

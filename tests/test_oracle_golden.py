@@ -132,3 +132,33 @@ def test_conv3d_layer_restatement_vs_torch():
     assert rel_err(out, ref.numpy()) < 1e-5
     y = torch.randn(1, 3, 2, 6, 8, generator=g)
     assert np.array_equal(co.maxpool_hw2(y.numpy()), F.max_pool3d(y, (1, 2, 2)).numpy())
+
+
+# ---- F2: dense photometric alignment (dense_align/dense_align.py), golden = the reference executed on the seeded case ----
+def _da_case():
+    from oracle.gen_golden import dense_align_case
+    return dense_align_case()
+
+
+def test_dense_align_sample_bit_exact():
+    g = golden("dense_align")
+    img_l, _, calib, _, box, borders, poses = _da_case()
+    H, W = img_l.shape[:2]
+    f, cx, cy = calib.p2[0, 0] * 2, calib.p2[0, 2] * 2, calib.p2[1, 2] * 2
+    uvz, wgt, cnt = co.da_sample(box * 2, borders * 2, poses, float(f), float(cx), float(cy), 2 * H, 2 * W)
+    assert np.array_equal(wgt, g["weight"])                 # same pixels kept, same row-major order, same padding
+    assert np.array_equal(uvz, g["uvz"])
+    assert list(cnt) == [int(v) for v in g["weight"].sum(1)] and cnt[1] == 0
+
+
+def test_dense_align_prep_and_enumeration():
+    g = golden("dense_align")
+    img_l, img_r, _, opt, _, _, _ = _da_case()
+    assert np.array_equal(img_l, g["img_l"]) and np.array_equal(img_r, g["img_r"])
+    L, R = co.da_prep_u8(img_l, opt.mean, opt.std), co.da_prep_u8(img_r, opt.mean, opt.std)
+    assert np.abs(L.reshape(3, -1)[:, g["im_pos"]] - g["im_l_s"]).max() < 2e-6          # ATen's interpolate: <= 2 ulp
+    assert np.abs(R.reshape(3, -1)[:, g["im_pos"]] - g["im_r_s"]).max() < 2e-6
+    err, best, idx = co.da_enum(L, R, g["uvz"], g["weight"], g["depth_enum"], float(g["fb"]))
+    assert rel_err(err, g["err_sum"]) < 1e-5
+    assert np.array_equal(best, g["best_depth"])
+    assert np.array_equal(idx, g["err_sum"].argmin(0))
