@@ -557,7 +557,7 @@ def main():
 
     # ---- BASELINE config #4 as written: 32 pairs TOTAL over the ranks (strong scaling) ----
     strong = None
-    if 32 % world == 0:
+    if 32 % world == 0 and 32 // world <= P:
         ps = 32 // world
         ms_s = min(mb, ps)
         if ps == P and ms_s == mb:
