@@ -369,6 +369,50 @@ int side_dense_align_enum(const float *imL_packed, const float *imR_packed, cons
                           const float *depth_enum, float fb, int rois, int pixels, int iters, int H, int W, int flags,
                           float *err_sum, float *best_depth, int *best_idx, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Detector input preparation.  Replaces stereoDetector.pre_process's host work
+ * (src/lib/modules/stereoDetector.py:45-82): cv2.warpAffine(INTER_LINEAR, constant border 0) of the raw uint8 image,
+ * ((x / 255) - mean) / std and the HWC -> CHW transpose, for the left and right image in one launch.
+ *   img_*      uint8 [src_h, src_w, 3] device pointers (img_right / out_right may be NULL)
+ *   inv_map6   HOST pointer: the 2x3 map from DESTINATION to SOURCE pixels (cv2.invertAffineTransform(trans_input))
+ *   mean3/std3 HOST pointers
+ *   out_*      float [3, dst_h, dst_w]
+ * OpenCV's 8-bit fixed-point algorithm is restated (1/32-pixel positions, 15-bit weights); cv2 is not in the image, so
+ * this entry's parity is pinned only by the repo's own numpy restatement (oracle/torch_port.py:warp_affine_u8).
+ * --------------------------------------------------------------------------------------------- */
+int side_preprocess_u8(const unsigned char *img_left, const unsigned char *img_right, int src_h, int src_w,
+                       const double *inv_map6, const float *mean3, const float *std3, float *out_left, float *out_right,
+                       int dst_h, int dst_w, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Instance voxel volume of the stereo_network_new variant.
+ * Replaces get_voxel (src/lib/models/networks/stereo_network_new.py:160-283, a host-side loop over images and RoIs) and
+ * the per-image F.grid_sample / mask / cat sequence of stereo_network.forward (:409-449).
+ *   left, right [N,5] boxes (b, x1, y1, x2, y2) in feature pixels; p2, p3 [B,3,4]; fb [B]; trans, trans_inv [B,2,3]
+ *   input_h, input_w: the module constants the reference normalises with (u_max = input_w/4 - 1, v_max = input_h/4 - 1)
+ *   side_voxel_coords      get_voxel's outputs: norm3 [N,10,10,10,3] + valid3 [N,10,10,10] (need depth_bins [N,D]; pass NULL for
+ *                          all three to skip them), normL / normR [N,10,10,10,2], validL / validR [N,10,10,10], depth_ori [N]
+ *   side_voxel_volume_fwd  featL, featR [B,64,H,W] -> voxel [N, 192, 10,10,10] = cat(L - R, L, R) of the bilinear samples
+ *                          (padding zeros; voxels outside [-1,1] are zero), depth_ori [N] (may be NULL).
+ *                          flags: SIDE_VOXEL_ALIGN_CORNERS = grid_sample(align_corners=True); 0 = False (torch >= 1.3 default,
+ *                          what the reference computes today).  ws: side_voxel_volume_ws_bytes(B,C,H,W) bytes.
+ *   side_voxel_volume_bwd  gvoxel -> gfeatL, gfeatR [B,64,H,W] (OVERWRITTEN; fp32 atomics inside).
+ * --------------------------------------------------------------------------------------------- */
+#define SIDE_VOXEL_ALIGN_CORNERS (1 << 0)
+int side_voxel_coords(const float *left, const float *right, const float *p2, const float *p3, const float *fb,
+                      const float *trans, const float *trans_inv, const float *depth_bins, int N, int B, int D, int H,
+                      int W, int input_h, int input_w, float *norm3, float *valid3, float *normL, float *validL,
+                      float *normR, float *validR, float *depth_ori, void *stream);
+size_t side_voxel_volume_ws_bytes(int B, int C, int H, int W);
+int side_voxel_volume_fwd(const float *featL, const float *featR, const float *left, const float *right, const float *p2,
+                          const float *p3, const float *fb, const float *trans, const float *trans_inv, float *voxel,
+                          float *depth_ori, int N, int B, int C, int H, int W, int input_h, int input_w, int flags,
+                          void *ws, size_t ws_bytes, void *stream);
+int side_voxel_volume_bwd(const float *gvoxel, const float *left, const float *right, const float *p2, const float *p3,
+                          const float *fb, const float *trans, const float *trans_inv, float *gfeatL, float *gfeatR,
+                          int N, int B, int C, int H, int W, int input_h, int input_w, int flags, void *ws,
+                          size_t ws_bytes, void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

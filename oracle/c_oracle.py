@@ -227,3 +227,32 @@ def da_enum(imL, imR, uvz, weight, depth_enum, fb, align_corners=False):
                            err.ctypes.data_as(P), best.ctypes.data_as(P), idx.ctypes.data_as(C.POINTER(C.c_int))),
          "orc_da_enum")
     return err, best, idx
+
+
+# ---- F3: stereo_network_new voxel volume (models/networks/stereo_network_new.py:160-283, 409-449) ----
+def voxel_coords(left, right, p2, p3, fb, trans, trans_inv, depth_bins, input_h=384, input_w=1280):
+    left, pl = _f(left); right, pr = _f(right); p2, pp2 = _f(p2); p3, pp3 = _f(p3); fb, pf = _f(fb)
+    trans, pt = _f(trans); trans_inv, pti = _f(trans_inv); depth_bins, pd = _f(depth_bins)
+    N, B, D = left.shape[0], fb.shape[0], depth_bins.shape[1]
+    P = C.POINTER(C.c_float)
+    norm3 = np.empty((N, 10, 10, 10, 3), np.float32); valid3 = np.empty((N, 10, 10, 10), np.float32)
+    normL = np.empty((N, 10, 10, 10, 2), np.float32); validL = np.empty((N, 10, 10, 10), np.float32)
+    normR = np.empty((N, 10, 10, 10, 2), np.float32); validR = np.empty((N, 10, 10, 10), np.float32)
+    dori = np.empty((N,), np.float32)
+    _chk(lib().orc_voxel_coords(pl, pr, pp2, pp3, pf, pt, pti, pd, N, B, D, input_h, input_w, norm3.ctypes.data_as(P),
+                                valid3.ctypes.data_as(P), normL.ctypes.data_as(P), validL.ctypes.data_as(P),
+                                normR.ctypes.data_as(P), validR.ctypes.data_as(P), dori.ctypes.data_as(P)), "orc_voxel_coords")
+    return norm3, valid3, normL, validL, normR, validR, dori
+
+
+def voxel_volume(featL, featR, left, right, p2, p3, fb, trans, trans_inv, input_h=384, input_w=1280, align_corners=False):
+    featL, pfl = _f(featL); featR, pfr = _f(featR)
+    left, pl = _f(left); right, pr = _f(right); p2, pp2 = _f(p2); p3, pp3 = _f(p3); fb, pf = _f(fb)
+    trans, pt = _f(trans); trans_inv, pti = _f(trans_inv)
+    N = left.shape[0]
+    B, Cc, H, W = featL.shape
+    P = C.POINTER(C.c_float)
+    voxel = np.empty((N, 3 * Cc, 10, 10, 10), np.float32); dori = np.empty((N,), np.float32)
+    _chk(lib().orc_voxel_volume(pfl, pfr, pl, pr, pp2, pp3, pf, pt, pti, N, B, Cc, H, W, input_h, input_w,
+                                1 if align_corners else 0, voxel.ctypes.data_as(P), dori.ctypes.data_as(P)), "orc_voxel_volume")
+    return voxel, dori

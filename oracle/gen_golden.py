@@ -256,6 +256,65 @@ def gen_dense_align(R):
          im_r_s=npy(im_r).reshape(3, -1)[:, pos])
 
 
+def voxel_new_case():
+    """Seeded inputs of the stereo_network_new fixture (numpy only; shared with the tests).  A quarter-size configuration
+    (network input 96 x 320, features 24 x 80) keeps the fixture small: the reference module's size constants
+    ``input_h, input_w`` (stereo_network_new.py:20) are set to 96, 320 for the run -- a configuration value, no code changes."""
+    from side_b200.preprocess import get_affine_transform
+    H_in, W_in = 96, 320
+    p2 = np.array([[721.54, 0, 609.56, 44.86], [0, 721.54, 172.85, 0.216], [0, 0, 1, 0.00275]], np.float32)
+    p3 = p2.copy()
+    p3[0, 3] = -339.52
+    c, s = np.array([621., 187.5], np.float32), np.array([1242, 375], np.int32)
+    trans = get_affine_transform(c, s, 0, [W_in // 4, H_in // 4]).astype(np.float32)
+    trans_inv = get_affine_transform(c, s, 0, [W_in // 4, H_in // 4], inv=1).astype(np.float32)
+    B = 2
+    fb = np.full((B,), 721.54 * 0.5327, np.float32)
+    # boxes in feature pixels (80 x 24): (image, x1, y1, x2, y2); right box = left shifted by the disparity of 12 .. 40 m
+    left = np.array([[0, 30.0, 10.0, 36.0, 14.0], [0, 52.5, 11.0, 56.0, 13.5], [0, 2.0, 9.0, 9.5, 15.0],
+                     [1, 41.0, 10.5, 45.0, 13.0], [1, 70.0, 9.5, 78.5, 15.5]], np.float32)
+    disp = np.array([1.9, 0.9, 2.0, 1.2, 0.62], np.float32)
+    right = left.copy()
+    right[:, 1] -= disp
+    right[:, 3] -= disp
+    stack = lambda a: np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape)).astype(np.float32)
+    return dict(H_in=H_in, W_in=W_in, p2=stack(p2), p3=stack(p3), trans=stack(trans), trans_inv=stack(trans_inv), fb=fb,
+                left=left, right=right)
+
+
+def gen_voxel_new(R):
+    """F3: the reference's get_proposal_shift / get_voxel executed directly, and stereo_network.forward of the voxel variant
+    executed with ground-truth RoIs; the voxel tensor is captured at the input of self.pointNet, the reduced features at
+    the output of self.feaRuduce (forward hooks: no reference code is changed)."""
+    import importlib
+    import warnings
+    rn = importlib.import_module("models.networks.stereo_network_new")
+    c = voxel_new_case()
+    rn.input_h, rn.input_w = float(c["H_in"]), float(c["W_in"])
+    t = lambda k: torch.from_numpy(c[k])
+    with warnings.catch_warnings(), torch.no_grad():
+        warnings.simplefilter("ignore")
+        pro_l, pro_r, depth_bin = rn.get_proposal_shift(t("left"), t("right"), 20, t("fb"), t("trans_inv"))
+        vox = rn.get_voxel(t("left"), t("right"), t("p2"), t("p3"), t("fb"), depth_bin, t("trans"), t("trans_inv"))
+        torch.manual_seed(7)
+        heads = {'hm': 3, 'wh': 3, 'reg': 3, 'dim': 3, 'orien': 2, 'kept_type': 168}
+        net = rn.get_pose_net(34, heads, 256).eval()
+        seen = {"fea": []}
+        net.feaRuduce.register_forward_hook(lambda m, i, o: seen["fea"].append(o.detach().clone()))
+        net.pointNet.register_forward_hook(lambda m, i, o: seen.update(voxel=i[0].detach().clone(), disp=o.detach().clone()))
+        g = torch.Generator().manual_seed(11)
+        batch = {'input': torch.randn(2, 3, c["H_in"], c["W_in"], generator=g), 'input_right': torch.randn(2, 3, c["H_in"], c["W_in"], generator=g),
+                 'fb': t("fb"), 'p2': t("p2"), 'p3': t("p3"), 'trans': t("trans"), 'trans_inv': t("trans_inv")}
+        z = net(batch, True, (t("left"), t("right"), torch.Size([2, 50, 1])))[0]
+    voxel = npy(seen["voxel"])                                       # [5, 192, 1000]
+    pos = np.random.RandomState(2).randint(0, voxel.size, 20000)
+    save("voxel_new", pro_left=npy(pro_l), pro_right=npy(pro_r), depth_bin=npy(depth_bin),
+         norm3=npy(vox[0]), valid3=npy(vox[1]), normL=npy(vox[2]), validL=npy(vox[3]), normR=npy(vox[4]), validR=npy(vox[5]),
+         depth_ori=npy(vox[6]), feaL=npy(seen["fea"][0]), feaR=npy(seen["fea"][1]), voxel_sha256=np.array(sha(voxel)),
+         voxel_pos=pos, voxel_s=voxel.reshape(-1)[pos], voxel_absmax=np.float32(np.abs(voxel).max()),
+         voxel_nonzero=np.int64((voxel != 0).sum()), disp=npy(seen["disp"]), depth=npy(z["depth"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
@@ -264,6 +323,7 @@ def main():
     gen_decode(R)
     gen_e2e(R)
     gen_dense_align(R)
+    gen_voxel_new(R)
 
 
 if __name__ == "__main__":

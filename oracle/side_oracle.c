@@ -875,3 +875,132 @@ ORC_API int orc_da_enum(const float *imL, const float *imR, const float *uvz, co
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * F3: instance voxel volume of the stereo_network_new variant (models/networks/stereo_network_new.py).
+ * get_voxel (:160-283) and the sampling of forward (:409-449).  Pinned by tests/golden/voxel_new.npz, generated by
+ * EXECUTING the reference's get_voxel and stereo_network.forward (the voxel tensor is captured at the input of
+ * self.pointNet).  F.grid_sample is an ATen op (bilinear, zeros padding, align_corners=False under torch 2.11).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct { float x, y, z, depth; int b; } orc_vx_roi;
+static orc_vx_roi orc_vx_roi_of(const float *lb, const float *rb, const float *p2, const float *fb, const float *trans_inv, int B)
+{
+    orc_vx_roi r;
+    r.b = (int)lb[0];
+    if (r.b < 0) r.b = 0;
+    if (r.b > B - 1) r.b = B - 1;
+    const float *ti = trans_inv + 6 * r.b, *P = p2 + 12 * r.b;
+#define ORC_TX(x, y) (((x) * ti[0] + (y) * ti[1]) + ti[2])
+#define ORC_TY(x, y) (((x) * ti[3] + (y) * ti[4]) + ti[5])
+    const float cx = (ORC_TX(lb[1], lb[2]) + ORC_TX(lb[3], lb[4])) / 2.f;
+    const float cy = (ORC_TY(lb[1], lb[2]) + ORC_TY(lb[3], lb[4])) / 2.f;
+    const float cxr = (ORC_TX(rb[1], rb[2]) + ORC_TX(rb[3], rb[4])) / 2.f;
+#undef ORC_TX
+#undef ORC_TY
+    r.depth = fb[r.b] / (cx - cxr);
+    r.z = r.depth - P[11];
+    r.x = ((cx * r.depth - P[3]) - P[2] * r.z) / P[0];
+    r.y = ((cy * r.depth - P[7]) - P[6] * r.z) / P[5];
+    return r;
+}
+static void orc_vx_project(const float *P, const float *tr, float X, float Y, float Z, float *uf, float *vf)
+{
+    const float a = ((X * P[0] + Y * P[1]) + Z * P[2]) + P[3];
+    const float b = ((X * P[4] + Y * P[5]) + Z * P[6]) + P[7];
+    const float w = ((X * P[8] + Y * P[9]) + Z * P[10]) + P[11];
+    const float u = a / w, v = b / w, one = w / w;
+    *uf = (u * tr[0] + v * tr[1]) + one * tr[2];
+    *vf = (u * tr[3] + v * tr[4]) + one * tr[5];
+}
+static void orc_vx_voxel(const orc_vx_roi *r, int v, float *X, float *Y, float *Z)
+{
+    const int ix = v / 100, iy = (v / 10) % 10, iz = v % 10;
+    *X = ((-2.5f + 0.5f * (float)ix) + 0.25f) + r->x;
+    *Y = ((-2.5f + 0.5f * (float)iy) + 0.25f) + r->y;
+    *Z = ((-5.f + (float)iz) + 0.5f) + r->z;
+}
+ORC_API int orc_voxel_coords(const float *left, const float *right, const float *p2, const float *p3, const float *fb,
+                             const float *trans, const float *trans_inv, const float *depth_bins, int N, int B, int D,
+                             int input_h, int input_w, float *norm3, float *valid3, float *normL, float *validL, float *normR,
+                             float *validR, float *depth_ori)
+{
+    const float umax = (float)(input_w / 4.0 - 1.0), vmax = (float)(input_h / 4.0 - 1.0);
+    for (int n = 0; n < N; ++n) {
+        const float *lb = left + 5 * n;
+        const orc_vx_roi r = orc_vx_roi_of(lb, right + 5 * n, p2, fb, trans_inv, B);
+        depth_ori[n] = r.depth;
+        float dmin = depth_bins[(size_t)n * D], dmax = dmin;
+        for (int i = 1; i < D; ++i) {
+            const float d = depth_bins[(size_t)n * D + i];
+            if (d < dmin) dmin = d;
+            if (d > dmax) dmax = d;
+        }
+        for (int v = 0; v < 1000; ++v) {
+            float X, Y, Z, uf, vf, ufr, vfr;
+            orc_vx_voxel(&r, v, &X, &Y, &Z);
+            orc_vx_project(p2 + 12 * r.b, trans + 6 * r.b, X, Y, Z, &uf, &vf);
+            orc_vx_project(p3 + 12 * r.b, trans + 6 * r.b, X, Y, Z, &ufr, &vfr);
+            const size_t o = (size_t)n * 1000 + v;
+            const float a = (uf - lb[1]) / (lb[3] - lb[1]) * 2.f - 1.f, b = (vf - lb[2]) / (lb[4] - lb[2]) * 2.f - 1.f;
+            const float c = (Z - dmin) / (dmax - dmin) * 2.f - 1.f;
+            norm3[3 * o] = a; norm3[3 * o + 1] = b; norm3[3 * o + 2] = c;
+            valid3[o] = (a >= -1.f && a <= 1.f && b >= -1.f && b <= 1.f && c >= -1.f && c <= 1.f) ? 1.f : 0.f;
+            const float lu = uf / umax * 2.f - 1.f, lv = vf / vmax * 2.f - 1.f, ru = ufr / umax * 2.f - 1.f, rv = vfr / vmax * 2.f - 1.f;
+            normL[2 * o] = lu; normL[2 * o + 1] = lv; normR[2 * o] = ru; normR[2 * o + 1] = rv;
+            validL[o] = (lu >= -1.f && lu <= 1.f && lv >= -1.f && lv <= 1.f) ? 1.f : 0.f;
+            validR[o] = (ru >= -1.f && ru <= 1.f && rv >= -1.f && rv <= 1.f) ? 1.f : 0.f;
+        }
+    }
+    return 0;
+}
+/* grid_sample(bilinear, zeros, align_corners) of all C channels of one NCHW image at normalised (gx, gy) */
+static void orc_gs_zeros(const float *im, int C, int H, int W, float gx, float gy, int align, float *out, size_t ostride)
+{
+    const float x = align ? ((gx + 1.f) / 2.f) * (float)(W - 1) : ((gx + 1.f) * (float)W - 1.f) / 2.f;
+    const float y = align ? ((gy + 1.f) / 2.f) * (float)(H - 1) : ((gy + 1.f) * (float)H - 1.f) / 2.f;
+    const float xw = floorf(x), yn = floorf(y);
+    const float we = x - xw, ww = 1.f - we, ws = y - yn, wn = 1.f - ws;
+    const int ix = (int)xw, iy = (int)yn;
+    const float w4[4] = {wn * ww, wn * we, ws * ww, ws * we};
+    for (int c = 0; c < C; ++c) {
+        const float *p = im + (size_t)c * H * W;
+        float acc = 0.f;
+        for (int k = 0; k < 4; ++k) {
+            const int xx = ix + (k & 1), yy = iy + (k >> 1);
+            if (xx >= 0 && xx < W && yy >= 0 && yy < H) acc += p[(size_t)yy * W + xx] * w4[k];
+        }
+        out[(size_t)c * ostride] = acc;
+    }
+}
+/* forward (:409-449): voxel [N, 3C, 1000] = cat(L - R, L, R), samples of invalid voxels zeroed */
+ORC_API int orc_voxel_volume(const float *featL, const float *featR, const float *left, const float *right, const float *p2,
+                             const float *p3, const float *fb, const float *trans, const float *trans_inv, int N, int B, int C,
+                             int H, int W, int input_h, int input_w, int align, float *voxel, float *depth_ori)
+{
+    const float umax = (float)(input_w / 4.0 - 1.0), vmax = (float)(input_h / 4.0 - 1.0);
+    float *l = (float *)malloc(sizeof(float) * 2 * (size_t)C), *rr = l + C;
+    if (!l) return -1;
+    for (int n = 0; n < N; ++n) {
+        const orc_vx_roi r = orc_vx_roi_of(left + 5 * n, right + 5 * n, p2, fb, trans_inv, B);
+        depth_ori[n] = r.depth;
+        for (int v = 0; v < 1000; ++v) {
+            float X, Y, Z, uf, vf, ufr, vfr;
+            orc_vx_voxel(&r, v, &X, &Y, &Z);
+            orc_vx_project(p2 + 12 * r.b, trans + 6 * r.b, X, Y, Z, &uf, &vf);
+            orc_vx_project(p3 + 12 * r.b, trans + 6 * r.b, X, Y, Z, &ufr, &vfr);
+            const float lu = uf / umax * 2.f - 1.f, lv = vf / vmax * 2.f - 1.f, ru = ufr / umax * 2.f - 1.f, rv = vfr / vmax * 2.f - 1.f;
+            const int okl = lu >= -1.f && lu <= 1.f && lv >= -1.f && lv <= 1.f, okr = ru >= -1.f && ru <= 1.f && rv >= -1.f && rv <= 1.f;
+            for (int c = 0; c < C; ++c) l[c] = rr[c] = 0.f;
+            if (okl) orc_gs_zeros(featL + (size_t)r.b * C * H * W, C, H, W, lu, lv, align, l, 1);
+            if (okr) orc_gs_zeros(featR + (size_t)r.b * C * H * W, C, H, W, ru, rv, align, rr, 1);
+            float *o = voxel + (size_t)n * 3 * C * 1000 + v;
+            for (int c = 0; c < C; ++c) {
+                o[(size_t)c * 1000] = l[c] - rr[c];
+                o[(size_t)(C + c) * 1000] = l[c];
+                o[(size_t)(2 * C + c) * 1000] = rr[c];
+            }
+        }
+    }
+    free(l);
+    return 0;
+}

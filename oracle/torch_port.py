@@ -204,6 +204,51 @@ def dw_deconv(x, w, stride, pad):
     return F.conv_transpose2d(x, w, None, stride=stride, padding=pad, groups=x.shape[1])
 
 
+# ---- F3: stereo_network_new voxel volume (models/networks/stereo_network_new.py:160-283, 409-449) ----
+def voxel_volume(featL, featR, left, right, p2, p3, fb, trans, trans_inv, input_h=384, input_w=1280):
+    """The reference's op sequence on torch tensors (any device): get_voxel's projection of the 10^3 metric grid into both views,
+    F.grid_sample per RoI, validity masks, cat(L - R, L, R).  Returns (voxel [N, 3C, 10, 10, 10], depth_ori [N])."""
+    F = torch.nn.functional
+    N = left.shape[0]
+    bi = left[:, 0].long()
+    ti, P2, P3, tr = trans_inv.float()[bi], p2.float()[bi], p3.float()[bi], trans.float()[bi]
+    ox = lambda x, y: x * ti[:, 0, 0] + y * ti[:, 0, 1] + ti[:, 0, 2]
+    oy = lambda x, y: x * ti[:, 1, 0] + y * ti[:, 1, 1] + ti[:, 1, 2]
+    cx = (ox(left[:, 1], left[:, 2]) + ox(left[:, 3], left[:, 4])) / 2
+    cy = (oy(left[:, 1], left[:, 2]) + oy(left[:, 3], left[:, 4])) / 2
+    cxr = (ox(right[:, 1], right[:, 2]) + ox(right[:, 3], right[:, 4])) / 2
+    depth = fb.float().reshape(-1)[bi] / (cx - cxr)
+    z = depth - P2[:, 2, 3]
+    x = (cx * depth - P2[:, 0, 3] - P2[:, 0, 2] * z) / P2[:, 0, 0]
+    y = (cy * depth - P2[:, 1, 3] - P2[:, 1, 2] * z) / P2[:, 1, 1]
+    stride = 0.5
+    dev = left.device
+    xs = (torch.arange(-2.5, 2.5, stride, device=dev) + stride / 2).view(1, 10, 1, 1) + x.view(N, 1, 1, 1)
+    ys = (torch.arange(-2.5, 2.5, stride, device=dev) + stride / 2).view(1, 1, 10, 1) + y.view(N, 1, 1, 1)
+    zs = (torch.arange(-5., 5., 1., device=dev) + 0.5).view(1, 1, 1, 10) + z.view(N, 1, 1, 1)
+    X, Y, Z = torch.broadcast_tensors(xs, ys, zs)
+
+    def view(P):
+        e = lambda r, c: P[:, r, c].view(N, 1, 1, 1)
+        a = X * e(0, 0) + Y * e(0, 1) + Z * e(0, 2) + e(0, 3)
+        b = X * e(1, 0) + Y * e(1, 1) + Z * e(1, 2) + e(1, 3)
+        w = X * e(2, 0) + Y * e(2, 1) + Z * e(2, 2) + e(2, 3)
+        u, v, one = a / w, b / w, w / w
+        t = lambda r, c: tr[:, r, c].view(N, 1, 1, 1)
+        uf = u * t(0, 0) + v * t(0, 1) + one * t(0, 2)
+        vf = u * t(1, 0) + v * t(1, 1) + one * t(1, 2)
+        g = torch.stack([uf / (input_w / 4 - 1.) * 2. - 1., vf / (input_h / 4 - 1.) * 2. - 1.], -1)       # [N,10,10,10,2]
+        ok = ((g[..., 0] >= -1.) & (g[..., 0] <= 1.) & (g[..., 1] >= -1.) & (g[..., 1] <= 1.)).float()
+        return g * ok.unsqueeze(4), ok
+    gl, okl = view(P2)
+    gr, okr = view(P3)
+    L = torch.cat([F.grid_sample(featL[int(bi[n]):int(bi[n]) + 1], gl[n].reshape(1, 1, -1, 2), align_corners=False)
+                   for n in range(N)], 0).reshape(N, -1, 10, 10, 10) * okl.unsqueeze(1)
+    R = torch.cat([F.grid_sample(featR[int(bi[n]):int(bi[n]) + 1], gr[n].reshape(1, 1, -1, 2), align_corners=False)
+                   for n in range(N)], 0).reshape(N, -1, 10, 10, 10) * okr.unsqueeze(1)
+    return torch.cat([L - R, L, R], 1), depth
+
+
 # ---------------------------------------------------------------------------------------------
 @contextlib.contextmanager
 def reference_ops():
@@ -217,7 +262,7 @@ def reference_ops():
     repl = dict(dcn_v2_conv=dcn_v2_conv, dcn_fused=fused, dcn_fused_infer=dcn_fused_infer, proposal_shift=proposal_shift,
                 inst_costvol=inst_costvol, xcross_gate=xcross_gate, softargmin=softargmin,
                 bbox_decode_raw=bbox_decode_raw, ddd_decode_raw=ddd_decode_raw, concat_volume=concat_volume,
-                gwc_volume=gwc_volume, dw_deconv=dw_deconv)
+                gwc_volume=gwc_volume, dw_deconv=dw_deconv, voxel_volume=voxel_volume)
     saved = {k: getattr(ops, k) for k in repl}
     saved_dcn = dcn_mod.dcn_v2_conv
     try:
@@ -229,3 +274,41 @@ def reference_ops():
         for k, v in saved.items():
             setattr(ops, k, v)
         dcn_mod.dcn_v2_conv = saved_dcn
+
+
+# ---- F4: detector input preparation (modules/stereoDetector.py:45-82) ----
+def warp_affine_u8(img, inv_map, out_hw):
+    """TEST INFRASTRUCTURE.  numpy restatement of cv2.warpAffine(img, M, (w, h), flags=INTER_LINEAR) for 8-bit images with
+    the default constant border 0, from OpenCV's published algorithm (imgwarp.cpp: WarpAffineInvoker + remapBilinear);
+    ``inv_map`` is the destination -> source map (what warpAffine computes from M).  cv2 is not installed in the build
+    image: PARITY UNPINNED against the real library."""
+    import numpy as np
+    img = np.asarray(img)
+    H, W = img.shape[:2]
+    h, w = out_hw
+    m = np.asarray(inv_map, np.float64).reshape(-1)
+    rnd = lambda v: np.clip(np.rint(v), -2147483648.0, 2147483647.0).astype(np.int64)
+    xs, ys = np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64)
+    X0 = rnd((m[1] * ys + m[2]) * 1024.0) + 16
+    Y0 = rnd((m[4] * ys + m[5]) * 1024.0) + 16
+    X = (X0[:, None] + rnd(m[0] * xs * 1024.0)[None, :]) >> 5
+    Y = (Y0[:, None] + rnd(m[3] * xs * 1024.0)[None, :]) >> 5
+    sx, sy, ax, ay = X >> 5, Y >> 5, X & 31, Y & 31
+    out = np.zeros((h, w, img.shape[2]), np.int64)
+    for dy, wy in ((0, 32 - ay), (1, ay)):
+        for dx, wx in ((0, 32 - ax), (1, ax)):
+            yy, xx = sy + dy, sx + dx
+            ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+            pix = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64) * ok[..., None]
+            out += pix * (wy * wx * 32)[..., None]
+    return np.clip((out + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def pre_process_ref(image, trans_input, out_hw, mean, std):
+    """The host pipeline of stereoDetector.pre_process on top of ``warp_affine_u8``: float32 1 x 3 x h x w."""
+    import numpy as np
+    from side_b200.preprocess import invert_affine
+    inp = warp_affine_u8(image, invert_affine(trans_input), out_hw)
+    inp = (inp.astype(np.float32) / 255.)
+    inp = (inp - np.array(mean, dtype=np.float32).reshape(1, 1, 3)) / np.array(std, dtype=np.float32).reshape(1, 1, 3)
+    return inp.transpose(2, 0, 1)[np.newaxis, ...]

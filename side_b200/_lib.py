@@ -63,6 +63,11 @@ SIGNATURES = {
     "side_conv_tc_set_mode": (_i, [_i]),
     "side_tc_range_guard": (_i, [_vp, _i]),
     "side_stem_conv_fwd": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "side_voxel_coords": (_i, [_vp] * 8 + [_i] * 7 + [_vp] * 8),
+    "side_voxel_volume_ws_bytes": (_sz, [_i] * 4),
+    "side_voxel_volume_fwd": (_i, [_vp] * 11 + [_i] * 8 + [_vp, _sz, _vp]),
+    "side_voxel_volume_bwd": (_i, [_vp] * 10 + [_i] * 8 + [_vp, _sz, _vp]),
+    "side_preprocess_u8": (_i, [_vp] * 2 + [_i] * 2 + [C.POINTER(C.c_double)] + [C.POINTER(_f)] * 2 + [_vp] * 2 + [_i] * 2 + [_vp]),
     "side_dense_align_prep_u8": (_i, [_vp] * 2 + [_i] * 2 + [C.POINTER(_f)] * 2 + [_vp]),
     "side_dense_align_up2_pack": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
     "side_dense_align_pack": (_i, [_vp] * 2 + [_i] * 2 + [_vp]),
@@ -87,6 +92,7 @@ VOL_XCROSS = 1 << 3
 VOL_BWD_SCALAR = 1 << 4
 DECODE_HEAT_IS_LOGIT = 1 << 0
 DA_ALIGN_CORNERS = 1 << 0
+VOXEL_ALIGN_CORNERS = 1 << 0
 
 _lib = None
 

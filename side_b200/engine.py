@@ -38,6 +38,12 @@ class StereoDetector:
         self.last_heads = None
         self.range_fallbacks = 0     # steps process_checked() had to repeat in 3xTF32
 
+    def pre_process(self, opt, image, image_right, calib, device="cuda"):
+        """stereoDetector.pre_process (modules/stereoDetector.py:45-82): raw uint8 H x W x 3 images -> normalised network inputs
+        on the device + the ``meta`` dict (one kernel for both images, see side_b200/preprocess.py)."""
+        from .preprocess import pre_process
+        return pre_process(opt, image, image_right, calib, device)
+
     @torch.no_grad()
     def process(self, batch):
         out = self.model(batch, useCostVolume=self.use_cost_volume, wh_scale=self.wh_scale)[-1]

@@ -835,3 +835,76 @@ def dcn_fwd_cl(x_nhwc, om_cl, weight, bias, stride, padding, dilation, scale=Non
                                    _p(shift), y.data_ptr(), B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, flags,
                                    ws.data_ptr(), nws, _stream()), "side_dcn_fwd_cl")
     return y
+
+
+# ----------------------------------------------------------------------------------------------
+# stereo_network_new: instance voxel volume
+# ----------------------------------------------------------------------------------------------
+voxel_align_corners = False      # grid_sample convention of the voxel sampler; False = torch >= 1.3 default
+
+
+def voxel_coords(left, right, p2, p3, fb, trans, trans_inv, depth_bins, input_h=384, input_w=1280):
+    """get_voxel (stereo_network_new.py:160-283) on the device: returns the reference's seven tensors
+    (norm_coord_imgs, valids, norm_coord_left_imgs2ds, valids_left, norm_coord_right_imgs2ds, valids_right, depth_ori)."""
+    lib = _lib.load()
+    args = [_chk(t.to(_F32) if t.is_cuda else t, n) for t, n in ((left, "left_boxes"), (right, "right_boxes"), (p2, "p2"), (p3, "p3"),
+                                                                 (fb.reshape(-1), "fb"), (trans, "trans"), (trans_inv, "trans_inv"),
+                                                                 (depth_bins, "depth_bins"))]
+    left, right, p2, p3, fb, trans, trans_inv, depth_bins = args
+    N, B, D = left.shape[0], fb.shape[0], depth_bins.shape[1]
+    dev = left.device
+    e = lambda *s: torch.empty(s, device=dev, dtype=_F32)
+    norm3, valid3, normL, validL = e(N, 10, 10, 10, 3), e(N, 10, 10, 10), e(N, 10, 10, 10, 2), e(N, 10, 10, 10)
+    normR, validR, dori = e(N, 10, 10, 10, 2), e(N, 10, 10, 10), e(N)
+    _lib.check(lib.side_voxel_coords(left.data_ptr(), right.data_ptr(), p2.data_ptr(), p3.data_ptr(), fb.data_ptr(),
+                                     trans.data_ptr(), trans_inv.data_ptr(), depth_bins.data_ptr(), N, B, D, 0, 0, int(input_h),
+                                     int(input_w), norm3.data_ptr(), valid3.data_ptr(), normL.data_ptr(), validL.data_ptr(),
+                                     normR.data_ptr(), validR.data_ptr(), dori.data_ptr(), _stream()), "side_voxel_coords")
+    return norm3, valid3, normL, validL, normR, validR, dori
+
+
+class _VoxelVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, featL, featR, left, right, p2, p3, fb, trans, trans_inv, input_h, input_w):
+        lib = _lib.load()
+        featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
+        geo = [_chk(t, n) for t, n in ((left, "left_boxes"), (right, "right_boxes"), (p2, "p2"), (p3, "p3"), (fb, "fb"),
+                                        (trans, "trans"), (trans_inv, "trans_inv"))]
+        B, C, H, W = featL.shape
+        N = geo[0].shape[0]
+        voxel = torch.empty((N, 3 * C, 10, 10, 10), device=featL.device, dtype=_F32)
+        dori = torch.empty((N,), device=featL.device, dtype=_F32)
+        nws = lib.side_voxel_volume_ws_bytes(B, C, H, W)
+        ws = torch.empty((max(nws, 16),), device=featL.device, dtype=torch.uint8)
+        flags = _lib.VOXEL_ALIGN_CORNERS if voxel_align_corners else 0
+        _lib.check(lib.side_voxel_volume_fwd(featL.data_ptr(), featR.data_ptr(), *[g.data_ptr() for g in geo], voxel.data_ptr(),
+                                             dori.data_ptr(), N, B, C, H, W, int(input_h), int(input_w), flags, ws.data_ptr(), nws,
+                                             _stream()), "side_voxel_volume_fwd")
+        ctx.save_for_backward(*geo)
+        ctx.meta = (B, C, H, W, int(input_h), int(input_w), flags)
+        ctx.mark_non_differentiable(dori)
+        return voxel, dori
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gvoxel, _gd):
+        lib = _lib.load()
+        geo = ctx.saved_tensors
+        B, C, H, W, ih, iw, flags = ctx.meta
+        gvoxel = _chk(gvoxel, "grad_voxel")
+        N = geo[0].shape[0]
+        gL = torch.empty((B, C, H, W), device=gvoxel.device, dtype=_F32)
+        gR = torch.empty((B, C, H, W), device=gvoxel.device, dtype=_F32)
+        nws = lib.side_voxel_volume_ws_bytes(B, C, H, W)
+        ws = torch.empty((max(nws, 16),), device=gvoxel.device, dtype=torch.uint8)
+        _lib.check(lib.side_voxel_volume_bwd(gvoxel.data_ptr(), *[g.data_ptr() for g in geo], gL.data_ptr(), gR.data_ptr(), N, B, C,
+                                             H, W, ih, iw, flags, ws.data_ptr(), nws, _stream()), "side_voxel_volume_bwd")
+        return (gL, gR) + (None,) * 9
+
+
+def voxel_volume(featL, featR, left, right, p2, p3, fb, trans, trans_inv, input_h=384, input_w=1280):
+    """Fused get_voxel + grid_sample + mask + cat of stereo_network_new.forward (:409-449):
+    feats [B,64,H,W], boxes [N,5] -> (voxel [N,192,10,10,10] = cat(L - R, L, R), depth_ori [N])."""
+    f32 = lambda t: t.to(_F32).contiguous()
+    return _VoxelVolume.apply(featL, featR, f32(left), f32(right), f32(p2), f32(p3), f32(fb.reshape(-1)), f32(trans), f32(trans_inv),
+                              input_h, input_w)

@@ -162,3 +162,37 @@ def test_dense_align_prep_and_enumeration():
     assert rel_err(err, g["err_sum"]) < 1e-5
     assert np.array_equal(best, g["best_depth"])
     assert np.array_equal(idx, g["err_sum"].argmin(0))
+
+
+# ---- F3: stereo_network_new voxel volume; golden = the reference's get_voxel / forward executed on the seeded case ----
+def test_voxel_new_coords_and_volume_vs_reference():
+    from oracle.gen_golden import voxel_new_case
+    g, c = golden("voxel_new"), voxel_new_case()
+    out = co.voxel_coords(c["left"], c["right"], c["p2"], c["p3"], c["fb"], c["trans"], c["trans_inv"], g["depth_bin"],
+                          c["H_in"], c["W_in"])
+    for mine, key in zip(out, ("norm3", "valid3", "normL", "validL", "normR", "validR", "depth_ori")):
+        if key.startswith("valid"):
+            assert np.array_equal(mine, g[key]), key
+        else:
+            assert np.abs(mine - g[key]).max() < 1e-5, key            # torch.mm's summation order: measured 4e-6
+    voxel, dori = co.voxel_volume(g["feaL"], g["feaR"], c["left"], c["right"], c["p2"], c["p3"], c["fb"], c["trans"],
+                                  c["trans_inv"], c["H_in"], c["W_in"])
+    assert np.abs(dori - g["depth_ori"]).max() < 1e-5 * np.abs(g["depth_ori"]).max()
+    d = np.abs(voxel.reshape(-1)[g["voxel_pos"]] - g["voxel_s"])
+    assert d.max() < 1e-5 * float(g["voxel_absmax"])                # measured 1e-8 absolute
+    assert abs(int((voxel != 0).sum()) - int(g["voxel_nonzero"])) < 1e-4 * voxel.size
+
+
+def test_voxel_new_torch_port_and_proposals():
+    from oracle.gen_golden import voxel_new_case
+    from side_b200.networks import stereo_network_new as sn
+    g, c = golden("voxel_new"), voxel_new_case()
+    t = lambda k: torch.from_numpy(c[k])
+    pl, pr, db = sn.get_proposal_shift(t("left"), t("right"), 20, t("fb"), t("trans_inv"))
+    assert np.abs(db.numpy() - g["depth_bin"]).max() < 1e-5 * 90
+    assert np.abs(pl.numpy() - g["pro_left"]).max() < 1e-5 * 80 and np.abs(pr.numpy() - g["pro_right"]).max() < 1e-5 * 80
+    voxel, dori = tp.voxel_volume(torch.from_numpy(g["feaL"]), torch.from_numpy(g["feaR"]), t("left"), t("right"), t("p2"), t("p3"),
+                                  t("fb"), t("trans"), t("trans_inv"), c["H_in"], c["W_in"])
+    d = np.abs(voxel.numpy().reshape(-1)[g["voxel_pos"]] - g["voxel_s"])
+    assert (d > 1e-4 * float(g["voxel_absmax"])).mean() < 2e-3
+    assert np.abs(dori.numpy() - g["depth_ori"]).max() < 1e-5 * 40

@@ -102,3 +102,40 @@ def test_training_glue_vs_reference_losses_and_gt_rois(R):
     bl, br, shp, k8 = T.gt_rois(t, 320)
     assert torch.equal(k8.bool(), keep) and tuple(shp) == tuple(bbox.shape)
     assert torch.equal(bl[keep], bbox.view(-1, 5)[keep]) and torch.equal(br[keep], bbox_right.view(-1, 5)[keep])
+
+
+def test_voxel_variant_reproduces_reference_network(R):
+    """stereo_network_new (voxel / PointNet head): same state-dict keys, and the product's module tree with the port ops ==
+    the reference network on the same weights (quarter-size configuration, ground-truth RoIs)."""
+    import importlib
+    import warnings
+    from oracle import torch_port
+    from oracle.gen_golden import voxel_new_case
+    from side_b200.networks import stereo_network_new as sn
+    from side_b200.utils.synthetic import HEADS
+    rn = importlib.import_module("models.networks.stereo_network_new")
+    c = voxel_new_case()
+    old = (rn.input_h, rn.input_w, sn.input_h, sn.input_w)
+    rn.input_h, rn.input_w = float(c["H_in"]), float(c["W_in"])
+    sn.input_h, sn.input_w = c["H_in"], c["W_in"]
+    try:
+        torch.manual_seed(3)
+        ref = rn.get_pose_net(34, HEADS, 256).eval()
+        mine = sn.get_pose_net(34, HEADS, 256).eval()
+        assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+        mine.load_state_dict(ref.state_dict())
+        t = lambda k: torch.from_numpy(c[k])
+        g = torch.Generator().manual_seed(5)
+        batch = {'input': torch.randn(2, 3, c["H_in"], c["W_in"], generator=g), 'input_right': torch.randn(2, 3, c["H_in"], c["W_in"], generator=g),
+                 'fb': t("fb"), 'p2': t("p2"), 'p3': t("p3"), 'trans': t("trans"), 'trans_inv': t("trans_inv")}
+        target = (t("left"), t("right"), torch.Size([2, 50, 1]))
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            zr = ref(batch, True, target)[0]
+            with torch_port.reference_ops():
+                zm = mine(batch, True, target)[0]
+        for k in zr:
+            err = (zr[k] - zm[k]).abs().max().item() / max(zr[k].abs().max().item(), 1e-30)
+            assert err < 1e-4, (k, err)
+    finally:
+        rn.input_h, rn.input_w, sn.input_h, sn.input_w = old
