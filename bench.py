@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--train-batch", type=int, default=2, help="pairs per GPU per training step (config #5: 16 pairs / 8 GPUs)")
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per GPU per step (config #4: batch 32)")
     ap.add_argument("--micro-batch", type=int, default=8)
-    ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"), choices=["fp32", "3xtf32", "tf32"],
-                    help="3xtf32 (default): tcgen05 with the exact hi/lo split, fp32-class accuracy (<= 1e-4 rel); fp32: SIMT")
+    ap.add_argument("--dcn-precision", default=os.environ.get("SIDE_DCN_PRECISION", "3xfp16"), choices=["fp32", "3xtf32", "3xfp16", "tf32"],
+                    help="3xfp16 (default): tcgen05 kind::f16 on fp16 hi/lo pairs under the range guard; 3xtf32: the exact tf32 hi/lo split "
+                         "(both fp32-class, <= 1e-4 rel); tf32: single pass; fp32: SIMT")
     ap.add_argument("--tc-format", default="f16", choices=["tf32", "f16"],
                     help="operand format of the tensor-core convolutions: 3xTF32 or 3xFP16 (kind::f16 MMAs "
                          "on fp16 hi/lo pairs, the same 22-bit operands at twice the tensor rate)")
@@ -549,10 +550,13 @@ def main():
     if not args.cudnn_only:
         other_fmt = "tf32" if args.tc_format == "f16" else "f16"
         ops.set_tc_format(other_fmt)
+        if args.dcn_precision == "3xfp16":                 # the two lines are "everything on fp16 pairs" / "everything on tf32 pairs"
+            ops.set_dcn_precision("3xtf32" if other_fmt == "tf32" else "3xfp16")
         step_resident()
         n_o = max(1, min(args.steps, 2))
         fmt_values[other_fmt] = world * P * n_o / (timed(step_resident, n_o) / 1000.0)
         ops.set_tc_format(args.tc_format)
+        ops.set_dcn_precision(args.dcn_precision)
         step_resident()
 
     # ---- BASELINE config #4 as written: 32 pairs TOTAL over the ranks (strong scaling) ----
@@ -625,7 +629,8 @@ def main():
                 "fraction" if f16 else
                 "3xTF32: tf32 rate is half of bf16 and every product takes 3 MMAs, so 1/6 = 0.167 is the ceiling of this fraction")
         return {"kernel": "%s, %d launches in the timed region" % (label, summ["calls"]), "bound": "tensor", "achieved": tf,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "traffic": traffic.get(name),
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"],
+                "traffic": (traffic.get(name) or {}).get("bytes"), "traffic_detail": traffic.get(name),
                 "peak_source": pk["src"] + " bf16 sustained (cuBLAS); this kernel is " + note,
                 "share_of_step": summ["ms"] / ms_res, "algorithmic_flop_per_step": summ["work"] / max(args.steps, 1)}
 
@@ -659,7 +664,8 @@ def main():
             "cost_volume": None if not vol["calls"] else {
                 "kernel": "inst_costvol_cl_kernel (gated channels-last fp16 pairs), %d launches in the timed region" % vol["calls"],
                 "bound": "hbm", "achieved": vol["work"] / (vol["ms"] / 1000.0) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": vol["work"] / (vol["ms"] / 1000.0) / 1e9 / pk["hbm"], "traffic": traffic.get("inst_costvol_cl_kernel"),
+                "frac": vol["work"] / (vol["ms"] / 1000.0) / 1e9 / pk["hbm"],
+                "traffic": (traffic.get("inst_costvol_cl_kernel") or {}).get("bytes"), "traffic_detail": traffic.get("inst_costvol_cl_kernel"),
                 "ms_per_launch": vol["ms"] / vol["calls"], "algorithmic_bytes_per_launch": vol["work"] / vol["calls"],
                 "share_of_step": vol["ms"] / ms_res, "peak_source": pk["src"] + " copy bandwidth"},
             "tc_formats": {("3xfp16" if k == "f16" else "3xtf32") + "_pairs_per_s": v for k, v in fmt_values.items()},

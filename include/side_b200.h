@@ -49,6 +49,9 @@ enum {
     SIDE_DCN_PREC_3XTF32   = 1 << 4, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs: fp32-class accuracy (<=1e-4 rel); falls back to
                                         the SIMT kernel for shapes tcgen05 cannot tile.  What callers should pass. */
     SIDE_DCN_PREC_TF32     = 2 << 4, /* tcgen05 kind::tf32 single pass (~1e-3 rel, opt-in) */
+    SIDE_DCN_PREC_3XFP16   = 3 << 4, /* tcgen05 kind::f16 on fp16 (hi, lo * 2^11) operand pairs, 3 MMAs at twice the tf32 rate: fp32-class
+                                        accuracy (<=1e-4 rel) while |x|, |w| stay in fp16's range -- reported through
+                                        side_tc_range_guard; Cin % 64 != 0 runs as 3xTF32 */
     SIDE_DCN_PREC_MASK     = 3 << 4,
     SIDE_DCN_BWD_SIMT_GEMM = 1 << 9, /* side_dcn_bwd: keep the column GEMM of the channels-last path on the fp32 SIMT kernel
                                         (default: tcgen05 3xTF32 when Cout % 32 == 0 and the pixel count tiles by 128) */

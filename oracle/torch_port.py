@@ -15,7 +15,7 @@ restatements, which turns the product's ``nn.Module`` tree (pure torch structure
 into a runnable port of ``stereo_network_old``.  It is only ever entered from ``tests/`` and from
 ``bench.py``'s CPU legs; the product itself never imports this package.
 
-Pinned against the real reference in the build container by ``tests/test_oracle_vs_reference.py``
+Pinned against the real reference in the build container by ``tests/test_reference_live.py``
 and the committed golden vectors (``oracle/gen_golden.py``).
 """
 import contextlib

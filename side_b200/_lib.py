@@ -83,6 +83,7 @@ DCN_FUSE_RELU = 1 << 2
 DCN_PREC_FP32 = 0 << 4
 DCN_PREC_3XTF32 = 1 << 4
 DCN_PREC_TF32 = 2 << 4
+DCN_PREC_3XFP16 = 3 << 4
 DCN_BWD_SCALAR = 1 << 8
 DCN_BWD_SIMT_GEMM = 1 << 9
 VOL_GATE = 1 << 0

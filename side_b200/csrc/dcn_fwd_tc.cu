@@ -58,6 +58,31 @@ __global__ void dcn_tc_weight_prep_kernel(const float *__restrict__ w, float *__
     }
 }
 
+// fp16-pair variant (SIDE_DCN_PREC_3XFP16): k-block = 64 channels (64 halfs = one 128-byte swizzle row), part 0 = hi = fp16(w),
+// part 1 = lo' = fp16((w - hi) * 2^11) (tc_common.cuh).  max |w| goes to the range-guard slot.
+__global__ void dcn_tc_weight_prep_f16_kernel(const float *__restrict__ w, __half *__restrict__ wp, int Cout, int Cin, int KK,
+                                              uint32_t *rs)
+{
+    const long long total = (long long)KK * Cin * Cout;
+    const int ncb = Cin / 64;
+    float amax = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % 64);
+        const int n = (int)((i / 64) % Cout);
+        const int kb = (int)(i / ((long long)64 * Cout));
+        const int tap = kb / ncb, cb = kb - tap * ncb;
+        const float v = __ldg(w + ((size_t)n * Cin + cb * 64 + kk) * KK + tap);
+        amax = fmaxf(amax, fabsf(v));
+        const size_t tile = (size_t)kb * 2 * Cout * 64;                       // halfs
+        const uint32_t off = (sw128(n, kk >> 3) >> 1) + (kk & 7);
+        __half h, l;
+        f16_split(v, h, l);
+        wp[tile + off] = h;
+        wp[tile + (size_t)Cout * 64 + off] = l;
+    }
+    if (rs) range_commit(rs, amax);
+}
+
 // sample geometry of one (pixel, tap), ready for the channels-last gather: element offsets into the NHWC copy of x
 // (batch folded in) and bilinear weights pre-multiplied by the modulation mask
 struct TapRec {
@@ -83,11 +108,17 @@ struct TcSplitK {
     unsigned int *tickets;     // [tiles], zeroed before the launch
 };
 
-template <bool SPLIT>
+// F16: operands are fp16 (hi, lo' = lo * 2^11) pairs, kind::f16 -- a k-block is 64 channels (the same 128-byte rows), so the
+// tile takes half the MMA instructions, half the operand bytes and half the barrier round trips of the tf32 pairs.
+template <bool SPLIT, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a, const float *__restrict__ wp,
                                                                   const float *__restrict__ xt, int stages, uint32_t idesc,
-                                                                  uint32_t tmem_cols, TcTiling tl, int tap_group, TcSplitK sk)
+                                                                  uint32_t tmem_cols, TcTiling tl, int tap_group, TcSplitK sk,
+                                                                  uint32_t *rs)
 {
+    static_assert(SPLIT || !F16, "fp16 operands are always hi/lo pairs");
+    constexpr int kKbCh = F16 ? 64 : kTcBK;            // channels per k-block
+    constexpr int kSub = F16 ? 2 : 1;                  // 32-channel producer passes per k-block
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kTcMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kTcMaxStages];
@@ -106,7 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     TapRec *tapbuf = reinterpret_cast<TapRec *>(tiles + (size_t)stages * stage_bytes);      // [tap_group][128]
 
-    const int ncb = s.Cin / kTcBK;
+    const int ncb = s.Cin / kKbCh;
     const int tile = (int)blockIdx.x / sk.ksplit, split = (int)blockIdx.x - tile * sk.ksplit;
     const int tap_lo = split * s.KK / sk.ksplit, tap_hi = (split + 1) * s.KK / sk.ksplit;      // this CTA's taps
     const int nkb = (tap_hi - tap_lo) * ncb;
@@ -177,10 +208,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 tapbuf[tt * kTcBM + m] = tr;
             }
         };
-        // issue the 8 corner loads of k-block (tap slot `slot` of the table, channel block cb)
+        // issue the 8 corner loads of one 32-channel pass (tap slot `slot` of the table, 32-channel block cb)
         auto prefetch = [&](int slot, int cb) {
             const TapRec *tb = tapbuf + slot * kTcBM;
-            const char *xc = reinterpret_cast<const char *>(xt + cb * kTcBK + 4 * c4);   // one 64-bit base per k-block,
+            const char *xc = reinterpret_cast<const char *>(xt + cb * kTcBK + 4 * c4);   // one 64-bit base per pass,
 #pragma unroll
             for (int i = 0; i < 2; ++i) {                                                // unsigned 32-bit byte offsets per corner
                 const uint4 o = *reinterpret_cast<const uint4 *>(&tb[r0 + 64 * i]);
@@ -193,10 +224,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         geometry(tap_lo);
         asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");
         prefetch(0, 0);
-        // all loop state is carried incrementally: no integer division in the k loop
+        // all loop state is carried incrementally: no integer division in the k loop.  cb counts 32-channel passes of the tap
+        const int npass = ncb * kSub;
+        float amax = 0.f;
         int st = 0, tp = tap_lo, cb = 0, slot = 0;
         uint32_t eph = 1;                        // parity to wait for on empty_bar[st] (first pass falls through)
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb * kSub; ++kb) {
             const TapRec *tb = tapbuf + slot * kTcBM;
             float4 v[2];
 #pragma unroll
@@ -210,11 +243,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
             }
             // advance (tap, channel block) to the next k-block and start its loads while this one is stored
             int ncbi = cb + 1, ntp = tp, nslot = slot;
-            if (ncbi == ncb) {
+            if (ncbi == npass) {
                 ncbi = 0; ++ntp;
                 if (++nslot == tap_group) nslot = 0;
             }
-            if (kb + 1 < nkb) {
+            if (kb + 1 < nkb * kSub) {
                 if (ntp != tp && nslot == 0) {              // the next k-block starts a new tap group: recompute the table
                     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducerThreads) : "memory");   // everyone is done with the old one
                     geometry(ntp);
@@ -222,10 +255,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 }
                 prefetch(nslot, ncbi);
             }
-            mbar_wait(&empty_bar[st], eph);
+            const int half = F16 ? (cb & 1) : 0;                 // which 32 channels of the 64-channel k-block
+            if (!F16 || half == 0) mbar_wait(&empty_bar[st], eph);
             unsigned char *sa = tiles + (size_t)st * stage_bytes;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
+                if (F16) {
+                    // 4 channels = 8 bytes of the row's 128: chunk 4 half + c4 / 2, upper or lower 8 bytes
+                    const uint32_t off = sw128(r0 + 64 * i, 4 * half + (c4 >> 1)) + ((c4 & 1) << 3);
+                    uint2 hi, lo;
+                    f16_split2(v[i].x, v[i].y, hi.x, lo.x);
+                    f16_split2(v[i].z, v[i].w, hi.y, lo.y);
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+                    *reinterpret_cast<uint2 *>(sa + off) = hi;
+                    *reinterpret_cast<uint2 *>(sa + kATileBytes + off) = lo;
+                    continue;
+                }
                 const uint32_t off = sw128(r0 + 64 * i, c4);
                 if (SPLIT) {
                     float4 hi, lo;
@@ -239,12 +284,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                     *reinterpret_cast<float4 *>(sa + off) = v[i];
                 }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[st]);   // one arrival per producer warp
-            if (++st == stages) { st = 0; eph ^= 1u; }
+            if (!F16 || half == 1) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[st]);   // one arrival per producer warp
+                if (++st == stages) { st = 0; eph ^= 1u; }
+            }
             cb = ncbi; tp = ntp; slot = nslot;
         }
+        if (F16 && rs) range_commit(rs, amax);
 
         // ================= epilogue: TMEM -> registers -> NCHW =================
         mbar_wait(&tmem_full_bar, 0);
@@ -267,7 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 float accx[8];
                 tc_ld8(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(N + c), accx);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += accx[j];
+                for (int j = 0; j < 8; ++j) acc[j] = F16 ? fmaf(accx[j], kF16LoInv, acc[j]) : acc[j] + accx[j];
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -291,21 +339,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
             if (s_ticket == (unsigned)sk.ksplit - 1u) {
                 __threadfence();
                 const size_t split_stride = (size_t)s.B * s.Cout * s.P;
-                for (int n = cbeg; n < cend; ++n) {
-                    float o = 0.f;
-                    if (pix_ok)
-                        for (int k = 0; k < sk.ksplit; ++k) o += __ldcg(sk.partial + (size_t)k * split_stride + pix_off + (size_t)n * s.P);
-                    o += a.bias ? __ldg(a.bias + n) : 0.f;
-                    if (affine) o = fmaf(o, __ldg(a.scale + n), __ldg(a.shift + n));
-                    if (relu) o = fmaxf(o, 0.f);
-                    if (pix_ok) yp[(size_t)n * s.P] = o;
+                // 4 channels x up to 9 partials = 36 independent loads in flight per thread (a loop with a run-time trip count
+                // serialised them: ~600 cycles of L2 latency per load made this tail longer than the contraction itself);
+                // the partials are still added in split order, so the result does not depend on which CTA finishes last
+                for (int n0 = cbeg; n0 < cend; n0 += 4) {
+                    float v[4][9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            v[j][k] = (pix_ok && k < sk.ksplit && n0 + j < cend)
+                                          ? __ldcg(sk.partial + (size_t)k * split_stride + pix_off + (size_t)(n0 + j) * s.P) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = n0 + j;
+                        if (n >= cend) break;
+                        float o = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) o += v[j][k];
+                        o += a.bias ? __ldg(a.bias + n) : 0.f;
+                        if (affine) o = fmaf(o, __ldg(a.scale + n), __ldg(a.shift + n));
+                        if (relu) o = fmaxf(o, 0.f);
+                        if (pix_ok) yp[(size_t)n * s.P] = o;
+                    }
                 }
             }
         }
     } else if (warp == 16) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc2 = tc_idesc_tf32(kTcBM, 2 * N <= 256 ? 2 * N : N);
+            const uint32_t idesc2 = tc_idesc<F16>(kTcBM, 2 * N <= 256 ? 2 * N : N);
             int st = 0;
             uint32_t fph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -321,19 +384,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                         // ONE instruction of width 2N against the adjacent [B_hi | B_lo] tiles (main -> columns 0..N, cross ->
                         // N..2N), lo*hi then accumulates onto the cross columns: 2 instructions per k-step instead of 3
                         const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
-                        tc_mma_tf32(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, 1u);
+                        tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, 1u);
                         continue;
                     }
-                    tc_mma_tf32(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_mma<F16>(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
                     if (SPLIT) {
                         // The two small cross terms go to a SECOND accumulator (columns N..2N): the tensor core adds
                         // into fp32 with truncation, ~0.5 ulp of the accumulator per MMA, so keeping them out of the
                         // main accumulator cuts that systematic bias 3x; the epilogue adds the two.
                         const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
                         const uint64_t b_lo = tc_smem_desc(sb + b_part_bytes + k * 32);
-                        tc_mma_tf32(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma_tf32(tmem_d + (uint32_t)N, a_hi, b_lo, idesc, 1u);
+                        tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma<F16>(tmem_d + (uint32_t)N, a_hi, b_lo, idesc, 1u);
                     }
                 }
                 tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
@@ -377,9 +440,16 @@ bool dcn_fwd_tc_supported(int Cin, int Cout, int dg)
     return dg == 1 && Cin % kTcBK == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
 }
 
+// fp16 pairs need whole 64-channel k-blocks; other channel counts run the request as 3xTF32
+static int tc_precision(int Cin, int flags)
+{
+    const int prec = flags & SIDE_DCN_PREC_MASK;
+    return (prec == SIDE_DCN_PREC_3XFP16 && Cin % 64 != 0) ? SIDE_DCN_PREC_3XTF32 : prec;
+}
 static size_t tc_weight_bytes(int Cin, int Cout, int KK, int flags)
 {
-    const bool split = (flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
+    // hi + lo tf32 words (3xTF32), hi + lo fp16 halves (3xFP16: half of that), or the plain fp32 words (TF32 single pass)
+    const bool split = tc_precision(Cin, flags) != SIDE_DCN_PREC_TF32;
     return (sizeof(float) * (split ? 2 : 1) * (size_t)Cin * Cout * KK + 255) & ~(size_t)255;
 }
 
@@ -414,7 +484,8 @@ size_t dcn_fwd_tc_ws_bytes(int B, int Cin, int H, int W, int Cout, int KK, int f
 int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_nhwc)
 {
     const DcnShape &s = a.s;
-    const bool split = (s.flags & SIDE_DCN_PREC_MASK) == SIDE_DCN_PREC_3XTF32;
+    const int prec = tc_precision(s.Cin, s.flags);
+    const bool f16 = prec == SIDE_DCN_PREC_3XFP16, split = prec != SIDE_DCN_PREC_TF32;
     if (!dcn_fwd_tc_supported(s.Cin, s.Cout, s.dg)) {
         set_error("side_dcn_fwd: tcgen05 path needs dg == 1, Cin %% 32 == 0, Cout %% 16 == 0, 16 <= Cout <= 256");
         return SIDE_ERR_UNSUPPORTED;
@@ -433,7 +504,14 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     int rc = SIDE_OK;
     if (x_nhwc) xt = const_cast<float *>(x_nhwc);           // the caller already holds the channels-last copy
     else if ((rc = launch_nchw_to_nhwc(a.x, xt, s.B, s.Cin, s.H * s.W, st))) return rc;
-    if ((rc = launch_tc_weight_prep(w, wp, s.Cout, s.Cin, s.KK, split ? 1 : 0, st))) return rc;
+    uint32_t *rs = f16 ? range_slot_next() : nullptr;
+    if (f16) {
+        const long long nW = (long long)s.Cout * s.Cin * s.KK;
+        dcn_tc_weight_prep_f16_kernel<<<(unsigned)std::min<long long>(1184, (nW + 255) / 256), 256, 0, st>>>(
+            w, reinterpret_cast<__half *>(wp), s.Cout, s.Cin, s.KK, rs);
+        SIDE_LAUNCH_CHECK("dcn_tc_weight_prep_f16_kernel");
+        rs = range_slot_next();                     // the gathered activations report into their own slot
+    } else if ((rc = launch_tc_weight_prep(w, wp, s.Cout, s.Cin, s.KK, split ? 1 : 0, st))) return rc;
 
     const uint32_t stage_bytes = (split ? 2u : 1u) * (kATileBytes + (uint32_t)s.Cout * 128u);
     // operand stages: the gather, not the MMA, bounds this kernel, so 2-3 stages are enough; what is left of the 228 KB
@@ -448,7 +526,7 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
     }
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < (split ? 2 : 1) * s.Cout) tmem_cols <<= 1;
-    const uint32_t idesc = tc_idesc_tf32(kTcBM, s.Cout);
+    const uint32_t idesc = f16 ? tc_idesc_f16(kTcBM, s.Cout) : tc_idesc_tf32(kTcBM, s.Cout);
     TcTiling tl;
     unsigned grid;
     if (s.Ho % 8 == 0 && s.Wo % 16 == 0) {
@@ -473,12 +551,15 @@ int dcn_fwd_tc(const DcnFwdArgs &a, const float *w, void *ws, size_t ws_bytes, c
             grid *= (unsigned)ks;
         }
     }
-    if (split) {
-        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true>, smem))) return rc;
-        dcn_fwd_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk);
+    if (f16) {
+        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true, true>, smem))) return rc;
+        dcn_fwd_tc_kernel<true, true><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk, rs);
+    } else if (split) {
+        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<true, false>, smem))) return rc;
+        dcn_fwd_tc_kernel<true, false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk, rs);
     } else {
-        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false>, smem))) return rc;
-        dcn_fwd_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk);
+        if ((rc = set_smem_attr((const void *)dcn_fwd_tc_kernel<false, false>, smem))) return rc;
+        dcn_fwd_tc_kernel<false, false><<<grid, kTcThreads, smem, st>>>(a, wp, xt, stages, idesc, tmem_cols, tl, tap_group, sk, rs);
     }
     SIDE_LAUNCH_CHECK("dcn_fwd_tc_kernel");
     return SIDE_OK;

@@ -62,17 +62,21 @@ class StereoDetector:
         the step is repeated with the 3xTF32 kernels (8-bit exponent, same accuracy class, half the tensor rate).  Costs one
         4-byte device-to-host copy per step -- free in a serving loop that reads the detections anyway."""
         dev = batch['input'].device
-        if not batch['input'].is_cuda or ops.get_tc_format() != "f16":
+        fmt, prec = ops.get_tc_format(), ops.get_dcn_precision()
+        if not batch['input'].is_cuda or (fmt != "f16" and prec != "3xfp16"):
             return self.process(batch)
         ops.tc_range_status(dev)                         # clear what earlier work left behind
         out = self.process(batch)
         if ops.tc_range_status(dev):
             self.range_fallbacks += 1
             ops.set_tc_format("tf32")
+            if prec == "3xfp16":
+                ops.set_dcn_precision("3xtf32")
             try:
                 out = self.process(batch)
             finally:
-                ops.set_tc_format("f16")
+                ops.set_tc_format(fmt)
+                ops.set_dcn_precision(prec)
         return out
 
     # -- CUDA graph path -----------------------------------------------------------------------

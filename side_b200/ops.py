@@ -65,14 +65,17 @@ def _pair(v):
 # ----------------------------------------------------------------------------------------------
 # DCNv2
 # ----------------------------------------------------------------------------------------------
-PRECISIONS = {"fp32": _lib.DCN_PREC_FP32, "3xtf32": _lib.DCN_PREC_3XTF32, "tf32": _lib.DCN_PREC_TF32}
+PRECISIONS = {"fp32": _lib.DCN_PREC_FP32, "3xtf32": _lib.DCN_PREC_3XTF32, "tf32": _lib.DCN_PREC_TF32,
+              "3xfp16": _lib.DCN_PREC_3XFP16}
 _default_precision = "3xtf32"
 
 
 def set_dcn_precision(name):
     """Selects the arithmetic of the DCN contraction: '3xtf32' (default: tcgen05 with the exact hi/lo split, fp32-class
     accuracy <= 1e-4 rel.; shapes the tensor-core kernel cannot tile -- Cin % 32, Cout % 16, Cout > 256, dg > 1 -- run the fp32
-    SIMT kernel), 'fp32' (always SIMT FMA) or 'tf32' (tcgen05 single pass, ~1e-3 relative, opt-in)."""
+    SIMT kernel), '3xfp16' (tcgen05 kind::f16 on fp16 (hi, lo) pairs: the same 22 significand bits at twice the MMA rate and
+    half the operand bytes, valid while |x|, |w| stay inside fp16's range -- watched by the range guard, see tc_range_status;
+    Cin % 64 != 0 runs as 3xtf32), 'fp32' (always SIMT FMA) or 'tf32' (tcgen05 single pass, ~1e-3 relative, opt-in)."""
     global _default_precision
     if name not in PRECISIONS:
         raise ValueError("unknown DCN precision %r" % (name,))
@@ -100,6 +103,8 @@ def dcn_forward_raw(x, offset_t, mask_t, weight, bias, stride, padding, dilation
     Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
     Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
     flags |= PRECISIONS[precision or _default_precision]
+    if (precision or _default_precision) == "3xfp16":
+        _range_guard(x.device)
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=_F32)
     nws = lib.side_dcn_fwd_ws_bytes(B, Cin, H, W, Cout, kh, kw, flags)
     ws = torch.empty((max(nws, 16),), device=x.device, dtype=torch.uint8)
@@ -824,6 +829,8 @@ def dcn_fwd_cl(x_nhwc, om_cl, weight, bias, stride, padding, dilation, scale=Non
     Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
     prec = precision or _default_precision
     flags = PRECISIONS["3xtf32" if prec == "fp32" else prec]
+    if prec == "3xfp16":
+        _range_guard(x_nhwc.device)
     if scale is not None:
         flags |= _lib.DCN_FUSE_AFFINE
     if relu:

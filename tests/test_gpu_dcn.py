@@ -182,12 +182,13 @@ def test_errors_mirror_reference(lib):
                     torch.zeros(2).cuda(), 1, 1, 1, 1)
 
 
-@pytest.mark.parametrize("prec,tol", [("3xtf32", 1e-4), ("tf32", 5e-3)])
+@pytest.mark.parametrize("prec,tol", [("3xtf32", 1e-4), ("3xfp16", 1e-4), ("tf32", 5e-3)])
 def test_tensor_core_paths(lib, prec, tol):
     """tcgen05 / TMEM paths: 3xTF32 must meet the fp32 bar (1e-4 relative); single-pass TF32 has its own stated
     tolerance (5e-3 relative to the output range).  Skipped while the path reports 'not built'."""
     from side_b200 import ops
-    for (Cin, Cout, H, W, B) in [(64, 64, 24, 40, 2), (128, 64, 12, 20, 1), (256, 128, 12, 20, 1), (64, 256, 9, 13, 1)]:
+    for (Cin, Cout, H, W, B) in [(64, 64, 24, 40, 2), (128, 64, 12, 20, 1), (256, 128, 12, 20, 1), (64, 256, 9, 13, 1),
+                                 (96, 32, 16, 32, 1), (512, 256, 12, 40, 2), (64, 16, 8, 16, 3)]:       # 96: fp16 pairs -> 3xtf32
         torch.manual_seed(Cin + Cout)
         x = torch.randn(B, Cin, H, W, device="cuda")
         off = torch.randn(B, 18, H, W, device="cuda") * 2
@@ -412,3 +413,28 @@ def test_backward_tensor_core_column_gemm_cin_192(lib):
     ref = ops.dcn_backward_raw(x, off, mask, w, gy, 1, 1, 1, 1, flags=_lib.DCN_BWD_SCALAR)
     for a, c, n in zip(fast, ref, "gx goff gmask gw gb".split()):
         assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 1e-4, n
+
+
+def test_fp16_pair_dcn_range_guard(lib):
+    """3xFP16 DCN operands: O(1) data leaves the guard quiet and meets the fp32 bar on every DLA up-path shape; activations beyond
+    fp16's range raise the saturation flag (the caller then reruns in 3xTF32); tiny weights raise the underflow flag."""
+    from side_b200 import ops
+    dev = torch.device("cuda")
+    for (Cin, Cout, H, W) in [(512, 256, 12, 40), (256, 128, 24, 80), (128, 64, 48, 160), (64, 64, 96, 320)]:
+        torch.manual_seed(Cin)
+        x = torch.randn(2, Cin, H, W, device="cuda").relu_() * 3
+        off = torch.randn(2, 18, H, W, device="cuda") * 2
+        mask = torch.sigmoid(torch.randn(2, 9, H, W, device="cuda"))
+        w = (torch.rand(Cout, Cin, 3, 3, device="cuda") * 2 - 1) / (9 * Cin) ** 0.5
+        ops.tc_range_status(dev)
+        y = ops.dcn_forward_raw(x, off, mask, w, None, 1, 1, 1, 1, precision="3xfp16")
+        assert ops.tc_range_status(dev) == 0
+        ref = ops.dcn_forward_raw(x, off, mask, w, None, 1, 1, 1, 1, precision="fp32")
+        assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-4, (Cin, Cout)
+        e = (y - ref).abs() / ref.abs().clamp_min(0.05 * float(ref.abs().max()))          # element-wise, away from zero
+        assert float(e.max()) < 1e-4
+    ops.dcn_forward_raw(x * 1e5, off, mask, w, None, 1, 1, 1, 1, precision="3xfp16")
+    assert ops.tc_range_status(dev) & ops.TC_RANGE_SATURATED
+    ops.dcn_forward_raw(x, off, mask, w * 1e-7, None, 1, 1, 1, 1, precision="3xfp16")
+    assert ops.tc_range_status(dev) & ops.TC_RANGE_UNDERFLOW
+    assert ops.tc_range_status(dev) == 0

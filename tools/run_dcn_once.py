@@ -12,6 +12,6 @@ off = torch.zeros(B, 18, H, W, device=dev) if zero else torch.randn(B, 18, H, W,
 mask = torch.sigmoid(torch.randn(B, 9, H, W, device=dev)); w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
 b = torch.rand(Cout, device=dev)
 for _ in range(3):
-    ops.dcn_forward_raw(x, off, mask, w, b, 1, 1, 1, 1, precision="3xtf32")
+    ops.dcn_forward_raw(x, off, mask, w, b, 1, 1, 1, 1, precision=os.environ.get("SIDE_DCN_PRECISION", "3xtf32"))
 torch.cuda.synchronize()
 print("ok")
