@@ -285,6 +285,83 @@ def kernel_rooflines(pk, precision):
             rec["torchvision"] = "unavailable: %s" % str(e)[:60]
         dcn["%dx%d@%dx%d" % (Cin, Cout, H, W)] = rec
     out["dcn_fwd_" + precision] = dcn
+    out.update(widened_rows(pk, flush))
+    return out
+
+
+def widened_rows(pk, flush):
+    """The rows SURVEY.md 8(f) marks "next", at BASELINE sizes: stereo_network_new voxel volume (F3), dense photometric
+    alignment (F2), detector input preparation (F4).  The CPU figures are the oracle's C restatement on one host thread over
+    a bounded sample (reported beside the kernel, never the product path)."""
+    import time
+    import types
+    import numpy as np
+    from oracle import c_oracle as co
+    from side_b200 import dense_align as da, ops, preprocess as pp
+    dev = torch.device("cuda")
+    out = {}
+    rng = np.random.RandomState(0)
+    p2 = np.array([[721.54, 0, 609.56, 44.86], [0, 721.54, 172.85, 0.216], [0, 0, 1, 0.00275]], np.float32)
+    p3 = p2.copy(); p3[0, 3] = -339.52
+    # ---- F3: voxel volume, 8 images x 100 RoIs, features 64 x 96 x 320 ----
+    B, N = 8, 800
+    c, s = np.array([621., 187.5], np.float32), np.array([1242, 375], np.int32)
+    tr = pp.get_affine_transform(c, s, 0, [320, 96]).astype(np.float32)
+    tri = pp.get_affine_transform(c, s, 0, [320, 96], inv=1).astype(np.float32)
+    st = lambda a: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))).float().to(dev)
+    x1 = rng.uniform(0, 290, N); w = rng.uniform(6, 50, N); y1 = rng.uniform(25, 70, N); h = rng.uniform(5, 25, N)
+    left = np.stack([np.repeat(np.arange(B), N // B), x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+    right = left.copy(); d = rng.uniform(1.0, 12.0, N).astype(np.float32); right[:, 1] -= d; right[:, 3] -= d
+    fL, fR = torch.randn(B, 64, 96, 320, device=dev), torch.randn(B, 64, 96, 320, device=dev)
+    tl, trr, fb = torch.from_numpy(left).to(dev), torch.from_numpy(right).to(dev), torch.full((B,), 384.38, device=dev)
+    P2, P3, TR, TRI = st(p2), st(p3), st(tr), st(tri)
+    ms = time_op(lambda: ops.voxel_volume(fL, fR, tl, trr, P2, P3, fb, TR, TRI), flush=flush)
+    byts = N * 192 * 1000 * 4 + 2 * B * 64 * 96 * 320 * 4
+    t0 = time.time()
+    co.voxel_volume(fL[:1].cpu().numpy(), fR[:1].cpu().numpy(), left[:20], right[:20], p2[None], p3[None], np.array([384.38], np.float32),
+                    tr[None], tri[None])
+    out["voxel_volume_fwd"] = {"ms": ms, "GBs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm"], "alg_bytes": byts,
+                               "rois": N, "cpu_oracle_ms_per_roi": 1000 * (time.time() - t0) / 20,
+                               "note": "fused get_voxel + 2 x grid_sample + mask + cat(L-R, L, R), stereo_network_new.py:160-283,409-449"}
+    # ---- F2: dense alignment, one 384 x 1280 frame (sampled at 768 x 2560), 100 RoIs, 50 + 20 hypotheses ----
+    Hh, Ww, n = 384, 1280, 100
+    img_l = rng.randint(0, 256, (Hh, Ww, 3), dtype=np.uint8)
+    img_r = np.ascontiguousarray(np.roll(img_l, -10, axis=1))
+    calib = types.SimpleNamespace(p2=p2, p3=p3)
+    opt = types.SimpleNamespace(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    xs = rng.uniform(-10, 10, n); zs = rng.uniform(8, 50, n)
+    poses = np.stack([xs, np.full(n, 1.6), zs, np.full(n, 1.6), np.full(n, 1.5), np.full(n, 3.9), rng.uniform(-1.5, 1.5, n)], 1).astype(np.float32)
+    u = 721.54 * xs / zs + 609.56; v = 721.54 * 1.6 / zs + 172.85; hw = 721.54 * 2.2 / zs
+    box = np.stack([u - hw, v - 1.6 * hw, u + hw, v + 0.1 * hw], 1).astype(np.float32)
+    borders = np.stack([u - 0.9 * hw, u + 0.9 * hw], 1).astype(np.float32)
+    gl, gr = torch.from_numpy(img_l).to(dev), torch.from_numpy(img_r).to(dev)
+    tb, tbd, tp_ = torch.from_numpy(box).to(dev), torch.from_numpy(borders).to(dev), torch.from_numpy(poses).to(dev)
+    ms = time_op(lambda: da.align_parallel(calib, opt, gl, gr, tb, tbd, tp_), flush=flush, iters=5)
+    L = da.prepare_image(gl, opt.mean, opt.std); R = da.prepare_image(gr, opt.mean, opt.std)
+    uvz, wgt, cnt = da._sample_fixed(p2[0, 0] * 2, p2[0, 2] * 2, p2[1, 2] * 2, L.H, L.W, tb * 2, tp_, tbd * 2)
+    pix = int(cnt.sum().item())
+    m = int(cnt.max().item())
+    uvz, wgt = uvz[:, :m].contiguous(), wgt[:, :m].contiguous()
+    de = (torch.linspace(-12.5, 12, 50, device=dev).unsqueeze(1) + tp_[:, 2].unsqueeze(0)).clamp_min(1.5).contiguous()
+    fbv = float(p2[0, 0] * 2 * ((p2[0, 3] - p3[0, 3]) * 2 / (p2[0, 0] * 2)))
+    ms_enum = time_op(lambda: da.enumeration_depth(L, R, uvz, wgt, de, fbv), flush=flush, iters=5)
+    Lp, Rp = L.planar()[0].cpu().numpy(), R.planar()[0].cpu().numpy()
+    t0 = time.time()
+    co.da_enum(Lp, Rp, uvz[:4].cpu().numpy(), wgt[:4].cpu().numpy(), de[:, :4].cpu().numpy(), fbv)
+    cpu4 = 1000 * (time.time() - t0)
+    out["dense_align"] = {"align_parallel_ms": ms, "rois": n, "valid_pixels": pix, "hypotheses": 70,
+                          "enumeration_50_ms": ms_enum, "bilinear_samples_per_s": pix * 51 / (ms_enum / 1000.0),
+                          "cpu_oracle_enumeration_50_ms_per_roi": cpu4 / 4,
+                          "note": "align_parallel = 2 image preparations + sample + 2 enumerations (dense_align.py:240-312); "
+                                  "latency-bound (a few MB touched), reported in ms"}
+    # ---- F4: detector input preparation, one KITTI pair 375 x 1242 -> 384 x 1280 ----
+    ol = types.SimpleNamespace(input_h=384, input_w=1280, output_h=96, output_w=320, down_ratio=4, keep_res=False,
+                               mean=np.array(opt.mean, np.float32).reshape(1, 1, 3), std=np.array(opt.std, np.float32).reshape(1, 1, 3))
+    kl = torch.from_numpy(rng.randint(0, 256, (375, 1242, 3), dtype=np.uint8)).to(dev)
+    kr = torch.from_numpy(rng.randint(0, 256, (375, 1242, 3), dtype=np.uint8)).to(dev)
+    out["pre_process_pair"] = {"us": 1000 * time_op(lambda: pp.pre_process(ol, kl, kr, None), flush=flush),
+                               "note": "warpAffine + normalise + transpose of both images in one launch (stereoDetector.py:45-82); "
+                                       "images resident as uint8"}
     return out
 
 

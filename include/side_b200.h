@@ -416,6 +416,21 @@ int side_voxel_volume_bwd(const float *gvoxel, const float *left, const float *r
                           int N, int B, int C, int H, int W, int input_h, int input_w, int flags, void *ws,
                           size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight gradient of the plain convolutions on tcgen05 (training side of SURVEY.md 8f rows F1 / F4; the reference gets it
+ * from cuDNN: nn.Conv2d / nn.Conv3d backward under stereoTrainer.py:254-319).
+ *   x_hi, x_lo  the fp16 (hi, lo * 2^11) channels-last activation pairs the forward consumed, [N, D, H, W, Cp] halves
+ *               (side_ncdhw_to_cl_split_f16; Cp = Cin rounded up to 32, padded channels are zero)
+ *   gy          [N, Cout, Do, Ho, Wo] fp32 (NCDHW; 2-D convolutions: D = 1 with the batch as N, or N = 1 with the batch as D)
+ *   gw          [Cout][taps][Cq] fp32, Cq = Cp rounded up to 64, OVERWRITTEN (tap-major: permute to [Cout, Cin, taps] and drop
+ *               the padded channels)
+ *   kernels 1x1x1, 1x3x3, 3x3x3 with padding (k - 1) / 2; stride (H, W) 1 or 2.  Needs Do*Ho*Wo % 8 == 0 and Cout % 8 == 0, else
+ *   SIDE_ERR_UNSUPPORTED (the caller keeps cuDNN).  3xFP16 pairs, gy range-scaled by a power of two.
+ * --------------------------------------------------------------------------------------------- */
+size_t side_conv_wgrad_tc_ws_bytes(int N, int D, int H, int W, int Cp, int Cout, int kd, int kh, int kw, int stride);
+int side_conv_wgrad_tc(const void *x_hi, const void *x_lo, const float *gy, float *gw, int N, int D, int H, int W, int Cp,
+                       int Cout, int kd, int kh, int kw, int stride, void *ws, size_t ws_bytes, void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) dcn_bwd_wprep_tc_kernel(const float *__re
 int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, float *y, long long ldy, long long rows, int K,
                       int Ncols, int Nt, cudaStream_t st);
 // weight gradient on tcgen05 (dcn_gw_tc.cu)
-bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows);
+bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows, bool partial_ok = false);
 int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, cudaStream_t st);
 int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, float *gw, int B, int b0, int nb, int Cout, int Kp,
                   int P, cudaStream_t st);

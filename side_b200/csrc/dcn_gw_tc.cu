@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
     const int per = (p.kb_total + p.ksplits - 1) / p.ksplits;
     const int kb0 = ks * per, kb1 = min(p.kb_total, kb0 + per);
     const int nkb = kb1 - kb0;
-    const int kpi = p.P / 64;                                        // k-blocks per sample
+    const int kpi = (p.P + 63) / 64;                                 // k-blocks per sample; a partial last block is zero-filled
+                                                                     // on the gy side (TMA), which cancels whatever rows B holds
 
     if (tid == 0) {
         for (int i = 0; i < kGwStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -225,9 +226,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 gw_encode_fn()
     return fn;
 }
 
-bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows)
+bool dcn_gw_tc_supported(int Cout, int Cin, int KK, int P, long long rows, bool partial_ok)
 {
-    return P % 64 == 0 && Cout % 8 == 0 && (Cin * KK) % 64 == 0 && rows < (1ll << 31) && gw_encode_fn() != nullptr;
+    // partial_ok: P only needs the 16-byte row alignment of the gy tensor map (P % 8); the last 64-pixel k-block of a sample then
+    // hangs over its end, where TMA zero-fills the gy operand
+    return (partial_ok ? P % 8 == 0 : P % 64 == 0) && Cout % 8 == 0 && (Cin * KK) % 64 == 0 && rows < (1ll << 31) && gw_encode_fn() != nullptr;
 }
 
 // halves needed for the gy pairs (the column pairs are written by the scatter kernel into the caller's buffers)
@@ -283,7 +286,7 @@ int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, 
     p.gw = gw; p.Cout = Cout; p.Kp = Kp; p.P = P; p.nb = nb;
     p.gy_absmax = reinterpret_cast<const uint32_t *>(gl + (size_t)B * Cout * P);
     p.n_ntiles = (Kp + 255) / 256; p.n_mtiles = (Cout + 127) / 128;
-    p.kb_total = nb * (P / 64);
+    p.kb_total = nb * ((P + 63) / 64);
     const int tiles = p.n_ntiles * p.n_mtiles;
     p.ksplits = std::max(1, std::min(p.kb_total, (296 + tiles - 1) / tiles));
     const size_t smem = (size_t)kGwStages * kGwStage + 1024;

@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from .. import ops
+from ..conv_train import TCConv2d
 from ..dcn_v2 import DCN
 
 BN_MOMENTUM = 0.1
@@ -26,10 +27,10 @@ def _bn(c):
 class BasicBlock(nn.Module):
     def __init__(self, inplanes, planes, stride=1, dilation=1):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=dilation, bias=False, dilation=dilation)
+        self.conv1 = TCConv2d(inplanes, planes, 3, stride=stride, padding=dilation, bias=False, dilation=dilation)
         self.bn1 = _bn(planes)
         self.relu = nn.ReLU(inplace=True)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=dilation, bias=False, dilation=dilation)
+        self.conv2 = TCConv2d(planes, planes, 3, stride=1, padding=dilation, bias=False, dilation=dilation)
         self.bn2 = _bn(planes)
         self.stride = stride
 
@@ -44,7 +45,7 @@ class BasicBlock(nn.Module):
 class Root(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, residual):
         super().__init__()
-        self.conv = nn.Conv2d(in_channels, out_channels, 1, stride=1, bias=False, padding=(kernel_size - 1) // 2)
+        self.conv = TCConv2d(in_channels, out_channels, 1, stride=1, bias=False, padding=(kernel_size - 1) // 2)
         self.bn = _bn(out_channels)
         self.relu = nn.ReLU(inplace=True)
         self.residual = residual
@@ -79,7 +80,7 @@ class Tree(nn.Module):
         self.downsample = nn.MaxPool2d(stride, stride=stride) if stride > 1 else None
         self.project = None
         if in_channels != out_channels:
-            self.project = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1, stride=1, bias=False), _bn(out_channels))
+            self.project = nn.Sequential(TCConv2d(in_channels, out_channels, 1, stride=1, bias=False), _bn(out_channels))
 
     def forward(self, x, residual=None, children=None):
         children = [] if children is None else children
@@ -111,7 +112,7 @@ class DLA(ops.PreparedStateOwner, nn.Module):
     def _conv_level(inplanes, planes, convs, stride=1, dilation=1):
         mods = []
         for i in range(convs):
-            mods += [nn.Conv2d(inplanes, planes, 3, stride=stride if i == 0 else 1, padding=dilation, bias=False,
+            mods += [TCConv2d(inplanes, planes, 3, stride=stride if i == 0 else 1, padding=dilation, bias=False,
                                dilation=dilation), _bn(planes), nn.ReLU(inplace=True)]
             inplanes = planes
         return nn.Sequential(*mods)

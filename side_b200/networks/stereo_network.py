@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
+from ..conv_train import TCConv2d, TCConv3d
 from ..decode import bbox_decode  # noqa: F401  (same import the reference module exposes)
 from .feature_extraction_dla34 import feature_extraction_dla34
 
@@ -30,7 +31,7 @@ input_h, input_w = 384., 1280.   # reference module constants (stereo_network_ol
 
 
 def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
-    return nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=pad, bias=False)
+    return TCConv3d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=pad, bias=False)
 
 
 def get_proposal_shift(left_boxes, right_boxes, depth_rate, fbs, trans_invs=None):
@@ -55,7 +56,7 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
                                  convbn_3d(cmid, cout, 3, 1, 1), nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
 
         self.dres0 = block(c3, 64, 64)
-        self.strAM_2D = nn.Sequential(nn.Conv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64))
+        self.strAM_2D = nn.Sequential(TCConv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64))
         self.dres1 = block(64, 64, 128)
         self.max_pool1 = nn.MaxPool3d((1, 2, 2))
         self.dres2 = block(128, 128, 128)
@@ -165,7 +166,7 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         cf = channels[self.first_level]
         self.roiSize = 16          # RoIAlign output size AND number of depth candidates (reference :270, F6)
         self.depth_candidates = None   # None -> roiSize (reference behaviour)
-        self.feaRuduce = nn.Sequential(nn.Conv2d(cf, 32, kernel_size=1, padding=0, bias=False),
+        self.feaRuduce = nn.Sequential(TCConv2d(cf, 32, kernel_size=1, padding=0, bias=False),
                                        nn.BatchNorm2d(32, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))
         self.reduced_channel = 32
         self.depth_estimator = cost_volume(cf)
@@ -175,11 +176,11 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         for head in self.heads:
             classes = self.heads[head]
             if head in self.left_only:
-                mods = [nn.Conv2d(cf, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+                mods = [TCConv2d(cf, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
                 for _ in range(4):
-                    mods += [nn.Conv2d(256, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+                    mods += [TCConv2d(256, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
             else:
-                mods = [nn.Conv2d(cf * 2, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
+                mods = [TCConv2d(cf * 2, 256, kernel_size=3, padding=1, bias=False), nn.ReLU(inplace=True)]
             mods.append(nn.Conv2d(256, classes, kernel_size=final_kernel, stride=1, padding=final_kernel // 2, bias=True))
             fc = nn.Sequential(*mods)
             if 'hm' in head:

@@ -633,7 +633,7 @@ def dw_deconv(x, w, stride, pad):
 # ----------------------------------------------------------------------------------------------
 # aggregation network on the tensor cores (channels-last activations, tf32 hi/lo split)
 # ----------------------------------------------------------------------------------------------
-def conv_tc_prepare(weight, fmt=None):
+def conv_tc_prepare(weight, fmt=None, normalize=True):
     """nn.Conv3d / nn.Conv2d weight [Cout, Cin, *k] -> swizzled per-k-block tiles (hi, lo) for side_conv3d_tc_fwd.
     fmt="f16": fp16 pairs for the kind::f16 ("3xFP16") variant, returned as a float16 tensor."""
     lib = _lib.load()
@@ -646,7 +646,7 @@ def conv_tc_prepare(weight, fmt=None):
     if fmt == "f16":
         # fp16 pairs resolve 2^-24 .. 65504: weights far from O(1) are normalised by an exact power of two that conv3d_tc folds
         # back into the epilogue's per-channel scale (never taken by networks with sane initialisation: one host sync here)
-        amax = float(weight.abs().max())
+        amax = float(weight.abs().max()) if normalize else 1.0       # normalize=False: no host sync (training steps)
         inv_scale = 1.0
         if amax > 0.0 and not (2.0 ** -8 <= amax <= 2.0 ** 8):
             import math
@@ -915,3 +915,24 @@ def voxel_volume(featL, featR, left, right, p2, p3, fb, trans, trans_inv, input_
     f32 = lambda t: t.to(_F32).contiguous()
     return _VoxelVolume.apply(featL, featR, f32(left), f32(right), f32(p2), f32(p3), f32(fb.reshape(-1)), f32(trans), f32(trans_inv),
                               input_h, input_w)
+
+
+def conv_wgrad_tc(x_hi, x_lo, gy, Cin, ksize, stride=1):
+    """Weight gradient of a convolution from the fp16 (hi, lo) channels-last input pairs the forward used and grad_output
+    [N, Cout, Do, Ho, Wo] (side_conv_wgrad_tc): -> [Cout, Cin, kd, kh, kw]."""
+    lib = _lib.load()
+    x_hi, x_lo = _chk(x_hi, "x_hi", torch.float16), _chk(x_lo, "x_lo", torch.float16)
+    gy = _chk(gy, "grad_output")
+    N, D, H, W, Cp = x_hi.shape
+    Cout = gy.shape[1]
+    kd, kh, kw = ksize
+    taps = kd * kh * kw
+    nws = lib.side_conv_wgrad_tc_ws_bytes(N, D, H, W, Cp, Cout, kd, kh, kw, int(stride))
+    if nws == 0:
+        raise RuntimeError("side_conv_wgrad_tc failed (code -5): unsupported shape")
+    ws = torch.empty((nws + 256,), device=gy.device, dtype=torch.uint8)
+    off = (-ws.data_ptr()) % 256
+    gw = torch.empty((Cout, taps, (Cp + 63) // 64 * 64), device=gy.device, dtype=_F32)
+    _lib.check(lib.side_conv_wgrad_tc(x_hi.data_ptr(), x_lo.data_ptr(), gy.data_ptr(), gw.data_ptr(), N, D, H, W, Cp, Cout, kd, kh, kw,
+                                      int(stride), ws.data_ptr() + off, nws, _stream()), "side_conv_wgrad_tc")
+    return gw[:, :, :Cin].permute(0, 2, 1).reshape(Cout, Cin, kd, kh, kw).contiguous()
