@@ -427,6 +427,10 @@ int side_voxel_volume_bwd(const float *gvoxel, const float *left, const float *r
  *   kernels 1x1x1, 1x3x3, 3x3x3 with padding (k - 1) / 2; stride (H, W) 1 or 2.  Needs Do*Ho*Wo % 8 == 0 and Cout % 8 == 0, else
  *   SIDE_ERR_UNSUPPORTED (the caller keeps cuDNN).  3xFP16 pairs, gy range-scaled by a power of two.
  * --------------------------------------------------------------------------------------------- */
+/* Power-of-two range scale of a gradient tensor for the fp16 pairs: s = 2^k with max |x| * s in [2^10, 2^11) (1 for all-zero x);
+ * scale_out[0 .. n_scale) = s, inv_out[0 .. n_inv) = 1 / s; scratch_word: 4 bytes of device memory.  No host synchronisation. */
+int side_pow2_range_scale(const float *x, long long n, float *scale_out, int n_scale, float *inv_out, int n_inv,
+                          void *scratch_word, void *stream);
 size_t side_conv_wgrad_tc_ws_bytes(int N, int D, int H, int W, int Cp, int Cout, int kd, int kh, int kw, int stride);
 int side_conv_wgrad_tc(const void *x_hi, const void *x_lo, const float *gy, float *gw, int N, int D, int H, int W, int Cp,
                        int Cout, int kd, int kh, int kw, int stride, void *ws, size_t ws_bytes, void *stream);

@@ -35,12 +35,13 @@ def _try(piece, key, fn):
         raise
 
 
-def _pow2_scale(g):
-    """Device scalar 2^s that brings max |g| into [2^10, 2^11) (1 where g is all zero): fp16 pairs resolve 2^-24 .. 65504."""
-    amax = g.abs().max()
-    e = torch.floor(torch.log2(amax.clamp_min(1e-38)))
-    s = torch.exp2(10.0 - e)
-    return torch.where(amax > 0, s, torch.ones_like(s))
+def _pow2_scale(g, n_scale, n_inv):
+    """Power-of-two s that brings max |g| into [2^10, 2^11) (1 where g is all zero; fp16 pairs resolve 2^-24 .. 65504), computed
+    on the device: returns (s repeated n_scale times, 1 / s repeated n_inv times)."""
+    buf = torch.empty((n_scale + n_inv + 1,), device=g.device, dtype=torch.float32)
+    _lib.check(_lib.load().side_pow2_range_scale(g.data_ptr(), g.numel(), buf.data_ptr(), n_scale, buf[n_scale:].data_ptr(), n_inv,
+                                                 buf[n_scale + n_inv:].data_ptr(), ops._stream()), "side_pow2_range_scale")
+    return buf[:n_scale], buf[n_scale:n_scale + n_inv]
 
 
 class _ConvTC(torch.autograd.Function):
@@ -96,12 +97,11 @@ def _dgrad_tc(gy, weight, ksize):
     """grad_input of a stride-1 convolution = the convolution of grad_output with the flipped, transposed weights."""
     N, Cout, D, H, W = gy.shape
     Cin = weight.shape[1]
-    s = _pow2_scale(gy)
-    hi, lo = ops.ncdhw_to_cl_split(gy, scale=s.expand(N, D).contiguous(), fmt="f16")
+    s, inv = _pow2_scale(gy, N * D, Cin)
+    hi, lo = ops.ncdhw_to_cl_split(gy, scale=s.view(N, D), fmt="f16")
     wt = weight.detach().flip(2, 3, 4).transpose(0, 1).contiguous()                       # [Cin, Cout, kd, kh, kw]
     wp = ops.conv_tc_prepare(wt, fmt="f16", normalize=False)
-    inv = (1.0 / s).expand(Cin).contiguous()
-    gx, _, _ = ops.conv3d_tc(hi, lo, wp, Cin, ksize=ksize, scale=inv, shift=torch.zeros_like(inv), full=True, split=False)
+    gx, _, _ = ops.conv3d_tc(hi, lo, wp, Cin, ksize=ksize, scale=inv, full=True, split=False)          # shift NULL = 0
     return ops.cl_to_nchw(gx, N, Cin, (D, H, W))
 
 

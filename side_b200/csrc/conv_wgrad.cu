@@ -57,6 +57,30 @@ __global__ void __launch_bounds__(256) conv_im2col_pairs_kernel(Im2colParams p)
     }
 }
 
+// max |x| -> power-of-two range scale for the fp16 pairs of a back-propagated gradient (input-gradient convolution): s brings the
+// largest element into [2^10, 2^11); s goes to scale_out[0 .. n_scale), 1 / s to inv_out[0 .. n_inv); all-zero / non-finite -> 1
+__global__ void __launch_bounds__(256) range_absmax_kernel(const float *__restrict__ x, long long n, uint32_t *__restrict__ bits)
+{
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
+}
+__global__ void range_scale_fill_kernel(const uint32_t *__restrict__ bits, float *__restrict__ scale_out, int n_scale,
+                                        float *__restrict__ inv_out, int n_inv)
+{
+    const uint32_t b = *bits;
+    int e = (int)(b >> 23) - 127;
+    if (b < 0x00800000u || b >= 0x7F800000u) e = 10;
+    const int sh = max(-126, min(126, 10 - e));
+    const float s = __uint_as_float((uint32_t)(127 + sh) << 23), inv = __uint_as_float((uint32_t)(127 - sh) << 23);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(n_scale, n_inv); i += gridDim.x * blockDim.x) {
+        if (i < n_scale) scale_out[i] = s;
+        if (i < n_inv) inv_out[i] = inv;
+    }
+}
+
 constexpr size_t kWgradColBudget = (size_t)768 << 20;      // bytes of patch matrix (hi + lo) per chunk of samples
 
 static int wgrad_chunk(int N, long long P, int Kp)
@@ -123,5 +147,23 @@ extern "C" int side_conv_wgrad_tc(const void *x_hi, const void *x_lo, const floa
         SIDE_LAUNCH_CHECK("conv_im2col_pairs_kernel");
         if ((rc = dcn_gw_tc_run(gy_pairs, col_hi, col_lo, gw, N, b0, nb, Cout, Kp, (int)P, st))) return rc;
     }
+    return SIDE_OK;
+}
+
+extern "C" int side_pow2_range_scale(const float *x, long long n, float *scale_out, int n_scale, float *inv_out, int n_inv,
+                                     void *scratch_word, void *stream)
+{
+    SIDE_REQUIRE(n > 0 && n_scale >= 0 && n_inv >= 0, "side_pow2_range_scale: bad sizes");
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(scratch_word);
+    if (n_scale) SIDE_REQUIRE_DEV(scale_out);
+    if (n_inv) SIDE_REQUIRE_DEV(inv_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(scratch_word);
+    SIDE_CUDA(cudaMemsetAsync(bits, 0, sizeof(uint32_t), st));
+    range_absmax_kernel<<<(unsigned)std::min<long long>((n + 1023) / 1024, 148 * 8), 256, 0, st>>>(x, n, bits);
+    SIDE_LAUNCH_CHECK("range_absmax_kernel");
+    range_scale_fill_kernel<<<(unsigned)std::max(1, std::min(64, (std::max(n_scale, n_inv) + 255) / 256)), 256, 0, st>>>(bits, scale_out,
+                                                                                                                    n_scale, inv_out, n_inv);
+    SIDE_LAUNCH_CHECK("range_scale_fill_kernel");
     return SIDE_OK;
 }
