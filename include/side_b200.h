@@ -435,6 +435,24 @@ size_t side_conv_wgrad_tc_ws_bytes(int N, int D, int H, int W, int Cp, int Cout,
 int side_conv_wgrad_tc(const void *x_hi, const void *x_lo, const float *gy, float *gw, int N, int D, int H, int W, int Cp,
                        int Cout, int kd, int kh, int kw, int stride, void *ws, size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm (training side of SURVEY.md 8f rows F1 / F4): nn.BatchNorm2d / nn.BatchNorm3d in train() mode
+ * (feature_extraction_dla34.py:31-95, stereo_network_old.py:139-171; cuDNN bn_fw_tr / bn_bw kernels in the reference).
+ *   x, y, gy, gx [N, C, S] (NCHW / NCDHW, S = product of the spatial sizes); gamma, beta [C] (NULL = 1 / 0)
+ *   fwd: batch mean and biased variance per channel (double accumulation), y = gamma (x - mean) / sqrt(var + eps) + beta,
+ *        save_mean / save_invstd [C] for the backward, running_mean / running_var (NULL = not tracked) updated with `momentum`
+ *        and the unbiased variance, as torch does.
+ *   bwd: gx = (gy - sum(gy)/M - (x - mean) invstd^2 sum(gy (x - mean))/M) invstd gamma, ggamma, gbeta (any of the three may be NULL).
+ *   N * C <= 65535.  ws: side_bn_train_ws_bytes(N, C, S) bytes, 8-byte aligned.
+ * --------------------------------------------------------------------------------------------- */
+size_t side_bn_train_ws_bytes(int N, int C, long long S);
+int side_bn_train_fwd(const float *x, const float *gamma, const float *beta, float *running_mean, float *running_var,
+                      float *y, float *save_mean, float *save_invstd, int N, int C, long long S, float eps, float momentum,
+                      void *ws, size_t ws_bytes, void *stream);
+int side_bn_train_bwd(const float *x, const float *gy, const float *gamma, const float *save_mean, const float *save_invstd,
+                      float *gx, float *ggamma, float *gbeta, int N, int C, long long S, void *ws, size_t ws_bytes,
+                      void *stream);
+
 /* Number of kernels launched by this library by the process since the last reset
  * (bench.py's "gpu_launches"). */
 long long side_launch_count(int reset);

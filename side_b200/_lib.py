@@ -67,6 +67,9 @@ SIGNATURES = {
     "side_voxel_volume_ws_bytes": (_sz, [_i] * 4),
     "side_voxel_volume_fwd": (_i, [_vp] * 11 + [_i] * 8 + [_vp, _sz, _vp]),
     "side_voxel_volume_bwd": (_i, [_vp] * 10 + [_i] * 8 + [_vp, _sz, _vp]),
+    "side_bn_train_ws_bytes": (_sz, [_i, _i, _ll]),
+    "side_bn_train_fwd": (_i, [_vp] * 8 + [_i, _i, _ll, _f, _f, _vp, _sz, _vp]),
+    "side_bn_train_bwd": (_i, [_vp] * 8 + [_i, _i, _ll, _vp, _sz, _vp]),
     "side_pow2_range_scale": (_i, [_vp, _ll, _vp, _i, _vp, _i, _vp, _vp]),
     "side_conv_wgrad_tc_ws_bytes": (_sz, [_i] * 10),
     "side_conv_wgrad_tc": (_i, [_vp] * 4 + [_i] * 10 + [_vp, _sz, _vp]),

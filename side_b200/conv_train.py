@@ -139,3 +139,65 @@ class TCConv3d(nn.Conv3d):
             if y is not None:
                 return y if self.bias is None else y + self.bias.view(1, -1, 1, 1, 1)
         return super().forward(x)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# training-mode BatchNorm (side_bn_train_fwd / _bwd, csrc/batchnorm.cu)
+# ----------------------------------------------------------------------------------------------------------------------------
+class _BNTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, rm_ptr, rv_ptr, eps, momentum):
+        # rm_ptr / rv_ptr: data pointers of the running statistics (buffers outside the graph, updated in place by the kernel)
+        lib = _lib.load()
+        x = x.contiguous()
+        N, C = x.shape[:2]
+        S = x.numel() // (N * C)
+        y = torch.empty_like(x)
+        stat = torch.empty((2, C), device=x.device, dtype=torch.float32)
+        nws = lib.side_bn_train_ws_bytes(N, C, S)
+        ws = torch.empty((nws // 8 + 1,), device=x.device, dtype=torch.float64)
+        _lib.check(lib.side_bn_train_fwd(x.data_ptr(), ops._p(weight), ops._p(bias), rm_ptr, rv_ptr,
+                                         y.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), N, C, S, float(eps), float(momentum),
+                                         ws.data_ptr(), nws, ops._stream()), "side_bn_train_fwd")
+        ctx.save_for_backward(x, weight, stat)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, weight, stat = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, C = x.shape[:2]
+        S = x.numel() // (N * C)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gwb = torch.empty((2, C), device=x.device, dtype=torch.float32)
+        nws = lib.side_bn_train_ws_bytes(N, C, S)
+        ws = torch.empty((nws // 8 + 1,), device=x.device, dtype=torch.float64)
+        _lib.check(lib.side_bn_train_bwd(x.data_ptr(), gy.data_ptr(), ops._p(weight), stat[0].data_ptr(), stat[1].data_ptr(), ops._p(gx),
+                                         gwb[0].data_ptr(), gwb[1].data_ptr(), N, C, S, ws.data_ptr(), nws, ops._stream()),
+                   "side_bn_train_bwd")
+        return gx, (gwb[0] if weight is not None else None), gwb[1], None, None, None, None
+
+
+class _TCBatchNorm:
+    """Mixin over nn.BatchNorm2d / nn.BatchNorm3d: train()-mode forward / backward through side_bn_train_* (batch statistics,
+    running-statistics update and num_batches_tracked exactly as the parent); eval mode and unsupported shapes use the parent."""
+
+    def forward(self, x):
+        if (self.training and enabled and x.is_cuda and x.dtype == torch.float32 and self.momentum is not None
+                and self.track_running_stats and self.affine and x.shape[0] * x.shape[1] <= 65535 and x.numel() > 0):
+            self._check_input_dim(x)
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return _BNTrain.apply(x, self.weight, self.bias, self.running_mean.data_ptr(), self.running_var.data_ptr(), self.eps,
+                                  self.momentum)
+        return super().forward(x)
+
+
+class TCBatchNorm2d(_TCBatchNorm, nn.BatchNorm2d):
+    pass
+
+
+class TCBatchNorm3d(_TCBatchNorm, nn.BatchNorm3d):
+    pass

@@ -14,14 +14,14 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..conv_train import TCConv2d
+from ..conv_train import TCBatchNorm2d, TCConv2d
 from ..dcn_v2 import DCN
 
 BN_MOMENTUM = 0.1
 
 
 def _bn(c):
-    return nn.BatchNorm2d(c, momentum=BN_MOMENTUM)
+    return TCBatchNorm2d(c, momentum=BN_MOMENTUM)
 
 
 class BasicBlock(nn.Module):

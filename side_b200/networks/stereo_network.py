@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from ..conv_train import TCConv2d, TCConv3d
+from ..conv_train import TCBatchNorm2d, TCBatchNorm3d, TCConv2d, TCConv3d
 from ..decode import bbox_decode  # noqa: F401  (same import the reference module exposes)
 from .feature_extraction_dla34 import feature_extraction_dla34
 
@@ -52,16 +52,16 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
         c3 = 3 * reduced_channel   # 96 in the reference (hard-coded, :139)
 
         def block(cin, cmid, cout):
-            return nn.Sequential(convbn_3d(cin, cmid, 3, 1, 1), nn.BatchNorm3d(cmid), nn.ReLU(inplace=True),
-                                 convbn_3d(cmid, cout, 3, 1, 1), nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+            return nn.Sequential(convbn_3d(cin, cmid, 3, 1, 1), TCBatchNorm3d(cmid), nn.ReLU(inplace=True),
+                                 convbn_3d(cmid, cout, 3, 1, 1), TCBatchNorm3d(cout), nn.ReLU(inplace=True))
 
         self.dres0 = block(c3, 64, 64)
-        self.strAM_2D = nn.Sequential(TCConv2d(64, 64, 3, 1, 1), nn.BatchNorm2d(64))
+        self.strAM_2D = nn.Sequential(TCConv2d(64, 64, 3, 1, 1), TCBatchNorm2d(64))
         self.dres1 = block(64, 64, 128)
         self.max_pool1 = nn.MaxPool3d((1, 2, 2))
         self.dres2 = block(128, 128, 128)
         self.max_pool2 = nn.MaxPool3d((1, 2, 2))
-        self.classify = nn.Sequential(convbn_3d(128, 64, 3, 1, 1), nn.BatchNorm3d(64), nn.ReLU(inplace=True),
+        self.classify = nn.Sequential(convbn_3d(128, 64, 3, 1, 1), TCBatchNorm3d(64), nn.ReLU(inplace=True),
                                       nn.Conv3d(64, 1, kernel_size=3, padding=1, stride=1, bias=False))
         self.avg_pool = nn.AvgPool2d(4, 4)
         for m in self.modules():
@@ -167,7 +167,7 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         self.roiSize = 16          # RoIAlign output size AND number of depth candidates (reference :270, F6)
         self.depth_candidates = None   # None -> roiSize (reference behaviour)
         self.feaRuduce = nn.Sequential(TCConv2d(cf, 32, kernel_size=1, padding=0, bias=False),
-                                       nn.BatchNorm2d(32, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))
+                                       TCBatchNorm2d(32, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))
         self.reduced_channel = 32
         self.depth_estimator = cost_volume(cf)
         self.left_only = ['kept_type']

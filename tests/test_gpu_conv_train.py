@@ -90,3 +90,31 @@ def test_eval_mode_is_plain_conv(lib):
     y = m(x.requires_grad_(True))                     # autograd on: tensor-core path, bias added afterwards
     ref = F.conv2d(x.double(), m.weight.double(), m.bias.double(), 1, 1)
     assert _err(y.detach(), ref.detach()) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 96, 320), (4, 512, 12, 40), (16, 128, 16, 8, 8), (16, 64, 16, 16, 16), (3, 32, 7, 9)])
+def test_batchnorm_train_matches_torch(lib, shape):
+    """TCBatchNorm (side_bn_train_fwd / _bwd) against nn.BatchNorm in float64: output, running statistics, all three gradients."""
+    from side_b200 import conv_train as ct
+    torch.manual_seed(shape[1])
+    C = shape[1]
+    cls, ref_cls = (ct.TCBatchNorm2d, torch.nn.BatchNorm2d) if len(shape) == 4 else (ct.TCBatchNorm3d, torch.nn.BatchNorm3d)
+    m = cls(C, momentum=0.1).cuda().train()
+    ref = ref_cls(C, momentum=0.1).cuda().double().train()
+    with torch.no_grad():
+        m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+        ref.weight.copy_(m.weight); ref.bias.copy_(m.bias)
+    x = (torch.randn(shape, device="cuda") * 2 + 0.7).requires_grad_(True)
+    xd = x.detach().double().requires_grad_(True)
+    y = m(x)
+    yr = ref(xd)
+    gy = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, (x, m.weight, m.bias), gy)
+    rgx, rgw, rgb = torch.autograd.grad(yr, (xd, ref.weight, ref.bias), gy.double())
+    for a, b, name in ((y, yr, "y"), (gx, rgx, "gx"), (gw, rgw, "gweight"), (gb, rgb, "gbias"),
+                       (m.running_mean, ref.running_mean, "running_mean"), (m.running_var, ref.running_var, "running_var")):
+        assert _err(a.detach(), b.detach()) < 1e-5, name
+    assert int(m.num_batches_tracked) == 1
+    m.eval()
+    with torch.no_grad():
+        assert _err(m(x), ref.eval()(xd)) < 1e-5
