@@ -295,6 +295,7 @@ int side_conv_tc_set_mode(int mode);
 int side_ncdhw_to_cl_split(const float *x, const float *scale, float *full, float *hi, float *lo, int N, int C, long long S,
                            int D, void *stream);   /* full (may be NULL): the unsplit channels-last copy as well */
 int side_tf32_split(const float *x, float *hi, float *lo, long long n, void *stream);
+int side_f16_split(const float *x, void *hi, void *lo, long long n, void *stream);   /* fp16 (hi, lo * 2^11) pairs, same layout */
 int side_gate_mul_split(const float *y, const float *gate, float *hi, float *lo, int N, int D, int H, int W, int C,
                         void *stream);
 int side_maxpool_hw2_cl(const float *x, float *y, float *hi, float *lo, int N, int D, int H, int W, int C, void *stream);
@@ -328,6 +329,8 @@ int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, 
 int side_tc_range_guard(void *status_words, int nwords);
 /* channels-last [B, HW, C] -> NCHW [B, C, HW]: hands a tensor-core convolution output back to NCHW consumers */
 int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream);
+/* same from rows of ld >= C floats: the first C channels of every row (outputs computed with padded channel counts) */
+int side_cl_to_nchw_ld(const float *x, int ld, float *y, int B, int C, long long HW, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DLA-34 stem: Conv2d(k, stride, padding (k-1)/2, bias=False) + eval-mode BatchNorm2d

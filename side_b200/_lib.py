@@ -56,10 +56,12 @@ SIGNATURES = {
     "side_maxpool_hw2_cl_f16": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_ncdhw_to_cl_split": (_i, [_vp] * 5 + [_i] * 2 + [_ll, _i, _vp]),
     "side_tf32_split": (_i, [_vp] * 3 + [_ll, _vp]),
+    "side_f16_split": (_i, [_vp] * 3 + [_ll, _vp]),
     "side_gate_mul_split": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_maxpool_hw2_cl": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_conv3d_c1_cl": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "side_cl_to_nchw": (_i, [_vp] * 2 + [_i] * 2 + [_ll, _vp]),
+    "side_cl_to_nchw_ld": (_i, [_vp, _i, _vp] + [_i] * 2 + [_ll, _vp]),
     "side_conv_tc_set_mode": (_i, [_i]),
     "side_tc_range_guard": (_i, [_vp, _i]),
     "side_stem_conv_fwd": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),

@@ -128,6 +128,23 @@ __global__ void tf32_split_kernel(const float4 *__restrict__ x, float4 *__restri
     }
 }
 
+// fp32 -> fp16 (hi, lo * 2^11) pairs of a tensor that is already in the consumer's layout
+__global__ void f16_split_kernel(const float4 *__restrict__ x, uint2 *__restrict__ hi, uint2 *__restrict__ lo, long long n4,
+                                 uint32_t *rs)
+{
+    float amax = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        uint2 h, l;
+        f16_split2(v.x, v.y, h.x, l.x);
+        f16_split2(v.z, v.w, h.y, l.y);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        hi[i] = h;
+        lo[i] = l;
+    }
+    if (rs) range_commit(rs, amax);
+}
+
 // y [N, D, H, W, C] * gate [N, D, W, C] (broadcast over H) -> hi, lo
 template <bool F16>
 __global__ void gate_mul_split_kernel(const float4 *__restrict__ y, const float4 *__restrict__ gate, float4 *__restrict__ hi,
@@ -276,6 +293,18 @@ extern "C" int side_tf32_split(const float *x, float *hi, float *lo, long long n
     tf32_split_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo), n / 4);
     SIDE_LAUNCH_CHECK("tf32_split_kernel");
+    return SIDE_OK;
+}
+
+extern "C" int side_f16_split(const float *x, void *hi, void *lo, long long n, void *stream)
+{
+    SIDE_REQUIRE(n >= 0 && n % 4 == 0, "side_f16_split: element count must be a multiple of 4");
+    if (n == 0) return SIDE_OK;
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
+    f16_split_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(x),
+                                                                           reinterpret_cast<uint2 *>(hi), reinterpret_cast<uint2 *>(lo),
+                                                                           n / 4, range_slot_next());
+    SIDE_LAUNCH_CHECK("f16_split_kernel");
     return SIDE_OK;
 }
 

@@ -25,16 +25,17 @@ __global__ void nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restr
 
 
 // channels-last [B, HW, C] -> NCHW [B, C, HW] (tensor-core convolution outputs handed back to NCHW consumers)
-__global__ void nhwc_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW)
+// ld: floats per channels-last row (>= C: the first C channels of every row are taken)
+__global__ void nhwc_to_nchw_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW, int ld)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const float *ip = in + (size_t)b * C * HW;
+    const float *ip = in + (size_t)b * ld * HW;
     float *op = out + (size_t)b * C * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int p = p0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (p < HW && c < C) ? __ldg(ip + (size_t)p * C + c) : 0.f;
+        tile[i][threadIdx.x] = (p < HW && c < C) ? __ldg(ip + (size_t)p * ld + c) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -56,22 +57,28 @@ int launch_nhwc_to_nchw(const float *in, float *out, int B, int C, int HW, cudaS
 {
     dim3 tg(ceil_div(HW, 32), ceil_div(C, 32), B), tb(32, 8);
     SIDE_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, "nhwc_to_nchw: grid too large");
-    nhwc_to_nchw_kernel<<<tg, tb, 0, st>>>(in, out, C, HW);
+    nhwc_to_nchw_kernel<<<tg, tb, 0, st>>>(in, out, C, HW, C);
     SIDE_LAUNCH_CHECK("nhwc_to_nchw_kernel");
     return SIDE_OK;
 }
 
 }  // namespace side
 
+extern "C" int side_cl_to_nchw_ld(const float *x, int ld, float *y, int B, int C, long long HW, void *stream);
 extern "C" int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream)
 {
+    return side_cl_to_nchw_ld(x, C, y, B, C, HW, stream);
+}
+
+extern "C" int side_cl_to_nchw_ld(const float *x, int ld, float *y, int B, int C, long long HW, void *stream)
+{
     using namespace side;
-    SIDE_REQUIRE(B >= 0 && C > 0 && HW > 0 && HW < (1ll << 31), "side_cl_to_nchw: bad shape");
+    SIDE_REQUIRE(B >= 0 && C > 0 && ld >= C && HW > 0 && HW < (1ll << 31), "side_cl_to_nchw: bad shape");
     if (B == 0) return SIDE_OK;
     SIDE_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, "side_cl_to_nchw: grid too large");
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(y);
     dim3 tg(ceil_div(HW, 32), ceil_div(C, 32), B), tb(32, 8);
-    nhwc_to_nchw_kernel<<<tg, tb, 0, (cudaStream_t)stream>>>(x, y, C, (int)HW);
+    nhwc_to_nchw_kernel<<<tg, tb, 0, (cudaStream_t)stream>>>(x, y, C, (int)HW, ld);
     SIDE_LAUNCH_CHECK("nhwc_to_nchw_kernel");
     return SIDE_OK;
 }

@@ -93,8 +93,10 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
                  (self.dres1[3], self.dres1[4]), (self.dres2[0], self.dres2[1]), (self.dres2[3], self.dres2[4]),
                  (self.classify[0], self.classify[1])]
         fmt = fmt or self.tc_format or ops.get_tc_format()
+        sconv, sbn = self.strAM_2D[0], self.strAM_2D[1]
         key = (ops.prep_epoch(), fmt) + tuple((c.weight.data_ptr(), c.weight._version, b.weight._version, b.bias._version,
-                                         b.running_mean._version, b.running_var._version) for c, b in convs)
+                                               b.running_mean._version, b.running_var._version)
+                                              for c, b in convs + [(sconv, sbn)]) + (sconv.bias._version,)
         st = getattr(self, "_tc_cache", None)
         if st is None or st[0] != key:
             layers = []
@@ -102,6 +104,11 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
                 scale = (b.weight / torch.sqrt(b.running_var + b.eps)).float().contiguous()
                 shift = (b.bias - b.running_mean * scale).float().contiguous()
                 layers.append((ops.conv_tc_prepare(c.weight.detach(), fmt=fmt), c.out_channels, scale, shift))
+            # strAM_2D (reference :207-210): Conv2d(64, 64, 3, padding 1, bias) + BatchNorm2d over the (D, W) plane, folded
+            c, b = self.strAM_2D[0], self.strAM_2D[1]
+            scale = (b.weight / torch.sqrt(b.running_var + b.eps)).float()
+            shift = (b.bias - b.running_mean * scale + (c.bias * scale if c.bias is not None else 0)).float().contiguous()
+            layers.append((ops.conv_tc_prepare(c.weight.detach().unsqueeze(2), fmt=fmt), c.out_channels, scale.contiguous(), shift))
             st = (key, layers)
             self._tc_cache = st
         return st[1]
@@ -127,8 +134,11 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
         _, hi, lo = conv(0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
-        isp = self.strAM_2D(y.mean(dim=2).permute(0, 3, 1, 2))                 # mean over H -> [N, 64, D, W]
-        gate = torch.sigmoid(isp).permute(0, 2, 3, 1).contiguous()             # [N, D, W, 64]
+        # strAM gate: mean over H stays channels-last [N, D, W, 64] = a batch of N (D x W) images for the same tcgen05 kernel
+        mh, ml = ops.split_pairs(y.mean(dim=2).unsqueeze(0), fmt)              # [1, N, D, W, 64]
+        isp, _, _ = ops.conv3d_tc(mh, ml, L[7][0], L[7][1], ksize=(1, 3, 3), scale=L[7][2], shift=L[7][3], relu=False,
+                                  full=True, split=False)
+        gate = torch.sigmoid(isp).squeeze(0)                                   # [N, D, W, 64]
         hi, lo = ops.gate_mul_split(y, gate, fmt=fmt)
         _, hi, lo = conv(2, hi, lo)
         p1, hi, lo = conv(3, hi, lo, full=True, split=True, pool=True)         # dres1 out + max_pool1 -> [N, D, 8, 8, 128]
@@ -236,16 +246,30 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
                 d["stereo_w"] = (ops.conv_tc_prepare(w0), w0.shape[0])
                 outs = [self.__getattr__(h)[-1] for h in stereo]
                 hid = [c.in_channels for c in outs]
-                blk = torch.zeros((sum(hid), sum(c.out_channels for c in outs)), device=w0.device)
+                n_out = sum(c.out_channels for c in outs)
+                n_pad = (n_out + 15) // 16 * 16
+                # the 1x1 outputs of all stereo heads = ONE 1x1 tcgen05 convolution with a block-diagonal weight (rows padded to 16)
+                w1 = torch.zeros((n_pad, sum(hid), 1, 1, 1), device=w0.device)
+                b1 = torch.zeros((n_pad,), device=w0.device)
                 r = c0 = 0
                 for c, hdim in zip(outs, hid):
-                    blk[r:r + hdim, c0:c0 + c.out_channels] = c.weight.detach().view(c.out_channels, hdim).t()
+                    w1[c0:c0 + c.out_channels, r:r + hdim, 0, 0, 0] = c.weight.detach().view(c.out_channels, hdim)
+                    b1[c0:c0 + c.out_channels] = c.bias.detach()
                     r += hdim
                     c0 += c.out_channels
-                d["stereo_out"] = (blk.contiguous(), torch.cat([c.bias.detach() for c in outs]), [c.out_channels for c in outs])
+                d["stereo_out"] = (ops.conv_tc_prepare(w1), n_pad, b1, [c.out_channels for c in outs])
             for h in mono:
                 mods = [m for m in self.__getattr__(h) if isinstance(m, nn.Conv2d)]
-                d["mono"][h] = ([(ops.conv_tc_prepare(c.weight.detach()), c.out_channels) for c in mods[:-1]], mods[-1])
+                last = mods[-1]
+                n_pad = (last.out_channels + 15) // 16 * 16
+                if n_pad > 128:
+                    n_pad = (n_pad + 127) // 128 * 128
+                w1 = torch.zeros((n_pad, last.in_channels, 1, 1, 1), device=last.weight.device)
+                w1[:last.out_channels, :, 0, 0, 0] = last.weight.detach().view(last.out_channels, last.in_channels)
+                b1 = torch.zeros((n_pad,), device=last.weight.device)
+                b1[:last.out_channels] = last.bias.detach()
+                d["mono"][h] = ([(ops.conv_tc_prepare(c.weight.detach().unsqueeze(2)), c.out_channels) for c in mods[:-1]],
+                                (ops.conv_tc_prepare(w1), n_pad, b1, last.out_channels))
             st = (key, d)
             self._heads_cache = st
         return st[1]
@@ -258,23 +282,21 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         if S["stereo"]:
             hi, lo = ops.ncdhw_to_cl_split(torch.cat((fl, fr), 1).unsqueeze(2))                  # [B, 1, H, W, 2C]
             wp, cout = S["stereo_w"]
-            y, _, _ = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=True, split=False)
-            blk, bias, widths = S["stereo_out"]
-            # [n_out, hidden] @ [hidden, H*W] per image: the transposed operand is a view, the result is NCHW
-            o = torch.baddbmm(bias.view(1, -1, 1), blk.t().unsqueeze(0).expand(B, -1, -1), y.view(B, H * W, cout).transpose(1, 2))
+            _, yh, yl = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=False, split=True)
+            wp1, n_pad, b1, widths = S["stereo_out"]
+            o, _, _ = ops.conv3d_tc(yh, yl, wp1, n_pad, ksize=(1, 1, 1), shift=b1, relu=False, full=True, split=False)
+            o = ops.cl_to_nchw(o, B, sum(widths), (H, W), ld=n_pad)                                # [B, sum(out), H, W]
             c0 = 0
             for h, wdt in zip(S["stereo"], widths):
-                z[h] = o[:, c0:c0 + wdt].reshape(B, wdt, H, W).contiguous()
+                z[h] = o[:, c0:c0 + wdt].contiguous()
                 c0 += wdt
         for h, (chain, last) in S["mono"].items():
             hi, lo = ops.ncdhw_to_cl_split(fl.unsqueeze(2))                                        # [B, 1, H, W, C]
-            y = None
-            for i, (wp, cout) in enumerate(chain):
-                final = i == len(chain) - 1
-                y, hi, lo = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=final, split=not final)
-            wl = last.weight.detach().view(1, last.out_channels, -1).expand(B, -1, -1)
-            o = torch.baddbmm(last.bias.detach().view(1, -1, 1), wl, y.view(B, H * W, y.shape[-1]).transpose(1, 2))
-            z[h] = o.view(B, last.out_channels, H, W)
+            for wp, cout in chain:
+                _, hi, lo = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=False, split=True)
+            wp1, n_pad, b1, n_out = last
+            o, _, _ = ops.conv3d_tc(hi, lo, wp1, n_pad, ksize=(1, 1, 1), shift=b1, relu=False, full=True, split=False)
+            z[h] = ops.cl_to_nchw(o, B, n_out, (H, W), ld=n_pad)
         return {h: z[h] for h in self.heads}
 
     fused_volume = True    # inference, fp16 pairs: volume builder writes the consumer format directly (ops.inst_costvol_cl)

@@ -735,6 +735,20 @@ def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt=None):
     return (full, hi, lo) if want_full else (hi, lo)
 
 
+def split_pairs(x, fmt=None):
+    """Operand pairs (hi, lo) of a tensor that already has the consumer's (channels-last) layout, in the given operand format."""
+    fmt = fmt or _tc_format
+    if fmt != "f16":
+        return tf32_split(x)
+    lib = _lib.load()
+    x = _chk(x, "x")
+    _range_guard(x.device)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.side_f16_split(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "side_f16_split")
+    return hi, lo
+
+
 def tf32_split(x):
     lib = _lib.load()
     x = _chk(x, "x")
@@ -805,15 +819,15 @@ def stem_conv(x, weight, scale=None, shift=None, stride=1, relu=True):
     return y
 
 
-def cl_to_nchw(x, B, C, spatial):
-    """channels-last buffer [B, *spatial, C] -> NCHW [B, C, *spatial]."""
+def cl_to_nchw(x, B, C, spatial, ld=None):
+    """channels-last buffer [B, *spatial, ld] -> NCHW [B, C, *spatial] (ld > C: rows computed with padded channels, first C taken)."""
     lib = _lib.load()
     x = _chk(x, "x")
     HW = 1
     for v in spatial:
         HW *= v
     y = torch.empty((B, C) + tuple(spatial), device=x.device, dtype=_F32)
-    _lib.check(lib.side_cl_to_nchw(x.data_ptr(), y.data_ptr(), B, C, HW, _stream()), "side_cl_to_nchw")
+    _lib.check(lib.side_cl_to_nchw_ld(x.data_ptr(), int(ld or C), y.data_ptr(), B, C, HW, _stream()), "side_cl_to_nchw")
     return y
 
 
