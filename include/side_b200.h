@@ -73,9 +73,11 @@ enum {
                                side_inst_costvol_fast_ws_bytes(...) bytes of workspace. */
     SIDE_VOL_XCROSS = 1 << 3, /* with SEPARABLE and without GATE: also return the gate scalar xcross[N, D] computed in the
                                same pass, WITHOUT applying it (the consumer, side_ncdhw_to_cl_split, multiplies) */
-    SIDE_VOL_BWD_SCALAR = 1 << 4 /* side_inst_costvol_bwd: force the scalar-atomic kernel (torchvision's roi_align backward
+    SIDE_VOL_BWD_SCALAR = 1 << 4, /* side_inst_costvol_bwd: force the scalar-atomic kernel (torchvision's roi_align backward
                                thread mapping, 32 atomics per volume element); default for P == 16, C % 8 == 0 is the
                                separable gather kernel that keeps the x-pass sums in registers */
+    SIDE_VOL_FEAT_NHWC = 1 << 5 /* side_inst_costvol_fwd_cl: featL / featR are already channels-last [B, H, W, C] (e.g. the output of
+                               side_conv3d_tc_fwd): the two staging copies are skipped */
 };
 
 /* decode flavour */

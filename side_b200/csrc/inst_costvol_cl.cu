@@ -404,7 +404,7 @@ extern "C" int side_inst_costvol_fwd_cl(const float *featL, const float *featR, 
     SIDE_REQUIRE(C == kClC && P == 16, "side_inst_costvol_fwd_cl: built for C == 32 channels per view and P == 16 (got C=%d, P=%d)", C, P);
     SIDE_REQUIRE(D >= 2 && D <= kClMaxD, "side_inst_costvol_fwd_cl: D must be in 2..%d", kClMaxD);
     SIDE_REQUIRE((long long)B * H * W * C < (1ll << 31) && W < 32768, "side_inst_costvol_fwd_cl: features too large");
-    SIDE_REQUIRE((flags & ~SIDE_VOL_GATE) == 0, "side_inst_costvol_fwd_cl: only SIDE_VOL_GATE is a valid flag");
+    SIDE_REQUIRE((flags & ~(SIDE_VOL_GATE | SIDE_VOL_FEAT_NHWC)) == 0, "side_inst_costvol_fwd_cl: valid flags are SIDE_VOL_GATE, SIDE_VOL_FEAT_NHWC");
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right); SIDE_REQUIRE_DEV(fb);
     SIDE_REQUIRE_DEV(cost_hi); SIDE_REQUIRE_DEV(cost_lo); SIDE_REQUIRE_DEV(depth_bin);
@@ -420,8 +420,12 @@ extern "C" int side_inst_costvol_fwd_cl(const float *featL, const float *featR, 
     float *nl = reinterpret_cast<float *>(ws), *nr = nl + fsz;
     int *counter = reinterpret_cast<int *>(nr + fsz);
     int rc;
-    if ((rc = launch_nchw_to_nhwc(featL, nl, B, C, H * W, st))) return rc;
-    if ((rc = launch_nchw_to_nhwc(featR, nr, B, C, H * W, st))) return rc;
+    if (flags & SIDE_VOL_FEAT_NHWC) {                       // the features arrive channels-last [B, H, W, C]: no staging copies
+        nl = const_cast<float *>(featL); nr = const_cast<float *>(featR);
+    } else {
+        if ((rc = launch_nchw_to_nhwc(featL, nl, B, C, H * W, st))) return rc;
+        if ((rc = launch_nchw_to_nhwc(featR, nr, B, C, H * W, st))) return rc;
+    }
     SIDE_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     ClParams p{};
     p.v = VolParams{featL, featR, left, right, fb, valid, nullptr, depth_bin, xcross, nullptr, nullptr, nullptr, N, B, C, H, W, D, P, x_clamp};

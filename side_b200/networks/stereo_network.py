@@ -236,7 +236,9 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         input cat(left, right)) are stacked into ONE convolution; their 1x1 outputs become one block-diagonal matmul."""
         stereo = [h for h in self.heads if h not in self.left_only]
         mono = [h for h in self.heads if h in self.left_only]
-        params = [p for h in self.heads for p in self.__getattr__(h).parameters()]
+        rc, rb = self.feaRuduce[0], self.feaRuduce[1]
+        params = [p for h in self.heads for p in self.__getattr__(h).parameters()] + [rc.weight, rb.weight, rb.bias,
+                                                                                      rb.running_mean, rb.running_var]
         key = (ops.prep_epoch(), ops.get_tc_format()) + tuple((p.data_ptr(), p._version) for p in params)
         st = getattr(self, "_heads_cache", None)
         if st is None or st[0] != key:
@@ -270,12 +272,27 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
                 b1[:last.out_channels] = last.bias.detach()
                 d["mono"][h] = ([(ops.conv_tc_prepare(c.weight.detach().unsqueeze(2)), c.out_channels) for c in mods[:-1]],
                                 (ops.conv_tc_prepare(w1), n_pad, b1, last.out_channels))
+            # feaRuduce (reference :260-264): Conv2d(cf, 32, 1x1, no bias) + BatchNorm2d (eval, folded) + ReLU
+            scale = (rb.weight / torch.sqrt(rb.running_var + rb.eps)).detach().float().contiguous()
+            shift = (rb.bias - rb.running_mean * scale).detach().float().contiguous()
+            d["reduce"] = (ops.conv_tc_prepare(rc.weight.detach().unsqueeze(2)), rc.out_channels, scale, shift)
             st = (key, d)
             self._heads_cache = st
         return st[1]
 
-    def _heads_tc(self, fl, fr):
-        """All head convolutions of forward (:343-348) as tcgen05 implicit GEMMs on channels-last activations."""
+    def _reduce_cl(self, pairs):
+        """feaRuduce of both views on the tcgen05 kernel from the batched [left; right] operand pairs: -> (featL, featR) channels-last
+        [B, H, W, 32], the layout the instance-volume kernel gathers from (no NCHW round trip)."""
+        hi, lo = pairs
+        wp, cout, scale, shift = self._heads_state()["reduce"]
+        y, _, _ = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 1, 1), scale=scale, shift=shift, relu=True, full=True, split=False)
+        B2, _, H, W, C = y.shape
+        y = y.view(B2, H, W, C)
+        return y[:B2 // 2], y[B2 // 2:]
+
+    def _heads_tc(self, fl, fr, pairs=None):
+        """All head convolutions of forward (:343-348) as tcgen05 implicit GEMMs on channels-last activations.
+        ``pairs``: operand pairs of the batched [left; right] features [2B, 1, H, W, C] when the caller already made them."""
         S = self._heads_state()
         B, C, H, W = fl.shape
         z = {}
@@ -291,7 +308,10 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
                 z[h] = o[:, c0:c0 + wdt].contiguous()
                 c0 += wdt
         for h, (chain, last) in S["mono"].items():
-            hi, lo = ops.ncdhw_to_cl_split(fl.unsqueeze(2))                                        # [B, 1, H, W, C]
+            if pairs is not None:
+                hi, lo = pairs[0][:B], pairs[1][:B]
+            else:
+                hi, lo = ops.ncdhw_to_cl_split(fl.unsqueeze(2))                                    # [B, 1, H, W, C]
             for wp, cout in chain:
                 _, hi, lo = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=False, split=True)
             wp1, n_pad, b1, n_out = last
@@ -302,8 +322,17 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
     fused_volume = True    # inference, fp16 pairs: volume builder writes the consumer format directly (ops.inst_costvol_cl)
     fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream
 
-    def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D):
+    def _fused_volume_ok(self, C, D):
         est = self.depth_estimator
+        return (self.fast_volume and self.fused_volume and est.tensor_core and not self.training and not torch.is_grad_enabled()
+                and self.roiSize == 16 and D % 8 == 0 and 3 * C == est.dres0[0].in_channels
+                and (est.tc_format or ops.get_tc_format()) == "f16" and ops.inst_costvol_cl_ok(C, D, 16))
+
+    def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D, nhwc=False):
+        est = self.depth_estimator
+        if nhwc:                                       # only taken when _fused_volume_ok: features channels-last [B, H, W, C]
+            hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid, nhwc=True)
+            return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16"), depth_bin)
         C = featL.shape[1]
         if (self.fast_volume and est.tensor_core and featL.is_cuda and not self.training and not torch.is_grad_enabled() and self.roiSize == 16
                 and D % 8 == 0 and D <= 256 and C % 8 == 0 and (3 * C) % 32 == 0 and 3 * C == est.dres0[0].in_channels
@@ -326,8 +355,13 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         left, right = batch['input'], batch['input_right']
         imgfea_left, imgfea_right = self._features(left, right)
 
+        pairs = None
         if self._heads_tc_ok(imgfea_left):
-            z = self._heads_tc(imgfea_left, imgfea_right)
+            base = imgfea_left._base
+            if (useCostVolume and target is None and base is not None and base is imgfea_right._base and base.is_contiguous()
+                    and base.shape[0] == 2 * imgfea_left.shape[0] and imgfea_left.data_ptr() == base.data_ptr()):
+                pairs = ops.ncdhw_to_cl_split(base.unsqueeze(2))        # [left; right] as one batch: mono head + feaRuduce share it
+            z = self._heads_tc(imgfea_left, imgfea_right, pairs)
         else:
             z = {}
             both = None
@@ -341,16 +375,20 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
 
         if useCostVolume:
             fb = batch['fb'].to(left.device, torch.float32).reshape(-1)
-            feaL = self.feaRuduce(imgfea_left).contiguous()
-            feaR = self.feaRuduce(imgfea_right).contiguous()
             D = self.depth_candidates or self.roiSize
             dev = left.device
+            nhwc = pairs is not None and self._fused_volume_ok(32, D)
+            if nhwc:
+                feaL, feaR = self._reduce_cl(pairs)                      # channels-last [B, H, W, 32]
+            else:
+                feaL = self.feaRuduce(imgfea_left).contiguous()
+                feaR = self.feaRuduce(imgfea_right).contiguous()
             if target is None and not self.training:
                 # fixed-shape path: all B*K decoded rows, validity mask instead of compaction (no host sync)
                 o = ops.bbox_decode_raw(z['hm'], z['wh'], z['reg'], K=self.K, wh_scale=float(wh_scale), heat_is_logit=True)
                 B, K = o['score'].shape
                 disp = self._depth_from_boxes(feaL, feaR, o['bbox'].view(-1, 5), o['bbox_right'].view(-1, 5), fb,
-                                              o['keep'], D)
+                                              o['keep'], D, nhwc=nhwc)
                 keep = o['keep'].bool()
                 depth = torch.zeros((B, K + 1), device=dev, dtype=disp.dtype)
                 slot = torch.where(keep.view(B, K), o['slot'].long(), torch.full_like(o['slot'], K, dtype=torch.long))

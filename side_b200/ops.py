@@ -389,15 +389,19 @@ def inst_costvol_cl_ok(C, D, P):
     return C == 32 and P == 16 and 2 <= D <= 64
 
 
-def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, gate=True):
+def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, gate=True, nhwc=False):
     """Inference-only: the (gated) volume straight in its consumer's format -> (hi, lo fp16 [N, D, P, P, 3C], depth_bin [N, D],
-    xcross [N, D]).  One pass over HBM; see include/side_b200.h side_inst_costvol_fwd_cl."""
+    xcross [N, D]).  One pass over HBM; see include/side_b200.h side_inst_costvol_fwd_cl.  nhwc=True: the features are already
+    channels-last [B, H, W, C]."""
     lib = _lib.load()
     featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
     left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
     if valid is not None:
         valid = _chk(valid, "valid", torch.uint8)
-    B, C, H, W = featL.shape
+    if nhwc:
+        B, H, W, C = featL.shape
+    else:
+        B, C, H, W = featL.shape
     N = left.shape[0]
     dev = featL.device
     _range_guard(dev)
@@ -409,7 +413,8 @@ def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, ga
     ws = torch.empty((nws,), device=dev, dtype=torch.uint8)
     _lib.check(lib.side_inst_costvol_fwd_cl(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(), fb.data_ptr(),
                                             _p(valid), hi.data_ptr(), lo.data_ptr(), depth_bin.data_ptr(), xc.data_ptr(), N, B, C, H,
-                                            W, D, P, float(x_clamp), _lib.VOL_GATE if gate else 0, ws.data_ptr(), nws, _stream()),
+                                            W, D, P, float(x_clamp), (_lib.VOL_GATE if gate else 0) | (_lib.VOL_FEAT_NHWC if nhwc else 0),
+                                            ws.data_ptr(), nws, _stream()),
                "side_inst_costvol_fwd_cl")
     return hi, lo, depth_bin, xc
 
