@@ -93,14 +93,19 @@ __device__ __forceinline__ void range_commit(uint32_t *slot, float amax)
     }
 }
 
-// split two values and pack the halves pairwise (little endian: a in the low 16 bits)
+// split two values and pack the halves pairwise (little endian: a in the low 16 bits).  Packed conversions: one
+// cvt.rn.satfinite.f16x2.f32 per pair of values for hi and for lo (same rounding as the scalar form, 8 instead of 12 instructions)
+__device__ __forceinline__ uint32_t f16x2_sat(float a, float b)
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t &hi, uint32_t &lo)
 {
-    __half ha, la, hb, lb;
-    f16_split(a, ha, la);
-    f16_split(b, hb, lb);
-    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+    hi = f16x2_sat(a, b);
+    const __half2 h2 = *reinterpret_cast<const __half2 *>(&hi);
+    lo = f16x2_sat((a - __low2float(h2)) * kF16LoScale, (b - __high2float(h2)) * kF16LoScale);
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
