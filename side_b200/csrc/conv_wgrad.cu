@@ -6,10 +6,12 @@
 //     gW[o][tap][c] = sum over (sample, output voxel) of gy[n][o][v] * x[n][v * stride + tap - pad][c]
 // runs as the split-K tensor-core GEMM of the DCN weight gradient (dcn_gw_tc.cu: gy is a K-major A operand as it lies in memory,
 // the pixel-major patch matrix is read in place as an MN-major B operand, 3xFP16 pairs with a power-of-two range scale on gy):
-//   conv_im2col_pairs_kernel  copies the fp16 (hi, lo) channels-last activation pairs the forward saved into the patch matrix
-//                             [sample * voxel][tap * Cp + c] (zeros for the padding) -- pure 16-byte copies, no conversion;
 //   dcn_gw_tc_split_gy        fp32 gy -> scaled fp16 pairs (once per call);
-//   dcn_gw_tc_kernel          the GEMM, over chunks of samples so that the patch matrix stays within the workspace.
+//   dcn_gw_tc_kernel, fused mode: a k-block = a box of 64 output voxels; the B operand of tap t is the SAME box of the saved
+//                             input pairs shifted by the tap (5-D TMA, traversal stride = convolution stride, out-of-bound fill =
+//                             the zero padding) -- the patch matrix never exists;
+//   conv_im2col_pairs_kernel + dcn_gw_tc_kernel: fallback for output maps that do not tile into 64-voxel boxes: the pairs are
+//                             copied into the patch matrix [sample * voxel][tap * Cq + c] in chunks of samples.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -21,6 +23,11 @@ size_t dcn_gw_tc_gy_halves(int B, int Cout, int P);
 int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, cudaStream_t st);
 int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, float *gw, int B, int b0, int nb, int Cout, int Kp,
                   int P, cudaStream_t st);
+bool dcn_gw_box(int Do, int Ho, int Wo, int &bw, int &bh, int &bd);
+int dcn_gw_tc_split_gy_box(const float *gy, void *gy_pairs, int N, int Cout, int Do, int Ho, int Wo, int bw, int bh, int bd,
+                           cudaStream_t st);
+int dcn_gw_tc_run_fused(const void *gy_pairs, const void *x_hi, const void *x_lo, float *gw, int N, int Cout, int Cp, int D, int H, int W,
+                        int Do, int Ho, int Wo, int kd, int kh, int kw, int stride, cudaStream_t st);
 
 struct Im2colParams {
     const uint4 *x_hi, *x_lo;          // [N, D, H, W, Cp] halves, 8 per uint4
@@ -137,6 +144,14 @@ extern "C" int side_conv_wgrad_tc(const void *x_hi, const void *x_lo, const floa
     __half *col_hi = reinterpret_cast<__half *>(w8 + gy_bytes), *col_lo = col_hi + (size_t)nbmax * P * Kp;
     SIDE_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Kp, st));
     int rc;
+    // first choice: the input is read in place through shifted TMA boxes (no patch matrix) against gy pairs written box-major;
+    // maps that do not tile into 64-voxel boxes (12 x 40 at D = 1) take the patch-matrix path below
+    int bw, bh, bd;
+    if (dcn_gw_box(Do, Ho, Wo, bw, bh, bd)) {
+        if ((rc = dcn_gw_tc_split_gy_box(gy, gy_pairs, N, Cout, Do, Ho, Wo, bw, bh, bd, st))) return rc;
+        rc = dcn_gw_tc_run_fused(gy_pairs, x_hi, x_lo, gw, N, Cout, Cp, D, H, W, Do, Ho, Wo, kd, kh, kw, stride, st);
+        if (rc != SIDE_ERR_UNSUPPORTED) return rc;
+    }
     if ((rc = dcn_gw_tc_split_gy(gy, gy_pairs, N, Cout, (int)P, st))) return rc;
     for (int b0 = 0; b0 < N; b0 += nbmax) {
         const int nb = std::min(nbmax, N - b0);

@@ -33,6 +33,9 @@ struct GwParams {
     const uint32_t *gy_absmax; // bits of max |gy| over the whole batch (gw_absmax_kernel): fixes the power-of-two range scale
     int Cout, Kp, P, nb;       // P % 64 == 0
     int n_ntiles, n_mtiles, ksplits, kb_total;     // kb_total = nb * P / 64
+    // fused convolution mode (conv_wgrad.cu): the B operand is the convolution INPUT read in place through shifted TMA boxes
+    // -- no patch matrix.  A k-block = one box of bw x bh x bd = 64 output voxels; gy map [W, H, D, Cout, N], x map [C, W, H, D, N]
+    int fused, bw, bh, bd, nbw, nbh, Cq, stride, kd, kh, kw;
 };
 
 __device__ __forceinline__ void gw_tma_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar)
@@ -40,6 +43,13 @@ __device__ __forceinline__ void gw_tma_3d(void *dst, const CUtensorMap *tm, int 
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+__device__ __forceinline__ void gw_tma_5d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, int c4, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
 }
 __device__ __forceinline__ void gw_tma_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
 {
@@ -128,6 +138,26 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
                 mbar_wait(&empty_bar[st], ph ^ 1u);
                 unsigned char *sa = tiles + (size_t)st * kGwStage;
                 mbar_expect_tx(&full_bar[st], bytes);
+                if (p.fused) {
+                    // box r of sample bl: output voxels (d0.., h0.., w0..); tap (td, th, tw) of column chunk j shifts the INPUT box
+                    const int r = kb - bl * kpi, bx = r % p.nbw, by = (r / p.nbw) % p.nbh, bz = r / (p.nbw * p.nbh);
+                    const int w0 = bx * p.bw, h0 = by * p.bh, d0 = bz * p.bd;
+                    // gy pairs were written box-major by gw_split_gy_box_kernel: the 64 voxels of box r are contiguous (a multi-
+                    // dimensional TMA box with an inner extent below 128 bytes is not laid out as one dense 128-byte K row)
+                    gw_tma_3d(sa, &tm_gy_hi, r * 64, mt * 128, bl, &full_bar[st]);
+                    gw_tma_3d(sa + kGwAPart, &tm_gy_lo, r * 64, mt * 128, bl, &full_bar[st]);
+                    unsigned char *sbf = sa + 2 * kGwAPart;
+                    for (int j = 0; j < Nw / 64; ++j) {
+                        const int kq = n0 + 64 * j, tap = kq / p.Cq, c0 = kq - tap * p.Cq;
+                        const int tw = tap % p.kw, th = (tap / p.kw) % p.kh, td = tap / (p.kw * p.kh);
+                        const int xi = w0 * p.stride + tw - (p.kw - 1) / 2, yi = h0 * p.stride + th - (p.kh - 1) / 2,
+                                  zi = d0 + td - (p.kd - 1) / 2;
+                        gw_tma_5d(sbf + (size_t)j * kGwBChunk, &tm_col_hi, c0, xi, yi, zi, bl, &full_bar[st]);
+                        gw_tma_5d(sbf + kGwBPart + (size_t)j * kGwBChunk, &tm_col_lo, c0, xi, yi, zi, bl, &full_bar[st]);
+                    }
+                    if (++st == kGwStages) { st = 0; ph ^= 1u; }
+                    continue;
+                }
                 gw_tma_3d(sa, &tm_gy_hi, p0, mt * 128, bl, &full_bar[st]);                 // rows past Cout: zero fill
                 gw_tma_3d(sa + kGwAPart, &tm_gy_lo, p0, mt * 128, bl, &full_bar[st]);
                 unsigned char *sb = sa + 2 * kGwAPart;
@@ -211,6 +241,56 @@ __global__ void __launch_bounds__(256) gw_split_gy_kernel(const float4 *__restri
     }
 }
 
+// gy [N][Cout][Do][Ho][Wo] fp32 -> fp16 pairs of (gy * 2^s) in BOX-MAJOR voxel order: position box * 64 + (dz * bh + dy) * bw + dx of
+// every (n, o) row holds voxel (bz * bd + dz, by * bh + dy, bx * bw + dx), box = (bz * nbh + by) * nbw + bx
+__global__ void __launch_bounds__(256) gw_split_gy_box_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo,
+                                                             long long rows, int Do, int Ho, int Wo, int bw, int bh, int bd,
+                                                             const uint32_t *__restrict__ absmax)
+{
+    const float sc = gw_range_scale(__ldg(absmax), false);
+    const long long P = (long long)Do * Ho * Wo, total = rows * P / 2;
+    const int nbw = Wo / bw, nbh = Ho / bh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = (2 * i) / P;
+        const int q = (int)(2 * i - row * P);                  // even position inside the row (bw is even: the pair shares a box row)
+        const int box = q >> 6, r = q & 63, dx = r % bw, dy = (r / bw) % bh, dz = r / (bw * bh);
+        const int bx = box % nbw, by = (box / nbw) % nbh, bz = box / (nbw * nbh);
+        const size_t src = (size_t)row * P + ((size_t)(bz * bd + dz) * Ho + by * bh + dy) * Wo + bx * bw + dx;
+        const float2 v = *reinterpret_cast<const float2 *>(x + src);
+        uint32_t h, l;
+        f16_split2(v.x * sc, v.y * sc, h, l);
+        reinterpret_cast<uint32_t *>(hi)[i] = h;
+        reinterpret_cast<uint32_t *>(lo)[i] = l;
+    }
+}
+
+// 64-voxel box of the fused convolution weight gradient: bw x bh x bd with bw | Wo, bh | Ho, bd | Do (powers of two, bw even)
+bool dcn_gw_box(int Do, int Ho, int Wo, int &bw, int &bh, int &bd)
+{
+    bw = 64;
+    while (bw > 1 && Wo % bw) bw >>= 1;
+    bh = 64 / bw;
+    while (bh > 1 && Ho % bh) bh >>= 1;
+    bd = 64 / (bw * bh);
+    return bw >= 2 && Do % bd == 0 && bw * bh * bd == 64;
+}
+
+int dcn_gw_tc_split_gy_box(const float *gy, void *gy_pairs, int N, int Cout, int Do, int Ho, int Wo, int bw, int bh, int bd,
+                           cudaStream_t st)
+{
+    const long long P = (long long)Do * Ho * Wo, n = (long long)N * Cout * P;
+    __half *hi = reinterpret_cast<__half *>(gy_pairs);
+    uint32_t *absmax = reinterpret_cast<uint32_t *>(hi + 2 * n);
+    SIDE_CUDA(cudaMemsetAsync(absmax, 0, sizeof(uint32_t), st));
+    const unsigned grid = (unsigned)std::min<long long>((n / 4 + 255) / 256, 148 * 16);
+    gw_absmax_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(gy), absmax, n / 4);
+    SIDE_LAUNCH_CHECK("gw_absmax_kernel");
+    gw_split_gy_box_kernel<<<(unsigned)std::min<long long>((n / 2 + 255) / 256, 148 * 16), 256, 0, st>>>(gy, hi, hi + n, (long long)N * Cout,
+                                                                                                     Do, Ho, Wo, bw, bh, bd, absmax);
+    SIDE_LAUNCH_CHECK("gw_split_gy_box_kernel");
+    return SIDE_OK;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 gw_encode_fn()
 {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -252,6 +332,66 @@ int dcn_gw_tc_split_gy(const float *gy, void *gy_pairs, int B, int Cout, int P, 
     return SIDE_OK;
 }
 
+// Fused convolution weight gradient: gw [Cout][taps * Cq] += gy (*) x, x = the fp16 pairs [N, D, H, W, Cp] of the convolution input read
+// through shifted (and, for stride 2, strided) TMA boxes; gy pairs [N, Cout, Do, Ho, Wo].  Returns SIDE_ERR_UNSUPPORTED when the
+// output map does not tile into 64-voxel boxes (the caller then builds the patch matrix).
+int dcn_gw_tc_run_fused(const void *gy_pairs, const void *x_hi, const void *x_lo, float *gw, int N, int Cout, int Cp, int D, int H, int W,
+                        int Do, int Ho, int Wo, int kd, int kh, int kw, int stride, cudaStream_t st)
+{
+    PFN_cuTensorMapEncodeTiled_v12000 enc = gw_encode_fn();
+    SIDE_REQUIRE(enc != nullptr, "dcn_gw_tc: cuTensorMapEncodeTiled is not available from the driver");
+    int bw, bh, bd;
+    if (!dcn_gw_box(Do, Ho, Wo, bw, bh, bd) || Cp % 8 != 0) {
+        set_error("dcn_gw_tc_run_fused: output map %dx%dx%d does not tile into 64-voxel boxes", Do, Ho, Wo);
+        return SIDE_ERR_UNSUPPORTED;
+    }
+    const long long P = (long long)Do * Ho * Wo;
+    const int Cq = (Cp + 63) / 64 * 64, taps = kd * kh * kw, Kp = taps * Cq;
+    const __half *gh = reinterpret_cast<const __half *>(gy_pairs), *gl = gh + (size_t)N * Cout * P;
+    CUtensorMap tm[4];
+    {   // gy pairs, box-major rows: [p' (inner), o, n], box {64, 128, 1}; rows past Cout are zero-filled
+        cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)Cout, (cuuint64_t)N};
+        cuuint64_t strides[2] = {(cuuint64_t)P * 2, (cuuint64_t)Cout * P * 2};
+        cuuint32_t box[3] = {64, 128, 1}, es[3] = {1, 1, 1};
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half *>(i ? gl : gh), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("dcn_gw_tc: cuTensorMapEncodeTiled(gy, fused) failed (CUresult %d)", (int)r); return SIDE_ERR_UNSUPPORTED; }
+        }
+    }
+    {   // input pairs [C (inner), W, H, D, N], box {64 channels, bw, bh, bd, 1}, traversal stride = the convolution stride on W, H
+        cuuint64_t dims[5] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t strides[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2, (cuuint64_t)D * H * W * Cp * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+        cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+        // with a traversal stride the box extent is given in INPUT elements spanned (b * stride, as conv_tc.cu does): it still
+        // delivers bw x bh positions
+        box[1] = (cuuint32_t)(bw * stride); box[2] = (cuuint32_t)(bh * stride);
+        for (int i = 0; i < 2; ++i) {
+            CUresult r = enc(&tm[2 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(i ? x_lo : x_hi), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("dcn_gw_tc: cuTensorMapEncodeTiled(x, fused) failed (CUresult %d)", (int)r); return SIDE_ERR_UNSUPPORTED; }
+        }
+    }
+    GwParams p{};
+    p.gw = gw; p.Cout = Cout; p.Kp = Kp; p.P = (int)P; p.nb = N;
+    p.gy_absmax = reinterpret_cast<const uint32_t *>(gl + (size_t)N * Cout * P);
+    p.n_ntiles = (Kp + 255) / 256; p.n_mtiles = (Cout + 127) / 128;
+    p.kb_total = N * (int)(P / 64);
+    p.fused = 1; p.bw = bw; p.bh = bh; p.bd = bd; p.nbw = Wo / bw; p.nbh = Ho / bh; p.Cq = Cq; p.stride = stride;
+    p.kd = kd; p.kh = kh; p.kw = kw;
+    const int tiles = p.n_ntiles * p.n_mtiles;
+    p.ksplits = std::max(1, std::min(p.kb_total, (296 + tiles - 1) / tiles));
+    const size_t smem = (size_t)kGwStages * kGwStage + 1024;
+    int rc;
+    if ((rc = set_smem_attr((const void *)dcn_gw_tc_kernel, smem))) return rc;
+    dcn_gw_tc_kernel<<<(unsigned)(tiles * p.ksplits), kGwThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], p);
+    SIDE_LAUNCH_CHECK("dcn_gw_tc_kernel<fused conv>");
+    return SIDE_OK;
+}
+
 int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, float *gw, int B, int b0, int nb, int Cout, int Kp,
                   int P, cudaStream_t st)
 {
@@ -282,7 +422,7 @@ int dcn_gw_tc_run(const void *gy_pairs, const void *col_hi, const void *col_lo, 
             if (r != CUDA_SUCCESS) { set_error("dcn_gw_tc: cuTensorMapEncodeTiled(col) failed (CUresult %d)", (int)r); return SIDE_ERR_CUDA; }
         }
     }
-    GwParams p;
+    GwParams p{};
     p.gw = gw; p.Cout = Cout; p.Kp = Kp; p.P = P; p.nb = nb;
     p.gy_absmax = reinterpret_cast<const uint32_t *>(gl + (size_t)B * Cout * P);
     p.n_ntiles = (Kp + 255) / 256; p.n_mtiles = (Cout + 127) / 128;
