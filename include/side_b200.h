@@ -343,6 +343,11 @@ int side_cl_to_nchw_ld(const float *x, int ld, float *y, int B, int C, long long
  * --------------------------------------------------------------------------------------------- */
 int side_stem_conv_fwd(const float *x, const float *w, const float *scale, const float *shift, float *y, int B, int Cin, int H,
                        int W, int Cout, int k, int stride, int relu, void *stream);
+/* base_layer only (3 -> 16, 7x7): the result as fp16 (hi, lo * 2^11) pairs in the 2x2 space-to-depth channels-last layout
+ * [B, H/2, W/2, 64], channel = (dy * 2 + dx) * 16 + o, so that level0 (16 -> 16, 3x3) and level1 (16 -> 32, 3x3, stride 2) run as
+ * 3x3 BLOCK convolutions (64 -> 64 and 64 -> 32, weights rearranged by the caller) on side_conv3d_tc_fwd_f16.  H, W even. */
+int side_stem_conv_fwd_s2d(const float *x, const float *w, const float *scale, const float *shift, void *y_hi, void *y_lo,
+                           int B, int H, int W, int relu, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense photometric alignment of the post-process path.

@@ -65,6 +65,7 @@ SIGNATURES = {
     "side_conv_tc_set_mode": (_i, [_i]),
     "side_tc_range_guard": (_i, [_vp, _i]),
     "side_stem_conv_fwd": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "side_stem_conv_fwd_s2d": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
     "side_voxel_coords": (_i, [_vp] * 8 + [_i] * 7 + [_vp] * 8),
     "side_voxel_volume_ws_bytes": (_sz, [_i] * 4),
     "side_voxel_volume_fwd": (_i, [_vp] * 11 + [_i] * 8 + [_vp, _sz, _vp]),

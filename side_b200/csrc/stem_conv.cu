@@ -8,16 +8,20 @@
 // and the odd input columns in separate half rows).
 // Eval-mode BatchNorm and ReLU are folded into the store.  cuDNN spends 3-4x longer on these three layers (its fp32
 // kernels are tuned for wide channels) plus separate BN / ReLU passes.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace side {
 
 constexpr int kStemTW = 64, kStemTH = 8;     // output tile; 256 threads, 2 pixels each
 
-template <int CIN, int COUT, int K, int S, int CCHUNK>
+// S2D: instead of NCHW fp32 the result leaves as fp16 (hi, lo * 2^11) operand pairs in the 2x2 space-to-depth channels-last layout
+// [B, Ho/2, Wo/2, 4 * COUT], channel = (dy * 2 + dx) * COUT + o -- the input format of the next two stem layers when they run as
+// 3x3 block convolutions on the tensor cores (DLA._stem_tc).  y = hi array, y2 = lo array.
+template <int CIN, int COUT, int K, int S, int CCHUNK, bool S2D = false>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ scale, const float *__restrict__ shift,
-                                                        float *__restrict__ y, int H, int W, int Ho, int Wo, int relu)
+                                                        float *__restrict__ y, int H, int W, int Ho, int Wo, int relu,
+                                                        void *__restrict__ y2 = nullptr, uint32_t *rs = nullptr)
 {
     constexpr int P = (K - 1) / 2;
     constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1;
@@ -75,6 +79,36 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
         }
     }
     const int oy = oy0 + ty, ox = ox0 + tx;
+    if (S2D) {
+        float amax = 0.f;
+        if (oy < Ho) {
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const int xo = ox + 32 * px;
+                if (xo >= Wo) continue;
+                const float *acc = px ? acc1 : acc0;
+                uint32_t hh[COUT / 2], ll[COUT / 2];
+#pragma unroll
+                for (int o = 0; o < COUT; o += 2) {
+                    float a = fmaf(acc[o], scale ? __ldg(scale + o) : 1.f, shift ? __ldg(shift + o) : 0.f);
+                    float c = fmaf(acc[o + 1], scale ? __ldg(scale + o + 1) : 1.f, shift ? __ldg(shift + o + 1) : 0.f);
+                    if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+                    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+                    f16_split2(a, c, hh[o / 2], ll[o / 2]);
+                }
+                const size_t off = ((((size_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1) + (xo >> 1)) * 4 + ((oy & 1) * 2 + (xo & 1))) * COUT;
+                uint4 *hp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(y) + off);
+                uint4 *lp = reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(y2) + off);
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) {
+                    hp[q] = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+                    lp[q] = make_uint4(ll[4 * q], ll[4 * q + 1], ll[4 * q + 2], ll[4 * q + 3]);
+                }
+            }
+        }
+        if (rs) range_commit(rs, amax);
+        return;
+    }
     if (oy < Ho && ox < Wo) {
         float *yp = y + ((size_t)b * COUT * Ho + oy) * Wo + ox;
         const bool two = ox + 32 < Wo;
@@ -121,4 +155,24 @@ extern "C" int side_stem_conv_fwd(const float *x, const float *w, const float *s
     set_error("side_stem_conv_fwd: only the DLA-34 stem shapes are built (3->16 k7 s1, 16->16 k3 s1, 16->32 k3 s2), got %d->%d k%d s%d",
               Cin, Cout, k, stride);
     return SIDE_ERR_UNSUPPORTED;
+}
+
+/* base_layer (3 -> 16, 7x7, stride 1, folded BatchNorm + ReLU) with the result written as fp16 operand pairs in the 2x2
+ * space-to-depth channels-last layout [B, H/2, W/2, 64] (channel = (dy * 2 + dx) * 16 + o): what DLA level0 / level1 read when they
+ * run as 3x3 block convolutions on side_conv3d_tc_fwd_f16.  H, W even. */
+extern "C" int side_stem_conv_fwd_s2d(const float *x, const float *w, const float *scale, const float *shift, void *y_hi, void *y_lo,
+                                      int B, int H, int W, int relu, void *stream)
+{
+    SIDE_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "side_stem_conv_fwd_s2d: bad shape");
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(y_hi); SIDE_REQUIRE_DEV(y_lo);
+    constexpr int CIN = 3, COUT = 16, K = 7, S = 1, CCHUNK = 3;
+    constexpr int IW = kStemTW * S + K - 1, IH = kStemTH * S + K - 1, IWP = IW | 1;
+    const size_t smem = sizeof(float) * ((size_t)CIN * K * K * COUT + (size_t)CCHUNK * IH * IWP);
+    int rc = set_smem_attr((const void *)stem_conv_kernel<CIN, COUT, K, S, CCHUNK, true>, smem);
+    if (rc) return rc;
+    dim3 grid(ceil_div(W, kStemTW), ceil_div(H, kStemTH), B);
+    stem_conv_kernel<CIN, COUT, K, S, CCHUNK, true><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        x, w, scale, shift, reinterpret_cast<float *>(y_hi), H, W, H, W, relu, y_lo, range_slot_next());
+    SIDE_LAUNCH_CHECK("stem_conv_kernel<s2d>");
+    return SIDE_OK;
 }

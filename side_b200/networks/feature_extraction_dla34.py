@@ -120,6 +120,9 @@ class DLA(ops.PreparedStateOwner, nn.Module):
     def forward(self, x):
         ys = []
         stem = self.direct_stem and x.is_cuda and not self.training and not torch.is_grad_enabled()
+        if stem and self.stem_block_convs and self.skip_stem_outputs and self._stem_tc_ok(x):
+            # levels 0 / 1 are not consumed downstream (first_level >= 2): the stem hands level 2 its channels-last operand pairs
+            return [None, None] + self._levels_tc_from(self._stem_tc(x), x.shape[0])
         x = self._stem(self.base_layer)(x) if stem else self.base_layer(x)
         for i in range(6):
             if i == 2 and self._tc_ok(x):
@@ -128,6 +131,69 @@ class DLA(ops.PreparedStateOwner, nn.Module):
             x = self._stem(level)(x) if (stem and i < 2) else level(x)
             ys.append(x)
         return ys
+
+    # -- stem on the tensor cores: base_layer (SIMT, 3 input channels) writes fp16 pairs in the 2x2 space-to-depth channels-last
+    #    layout [B, H/2, W/2, 64]; in that layout level0 (16 -> 16, 3x3) is a 3x3 BLOCK convolution 64 -> 64 and level1 (16 -> 32,
+    #    3x3, stride 2) a 3x3 block convolution 64 -> 32 at level-1 resolution (its stride disappears), both with 64-channel
+    #    k-blocks instead of the 16 channels that starve an MMA.  Weights are rearranged once (structural zeros included). ----
+    stem_block_convs = True
+    skip_stem_outputs = False      # set by feature_extraction_dla34 when the up path starts at level >= 2
+
+    def _stem_tc_ok(self, x):
+        B, C, H, W = x.shape
+        l0, l1 = list(self.level0), list(self.level1)
+        return (self.tensor_core and ops.get_tc_format() == "f16" and C == 3 and H % 32 == 0 and W % 256 == 0 and len(l0) == 3
+                and len(l1) == 3 and tuple(self.base_layer[0].weight.shape) == (16, 3, 7, 7) and tuple(l0[0].weight.shape) == (16, 16, 3, 3)
+                and tuple(l1[0].weight.shape) == (32, 16, 3, 3) and l1[0].stride == (2, 2) and l0[0].stride == (1, 1)
+                and self._tc_ok_shape(B, 32, H // 2, W // 2))
+
+    @staticmethod
+    def _block_weights(w, stride):
+        """w [Cout, 16, 3, 3] of a pixel-domain 3x3 convolution -> the 3x3 convolution over 2x2 pixel blocks it equals:
+        stride 1: [4 * Cout, 64, 3, 3] (output channel (dyo * 2 + dxo) * Cout + o), stride 2: [Cout, 64, 3, 3]; input channel
+        (dyi * 2 + dxi) * 16 + c; block tap (by + 1, bx + 1)."""
+        Cout, Cin = w.shape[:2]
+        outs = [(0, 0)] if stride == 2 else [(0, 0), (0, 1), (1, 0), (1, 1)]
+        wb = w.new_zeros((len(outs) * Cout, 4 * Cin, 3, 3))
+        for io, (dyo, dxo) in enumerate(outs):
+            for ky in range(3):
+                ry = dyo + ky - 1                       # input row relative to the block's first row
+                by, dyi = ry // 2, ry % 2
+                for kx in range(3):
+                    rx = dxo + kx - 1
+                    bx, dxi = rx // 2, rx % 2
+                    ci = (dyi * 2 + dxi) * Cin
+                    wb[io * Cout:(io + 1) * Cout, ci:ci + Cin, by + 1, bx + 1] = w[:, :, ky, kx]
+        return wb
+
+    def _stem_tc_state(self):
+        mods = [self.base_layer[0], self.base_layer[1], self.level0[0], self.level0[1], self.level1[0], self.level1[1]]
+        key = (ops.prep_epoch(),) + tuple((t.data_ptr(), t._version) for m in mods for t in list(m.parameters()) + list(m.buffers()))
+        st = self.__dict__.get("_stem_tc_cache")
+        if st is None or st[0] != key:
+            def affine(bn):
+                sc = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
+                return sc.contiguous(), (bn.bias - bn.running_mean * sc).detach().float().contiguous()
+            s0, h0 = affine(self.base_layer[1])
+            s1, h1 = affine(self.level0[1])
+            s2, h2 = affine(self.level1[1])
+            w1 = self._block_weights(self.level0[0].weight.detach().float(), 1).unsqueeze(2)       # [64, 64, 1, 3, 3]
+            w2 = self._block_weights(self.level1[0].weight.detach().float(), 2).unsqueeze(2)       # [32, 64, 1, 3, 3]
+            wp1, wp2 = ops.conv_tc_prepare(w1, fmt="f16"), ops.conv_tc_prepare(w2, fmt="f16")
+            wp1.cin_alg = wp2.cin_alg = 16         # algorithmic FLOPs (bench.py) are those of the 16-channel pixel-domain layers
+            st = (key, (self.base_layer[0].weight.detach().float().contiguous(), s0, h0),
+                  (wp1, 64, s1.repeat(4).contiguous(), h1.repeat(4).contiguous()), (wp2, 32, s2, h2))
+            self.__dict__["_stem_tc_cache"] = st
+        return st[1:]
+
+    def _stem_tc(self, x):
+        """-> (full, hi, lo) of the level-1 output, channels-last [1, B, H/2, W/2, 32]: the triple level 2 starts from."""
+        (w0, s0, h0), (wp1, c1, s1, h1), (wp2, c2, s2, h2) = self._stem_tc_state()
+        hi, lo = ops.stem_conv_s2d(x, w0, s0, h0, relu=True)                                      # [B, 1, H/2, W/2, 64]
+        _, hi, lo = ops.conv3d_tc(hi, lo, wp1, c1, ksize=(1, 3, 3), scale=s1, shift=h1, relu=True, full=False, split=True)
+        full, hi, lo = ops.conv3d_tc(hi, lo, wp2, c2, ksize=(1, 3, 3), scale=s2, shift=h2, relu=True, full=True, split=True)
+        B, _, H2, W2, C = hi.shape
+        return full.view(1, B, H2, W2, C), hi.view(1, B, H2, W2, C), lo.view(1, B, H2, W2, C)
 
     # -- stem (base_layer, level0, level1) as direct fp32 convolutions with BatchNorm + ReLU folded in, inference only -----
     direct_stem = True
@@ -173,6 +239,10 @@ class DLA(ops.PreparedStateOwner, nn.Module):
         if not (self.tensor_core and x.is_cuda and not self.training and not torch.is_grad_enabled()):
             return False
         B, C, H, W = x.shape
+        return self._tc_ok_shape(B, C, H, W)
+
+    def _tc_ok_shape(self, B, C, H, W):
+        """Level-1 output shape [B, C, H, W] from which levels 2-5 can run on the tensor cores."""
         if C % 32 or H % 16 or W % 16:
             return False
         return all(self._tiles(B, H >> k, W >> k) for k in (1, 2, 3, 4))
@@ -229,6 +299,10 @@ class DLA(ops.PreparedStateOwner, nn.Module):
             hi, lo = ops.ncdhw_to_cl_split(x.unsqueeze(2))           # [B, 1, H, W, C] channels-last halves
             hi, lo = hi.view(1, B, H, W, C), lo.view(1, B, H, W, C)
             t = (hi + lo, hi, lo)                                    # hi + lo == x exactly
+        return self._levels_tc_from(t, B)
+
+    def _levels_tc_from(self, t, B):
+        """Levels 2-5 from the channels-last (full, hi, lo) triple of the level-1 output [1, B, H, W, C]."""
         outs = []
         for i in range(2, 6):
             t = self._tree_tc(t, getattr(self, "level%d" % i))
@@ -336,6 +410,7 @@ class feature_extraction_dla34(nn.Module):
         self.first_level = int(np.log2(down_ratio))
         self.last_level = last_level
         self.base = dla34(pretrained=pretrained)
+        self.base.skip_stem_outputs = self.first_level >= 2       # DLAUp reads layers[first_level:] only
         self.channels = self.base.channels
         scales = [2 ** i for i in range(len(self.channels[self.first_level:]))]
         self.dla_up = DLAUp(self.first_level, self.channels[self.first_level:], scales)

@@ -824,6 +824,22 @@ def stem_conv(x, weight, scale=None, shift=None, stride=1, relu=True):
     return y
 
 
+def stem_conv_s2d(x, weight, scale=None, shift=None, relu=True):
+    """base_layer (3 -> 16, 7x7) + folded BatchNorm + ReLU -> fp16 operand pairs (hi, lo) [B, 1, H/2, W/2, 64] in the 2x2
+    space-to-depth channels-last layout (channel = (dy * 2 + dx) * 16 + o), see side_stem_conv_fwd_s2d."""
+    lib = _lib.load()
+    x, weight = _chk(x, "x"), _chk(weight, "weight")
+    B, Cin, H, W = x.shape
+    if tuple(weight.shape) != (16, 3, 7, 7) or H % 2 or W % 2:
+        raise RuntimeError("side_stem_conv_fwd_s2d failed (code -5): built for the 3 -> 16 7x7 base layer on even-sized images")
+    _range_guard(x.device)
+    hi = torch.empty((B, 1, H // 2, W // 2, 64), device=x.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.side_stem_conv_fwd_s2d(x.data_ptr(), weight.data_ptr(), _p(scale), _p(shift), hi.data_ptr(), lo.data_ptr(), B, H, W,
+                                          1 if relu else 0, _stream()), "side_stem_conv_fwd_s2d")
+    return hi, lo
+
+
 def cl_to_nchw(x, B, C, spatial, ld=None):
     """channels-last buffer [B, *spatial, ld] -> NCHW [B, C, *spatial] (ld > C: rows computed with padded channels, first C taken)."""
     lib = _lib.load()

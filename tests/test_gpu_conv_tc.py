@@ -488,3 +488,39 @@ def test_aggregate_tc_f16_scaled_volume_with_fallback(lib, scale):
     assert err < 1e-4, (scale, flags, err)
     if scale >= 1e5:
         assert flags & ops.TC_RANGE_SATURATED            # 1e5 * N(0,1) crosses 65504: the guard must have caught it
+
+
+def test_stem_block_convolutions_match_direct_stem(lib):
+    """DLA stem on the tensor cores (base layer -> 2x2 space-to-depth fp16 pairs, level0 / level1 as 3x3 BLOCK convolutions with
+    rearranged weights) against the plain modules in float64: the level-1 output that levels 2-5 start from."""
+    from side_b200 import ops
+    from side_b200.networks.feature_extraction_dla34 import dla34
+    torch.manual_seed(0)
+    m = dla34().cuda().eval()
+    for seq in (m.base_layer, m.level0, m.level1):
+        bn = seq[1]
+        with torch.no_grad():
+            bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.uniform_(0.7, 1.3); bn.bias.normal_(0, 0.2)
+    x = torch.randn(2, 3, 64, 256, device="cuda")
+    old = ops.get_tc_format()
+    ops.set_tc_format("f16")
+    try:
+        with torch.no_grad():
+            assert m._stem_tc_ok(x)
+            full, hi, lo = m._stem_tc(x)
+            md = dla34().double().cuda().eval()
+            md.load_state_dict(m.state_dict())
+            ref = md.level1(md.level0(md.base_layer(x.double())))                  # [2, 32, 32, 128]
+    finally:
+        ops.set_tc_format(old)
+    got = full[0].permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    pair = hi.float() + lo.float() / 2048.0
+    assert float((pair[0].permute(0, 3, 1, 2).double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    # the block weights are an exact rearrangement: every pixel-domain weight appears once per output sub-position
+    w = m.level0[0].weight.detach()
+    wb = m._block_weights(w, 1)
+    assert wb.shape == (64, 64, 3, 3) and float(wb.abs().sum()) == pytest.approx(4 * float(w.abs().sum()), rel=1e-6)
+    wb2 = m._block_weights(m.level1[0].weight.detach(), 2)
+    assert wb2.shape == (32, 64, 3, 3) and float(wb2.abs().sum()) == pytest.approx(float(m.level1[0].weight.abs().sum()), rel=1e-6)
