@@ -331,6 +331,9 @@ int side_conv3d_c1_cl(const float *x, const float *w, float *out, int N, int D, 
 int side_tc_range_guard(void *status_words, int nwords);
 /* channels-last [B, HW, C] -> NCHW [B, C, HW]: hands a tensor-core convolution output back to NCHW consumers */
 int side_cl_to_nchw(const float *x, float *y, int B, int C, long long HW, void *stream);
+/* channel concatenation of channels-last tensors: srcs[i] = [rows, row_bytes[i]] (host arrays of device pointers / byte counts, 1..8
+ * sources, rows multiples of 16 bytes) -> dst [rows, sum row_bytes]; 16-byte copies (Root inputs of the DLA trees) */
+int side_cl_concat(const void *const *srcs, const int *row_bytes, int nsrc, void *dst, long long rows, void *stream);
 /* same from rows of ld >= C floats: the first C channels of every row (outputs computed with padded channel counts) */
 int side_cl_to_nchw_ld(const float *x, int ld, float *y, int B, int C, long long HW, void *stream);
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "side_maxpool_hw2_cl": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_conv3d_c1_cl": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "side_cl_to_nchw": (_i, [_vp] * 2 + [_i] * 2 + [_ll, _vp]),
+    "side_cl_concat": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _ll, _vp]),
     "side_cl_to_nchw_ld": (_i, [_vp, _i, _vp] + [_i] * 2 + [_ll, _vp]),
     "side_conv_tc_set_mode": (_i, [_i]),
     "side_tc_range_guard": (_i, [_vp, _i]),

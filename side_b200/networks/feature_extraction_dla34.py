@@ -280,7 +280,7 @@ class DLA(ops.PreparedStateOwner, nn.Module):
             x1 = self._block_tc(t, residual, tree.tree1)
             x2 = self._block_tc(x1, x1[0], tree.tree2)
             xs = [x2, x1] + children
-            cat = (None, torch.cat([c[1] for c in xs], -1), torch.cat([c[2] for c in xs], -1))
+            cat = (None, ops.cl_concat([c[1] for c in xs]), ops.cl_concat([c[2] for c in xs]))
             y = self._conv_tc(cat, tree.root.conv, tree.root.bn, "after" if tree.root.residual else True,
                               residual=xs[0][0] if tree.root.residual else None)
             return y

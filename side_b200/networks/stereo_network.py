@@ -297,7 +297,10 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         B, C, H, W = fl.shape
         z = {}
         if S["stereo"]:
-            hi, lo = ops.ncdhw_to_cl_split(torch.cat((fl, fr), 1).unsqueeze(2))                  # [B, 1, H, W, 2C]
+            if pairs is not None:            # channel concatenation of the left / right halves of the batched pairs, 16-byte copies
+                hi, lo = ops.cl_concat([pairs[0][:B], pairs[0][B:]]), ops.cl_concat([pairs[1][:B], pairs[1][B:]])
+            else:
+                hi, lo = ops.ncdhw_to_cl_split(torch.cat((fl, fr), 1).unsqueeze(2))              # [B, 1, H, W, 2C]
             wp, cout = S["stereo_w"]
             _, yh, yl = ops.conv3d_tc(hi, lo, wp, cout, ksize=(1, 3, 3), relu=True, full=False, split=True)
             wp1, n_pad, b1, widths = S["stereo_out"]

@@ -840,6 +840,24 @@ def stem_conv_s2d(x, weight, scale=None, shift=None, relu=True):
     return hi, lo
 
 
+def cl_concat(tensors):
+    """torch.cat(tensors, -1) for channels-last tensors of one dtype whose rows are multiples of 16 bytes (one 16-byte-copy kernel)."""
+    lib = _lib.load()
+    ts = [_chk(t, "tensor", tensors[0].dtype) for t in tensors]
+    lead = ts[0].shape[:-1]
+    es = ts[0].element_size()
+    if len(ts) > 8 or any(t.shape[:-1] != lead or (t.shape[-1] * es) % 16 for t in ts):
+        return torch.cat(ts, -1)
+    rows = 1
+    for v in lead:
+        rows *= v
+    out = torch.empty(tuple(lead) + (sum(t.shape[-1] for t in ts),), device=ts[0].device, dtype=ts[0].dtype)
+    ptrs = (_lib._vp * len(ts))(*[t.data_ptr() for t in ts])
+    nb = (_lib._i * len(ts))(*[t.shape[-1] * es for t in ts])
+    _lib.check(lib.side_cl_concat(ptrs, nb, len(ts), out.data_ptr(), rows, _stream()), "side_cl_concat")
+    return out
+
+
 def cl_to_nchw(x, B, C, spatial, ld=None):
     """channels-last buffer [B, *spatial, ld] -> NCHW [B, C, *spatial] (ld > C: rows computed with padded channels, first C taken)."""
     lib = _lib.load()
