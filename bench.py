@@ -616,6 +616,7 @@ def main():
     dcn, dcn2 = tm.summary(), tm2.summary()
     dcn = {k: dcn[k] + dcn2[k] for k in ("calls", "ms", "work")}       # NCHW entry + channels-last entry of the same kernel
     cv, cv16 = tmc.summary("tf32"), tmc.summary("f16")
+    cv_big, cv_small = tmc.split_by_work(1e11, args.tc_format)      # >= 100 GFLOP per launch: aggregation layers, head convolutions
     vol = tmv.summary()
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)
@@ -712,9 +713,17 @@ def main():
                 "share_of_step": summ["ms"] / ms_res, "algorithmic_flop_per_step": summ["work"] / max(args.steps, 1)}
 
     r_dcn = roof("dcn_fwd_tc_kernel", "dcn_fwd (%s)" % args.dcn_precision, dcn)
-    label = "conv3d_tc %s (aggregation network + heads + DLA levels 2-5 + DCN offset convs: conv_tct_kernel / conv_tc_kernel)"
+    label = ("conv3d_tc %s (every convolution of the step except the 7x7 base layer: aggregation network, heads incl. 1x1 outputs, "
+             "DLA levels 0-5 incl. the stem block convolutions, DCN offset convs, strAM, feaRuduce: conv_tct_kernel / conv_tc_kernel)")
     r_cv = roof("conv_tc_kernel", label % "3xtf32", cv)
     r_cv16 = roof("conv_tc_kernel_f16", label % "3xfp16, kind::f16", cv16, f16=True)
+    for r in (r_cv16 if args.tc_format == "f16" else r_cv,):
+        for name, summ in (("launches_100gflop_and_more", cv_big), ("smaller_launches", cv_small)):
+            tf = summ["work"] / (summ["ms"] / 1000.0) / 1e12 if summ["ms"] > 0 else 0.0
+            r[name] = {"calls": summ["calls"], "achieved": tf, "frac": tf / pk["tf_sust"], "share_of_step": summ["ms"] / ms_res,
+                       "note": "aggregation network and head convolutions" if name.startswith("launches") else
+                               "DLA levels 2-5, stem block convolutions (algorithmic FLOPs of the 16-channel pixel-domain layers), "
+                               "DCN offset convolutions, 1x1 outputs, strAM / feaRuduce"}
     ranked = sorted([r_cv, r_cv16, r_dcn], key=lambda r: -r["share_of_step"])
     dominant, other, third = ranked
     if rank == 0:
@@ -727,9 +736,10 @@ def main():
                        "pairs_per_gpu_per_step": P, "micro_batch": mb, "parallelism": "pair-sharded x%d, all_gather(detections)" % world,
                        "dcn_precision": args.dcn_precision, "cudnn_tf32": bool(args.allow_tf32),
                        "tensor_core_convs": "cuDNN fp32 only" if args.cudnn_only else
-                       "3-D aggregation network, heads, DLA-34 levels 2-5 and the DCN offset convolutions on tcgen05 %s "
-                       "(fp32-class accuracy: 22-bit operands, fp32 accumulation, <= 1e-4 rel.); DLA stem as direct fp32 SIMT "
-                       "convolutions; strAM conv2d cuDNN fp32" % ("3xFP16 (kind::f16)" if args.tc_format == "f16" else "3xTF32"),
+                       "3-D aggregation network incl. the strAM gate convolution, heads incl. their 1x1 outputs, feaRuduce, DLA-34 levels "
+                       "0-5 (levels 0 / 1 as 2x2 space-to-depth block convolutions) and the DCN offset convolutions on tcgen05 %s "
+                       "(fp32-class accuracy: 22-bit operands, fp32 accumulation, <= 1e-4 rel.); the 7x7 base layer as a direct fp32 "
+                       "SIMT convolution; no cuDNN / cuBLAS kernel in the step" % ("3xFP16 (kind::f16)" if args.tc_format == "f16" else "3xTF32"),
                        "l2": "inputs larger than L2 (%.0f MB of images per step)" % (2 * P * 3 * H_IN * W_IN * 4 / 1e6)},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * 3 * H_IN * W_IN * 4,
                     "d2h_bytes_per_step": P * 100 * 22 * 4, "ms_per_step": ms_e2e / args.steps},

@@ -272,3 +272,12 @@ class OpTimer:
         ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
         work = sum(w for _, _, w, _ in recs)
         return dict(calls=len(recs), ms=ms, work=work)
+
+    def split_by_work(self, threshold, key=None):
+        """(summary of the calls with work >= threshold, summary of the others): large layers vs the many small launches."""
+        torch.cuda.synchronize()
+        out = []
+        for big in (True, False):
+            recs = [r for r in self.records if (key is None or r[3] == key) and ((r[2] >= threshold) == big)]
+            out.append(dict(calls=len(recs), ms=sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs), work=sum(r[2] for r in recs)))
+        return tuple(out)
