@@ -524,3 +524,11 @@ def test_stem_block_convolutions_match_direct_stem(lib):
     assert wb.shape == (64, 64, 3, 3) and float(wb.abs().sum()) == pytest.approx(4 * float(w.abs().sum()), rel=1e-6)
     wb2 = m._block_weights(m.level1[0].weight.detach(), 2)
     assert wb2.shape == (32, 64, 3, 3) and float(wb2.abs().sum()) == pytest.approx(float(m.level1[0].weight.abs().sum()), rel=1e-6)
+
+
+def test_cl_concat_matches_torch_cat(lib):
+    from side_b200 import ops
+    torch.manual_seed(1)
+    for dt, widths in ((torch.float16, (64, 64, 128)), (torch.float32, (32, 4, 96)), (torch.float16, (64, 12))):   # last: 24-byte rows -> torch.cat
+        ts = [torch.randn(2, 3, 5, 7, w, device="cuda").to(dt) for w in widths]
+        assert torch.equal(ops.cl_concat(ts), torch.cat(ts, -1))

@@ -166,3 +166,21 @@ def test_rejects_cpu_tensors(lib):
     with pytest.raises(RuntimeError):
         da.enumeration_depth(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8), torch.zeros(1, 4, 3), torch.zeros(1, 4),
                              torch.ones(2, 1), 1.0)
+
+
+def test_no_rois_and_no_pixels(lib):
+    """Empty RoI set and RoIs without a single valid pixel: shapes and the reference's early-exit values."""
+    from side_b200 import dense_align as da
+    img_l, img_r, calib, opt, box, borders, poses = dense_align_case()
+    e = lambda n: torch.zeros((0, n), device="cuda")
+    status, dis = da.align_parallel(calib, opt, img_l, img_r, e(4), e(2), e(7))
+    assert status.shape == (0,) and dis.shape == (0,)
+    L = da.prepare_image(img_l, opt.mean, opt.std, "cuda")
+    best, err, idx = da.enumeration_depth(L, L, torch.zeros(2, 0, 3, device="cuda"), torch.zeros(2, 0, device="cuda"),
+                                          torch.full((5, 2), 10.0, device="cuda"), 100.0, return_error=True)
+    assert float(err.abs().max()) == 0.0 and idx.cpu().tolist() == [0, 0] and best.cpu().tolist() == [10.0, 10.0]
+    # identical images: zero photometric error at every hypothesis for a far object (disparity below the sampling resolution)
+    uvz, w = da.sample(calib, 2, L.H, L.W, dev(box[:1] * 2), dev(poses[:1]), dev(borders[:1] * 2))
+    de = torch.full((3, 1), 1e6, device="cuda")
+    _, err, _ = da.enumeration_depth(L, L, uvz, w, de, float(calib.p2[0, 0] * 2 * 0.54), return_error=True)
+    assert float(err.max()) < 1e-3 * float(w.sum())

@@ -143,3 +143,17 @@ def test_voxel_variant_runs_on_gpu(lib):
         assert (z["depth"].cpu() - zc["depth"]).abs().max().item() < 1e-3 * zc["depth"].abs().max().item()
     finally:
         sn.input_h, sn.input_w = old
+
+
+def test_voxel_empty_and_bad_inputs(lib):
+    from side_b200 import ops
+    c = voxel_new_case()
+    f = torch.randn(2, 64, 24, 80, device="cuda")
+    args = [dev(c[k]) for k in ("p2", "p3", "fb", "trans", "trans_inv")]
+    empty = torch.zeros((0, 5), device="cuda")
+    vox, dori = ops.voxel_volume(f, f, empty, empty, *args, c["H_in"], c["W_in"])
+    assert vox.shape == (0, 192, 10, 10, 10) and dori.shape == (0,)
+    with pytest.raises(RuntimeError):                       # 32 channels: the kernel is built for the variant's 64
+        ops.voxel_volume(f[:, :32].contiguous(), f[:, :32].contiguous(), dev(c["left"]), dev(c["right"]), *args, c["H_in"], c["W_in"])
+    with pytest.raises(RuntimeError):                       # host tensors: no CPU path
+        ops.voxel_volume(f.cpu(), f.cpu(), dev(c["left"]), dev(c["right"]), *args, c["H_in"], c["W_in"])
