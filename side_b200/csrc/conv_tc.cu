@@ -30,7 +30,7 @@
 
 namespace side {
 
-constexpr int kCvThreads = 192;
+constexpr int kCvThreads = 320;        // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane group, alternating 16-column chunks)
 constexpr int kCvMaxStages = 6;
 constexpr int kCvBM = 128;
 constexpr int kCvMaxCout = 1536;       // all n-tiles' folded-BN vectors live in shared memory
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], 8);
             mbar_init(&fullA[i], 1);
             mbar_init(&emptyA[i], 1);
         }
@@ -289,14 +289,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
     } else {
         // ================= epilogue =================
+        // Low-K layers (DLA levels: 9 k-blocks per tile) are bound by this part, not by the MMAs (ncu: 34 % of the samples waited
+        // on the residual loads, tensor pipe 25 % active).  8 warps share a tile -- warps w and w + 4 read the same TMEM lane
+        // group (lanes 32 (w % 4) ..) and take alternating 16-column chunks -- and a warp requests the residual rows of its chunks
+        // BEFORE it waits for the accumulator.
         const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int chalf = (warp - 2) >> 2;       // which of the two warps of the lane group: chunks chalf, chalf + 2, ...
         const int m = lg * 32 + lane;
         int acc = 0;
         uint32_t acc_ph = 0;
         float amax = 0.f;                        // max |x| of what this thread splits into fp16 pairs (range guard)
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            mbar_wait(&tmem_full[acc], acc_ph);
-            tc_fence_after();
             const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
             int n, d0, h0, w0;
             conv_tile_origin(p, mt, n, d0, h0, w0);
@@ -307,9 +310,26 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             const size_t orow = !p.pool ? row
                                         : ((((size_t)n * p.D + d0 + dd) * (p.H >> 1) + ((h0 + hh) >> 1)) * (p.W >> 1) + ((w0 + ww) >> 1)) *
                                                   (size_t)p.ldy + (size_t)nt * N;       // pooled output voxel
+            float4 rres[4][4];                       // residual of this warp's chunks (N <= 128: 8 chunks over two warps)
+            if (p.residual && inb) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = (2 * q + chalf) * 16;
+                    if (c < N) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row + c);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rres[q][j] = __ldg(rp + j);
+                    }
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
             const int cbase = nt * N;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
-            for (int c = 0; c < ((p.dbg & 8) ? 0 : N); c += 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = (2 * q + chalf) * 16;
+                if (c >= N || (p.dbg & 8)) break;
                 float v[16], vx[16];
                 tc_ld16(taddr + (uint32_t)c, v);
                 tc_ld16(taddr + (uint32_t)(N + c), vx);
@@ -321,10 +341,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                     v[j] = o;
                 }
                 if (p.residual && inb) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(p.residual + row + c);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 rr = __ldg(rp + j);
+                        const float4 rr = rres[q][j];
                         v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
                     }
                 }

@@ -382,7 +382,7 @@ constexpr int kSepMaxD = 256;
 // the row stride is = 4 (mod 32) floats so the two rows a warp instruction touches are 4 banks apart: every shared load
 // of the slice loop is conflict-free whatever the box geometry.
 constexpr int kSepRowF = 4 * (kSepXq + 2) * kSepCC + 4;     // floats per ph row (1540): kSepXq real cells + 2 zero cells
-constexpr int kSepUSide = 16 * kSepRowF;                     // floats per side
+constexpr int kSepUSide = 16 * kSepRowF;                     // floats per side (ROWS = 16)
 
 // shared-memory load through a 32-bit shared-space address + immediate byte offset
 template <int IMM>
@@ -393,37 +393,42 @@ __device__ __forceinline__ float2 sep_lds2(uint32_t addr)
     return v;
 }
 
-template <bool WRITE, bool STATS, bool APPLY>
-__global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolParams p, const float *__restrict__ nhwcL,
-                                                                         const float *__restrict__ nhwcR,
-                                                                         float *__restrict__ partial)
+// ROWS = 16: one CTA of 512 threads per SM owns all 16 bin rows of (RoI, 8 channels).  ROWS = 8: the bin rows are split over
+// blockIdx.z = 0, 1; a CTA has 256 threads and half the window (98 KB), so TWO CTAs share an SM and the window build of one
+// (global loads, no stores) runs under the slice phase (stores) of the other -- the build is NOT repeated, each CTA builds
+// only its own rows.
+template <bool WRITE, bool STATS, bool APPLY, int ROWS>
+__global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(VolParams p, float *__restrict__ partial)
 {
-    extern __shared__ __align__(16) float U[];              // [2][16][kSepRowF]
+    constexpr int kThreads = 32 * ROWS, kUSide = ROWS * kSepRowF, kZ = 16 / ROWS;
+    extern __shared__ __align__(16) float U[];              // [2][ROWS][kSepRowF]
     __shared__ AxisTap ytab[32];
     __shared__ float4 geo[kSepMaxD];                         // lx1, bin_w(left), rx1, bin_w(right) per slice
     __shared__ short2 cellbuf[kSepMaxD][8];                  // (first, last) cell per slice and (side, quad)
     __shared__ int g_d1, g_win[8], g_wr[8];                  // current slice group: last slice, window start / width
     __shared__ int s_slow;
 
-    const int n = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x, c0 = chunk * kSepCC;
+    const int n = blockIdx.y, chunk = blockIdx.x, c0 = chunk * kSepCC;
+    const int ph0 = blockIdx.z * ROWS;                       // first bin row of this CTA
+    const int nslot = gridDim.x * kZ, slot = chunk * kZ + blockIdx.z;      // statistics partials: one slot per CTA of a RoI
     const int C = p.C, D = p.D, W = p.W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSepThreads >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kThreads >> 5;
     const size_t cs = (size_t)D * 256;
     float *outn = p.cost + ((size_t)n * 3 * C + c0) * cs;
 
     if (p.valid && !p.valid[n]) {
         if (WRITE) {
-            for (int i = tid; i < 3 * kSepCC * D * 64; i += kSepThreads) {
-                const int q4 = i & 63, rest = i >> 6, d = rest % D, ch = rest / D;     // ch = which * 8 + cc
-                st_cs(reinterpret_cast<float4 *>(outn + ((size_t)(ch >> 3) * C + (ch & 7)) * cs + (size_t)d * 256) + q4,
+            for (int i = tid; i < 3 * kSepCC * D * 4 * ROWS; i += kThreads) {
+                const int q4 = i % (4 * ROWS), rest = i / (4 * ROWS), d = rest % D, ch = rest / D;     // ch = which * 8 + cc
+                st_cs(reinterpret_cast<float4 *>(outn + ((size_t)(ch >> 3) * C + (ch & 7)) * cs + (size_t)d * 256 + ph0 * 16) + q4,
                       make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            if (chunk == 0)
-                for (int d = tid; d < D; d += kSepThreads) p.depth_bin[(size_t)n * D + d] = 0.f;
+            if (slot == 0)
+                for (int d = tid; d < D; d += kThreads) p.depth_bin[(size_t)n * D + d] = 0.f;
         }
         if (STATS)
-            for (int d = tid; d < D; d += kSepThreads)
-                *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int d = tid; d < D; d += kThreads)
+                *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
 
@@ -431,22 +436,22 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
     const int b = min(max((int)lb[0], 0), p.B - 1);
     const float fb = p.fb[b];
     if (tid == 0) s_slow = 0;
-    for (int d = tid; d < D; d += kSepThreads) {
+    for (int d = tid; d < D; d += kThreads) {
         float dbin, lx1, lx2, rx1, rx2, y1, y2;
         proposal_for(lb, rb, fb, d, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
         const float rwl = fmaxf(__fsub_rn(lx2, lx1), 1.0f), rwr = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
         geo[d] = make_float4(lx1, __fmul_rn(rwl, 0.0625f), rx1, __fmul_rn(rwr, 0.0625f));   // == rw / 16 exactly
-        if (WRITE && chunk == 0) p.depth_bin[(size_t)n * D + d] = dbin;
+        if (WRITE && slot == 0) p.depth_bin[(size_t)n * D + d] = dbin;
     }
     if (tid < 32) {
         float dbin, lx1, lx2, rx1, rx2, y1, y2;
         proposal_for(lb, rb, fb, 0, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
         const float rh = fmaxf(__fsub_rn(y2, y1), 1.0f);
-        ytab[tid] = to_tap(axis_sample(y1, __fmul_rn(rh, 0.0625f), tid >> 1, tid & 1, p.H), W * C);
+        ytab[tid] = to_tap(axis_sample(y1, __fmul_rn(rh, 0.0625f), tid >> 1, tid & 1, p.H), W);      // NCHW row offsets
     }
     __syncthreads();
     // cells touched by each lane-quad (x-samples 8q .. 8q+7) of each slice, both sides
-    for (int i = tid; i < D * 8; i += kSepThreads) {
+    for (int i = tid; i < D * 8; i += kThreads) {
         const int d = i >> 3, sq = i & 7, q = sq & 3;
         const float4 g4 = geo[d];
         int a0, a1;
@@ -457,8 +462,9 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
     __syncthreads();
 
     if (s_slow) {
-        const float *fLb = nhwcL + (size_t)b * p.H * W * C + c0;
-        const float *fRb = nhwcR + (size_t)b * p.H * W * C + c0;
+        const size_t plane = (size_t)p.H * W;
+        const float *fLb = p.featL + ((size_t)b * C + c0) * plane;
+        const float *fRb = p.featR + ((size_t)b * C + c0) * plane;
         // Very wide box (> ~90 feature columns, or garbage): the same formula evaluated straight from global memory,
         // one slice at a time.  Results are identical to the fast path's.
         float *red = U;
@@ -468,27 +474,27 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
             float g = 1.0f;
             if (APPLY) {
                 float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-                for (int j = 0; j < nchunk; ++j) {
-                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nchunk + j) * 4);
+                for (int j = 0; j < nslot; ++j) {
+                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nslot + j) * 4);
                     t0 += ps.x; t1 += ps.y; t2 += ps.z;
                 }
                 g = __fdiv_rn(t2, fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f));
-                if (chunk == 0 && tid == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+                if (slot == 0 && tid == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
             }
-            for (int idx = tid; idx < 256 * kSepCC; idx += kSepThreads) {
-                const int c1 = idx & 7, q = idx >> 3, ph = q >> 4, pw = q & 15;
+            for (int idx = tid; idx < 16 * ROWS * kSepCC; idx += kThreads) {
+                const int c1 = idx & 7, q = (idx >> 3) + ph0 * 16, ph = q >> 4, pw = q & 15;
                 const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
                 float lr[2];
 #pragma unroll
                 for (int side = 0; side < 2; ++side) {
-                    const float *f = (side ? fRb : fLb) + c1;
+                    const float *f = (side ? fRb : fLb) + (size_t)c1 * plane;
                     float t = 0.f;
 #pragma unroll
                     for (int ix = 0; ix < 2; ++ix) {
                         const AxisSample sx = axis_sample(side ? g4.z : g4.x, side ? g4.w : g4.y, pw, ix, W);
                         float ulo = 0.f, uhi = 0.f, wq = 0.f;
                         if (sx.lo >= 0) {
-                            const float *a = f + (size_t)sx.lo * C, *bq = f + (size_t)sx.hi * C;
+                            const float *a = f + sx.lo, *bq = f + sx.hi;
                             ulo = fmaf(t0.l, __ldg(a + t0.ohi), t0.h * __ldg(a + t0.olo)) + fmaf(t1.l, __ldg(a + t1.ohi), t1.h * __ldg(a + t1.olo));
                             uhi = fmaf(t0.l, __ldg(bq + t0.ohi), t0.h * __ldg(bq + t0.olo)) + fmaf(t1.l, __ldg(bq + t1.ohi), t1.h * __ldg(bq + t1.olo));
                             wq = 0.25f * sx.l;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
             if (STATS) {
                 block_sum<4>(sv, red);
                 if (tid == 0)
-                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(sv[0], sv[1], sv[2], 0.f);
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(sv[0], sv[1], sv[2], 0.f);
                 __syncthreads();
             }
         }
@@ -542,41 +548,72 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
         const int d1 = g_d1;
         // ---- build U: local cells 0..wr-1 real, cells wr and wr+1 = zeros (invalid samples read (wr, wr+1); a sample
         //      clamped at the right border reads (W-1, W) with weight 0 on the second) ----
+        //      The features are read as they are (NCHW, no staging copy): a task = (side, bin row, channel, 4 consecutive columns);
+        //      a warp covers 8 channels x 4 bin rows of one column group, loads the (up to) four feature rows of its y samples as
+        //      16-byte vectors ALONG x and scatters the four results into the sub-windows of the quads that contain the column
+        //      (bank = 4 ph + 8 quad + c: at most 2-way conflicts), so a column is loaded and interpolated once, not once per quad.
         {
-            int ncell = 0;
+            int win[8], wr[8], xa[2], nx4 = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ncell = max(ncell, g_wr[k]);
-            ncell += 2;
-            const size_t img = (size_t)b * p.H * W * C + c0;
-            const int per_side = 16 * ncell * 8;
-            // branch-free body (clamped address, value selected afterwards) so that the unrolled iterations' 16 loads
-            // are all in flight together: the build is latency-bound, not bandwidth-bound
+            for (int k = 0; k < 8; ++k) { win[k] = g_win[k]; wr[k] = g_wr[k]; }
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                int lo = win[4 * sd], hi = win[4 * sd] + wr[4 * sd];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) { lo = min(lo, win[4 * sd + k]); hi = max(hi, win[4 * sd + k] + wr[4 * sd + k]); }
+                xa[sd] = lo & ~3;
+                nx4 = max(nx4, (hi - xa[sd] + 3) >> 2);
+            }
+            const size_t plane = (size_t)p.H * W;
+            const size_t img = ((size_t)b * C + c0) * plane;
+            const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.featL) | reinterpret_cast<uintptr_t>(p.featR)) & 15) == 0;
+            const int ntask = 2 * ROWS * 8 * nx4;
+            // branch-light body so that the unrolled iterations' loads are all in flight together: the build is latency-bound
 #pragma unroll 4
-            for (int it = tid; it < 2 * per_side; it += kSepThreads) {
-                const int side = it >= per_side, i2 = it - side * per_side;
-                const int half = i2 & 1, q = (i2 >> 1) & 3, r2 = i2 >> 3, cell = r2 % ncell, ph = r2 / ncell;
-                const int wr = g_wr[4 * side + q];
-                const int x = g_win[4 * side + q] + cell;
-                const bool real = cell < wr && x <= W - 1;
-                const AxisTap t0 = ytab[2 * ph], t1 = ytab[2 * ph + 1];
-                const float *fx = (side ? nhwcR : nhwcL) + img + (size_t)min(x, W - 1) * C + 4 * half;
-                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(fx + t0.olo));
-                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(fx + t0.ohi));
-                // the two y sub-samples of a bin usually fall in the same cell or in adjacent ones: reuse the rows already
-                // loaded (ph is uniform across a warp except at row boundaries, so these branches do not diverge)
-                float4 b0 = a0, b1 = a1;
-                if (t1.olo != t0.olo || t1.ohi != t0.ohi) {
-                    b0 = (t1.olo == t0.ohi) ? a1 : __ldg(reinterpret_cast<const float4 *>(fx + t1.olo));
-                    b1 = __ldg(reinterpret_cast<const float4 *>(fx + t1.ohi));
+            for (int it = tid; it < ntask; it += kThreads) {
+                const int c = it & 7, ph = (it >> 3) & (ROWS - 1), r = it / (8 * ROWS), x4 = r % nx4, side = r / nx4;
+                const int x = xa[side] + 4 * x4;
+                const AxisTap t0 = ytab[2 * (ph0 + ph)], t1 = ytab[2 * (ph0 + ph) + 1];
+                const float *fx = (side ? p.featR : p.featL) + img + (size_t)c * plane;
+                float4 a0, a1, b0, b1;
+                if (vec) {
+                    const float *fv = fx + min(x, W - 4);
+                    a0 = __ldg(reinterpret_cast<const float4 *>(fv + t0.olo));
+                    a1 = __ldg(reinterpret_cast<const float4 *>(fv + t0.ohi));
+                    // the two y sub-samples of a bin usually fall in the same cell or in adjacent ones: reuse the rows already loaded
+                    b0 = a0; b1 = a1;
+                    if (t1.olo != t0.olo || t1.ohi != t0.ohi) {
+                        b0 = (t1.olo == t0.ohi) ? a1 : __ldg(reinterpret_cast<const float4 *>(fv + t1.olo));
+                        b1 = __ldg(reinterpret_cast<const float4 *>(fv + t1.ohi));
+                    }
+                } else {
+                    const int x0 = min(x, W - 1), x1 = min(x + 1, W - 1), x2 = min(x + 2, W - 1), x3 = min(x + 3, W - 1);
+                    a0 = make_float4(__ldg(fx + t0.olo + x0), __ldg(fx + t0.olo + x1), __ldg(fx + t0.olo + x2), __ldg(fx + t0.olo + x3));
+                    a1 = make_float4(__ldg(fx + t0.ohi + x0), __ldg(fx + t0.ohi + x1), __ldg(fx + t0.ohi + x2), __ldg(fx + t0.ohi + x3));
+                    b0 = make_float4(__ldg(fx + t1.olo + x0), __ldg(fx + t1.olo + x1), __ldg(fx + t1.olo + x2), __ldg(fx + t1.olo + x3));
+                    b1 = make_float4(__ldg(fx + t1.ohi + x0), __ldg(fx + t1.ohi + x1), __ldg(fx + t1.ohi + x2), __ldg(fx + t1.ohi + x3));
                 }
-                float4 u;
-                u.x = fmaf(t0.l, a1.x, t0.h * a0.x) + fmaf(t1.l, b1.x, t1.h * b0.x);
-                u.y = fmaf(t0.l, a1.y, t0.h * a0.y) + fmaf(t1.l, b1.y, t1.h * b0.y);
-                u.z = fmaf(t0.l, a1.z, t0.h * a0.z) + fmaf(t1.l, b1.z, t1.h * b0.z);
-                u.w = fmaf(t0.l, a1.w, t0.h * a0.w) + fmaf(t1.l, b1.w, t1.h * b0.w);
-                if (!real) u = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cell <= wr + 1)
-                    *reinterpret_cast<float4 *>(U + side * kSepUSide + (size_t)ph * kSepRowF + (4 * cell + q) * kSepCC + 4 * half) = u;
+                float u[4];
+                u[0] = fmaf(t0.l, a1.x, t0.h * a0.x) + fmaf(t1.l, b1.x, t1.h * b0.x);
+                u[1] = fmaf(t0.l, a1.y, t0.h * a0.y) + fmaf(t1.l, b1.y, t1.h * b0.y);
+                u[2] = fmaf(t0.l, a1.z, t0.h * a0.z) + fmaf(t1.l, b1.z, t1.h * b0.z);
+                u[3] = fmaf(t0.l, a1.w, t0.h * a0.w) + fmaf(t1.l, b1.w, t1.h * b0.w);
+                float *urow = U + side * kUSide + (size_t)ph * kSepRowF + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    const float v = xx <= W - 1 ? u[j] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cell = xx - (side ? win[4 + q] : win[q]);
+                        if (cell >= 0 && cell < (side ? wr[4 + q] : wr[q])) urow[(4 * cell + q) * kSepCC] = v;
+                    }
+                }
+            }
+            // the two zero cells behind each sub-window
+            for (int it = tid; it < 2 * 4 * ROWS * 2 * kSepCC; it += kThreads) {
+                const int c = it & 7, z = (it >> 3) & 1, q = (it >> 4) & 3, ph = (it >> 6) & (ROWS - 1), side = it >> (6 + (ROWS == 16 ? 4 : 3));
+                U[side * kUSide + (size_t)ph * kSepRowF + (4 * (g_wr[4 * side + q] + z) + q) * kSepCC + c] = 0.f;
             }
         }
         __syncthreads();
@@ -618,23 +655,23 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
             float g = 1.0f;
             if (APPLY) {
                 float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-                if (lane < nchunk) {
-                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nchunk + lane) * 4);
-                    t0 = ps.x; t1 = ps.y; t2 = ps.z;
+                for (int j = lane; j < nslot; j += 32) {
+                    const float4 ps = *reinterpret_cast<const float4 *>(partial + (((size_t)n * D + d) * nslot + j) * 4);
+                    t0 += ps.x; t1 += ps.y; t2 += ps.z;
                 }
                 t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
                 const float den = fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f);
                 g = __fdiv_rn(t2, den);
-                if (chunk == 0 && lane == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+                if (slot == 0 && lane == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
             }
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
             constexpr int kRowBytes = kSepRowF * 4;
-            constexpr int kR = kSepUSide * 4;                         // byte distance of the right-view table
+            constexpr int kR = kUSide * 4;                            // byte distance of the right-view table
             const size_t side_stride = (size_t)C * cs;                // L -> R -> L-R planes
             uint32_t uL = smem_u32(U + phsel * kSepRowF + 2 * ccl);   // this lane's channel pair (2 ccl, 2 ccl + 1)
-            float *o = outn + (size_t)(2 * ccl) * cs + (size_t)d * 256 + phsel * 16 + 4 * quad;
+            float *o = outn + (size_t)(2 * ccl) * cs + (size_t)d * 256 + (ph0 + phsel) * 16 + 4 * quad;
 #pragma unroll 1
-            for (int rp2 = 0; rp2 < 4; ++rp2, uL += 4 * kRowBytes, o += 64) {
+            for (int rp2 = 0; rp2 < ROWS / 4; ++rp2, uL += 4 * kRowBytes, o += 64) {
 #pragma unroll
                 for (int rp = 0; rp < 2; ++rp) {                      // row pair within this iteration
                     float l0[4], l1[4], r0[4], r1[4];                 // [bin] for the two channels, left / right view
@@ -690,7 +727,7 @@ __global__ void __launch_bounds__(kSepThreads, 1) inst_costvol_sep_kernel(VolPar
             if (STATS) {
                 s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
                 if (lane == 0)
-                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nchunk + chunk) * 4) = make_float4(s0, s1, s2, 0.f);
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(s0, s1, s2, 0.f);
             }
         }
         __syncthreads();
@@ -1113,7 +1150,8 @@ using namespace side;
 extern "C" size_t side_inst_costvol_fast_ws_bytes(int B, int C, int H, int W, int N, int D)
 {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0 || D <= 0) return 0;
-    return sizeof(float) * (2 * (size_t)B * C * H * W + 4 * (size_t)N * D * ((C + kSepCC - 1) / kSepCC));
+    // gate-statistics partials only (2 slots per 8-channel chunk); the separable kernel reads the NCHW features in place
+    return sizeof(float) * (8 * (size_t)N * D * ((C + kSepCC - 1) / kSepCC) + 64);
 }
 
 extern "C" size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W)
@@ -1158,30 +1196,35 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
             set_error("inst_costvol: the separable path needs side_inst_costvol_fast_ws_bytes(...) bytes of device workspace");
             return SIDE_ERR_WORKSPACE;
         }
-        float *nl = reinterpret_cast<float *>(ws), *nr = nl + (size_t)B * C * H * W, *partial = nr + (size_t)B * C * H * W;
-        if ((rc = launch_nchw_to_nhwc(featL, nl, B, C, H * W, st))) return rc;
-        if ((rc = launch_nchw_to_nhwc(featR, nr, B, C, H * W, st))) return rc;
-        const size_t smem = sizeof(float) * 2 * kSepUSide;
-        const dim3 sg((unsigned)(C / kSepCC), (unsigned)N);
+        float *partial = reinterpret_cast<float *>(ws);
         const bool want_xc = (flags & SIDE_VOL_XCROSS) && xcross != nullptr;
+        static const int rows_env = [] { const char *e = getenv("SIDE_SEP_ROWS"); return e ? atoi(e) : 0; }();
+        const int rows = rows_env == 16 ? 16 : 8;
+#define SIDE_SEP_LAUNCH(WR, ST, AP, what)                                                                                      \
+    do {                                                                                                                       \
+        if (rows == 16) {                                                                                                      \
+            const size_t smem = sizeof(float) * 2 * 16 * kSepRowF;                                                             \
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<WR, ST, AP, 16>, smem))) return rc;                  \
+            inst_costvol_sep_kernel<WR, ST, AP, 16><<<dim3((unsigned)(C / kSepCC), (unsigned)N, 1), 512, smem, st>>>(p, partial); \
+        } else {                                                                                                               \
+            const size_t smem = sizeof(float) * 2 * 8 * kSepRowF;                                                              \
+            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<WR, ST, AP, 8>, smem))) return rc;                   \
+            inst_costvol_sep_kernel<WR, ST, AP, 8><<<dim3((unsigned)(C / kSepCC), (unsigned)N, 2), 256, smem, st>>>(p, partial);  \
+        }                                                                                                                      \
+        SIDE_LAUNCH_CHECK(what);                                                                                               \
+    } while (0)
+        const int nslot = (C / kSepCC) * (16 / rows);
         if (gate) {
-            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<false, true, false>, smem))) return rc;
-            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, false, true>, smem))) return rc;
-            inst_costvol_sep_kernel<false, true, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
-            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<stats>");
-            inst_costvol_sep_kernel<true, false, true><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
-            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write, gate>");
+            SIDE_SEP_LAUNCH(false, true, false, "inst_costvol_sep_kernel<stats>");
+            SIDE_SEP_LAUNCH(true, false, true, "inst_costvol_sep_kernel<write, gate>");
         } else if (want_xc) {
-            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, true, false>, smem))) return rc;
-            inst_costvol_sep_kernel<true, true, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
-            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write, stats>");
-            sep_finish_xcross_kernel<<<ceil_div((long long)N * D, 128), 128, 0, st>>>(partial, valid, xcross, N * D, D, C / kSepCC);
+            SIDE_SEP_LAUNCH(true, true, false, "inst_costvol_sep_kernel<write, stats>");
+            sep_finish_xcross_kernel<<<ceil_div((long long)N * D, 128), 128, 0, st>>>(partial, valid, xcross, N * D, D, nslot);
             SIDE_LAUNCH_CHECK("sep_finish_xcross_kernel");
         } else {
-            if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<true, false, false>, smem))) return rc;
-            inst_costvol_sep_kernel<true, false, false><<<sg, kSepThreads, smem, st>>>(p, nl, nr, partial);
-            SIDE_LAUNCH_CHECK("inst_costvol_sep_kernel<write>");
+            SIDE_SEP_LAUNCH(true, false, false, "inst_costvol_sep_kernel<write>");
         }
+#undef SIDE_SEP_LAUNCH
         return SIDE_OK;
     }
     // channels-last fast path: needs the transposed copies (workspace), C % 4 == 0, P*P % 4 == 0 and the padded
