@@ -408,9 +408,12 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
     __shared__ int g_d1, g_win[8], g_wr[8];                  // current slice group: last slice, window start / width
     __shared__ int s_slow;
 
-    const int n = blockIdx.y, chunk = blockIdx.x, c0 = chunk * kSepCC;
-    const int ph0 = blockIdx.z * ROWS;                       // first bin row of this CTA
-    const int nslot = gridDim.x * kZ, slot = chunk * kZ + blockIdx.z;      // statistics partials: one slot per CTA of a RoI
+    // the row halves of a (RoI, chunk) are neighbours in dispatch order: they run at the same time and their 512-byte halves of
+    // every 1 KB output plane meet in L2 before they are written back
+    const int n = blockIdx.y, chunk = blockIdx.x / kZ, zhalf = blockIdx.x % kZ, nchunk = gridDim.x / kZ, c0 = chunk * kSepCC;
+    const int ph0 = zhalf * ROWS;                            // first bin row of this CTA
+    constexpr int kUnits = ROWS / 4;                         // groups of 4 bin rows
+    const int nslot = nchunk * kZ, slot0 = chunk * kZ + zhalf;             // statistics partials: one slot per CTA of a RoI
     const int C = p.C, D = p.D, W = p.W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kThreads >> 5;
     const size_t cs = (size_t)D * 256;
@@ -423,12 +426,12 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
                 st_cs(reinterpret_cast<float4 *>(outn + ((size_t)(ch >> 3) * C + (ch & 7)) * cs + (size_t)d * 256 + ph0 * 16) + q4,
                       make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            if (slot == 0)
+            if (slot0 == 0)
                 for (int d = tid; d < D; d += kThreads) p.depth_bin[(size_t)n * D + d] = 0.f;
         }
         if (STATS)
             for (int d = tid; d < D; d += kThreads)
-                *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot0) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
 
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
         proposal_for(lb, rb, fb, d, D, p.x_clamp, dbin, lx1, lx2, rx1, rx2, y1, y2);
         const float rwl = fmaxf(__fsub_rn(lx2, lx1), 1.0f), rwr = fmaxf(__fsub_rn(rx2, rx1), 1.0f);
         geo[d] = make_float4(lx1, __fmul_rn(rwl, 0.0625f), rx1, __fmul_rn(rwr, 0.0625f));   // == rw / 16 exactly
-        if (WRITE && slot == 0) p.depth_bin[(size_t)n * D + d] = dbin;
+        if (WRITE && slot0 == 0) p.depth_bin[(size_t)n * D + d] = dbin;
     }
     if (tid < 32) {
         float dbin, lx1, lx2, rx1, rx2, y1, y2;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
                     t0 += ps.x; t1 += ps.y; t2 += ps.z;
                 }
                 g = __fdiv_rn(t2, fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f));
-                if (slot == 0 && tid == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+                if (slot0 == 0 && tid == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
             }
             for (int idx = tid; idx < 16 * ROWS * kSepCC; idx += kThreads) {
                 const int c1 = idx & 7, q = (idx >> 3) + ph0 * 16, ph = q >> 4, pw = q & 15;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
             if (STATS) {
                 block_sum<4>(sv, red);
                 if (tid == 0)
-                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(sv[0], sv[1], sv[2], 0.f);
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot0) * 4) = make_float4(sv[0], sv[1], sv[2], 0.f);
                 __syncthreads();
             }
         }
@@ -578,9 +581,10 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
                 float4 a0, a1, b0, b1;
                 if (vec) {
                     const float *fv = fx + min(x, W - 4);
+                    // the two y sub-samples of a bin usually fall in the same row pair or in adjacent ones: reuse the rows already
+                    // loaded (unconditional loads of all four rows were measured: 10 % slower, the L1 pipe is the busy unit)
                     a0 = __ldg(reinterpret_cast<const float4 *>(fv + t0.olo));
                     a1 = __ldg(reinterpret_cast<const float4 *>(fv + t0.ohi));
-                    // the two y sub-samples of a bin usually fall in the same cell or in adjacent ones: reuse the rows already loaded
                     b0 = a0; b1 = a1;
                     if (t1.olo != t0.olo || t1.ohi != t0.ohi) {
                         b0 = (t1.olo == t0.ohi) ? a1 : __ldg(reinterpret_cast<const float4 *>(fv + t1.olo));
@@ -617,7 +621,8 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
             }
         }
         __syncthreads();
-        // ---- one warp per slice ----
+        // ---- one warp per slice (units of (slice, 4 bin rows) were measured: the repeated per-unit set-up costs more than the
+        //      better balance of the last round returns) ----
         for (int d = d0 + warp; d <= d1; d += nwarps) {
             const float4 g4 = geo[d];
             // x-sample `lane` of this slice (it belongs to quad lane >> 3): byte offset of its first cell inside that quad's
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
                 t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
                 const float den = fmaxf(__fmul_rn(sqrtf(t0), sqrtf(t1)), 0.01f);
                 g = __fdiv_rn(t2, den);
-                if (slot == 0 && lane == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
+                if (slot0 == 0 && lane == 0 && p.xcross) p.xcross[(size_t)n * D + d] = g;
             }
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
             constexpr int kRowBytes = kSepRowF * 4;
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
             uint32_t uL = smem_u32(U + phsel * kSepRowF + 2 * ccl);   // this lane's channel pair (2 ccl, 2 ccl + 1)
             float *o = outn + (size_t)(2 * ccl) * cs + (size_t)d * 256 + (ph0 + phsel) * 16 + 4 * quad;
 #pragma unroll 1
-            for (int rp2 = 0; rp2 < ROWS / 4; ++rp2, uL += 4 * kRowBytes, o += 64) {
+            for (int rp2 = 0; rp2 < kUnits; ++rp2, uL += 4 * kRowBytes, o += 64) {
 #pragma unroll
                 for (int rp = 0; rp < 2; ++rp) {                      // row pair within this iteration
                     float l0[4], l1[4], r0[4], r1[4];                 // [bin] for the two channels, left / right view
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(32 * ROWS, 16 / ROWS) inst_costvol_sep_kernel(
             if (STATS) {
                 s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
                 if (lane == 0)
-                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot) * 4) = make_float4(s0, s1, s2, 0.f);
+                    *reinterpret_cast<float4 *>(partial + (((size_t)n * D + d) * nslot + slot0) * 4) = make_float4(s0, s1, s2, 0.f);
             }
         }
         __syncthreads();
@@ -1150,8 +1155,8 @@ using namespace side;
 extern "C" size_t side_inst_costvol_fast_ws_bytes(int B, int C, int H, int W, int N, int D)
 {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0 || D <= 0) return 0;
-    // gate-statistics partials only (2 slots per 8-channel chunk); the separable kernel reads the NCHW features in place
-    return sizeof(float) * (8 * (size_t)N * D * ((C + kSepCC - 1) / kSepCC) + 64);
+    // gate-statistics partials only (up to 4 slots of 4 floats per 8-channel chunk); the separable kernel reads the NCHW features in place
+    return sizeof(float) * (16 * (size_t)N * D * ((C + kSepCC - 1) / kSepCC) + 64);
 }
 
 extern "C" size_t side_inst_costvol_ws_bytes(int B, int C, int H, int W)
@@ -1200,6 +1205,7 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
         const bool want_xc = (flags & SIDE_VOL_XCROSS) && xcross != nullptr;
         static const int rows_env = [] { const char *e = getenv("SIDE_SEP_ROWS"); return e ? atoi(e) : 0; }();
         const int rows = rows_env == 16 ? 16 : 8;
+
 #define SIDE_SEP_LAUNCH(WR, ST, AP, what)                                                                                      \
     do {                                                                                                                       \
         if (rows == 16) {                                                                                                      \
@@ -1209,7 +1215,7 @@ extern "C" int side_inst_costvol_fwd(const float *featL, const float *featR, con
         } else {                                                                                                               \
             const size_t smem = sizeof(float) * 2 * 8 * kSepRowF;                                                              \
             if ((rc = set_smem_attr((const void *)inst_costvol_sep_kernel<WR, ST, AP, 8>, smem))) return rc;                   \
-            inst_costvol_sep_kernel<WR, ST, AP, 8><<<dim3((unsigned)(C / kSepCC), (unsigned)N, 2), 256, smem, st>>>(p, partial);  \
+            inst_costvol_sep_kernel<WR, ST, AP, 8><<<dim3((unsigned)(2 * (C / kSepCC)), (unsigned)N, 1), 256, smem, st>>>(p, partial);  \
         }                                                                                                                      \
         SIDE_LAUNCH_CHECK(what);                                                                                               \
     } while (0)
