@@ -63,7 +63,11 @@ struct ConvTcParams {
     float acc_fix;                    // 1 + (MMA steps per accumulator) * 2^-26: undoes the accumulator's truncation bias
     int dbg;                          // timing experiments only (side_conv_tc_set_mode bits 1, 2): skip the B / A copies
     uint32_t a_part;                  // bytes of one half (hi or lo) of an A slot
+    int stg;                          // 1: epilogue staged through shared memory (coalesced global accesses), see the epilogue
+    uint32_t stg_off;                 // byte offset of the staging area behind the operand ring
 };
+constexpr int kCvStgRowF = 36;                              // floats per staged row: 32 columns + 4 pad (conflict-free 16-byte accesses)
+constexpr uint32_t kCvStgBytes = 8u * 32u * kCvStgRowF * 4u;   // 8 epilogue warps x 32 rows
 
 // m-tile -> first voxel coordinates of its box
 __device__ __forceinline__ void conv_tile_origin(const ConvTcParams &p, int mt, int &n, int &d0, int &h0, int &w0)
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ __align__(8) uint64_t tmem_full[2];
     __shared__ __align__(8) uint64_t tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_scale[kCvMaxCout], s_shift[kCvMaxCout];
+    __shared__ __align__(16) float s_scale[kCvMaxCout], s_shift[kCvMaxCout];
 
     constexpr int kKel = F16 ? 64 : 32;      // channels per 128-byte k-block row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -294,7 +298,119 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         // group (lanes 32 (w % 4) ..) and take alternating 16-column chunks -- and a warp requests the residual rows of its chunks
         // BEFORE it waits for the accumulator.
         const int lg = warp & 3;                 // TMEM lane group this warp may read
-        const int chalf = (warp - 2) >> 2;       // which of the two warps of the lane group: chunks chalf, chalf + 2, ...
+        const int chalf = (warp - 2) >> 2;       // which of the two warps of the lane group
+        if (p.stg) {
+            // ---- staged epilogue (2-D layers: few k-blocks per tile, the epilogue is what bounds them) ----
+            // With a thread per accumulator row, every global access of a warp touches 32 different 128-byte lines (32 L1
+            // wavefronts per instruction; ncu: the LSU, not the tensor pipe or DRAM, was the busy unit on the DLA layers).  Here a
+            // warp owns 32 rows x 32 columns: it dumps the raw accumulator sums into its private staging rows, and then walks the
+            // region with lanes ALONG the channels (8 lanes = 128 contiguous bytes of one output row): BatchNorm, residual, ReLU,
+            // the operand split and all global loads / stores happen in that coalesced phase (4 wavefronts per instruction).
+            float *stg = reinterpret_cast<float *>(tiles + p.stg_off) + (size_t)(warp - 2) * (32 * kCvStgRowF);
+            const int sr = lane >> 3, sc4 = (lane & 7) * 4;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            float amax = 0.f;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+                int n, d0, h0, w0;
+                conv_tile_origin(p, mt, n, d0, h0, w0);
+                size_t rowoff[8];                        // float offset of the first channel of the 8 rows this lane stores
+                uint32_t rin = 0;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int mm = lg * 32 + it * 4 + sr;
+                    const int ww = mm % p.bw, r1 = mm / p.bw, hh = r1 % p.bh, dd = r1 / p.bh;
+                    if (d0 + dd < p.D) rin |= 1u << it;
+                    rowoff[it] = ((((size_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww) * (size_t)p.ldy + (size_t)nt * N;
+                }
+                const int cbase = nt * N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
+                bool waited = false;
+                for (int c0 = 32 * chalf; ; c0 += 64) {
+                    const bool work = c0 < N;
+                    const bool active = work && c0 + sc4 < N;
+                    float4 rres[8];
+                    if (active && p.residual) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            if (rin >> it & 1) rres[it] = __ldg(reinterpret_cast<const float4 *>(p.residual + rowoff[it] + c0 + sc4));
+                    }
+                    if (!waited) {
+                        mbar_wait(&tmem_full[acc], acc_ph);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    if (!work) {
+                        if (32 * chalf >= N) {           // a warp without columns (N <= 32) still hands the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        }
+                        break;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = c0 + 16 * h;
+                        if (c < N) {
+                            float v[16], vx[16];
+                            tc_ld16(taddr + (uint32_t)c, v);
+                            tc_ld16(taddr + (uint32_t)(N + c), vx);
+                            float4 *sp = reinterpret_cast<float4 *>(stg + lane * kCvStgRowF + 16 * h);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 o;
+                                o.x = F16 ? fmaf(vx[4 * j], kF16LoInv, v[4 * j] * p.acc_fix) : fmaf(v[4 * j], p.acc_fix, vx[4 * j]);
+                                o.y = F16 ? fmaf(vx[4 * j + 1], kF16LoInv, v[4 * j + 1] * p.acc_fix) : fmaf(v[4 * j + 1], p.acc_fix, vx[4 * j + 1]);
+                                o.z = F16 ? fmaf(vx[4 * j + 2], kF16LoInv, v[4 * j + 2] * p.acc_fix) : fmaf(v[4 * j + 2], p.acc_fix, vx[4 * j + 2]);
+                                o.w = F16 ? fmaf(vx[4 * j + 3], kF16LoInv, v[4 * j + 3] * p.acc_fix) : fmaf(v[4 * j + 3], p.acc_fix, vx[4 * j + 3]);
+                                sp[j] = o;
+                            }
+                        }
+                    }
+                    if (c0 + 64 >= N) {                  // last region of this warp: the accumulator is free again
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    __syncwarp();
+                    if (active) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + cbase + c0 + sc4);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + cbase + c0 + sc4);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            if (!(rin >> it & 1)) continue;
+                            float4 v = *reinterpret_cast<const float4 *>(stg + (it * 4 + sr) * kCvStgRowF + sc4);
+                            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                            if (p.relu == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (p.residual) { v.x += rres[it].x; v.y += rres[it].y; v.z += rres[it].z; v.w += rres[it].w; }
+                            if (p.relu == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            const size_t o = rowoff[it] + c0 + sc4;
+                            if (p.y) *reinterpret_cast<float4 *>(p.y + o) = v;
+                            if (F16 && p.y_hi) {
+                                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                                uint32_t h0, l0, h1, l1;
+                                f16_split2(v.x, v.y, h0, l0);
+                                f16_split2(v.z, v.w, h1, l1);
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.y_hi) + o) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.y_lo) + o) = make_uint2(l0, l1);
+                            } else if (p.y_hi) {
+                                float4 h, l;
+                                h.x = tf32_hi(v.x); l.x = v.x - h.x;
+                                h.y = tf32_hi(v.y); l.y = v.y - h.y;
+                                h.z = tf32_hi(v.z); l.z = v.z - h.z;
+                                h.w = tf32_hi(v.w); l.w = v.w - h.w;
+                                *reinterpret_cast<float4 *>(p.y_hi + o) = h;
+                                *reinterpret_cast<float4 *>(p.y_lo + o) = l;
+                            }
+                        }
+                    }
+                    __syncwarp();                        // the staging rows are rewritten by the next region / tile
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            }
+            if (F16 && p.rs && p.y_hi) range_commit(p.rs, amax);
+        } else {
         const int m = lg * 32 + lane;
         int acc = 0;
         uint32_t acc_ph = 0;
@@ -397,6 +513,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
             if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         if (F16 && p.rs && p.y_hi) range_commit(p.rs, amax);
+        }
     }
 
     tc_fence_before();
@@ -633,11 +750,18 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     p.D = D; p.H = Ho; p.W = Wo; p.bw = bw; p.bh = bh; p.bd = bd; p.wt = Wo / bw; p.ht = Ho / bh; p.dt = dt;
     p.kd = kd; p.kh = kh; p.kw = kw; p.sh = stride_hw; p.sw = stride_hw;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
-    p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
+    // 2-D layers (few k-blocks per tile): coalescing epilogue staged through 36 KB of shared memory behind the operand ring
+    static const int stg_env = [] { const char *e = getenv("SIDE_CONV_STG"); return e ? atoi(e) : 1; }();
+    // (measured per layer shape, B = 16: 64->64 @ 96x320 194 -> 167 us, 64->128 @ 48x160 100 -> 71 us, 128->128 @ 48x160 128 -> 113 us;
+    // from 36 k-blocks per tile on, the MMAs hide the epilogue and the ring depth given up for the staging area costs 3 %)
+    p.stg = (stg_env && !pool && kd == 1 && !khv && !g_dbg && p.nkb <= 18 && p.N >= 64) ? 1 : 0;
+    const uint32_t ring_budget = 196u * 1024u - (p.stg ? kCvStgBytes : 0u);
+    p.stages = std::max(2, std::min((int)(ring_budget / stage_bytes), kCvMaxStages));
+    p.stg_off = (uint32_t)p.stages * stage_bytes;
     p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
     p.rs = f16 ? range_slot_next() : nullptr;
     p.acc_fix = tc_acc_fix(kd * kh * kw * ((p.ncb - 1) * 4 + p.klast));
-    const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + 1024;
+    const size_t smem = (khv ? (size_t)2 * 2 * a_part + (size_t)b_slots * b_slot : (size_t)p.stages * stage_bytes) + (p.stg ? kCvStgBytes : 0u) + 1024;
     if ((rc = set_smem_attr(f16 ? (const void *)conv_tc_kernel<true> : (const void *)conv_tc_kernel<false>, smem))) return rc;
     if (g_sm_count == 0) {
         int dev = 0;
@@ -676,7 +800,7 @@ int conv_tc_rows_gemm(const float *x_hi, const float *x_lo, const float *wp, flo
     p.kd = 1; p.kh = 1; p.kw = 1; p.sh = 1; p.sw = 1;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * (uint32_t)p.N * 128u;
     p.stages = std::max(2, std::min((int)((196u * 1024u) / stage_bytes), kCvMaxStages));
-    p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0; p.rs = nullptr;
+    p.khv = 0; p.a_slots = 2; p.b_slots = 0; p.a_part = 0; p.dbg = 0; p.rs = nullptr; p.stg = 0; p.stg_off = 0;
     p.acc_fix = tc_acc_fix(p.ncb * 4);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     if ((rc = set_smem_attr((const void *)conv_tc_kernel<false>, smem))) return rc;
