@@ -591,8 +591,13 @@ def main():
         w = a[2]
         return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
 
+    conv_desc = []                                             # one entry per timed convolution launch (SIDE_BENCH_CONV_TABLE)
+
     def conv_work(out, x_hi, x_lo, wp, Cout, ksize=(3, 3, 3), **k):
         cin = getattr(wp, "cin_alg", x_hi.shape[-1])          # zero-padded input channels (96 -> 128 for fp16) do not count
+        conv_desc.append("%s -> %d k%s s%s%s%s%s" % ("x".join(str(v) for v in x_hi.shape), Cout, "x".join(str(v) for v in ksize),
+                                                  k.get("stride", 1), " +res" if k.get("residual") is not None else "",
+                                                  " full" if k.get("full", True) else "", " split" if k.get("split") else ""))
         return 2.0 * (x_hi.numel() // x_hi.shape[-1]) * Cout * cin * ksize[0] * ksize[1] * ksize[2]
 
     def conv_fmt(x_hi, *a, **k):
@@ -618,6 +623,16 @@ def main():
     cv, cv16 = tmc.summary("tf32"), tmc.summary("f16")
     cv_big, cv_small = tmc.split_by_work(1e11, args.tc_format)      # >= 100 GFLOP per launch: aggregation layers, head convolutions
     vol = tmv.summary()
+    if os.environ.get("SIDE_BENCH_CONV_TABLE") and rank == 0:
+        # per-shape table of the convolution launches of the timed region (profiles/): calls, ms per step, TFLOP/s
+        tab = {}
+        for (e0, e1, w, _), d in zip(tmc.records, conv_desc):
+            t = tab.setdefault(d, [0, 0.0, 0.0])
+            t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += w
+        with open(os.environ["SIDE_BENCH_CONV_TABLE"], "w") as f:
+            f.write("| input (N x D x H x W x C) -> Cout | calls / step | ms / step | TFLOP/s |\n|---|---|---|---|\n")
+            for d, (n, ms_, w) in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+                f.write("| %s | %.0f | %.3f | %.1f |\n" % (d, n / args.steps, ms_ / args.steps, w / ms_ / 1e9 if ms_ > 0 else 0.0))
     launches = _lib.launch_count(reset=True)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop()
