@@ -359,9 +359,10 @@ __global__ void __launch_bounds__(kNhwcThreads) inst_costvol_fwd_nhwc_kernel(Vol
 // Separable fast path (SIDE_VOL_SEPARABLE).
 // The RoIAlign of depth candidate d samples the SAME 32 feature rows for every d of a RoI (the candidates only shift
 // the box along x, stereo_network_old.py:70-77), so the y half of the bilinear interpolation and the sum over the two
-// y sub-samples of a bin are shared by all D slices.  One CTA owns (RoI n, 8 channels): it builds
+// y sub-samples of a bin are shared by all D slices.  One CTA owns (RoI n, 8 channels, 8 of the 16 bin rows: ROWS below): it builds
 //     U[side][ph][x][c] = sum_{iy} ( hy * f[ylo][x][c] + ly * f[yhi][x][c] )          (once per group of slices)
-// in shared memory for the window of columns the group's shifted boxes touch, and every output bin is then 4 taps
+// in shared memory for the window of columns the group's shifted boxes touch (read straight from the NCHW features,
+// 16-byte vectors along x, a column interpolated once and scattered to the quads' sub-windows), and every output bin is then 4 taps
 //     bin = sum_{ix} ( 0.25*hx * U[ph][xlo] + 0.25*lx * U[ph][xhi] )
 // instead of 16 global taps and 33 rounded operations.  One warp per slice: lane = (channel pair, row of a pair, 4
 // consecutive bins), 8-byte conflict-free shared loads; the 32 x-sample table entries of the slice are computed one per lane and exchanged by shuffles; a quarter-warp's
