@@ -76,8 +76,12 @@ enum {
     SIDE_VOL_BWD_SCALAR = 1 << 4, /* side_inst_costvol_bwd: force the scalar-atomic kernel (torchvision's roi_align backward
                                thread mapping, 32 atomics per volume element); default for P == 16, C % 8 == 0 is the
                                separable gather kernel that keeps the x-pass sums in registers */
-    SIDE_VOL_FEAT_NHWC = 1 << 5 /* side_inst_costvol_fwd_cl: featL / featR are already channels-last [B, H, W, C] (e.g. the output of
+    SIDE_VOL_FEAT_NHWC = 1 << 5, /* side_inst_costvol_fwd_cl: featL / featR are already channels-last [B, H, W, C] (e.g. the output of
                                side_conv3d_tc_fwd): the two staging copies are skipped */
+    SIDE_VOL_NO_DIFF = 1 << 6  /* side_inst_costvol_fwd_cl: emit only the L and R planes, [N, D, P, P, 2C].  The third plane of
+                               cat(L, R, L - R) (stereo_network_old.py:374-376) is linear in the other two; the volume's only
+                               consumer, the first convolution of cost_volume.dres0 (:147-149), then runs with the folded
+                               weights (W_L + W_D, W_R - W_D) on 2C input channels: same function, <= 1e-6 of the output range */
 };
 
 /* decode flavour */

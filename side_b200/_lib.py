@@ -102,6 +102,7 @@ VOL_SEPARABLE = 1 << 2
 VOL_XCROSS = 1 << 3
 VOL_BWD_SCALAR = 1 << 4
 VOL_FEAT_NHWC = 1 << 5
+VOL_NO_DIFF = 1 << 6
 DECODE_HEAT_IS_LOGIT = 1 << 0
 DA_ALIGN_CORNERS = 1 << 0
 VOXEL_ALIGN_CORNERS = 1 << 0

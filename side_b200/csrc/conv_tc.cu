@@ -718,8 +718,9 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     int khv = (kh == 3 && stride_hw == 1 && bd == 1 && (bw % 8) == 0 && g_enable_khv) ? 1 : 0;
     int b_slots = 0;
     if (khv) {
-        b_slots = std::min(4, (int)((196u * 1024u - 2u * 2u * a_part) / b_slot));
-        if (2u * 2u * a_part >= 196u * 1024u || b_slots < 2) khv = 0;
+        const uint32_t budget = 196u * 1024u - kCvStgBytes;          // room for the staging area of the coalescing epilogue
+        b_slots = 2u * 2u * a_part < budget ? std::min(4, (int)((budget - 2u * 2u * a_part) / b_slot)) : 0;
+        if (b_slots < 2) khv = 0;
     }
     int rc;
     if (g_sm_count == 0) {
@@ -754,10 +755,10 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     static const int stg_env = [] { const char *e = getenv("SIDE_CONV_STG"); return e ? atoi(e) : 1; }();
     // (measured per layer shape, B = 16: 64->64 @ 96x320 194 -> 167 us, 64->128 @ 48x160 100 -> 71 us, 128->128 @ 48x160 128 -> 113 us;
     // from 36 k-blocks per tile on, the MMAs hide the epilogue and the ring depth given up for the staging area costs 3 %)
-    p.stg = (stg_env && !pool && kd == 1 && !khv && !g_dbg && p.nkb <= 18 && p.N >= 64) ? 1 : 0;
+    p.stg = (stg_env && !pool && kd == 1 && !g_dbg && p.nkb <= 18 && p.N >= 64) ? 1 : 0;
     const uint32_t ring_budget = 196u * 1024u - (p.stg ? kCvStgBytes : 0u);
     p.stages = std::max(2, std::min((int)(ring_budget / stage_bytes), kCvMaxStages));
-    p.stg_off = (uint32_t)p.stages * stage_bytes;
+    p.stg_off = khv ? 2u * 2u * a_part + (uint32_t)b_slots * b_slot : (uint32_t)p.stages * stage_bytes;
     p.khv = khv; p.a_slots = 2; p.b_slots = b_slots; p.a_part = a_part; p.dbg = g_dbg;
     p.rs = f16 ? range_slot_next() : nullptr;
     p.acc_fix = tc_acc_fix(kd * kh * kw * ((p.ncb - 1) * 4 + p.klast));

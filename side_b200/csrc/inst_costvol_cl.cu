@@ -21,6 +21,10 @@
 //       (cp.async.bulk shared -> global), double-buffered per warp.  No LSU store instruction touches the volume.
 // Boxes too wide for the window (a slice's x range > 38 columns) are processed in 2 .. 16 column tiles with a statistics
 // pass before the emitting pass (the gate needs the sums of the whole slice before its first value may be written).
+// OC = 64 (SIDE_VOL_NO_DIFF): only the L and R planes are emitted, [N, D, 16, 16, 2C].  The L - R plane of the reference's
+// cat(L, R, L - R) (stereo_network_old.py:374-376) is a linear function of the other two, so its consumer dres0.0 -- the only
+// reader of the volume -- folds it into the weights instead (W_L + W_D, W_R - W_D: side_b200/networks/stereo_network.py):
+// a third less volume to write and a 64-channel first convolution (one k-block per tap instead of one and a half).
 // Numerics: the same sample positions, validity rules, weights and operation order as inst_costvol_sep_kernel (<= 1e-5
 // relative to torchvision's RoIAlign order); the pair (hi, lo) carries 22 significand bits.
 #include <cuda_fp16.h>
@@ -88,26 +92,28 @@ __device__ __forceinline__ void cl_stage_plane(float x0, float x1, uint32_t hi_a
 // One chunk = NS steps of this warp's bin row (a step = 2 voxels, one per half-warp) -> staged -> two bulk stores of nbytes.
 // l[], r[]: the steps' values of this lane's channel pair; buf: this warp's staging buffer for the chunk ([hi][lo]);
 // slot0: staging slot of the lane's voxel in step 0 (step j uses slot0 + 2 j); vox: index of the chunk's first voxel.
-template <int NS>
+template <int NS, int OC>
 __device__ __forceinline__ void cl_emit_chunk(const float2 *l, const float2 *r, float g, unsigned char *buf, __half *ghi, __half *glo,
                                               size_t vox, uint32_t nbytes, int lane, int slot0)
 {
     if (lane == 0) bulk_wait_read<1>();          // the store issued from this buffer two chunks ago has read it
     __syncwarp();
-    const uint32_t base = smem_u32(buf) + (uint32_t)((slot0 * 48 + (lane & 15)) * 4);
+    // OC = 64: a voxel row is 32 words, the two half-warps fall on the same banks (2-way conflict on these stores)
+    const uint32_t base = smem_u32(buf) + (uint32_t)((slot0 * (OC / 2) + (lane & 15)) * 4);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        const uint32_t a = base + (uint32_t)(j * 2 * 192);
+        const uint32_t a = base + (uint32_t)(j * 2 * (OC * 2));
         const float2 lv = l[j], rv = r[j];
         cl_stage_plane(__fmul_rn(lv.x, g), __fmul_rn(lv.y, g), a, a + kClChunkB);
         cl_stage_plane(__fmul_rn(rv.x, g), __fmul_rn(rv.y, g), a + 64, a + 64 + kClChunkB);
-        cl_stage_plane(__fmul_rn(__fsub_rn(lv.x, rv.x), g), __fmul_rn(__fsub_rn(lv.y, rv.y), g), a + 128, a + 128 + kClChunkB);
+        if (OC == 96)
+            cl_stage_plane(__fmul_rn(__fsub_rn(lv.x, rv.x), g), __fmul_rn(__fsub_rn(lv.y, rv.y), g), a + 128, a + 128 + kClChunkB);
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-        bulk_s2g(ghi + vox * 96, buf, nbytes);
-        bulk_s2g(glo + vox * 96, buf + kClChunkB, nbytes);
+        bulk_s2g(ghi + vox * OC, buf, nbytes);
+        bulk_s2g(glo + vox * OC, buf + kClChunkB, nbytes);
         bulk_commit();
     }
 }
@@ -141,6 +147,7 @@ __device__ __forceinline__ float cl_gate(const float (*part)[4], int lane)
     return __fdiv_rn(t2, fmaxf(__fmul_rn(__fsqrt_rn(t0), __fsqrt_rn(t1)), 0.01f));
 }
 
+template <int OC>
 __global__ void __launch_bounds__(kClThreads, 1) inst_costvol_cl_kernel(ClParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -168,10 +175,10 @@ __global__ void __launch_bounds__(kClThreads, 1) inst_costvol_cl_kernel(ClParams
         __syncthreads();
         const int n = s_n;
         if (n >= N) break;
-        __half *ghi = p.hi + (size_t)n * D * 256 * 96, *glo = p.lo + (size_t)n * D * 256 * 96;
+        __half *ghi = p.hi + (size_t)n * D * 256 * OC, *glo = p.lo + (size_t)n * D * 256 * OC;
 
         if (v.valid && !v.valid[n]) {                // dropped row of the fixed-shape RoI set: an all-zero volume, depth_bin = 0
-            const int total = D * 256 * 96 * 2 / 16;
+            const int total = D * 256 * OC * 2 / 16;
             uint4 *a = reinterpret_cast<uint4 *>(ghi), *b = reinterpret_cast<uint4 *>(glo);
             for (int i = tid; i < total; i += kClThreads) {
                 __stcs(a + i, make_uint4(0u, 0u, 0u, 0u));
@@ -322,8 +329,8 @@ __global__ void __launch_bounds__(kClThreads, 1) inst_costvol_cl_kernel(ClParams
                                 const float g = p.gate ? xc : 1.0f;
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
-                                    cl_emit_chunk<2>(L + 2 * q, R + 2 * q, g, wstage + ((cc + q) & 1) * 2 * kClChunkB, ghi, glo,
-                                                     vox_row + 4 * q, 768u, lane, hw);
+                                    cl_emit_chunk<2, OC>(L + 2 * q, R + 2 * q, g, wstage + ((cc + q) & 1) * 2 * kClChunkB, ghi, glo,
+                                                         vox_row + 4 * q, (uint32_t)(4 * OC * 2), lane, hw);
                                 cc += 4;
                             } else {
                                 // tiled: bin columns [t PWT, (t+1) PWT) of the row, two per step (one per step when PWT == 1: both
@@ -349,8 +356,8 @@ __global__ void __launch_bounds__(kClThreads, 1) inst_costvol_cl_kernel(ClParams
                                         const float g = p.gate ? gtab[d] : 1.0f;
                                         unsigned char *buf = wstage + (cc & 1) * 2 * kClChunkB;
                                         const int nv = min(4, PWT - 2 * st);                     // voxels of this chunk: 4, 2 or 1
-                                        if (nv == 4) cl_emit_chunk<2>(l, r, g, buf, ghi, glo, vox_row + p0 + 2 * st, 768u, lane, hw);
-                                        else cl_emit_chunk<1>(l, r, g, buf, ghi, glo, vox_row + p0 + 2 * st, (uint32_t)nv * 192u, lane, hw);
+                                        if (nv == 4) cl_emit_chunk<2, OC>(l, r, g, buf, ghi, glo, vox_row + p0 + 2 * st, (uint32_t)(4 * OC * 2), lane, hw);
+                                        else cl_emit_chunk<1, OC>(l, r, g, buf, ghi, glo, vox_row + p0 + 2 * st, (uint32_t)(nv * OC * 2), lane, hw);
                                         ++cc;
                                     }
                                 }
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(kClThreads, 1) inst_costvol_cl_kernel(ClParams
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
     // |L - R| can reach twice the tracked maximum: report it when that is what would saturate
-    if (p.rs) range_commit(p.rs, 2.f * amax >= 65504.f ? 2.f * amax : amax);
+    if (p.rs) range_commit(p.rs, (OC == 96 && 2.f * amax >= 65504.f) ? 2.f * amax : amax);
 }
 
 }  // namespace side
@@ -404,7 +411,8 @@ extern "C" int side_inst_costvol_fwd_cl(const float *featL, const float *featR, 
     SIDE_REQUIRE(C == kClC && P == 16, "side_inst_costvol_fwd_cl: built for C == 32 channels per view and P == 16 (got C=%d, P=%d)", C, P);
     SIDE_REQUIRE(D >= 2 && D <= kClMaxD, "side_inst_costvol_fwd_cl: D must be in 2..%d", kClMaxD);
     SIDE_REQUIRE((long long)B * H * W * C < (1ll << 31) && W < 32768, "side_inst_costvol_fwd_cl: features too large");
-    SIDE_REQUIRE((flags & ~(SIDE_VOL_GATE | SIDE_VOL_FEAT_NHWC)) == 0, "side_inst_costvol_fwd_cl: valid flags are SIDE_VOL_GATE, SIDE_VOL_FEAT_NHWC");
+    SIDE_REQUIRE((flags & ~(SIDE_VOL_GATE | SIDE_VOL_FEAT_NHWC | SIDE_VOL_NO_DIFF)) == 0,
+                 "side_inst_costvol_fwd_cl: valid flags are SIDE_VOL_GATE, SIDE_VOL_FEAT_NHWC, SIDE_VOL_NO_DIFF");
     if (N == 0) return SIDE_OK;
     SIDE_REQUIRE_DEV(featL); SIDE_REQUIRE_DEV(featR); SIDE_REQUIRE_DEV(left); SIDE_REQUIRE_DEV(right); SIDE_REQUIRE_DEV(fb);
     SIDE_REQUIRE_DEV(cost_hi); SIDE_REQUIRE_DEV(cost_lo); SIDE_REQUIRE_DEV(depth_bin);
@@ -438,8 +446,13 @@ extern "C" int side_inst_costvol_fwd_cl(const float *featL, const float *featR, 
         SIDE_CUDA(cudaGetDevice(&dev));
         SIDE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    if ((rc = set_smem_attr((const void *)inst_costvol_cl_kernel, kClSmem))) return rc;
-    inst_costvol_cl_kernel<<<(unsigned)std::min(N, sm_count), kClThreads, kClSmem, st>>>(p);
+    if (flags & SIDE_VOL_NO_DIFF) {
+        if ((rc = set_smem_attr((const void *)inst_costvol_cl_kernel<64>, kClSmem))) return rc;
+        inst_costvol_cl_kernel<64><<<(unsigned)std::min(N, sm_count), kClThreads, kClSmem, st>>>(p);
+    } else {
+        if ((rc = set_smem_attr((const void *)inst_costvol_cl_kernel<96>, kClSmem))) return rc;
+        inst_costvol_cl_kernel<96><<<(unsigned)std::min(N, sm_count), kClThreads, kClSmem, st>>>(p);
+    }
     SIDE_LAUNCH_CHECK("inst_costvol_cl_kernel");
     return SIDE_OK;
 }

@@ -109,6 +109,13 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
             scale = (b.weight / torch.sqrt(b.running_var + b.eps)).float()
             shift = (b.bias - b.running_mean * scale + (c.bias * scale if c.bias is not None else 0)).float().contiguous()
             layers.append((ops.conv_tc_prepare(c.weight.detach().unsqueeze(2), fmt=fmt), c.out_channels, scale.contiguous(), shift))
+            # dres0.0 on the (L, R) planes only: the volume is cat(L, R, L - R) (reference :374-376) and this convolution is its
+            # only reader, so  W_L * L + W_R * R + W_D * (L - R) = (W_L + W_D) * L + (W_R - W_D) * R  -- the same function on 2C
+            # input channels (one 64-channel k-block per tap instead of one and a half, a third less volume to write and read)
+            w0 = self.dres0[0].weight.detach()
+            C = w0.shape[1] // 3
+            wf = torch.cat((w0[:, :C] + w0[:, 2 * C:], w0[:, C:2 * C] - w0[:, 2 * C:]), dim=1).contiguous()
+            layers.append((ops.conv_tc_prepare(wf, fmt=fmt), layers[0][1], layers[0][2], layers[0][3]))
             st = (key, layers)
             self._tc_cache = st
         return st[1]
@@ -126,13 +133,14 @@ class cost_volume(ops.PreparedStateOwner, nn.Module):
         hi, lo = ops.ncdhw_to_cl_split(cost, scale=xcross, fmt=fmt)            # [N, D, 16, 16, 3C]
         return self.aggregate_tc_pairs(hi, lo, fmt)
 
-    def aggregate_tc_pairs(self, hi, lo, fmt=None):
+    def aggregate_tc_pairs(self, hi, lo, fmt=None, folded=False):
         """``aggregate_tc`` from the gated volume already channels-last and split into operand pairs [N, D, 16, 16, 3C]
-        (what ops.inst_costvol_cl emits)."""
+        (what ops.inst_costvol_cl emits); ``folded``: the pairs hold only the (L, R) planes [N, D, 16, 16, 2C]
+        (``inst_costvol_cl(..., diff=False)``) and dres0.0 runs with the L - R plane folded into its weights."""
         fmt = fmt or self.tc_format or ops.get_tc_format()
         L = self._tc_state(fmt)
         conv = lambda i, hi, lo, **k: ops.conv3d_tc(hi, lo, L[i][0], L[i][1], scale=L[i][2], shift=L[i][3], relu=True, **k)
-        _, hi, lo = conv(0, hi, lo)
+        _, hi, lo = conv(8 if folded else 0, hi, lo)
         y, _, _ = conv(1, hi, lo, full=True, split=False)                      # dres0 out, [N, D, H, W, 64]
         # strAM gate: mean over H stays channels-last [N, D, W, 64] = a batch of N (D x W) images for the same tcgen05 kernel
         mh, ml = ops.split_pairs(y.mean(dim=2).unsqueeze(0), fmt)              # [1, N, D, W, 64]
@@ -323,6 +331,7 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
         return {h: z[h] for h in self.heads}
 
     fused_volume = True    # inference, fp16 pairs: volume builder writes the consumer format directly (ops.inst_costvol_cl)
+    fold_diff = True       # fused volume: emit (L, R) only, dres0.0 takes the L - R plane through folded weights
     fast_volume = True     # inference: separable volume builder (<= 1e-5 rel. of the bit-exact one), gate applied downstream
 
     def _fused_volume_ok(self, C, D):
@@ -334,8 +343,9 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
     def _depth_from_boxes(self, featL, featR, left, right, fb, valid, D, nhwc=False):
         est = self.depth_estimator
         if nhwc:                                       # only taken when _fused_volume_ok: features channels-last [B, H, W, C]
-            hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid, nhwc=True)
-            return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16"), depth_bin)
+            hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid, nhwc=True,
+                                                       diff=not self.fold_diff)
+            return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16", folded=self.fold_diff), depth_bin)
         C = featL.shape[1]
         if (self.fast_volume and est.tensor_core and featL.is_cuda and not self.training and not torch.is_grad_enabled() and self.roiSize == 16
                 and D % 8 == 0 and D <= 256 and C % 8 == 0 and (3 * C) % 32 == 0 and 3 * C == est.dres0[0].in_channels
@@ -343,8 +353,9 @@ class stereo_network(ops.PreparedStateOwner, nn.Module):
             fmt = est.tc_format or ops.get_tc_format()
             if self.fused_volume and fmt == "f16" and ops.inst_costvol_cl_ok(C, D, 16):
                 # the gated volume leaves the builder channels-last and split into the fp16 pairs dres0.0 reads: one HBM pass
-                hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid)
-                return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16"), depth_bin)
+                hi, lo, depth_bin, _ = ops.inst_costvol_cl(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid,
+                                                           diff=not self.fold_diff)
+                return ops.softargmin(est.aggregate_tc_pairs(hi, lo, "f16", folded=self.fold_diff), depth_bin)
             # one pass over the volume: [L, R, L-R] written ungated with the gate scalars on the side; the gate is applied
             # while the volume is re-laid out channels-last for the tensor-core convolutions
             cost, depth_bin, xc = ops.inst_costvol_ungated(featL, featR, left, right, fb, D, 16, input_w // 4 - 1., valid=valid)

@@ -389,10 +389,11 @@ def inst_costvol_cl_ok(C, D, P):
     return C == 32 and P == 16 and 2 <= D <= 64
 
 
-def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, gate=True, nhwc=False):
+def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, gate=True, nhwc=False, diff=True):
     """Inference-only: the (gated) volume straight in its consumer's format -> (hi, lo fp16 [N, D, P, P, 3C], depth_bin [N, D],
     xcross [N, D]).  One pass over HBM; see include/side_b200.h side_inst_costvol_fwd_cl.  nhwc=True: the features are already
-    channels-last [B, H, W, C]."""
+    channels-last [B, H, W, C].  diff=False (SIDE_VOL_NO_DIFF): only the L and R planes, [N, D, P, P, 2C] -- for a consumer that
+    folded the L - R plane into its weights (cost_volume.aggregate_tc_pairs(..., folded=True))."""
     lib = _lib.load()
     featL, featR = _chk(featL, "featL"), _chk(featR, "featR")
     left, right, fb = _chk(left, "left_boxes"), _chk(right, "right_boxes"), _chk(fb, "fb")
@@ -405,7 +406,7 @@ def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, ga
     N = left.shape[0]
     dev = featL.device
     _range_guard(dev)
-    hi = torch.empty((N, D, P, P, 3 * C), device=dev, dtype=torch.float16)
+    hi = torch.empty((N, D, P, P, (3 if diff else 2) * C), device=dev, dtype=torch.float16)
     lo = torch.empty_like(hi)
     depth_bin = torch.empty((N, D), device=dev, dtype=_F32)
     xc = torch.empty((N, D), device=dev, dtype=_F32)
@@ -413,7 +414,8 @@ def inst_costvol_cl(featL, featR, left, right, fb, D, P, x_clamp, valid=None, ga
     ws = torch.empty((nws,), device=dev, dtype=torch.uint8)
     _lib.check(lib.side_inst_costvol_fwd_cl(featL.data_ptr(), featR.data_ptr(), left.data_ptr(), right.data_ptr(), fb.data_ptr(),
                                             _p(valid), hi.data_ptr(), lo.data_ptr(), depth_bin.data_ptr(), xc.data_ptr(), N, B, C, H,
-                                            W, D, P, float(x_clamp), (_lib.VOL_GATE if gate else 0) | (_lib.VOL_FEAT_NHWC if nhwc else 0),
+                                            W, D, P, float(x_clamp), (_lib.VOL_GATE if gate else 0) | (_lib.VOL_FEAT_NHWC if nhwc else 0) |
+                                            (0 if diff else _lib.VOL_NO_DIFF),
                                             ws.data_ptr(), nws, _stream()),
                "side_inst_costvol_fwd_cl")
     return hi, lo, depth_bin, xc

@@ -396,3 +396,42 @@ def test_volume_channels_last_pairs_match_two_pass_path(lib):
         d0 = ops.softargmin(m.aggregate_tc_pairs(hi0, lo0, "f16"), db0)
         d1 = ops.softargmin(m.aggregate_tc_pairs(hi1, lo1, "f16"), db1)
     assert float(((d0 - d1).abs() / d0.abs()).max()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_volume_without_difference_plane_and_folded_first_convolution(lib):
+    """SIDE_VOL_NO_DIFF: the builder emits only the (L, R) planes -- bit-identical to the first 2C channels of the full volume --
+    and cost_volume.dres0.0 with the L - R plane folded into its weights (W_L + W_D, W_R - W_D; the volume is cat(L, R, L - R),
+    stereo_network_old.py:374-376, and this convolution is its only reader) gives the same logits and depth: <= 1e-5 of the logit
+    range, depth <= 1e-5 relative.  Also against the module's own fp64 convolution stack on the full volume."""
+    from side_b200 import ops
+    from side_b200.networks.stereo_network import cost_volume
+    from side_b200.utils.synthetic import make_boxes
+    torch.manual_seed(5)
+    fL, fR = torch.randn(2, 32, 96, 320, device="cuda"), torch.randn(2, 32, 96, 320, device="cuda")
+    left, right, _ = make_boxes(2, 12, seed=6)
+    left, right = left.cuda(), right.cuda()
+    fb = torch.tensor([384.38, 400.0], device="cuda")
+    valid = torch.ones(24, dtype=torch.uint8, device="cuda")
+    valid[5] = 0
+    hi3, lo3, db3, xc3 = ops.inst_costvol_cl(fL, fR, left, right, fb, 16, 16, 319.0, valid=valid)
+    hi2, lo2, db2, xc2 = ops.inst_costvol_cl(fL, fR, left, right, fb, 16, 16, 319.0, valid=valid, diff=False)
+    assert tuple(hi2.shape) == (24, 16, 16, 16, 64)
+    assert torch.equal(hi2, hi3[..., :64]) and torch.equal(lo2, lo3[..., :64])
+    assert torch.equal(db2, db3) and torch.equal(xc2, xc3)
+    m = cost_volume(64).cuda().eval()
+    with torch.no_grad():
+        for b in m.modules():                        # non-trivial folded BatchNorm
+            if isinstance(b, (torch.nn.BatchNorm3d, torch.nn.BatchNorm2d)):
+                b.running_mean.normal_(0, 0.1); b.running_var.uniform_(0.5, 1.5); b.weight.uniform_(0.5, 1.5); b.bias.normal_(0, 0.1)
+        l3 = m.aggregate_tc_pairs(hi3, lo3, "f16")
+        l2 = m.aggregate_tc_pairs(hi2, lo2, "f16", folded=True)
+        assert float((l3 - l2).abs().max()) <= 1e-5 * float(l3.abs().max())
+        keep = valid.bool()
+        d3, d2 = ops.softargmin(l3, db3)[keep], ops.softargmin(l2, db2)[keep]
+        assert float(((d3 - d2).abs() / d3.abs()).max()) < 1e-5
+        # fp64 module on the full [L, R, L - R] volume (NCDHW)
+        import copy
+        vol = (hi3.double() + lo3.double() / 2048.0).permute(0, 4, 1, 2, 3).contiguous().cpu()
+        ref = copy.deepcopy(m).cpu().double().aggregate(vol)
+        assert float((l2.double().cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
