@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ __align__(16) float s_scale[kCvMaxCout], s_shift[kCvMaxCout];
 
     constexpr int kKel = F16 ? 64 : 32;      // channels per 128-byte k-block row
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler as well
     const int N = p.N;
     const uint32_t b_part = (uint32_t)N * 128u;
     const uint32_t stage_bytes = 2 * kCvATile + 2 * b_part;
@@ -145,57 +146,65 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // All 32 lanes run the loops (uniform control flow, uniform operands); the elected lane issues -- see tc_elect_one().
+        const bool leader = tc_elect_one();
+        if (leader) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_lo) : "memory");
-            int st = 0;
-            uint32_t phs = 0;
-            if (p.khv) {
-                unsigned char *bring = tiles + (size_t)p.a_slots * 2 * p.a_part;
-                int sa_i = 0;
-                uint32_t pha = 0;
-                for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                    const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
-                    int n, d0, h0, w0;
-                    conv_tile_origin(p, mt, n, d0, h0, w0);
-                    const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
-                    for (int kdi = 0; kdi < p.kd; ++kdi)
-                        for (int kwi = 0; kwi < 3; ++kwi)
-                            for (int cb = 0; cb < p.ncb; ++cb) {
-                                mbar_wait(&emptyA[sa_i], pha ^ 1u);
-                                unsigned char *sa = tiles + (size_t)sa_i * 2 * p.a_part;
-                                mbar_expect_tx(&fullA[sa_i], 2 * p.a_part);
-                                tma_load_5d(sa, &tm_hi, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
-                                tma_load_5d(sa + p.a_part, &tm_lo, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
-                                if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
-                                for (int khi = 0; khi < 3; ++khi) {
-                                    const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
-                                    mbar_wait(&empty_bar[st], phs ^ 1u);
-                                    mbar_expect_tx(&full_bar[st], 2 * b_part);
-                                    bulk_g2s(bring + (size_t)st * 2 * b_part, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
-                                    if (++st == p.b_slots) { st = 0; phs ^= 1u; }
-                                }
-                            }
-                }
-            } else
+        }
+        int st = 0;
+        uint32_t phs = 0;
+        if (p.khv) {
+            unsigned char *bring = tiles + (size_t)p.a_slots * 2 * p.a_part;
+            int sa_i = 0;
+            uint32_t pha = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
                 int n, d0, h0, w0;
                 conv_tile_origin(p, mt, n, d0, h0, w0);
                 const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
-                // (kd, kh, kw, channel block) carried incrementally: this single thread's instruction latency is on the critical
-                // path of every k-block, integer divisions here cost more than the MMAs they feed
+                for (int kdi = 0; kdi < p.kd; ++kdi)
+                    for (int kwi = 0; kwi < 3; ++kwi)
+                        for (int cb = 0; cb < p.ncb; ++cb) {
+                            mbar_wait(&emptyA[sa_i], pha ^ 1u);
+                            unsigned char *sa = tiles + (size_t)sa_i * 2 * p.a_part;
+                            if (leader) {
+                                mbar_expect_tx(&fullA[sa_i], 2 * p.a_part);
+                                tma_load_5d(sa, &tm_hi, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                                tma_load_5d(sa + p.a_part, &tm_lo, cb * kKel, w0 + kwi - 1, h0 - 1, d0 + kdi - pd, n, &fullA[sa_i]);
+                            }
+                            if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
+                            for (int khi = 0; khi < 3; ++khi) {
+                                const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
+                                mbar_wait(&empty_bar[st], phs ^ 1u);
+                                if (leader) {
+                                    mbar_expect_tx(&full_bar[st], 2 * b_part);
+                                    bulk_g2s(bring + (size_t)st * 2 * b_part, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
+                                }
+                                if (++st == p.b_slots) { st = 0; phs ^= 1u; }
+                            }
+                        }
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+                int n, d0, h0, w0;
+                conv_tile_origin(p, mt, n, d0, h0, w0);
+                const float *wpt = p.wp + (size_t)nt * p.nkb * (2 * b_part / 4);
+                // (kd, kh, kw, channel block) carried incrementally: no integer divisions on the critical path of every k-block
                 int kdi = 0, khi = 0, kwi = 0, cb = 0;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&empty_bar[st], phs ^ 1u);
                     unsigned char *sa = tiles + (size_t)st * stage_bytes;
-                    mbar_expect_tx(&full_bar[st], ((p.dbg & 4) ? 0u : 2 * kCvATile) + ((p.dbg & 2) ? 0u : 2 * b_part));
                     const int cw = w0 * p.sw + kwi - pw, ch = h0 * p.sh + khi - ph;     // input coordinates of the box origin
-                    if (!(p.dbg & 4)) {
-                        tma_load_5d(sa, &tm_hi, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
-                        tma_load_5d(sa + kCvATile, &tm_lo, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                    if (leader) {
+                        mbar_expect_tx(&full_bar[st], ((p.dbg & 4) ? 0u : 2 * kCvATile) + ((p.dbg & 2) ? 0u : 2 * b_part));
+                        if (!(p.dbg & 4)) {
+                            tma_load_5d(sa, &tm_hi, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                            tma_load_5d(sa + kCvATile, &tm_lo, cb * kKel, cw, ch, d0 + kdi - pd, n, &full_bar[st]);
+                        }
+                        if (!(p.dbg & 2)) bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     }
-                    if (!(p.dbg & 2)) bulk_g2s(sa + 2 * kCvATile, wpt + (size_t)kb * (2 * b_part / 4), 2 * b_part, &full_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
                     if (++cb == p.ncb) {
                         cb = 0;
@@ -210,83 +219,83 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // hi*hi and hi*lo share their A operand: ONE MMA of width 2N against the adjacent [B_hi | B_lo] tiles writes
-            // main (columns 0..N) and the first cross term (N..2N) at once; lo*hi then accumulates onto N..2N.  The A tile
-            // is fetched from shared memory twice per k-step instead of three times (the kernel is smem-bandwidth bound:
-            // tf32 operands are 4 bytes, a 128 x N x 8 MMA reads (128 + N) * 32 bytes in 128 * N / 256 cycles).
-            const uint32_t idesc = tc_idesc<F16>(kCvBM, N), idesc2 = tc_idesc<F16>(kCvBM, 2 * N);
-            int st = 0, acc = 0;
-            uint32_t phs = 0, acc_ph = 0;
-            if (p.khv) {
-                const uint32_t bring = smem_u32(tiles + (size_t)p.a_slots * 2 * p.a_part);
-                const uint32_t view = (uint32_t)p.bw * 128u;          // bytes per halo row: tap kh starts kh rows further down
-                int sa_i = 0;
-                uint32_t pha = 0;
-                const int ngroups = p.kd * 3 * p.ncb;
-                for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                    mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
-                    const uint32_t tmem_x = tmem_d + (uint32_t)N;
-                    for (int g = 0; g < ngroups; ++g) {
-                        mbar_wait(&fullA[sa_i], pha);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(tiles + (size_t)sa_i * 2 * p.a_part);
-                        const int ksteps = (g % p.ncb == p.ncb - 1) ? p.klast : 4;    // zero-padded tail of the last channel block
-                        for (int khi = 0; khi < 3; ++khi) {
-                            mbar_wait(&full_bar[st], phs);
-                            tc_fence_after();
-                            const uint32_t sb = bring + (uint32_t)st * 2 * b_part;
-                            const uint32_t av = sa + (uint32_t)khi * view;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k >= ksteps) break;
-                                const uint64_t a_hi = tc_smem_desc(av + k * 32), b_hi = tc_smem_desc(sb + k * 32);
-                                const uint64_t a_lo = tc_smem_desc(av + p.a_part + k * 32);
-                                tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (g | khi | k) != 0 ? 1u : 0u);
-                                tc_mma<F16>(tmem_x, a_lo, b_hi, idesc, 1u);
-                            }
-                            tc_commit(&empty_bar[st]);
-                            if (++st == p.b_slots) { st = 0; phs ^= 1u; }
-                        }
-                        tc_commit(&emptyA[sa_i]);
-                        if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
-                    }
-                    tc_commit(&tmem_full[acc]);
-                    if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
-                }
-            } else
+        // hi*hi and hi*lo share their A operand: ONE MMA of width 2N against the adjacent [B_hi | B_lo] tiles writes main (columns
+        // 0..N) and the first cross term (N..2N) at once; lo*hi then accumulates onto N..2N.
+        // Two accumulators per tile: hi*hi in `tmem_d`, the two small cross terms in `tmem_x`.  The tensor core adds into the fp32
+        // accumulator with truncation (round toward zero), a bias of ~0.5 ulp of the accumulator per MMA; keeping the 2/3 of the
+        // MMAs that carry 2^-11-sized terms out of the main accumulator cuts that bias 3x (the cross accumulator is ~2^-10 of the
+        // main one, its ulp is negligible).
+        // All 32 lanes run the loops; the elected lane issues the MMAs and the commits (tc_elect_one(): the descriptors stay in
+        // uniform registers, 8 UTCHMMA back to back per k-block instead of ~45 single-thread instructions per K-step).
+        const bool leader = tc_elect_one();
+        const uint32_t idesc = tc_idesc<F16>(kCvBM, N), idesc2 = tc_idesc<F16>(kCvBM, 2 * N);
+        const uint64_t desc0 = tc_smem_desc(smem_u32(tiles));
+        int st = 0, acc = 0, cbm = 0;
+        uint32_t phs = 0, acc_ph = 0;
+        if (p.khv) {
+            const uint64_t bring = tc_desc_add(desc0, (uint32_t)p.a_slots * 2u * p.a_part);
+            const uint32_t view = (uint32_t)p.bw * 128u;          // bytes per halo row: tap kh starts kh rows further down
+            int sa_i = 0;
+            uint32_t pha = 0;
+            const int ngroups = p.kd * 3 * p.ncb;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
                 tc_fence_after();
-                // Two accumulators per tile: hi*hi in `tmem_d`, the two small cross terms in `tmem_x`.  The tensor core
-                // adds into the fp32 accumulator with truncation (round toward zero), a bias of ~0.5 ulp of the
-                // accumulator per MMA; keeping the 2/3 of the MMAs that carry 2^-11-sized terms out of the main
-                // accumulator cuts that bias 3x (the cross accumulator is ~2^-10 of the main one, its ulp is negligible).
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
                 const uint32_t tmem_x = tmem_d + (uint32_t)N;
-                int cbm = 0;
+                for (int g = 0; g < ngroups; ++g) {
+                    mbar_wait(&fullA[sa_i], pha);
+                    tc_fence_after();
+                    const uint64_t sa = tc_desc_add(desc0, (uint32_t)sa_i * 2u * p.a_part);
+                    const int ksteps = (cbm == p.ncb - 1) ? p.klast : 4;    // zero-padded tail of the last channel block
+                    if (++cbm == p.ncb) cbm = 0;
+                    for (int khi = 0; khi < 3; ++khi) {
+                        mbar_wait(&full_bar[st], phs);
+                        tc_fence_after();
+                        const uint64_t b_hi0 = tc_desc_add(bring, (uint32_t)st * 2u * b_part);
+                        const uint64_t a_hi0 = tc_desc_add(sa, (uint32_t)khi * view), a_lo0 = tc_desc_add(a_hi0, p.a_part);
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k >= ksteps) break;
+                                tc_mma<F16>(tmem_d, tc_desc_add(a_hi0, k * 32), tc_desc_add(b_hi0, k * 32), idesc2, (g | khi | k) != 0 ? 1u : 0u);
+                                tc_mma<F16>(tmem_x, tc_desc_add(a_lo0, k * 32), tc_desc_add(b_hi0, k * 32), idesc, 1u);
+                            }
+                            tc_commit(&empty_bar[st]);
+                        }
+                        if (++st == p.b_slots) { st = 0; phs ^= 1u; }
+                    }
+                    if (leader) tc_commit(&emptyA[sa_i]);
+                    if (++sa_i == p.a_slots) { sa_i = 0; pha ^= 1u; }
+                }
+                if (leader) tc_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 2 * N);
+                const uint32_t tmem_x = tmem_d + (uint32_t)N;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(&full_bar[st], phs);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
-                    const uint32_t sb = sa + 2 * kCvATile;
+                    const uint64_t a_hi0 = tc_desc_add(desc0, (uint32_t)st * stage_bytes);
+                    const uint64_t a_lo0 = tc_desc_add(a_hi0, kCvATile), b_hi0 = tc_desc_add(a_hi0, 2 * kCvATile);
                     const int ksteps = (cbm == p.ncb - 1) ? p.klast : 4;
                     if (++cbm == p.ncb) cbm = 0;
+                    if (leader && !(p.dbg & 16)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k >= ksteps) break;
-                        const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
-                        const uint64_t a_lo = tc_smem_desc(sa + kCvATile + k * 32);
-                        if (p.dbg & 16) continue;
-                        tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);     // [hi*hi | hi*lo]
-                        tc_mma<F16>(tmem_x, a_lo, b_hi, idesc, 1u);                          // + lo*hi
+                        for (int k = 0; k < 4; ++k) {
+                            if (k >= ksteps) break;
+                            tc_mma<F16>(tmem_d, tc_desc_add(a_hi0, k * 32), tc_desc_add(b_hi0, k * 32), idesc2, (kb | k) != 0 ? 1u : 0u);   // [hi*hi | hi*lo]
+                            tc_mma<F16>(tmem_x, tc_desc_add(a_lo0, k * 32), tc_desc_add(b_hi0, k * 32), idesc, 1u);                      // + lo*hi
+                        }
                     }
-                    tc_commit(&empty_bar[st]);
+                    if (leader) tc_commit(&empty_bar[st]);
                     if (++st == stages) { st = 0; phs ^= 1u; }
                 }
-                tc_commit(&tmem_full[acc]);
+                if (leader) tc_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
             }
         }
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * N);
                 bool waited = false;
                 for (int c0 = 32 * chalf; ; c0 += 64) {
-                    const bool work = c0 < N;
+                    const bool work = c0 < N && !(p.dbg & 8);
                     const bool active = work && c0 + sc4 < N;
                     float4 rres[8];
                     if (active && p.residual) {
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const __grid_con
                         waited = true;
                     }
                     if (!work) {
-                        if (32 * chalf >= N) {           // a warp without columns (N <= 32) still hands the accumulator back
+                        if (32 * chalf >= N || (p.dbg & 8)) {   // a warp without columns (N <= 32) still hands the accumulator back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -755,7 +764,7 @@ static int conv3d_tc_fwd_impl(const float *x_hi, const float *x_lo, const float 
     static const int stg_env = [] { const char *e = getenv("SIDE_CONV_STG"); return e ? atoi(e) : 1; }();
     // (measured per layer shape, B = 16: 64->64 @ 96x320 194 -> 167 us, 64->128 @ 48x160 100 -> 71 us, 128->128 @ 48x160 128 -> 113 us;
     // from 36 k-blocks per tile on, the MMAs hide the epilogue and the ring depth given up for the staging area costs 3 %)
-    p.stg = (stg_env && !pool && kd == 1 && !g_dbg && p.nkb <= 18 && p.N >= 64) ? 1 : 0;
+    p.stg = (stg_env && !pool && kd == 1 && p.nkb <= 18 && p.N >= 64) ? 1 : 0;
     const uint32_t ring_budget = 196u * 1024u - (p.stg ? kCvStgBytes : 0u);
     p.stages = std::max(2, std::min((int)(ring_budget / stage_bytes), kCvMaxStages));
     p.stg_off = khv ? 2u * 2u * a_part + (uint32_t)b_slots * b_slot : (uint32_t)p.stages * stage_bytes;

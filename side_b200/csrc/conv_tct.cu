@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_scale[kTtCout], s_shift[kTtCout];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler as well
     unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *xring = base;                                               // kTtXSlots x [X_hi halo box][X_lo halo box]
     unsigned char *wring = xring + (size_t)kTtXSlots * 2 * p.x_part;           // kTtWSlots x [zeros][W_hi][W_lo]
@@ -117,74 +118,83 @@ __global__ void __launch_bounds__(kTtThreads, 1) conv_tct_kernel(const __grid_co
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // all 32 lanes run the loops (uniform control flow and operands), the elected lane issues -- see tc_elect_one()
+        const bool leader = tc_elect_one();
+        if (leader) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_lo) : "memory");
-            int sx = 0, sw = 0;
-            uint32_t phx = 0, phw = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int n = tile / p.D, d0 = tile - n * p.D;
-                for (int kdi = 0; kdi < p.kd; ++kdi)
-                    for (int kwi = 0; kwi < 3; ++kwi)
-                        for (int cb = 0; cb < p.ncb; ++cb) {
-                            mbar_wait(&emptyX[sx], phx ^ 1u);
-                            unsigned char *xs = xring + (size_t)sx * 2 * p.x_part;
+        }
+        int sx = 0, sw = 0;
+        uint32_t phx = 0, phw = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int n = tile / p.D, d0 = tile - n * p.D;
+            for (int kdi = 0; kdi < p.kd; ++kdi)
+                for (int kwi = 0; kwi < 3; ++kwi)
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        mbar_wait(&emptyX[sx], phx ^ 1u);
+                        unsigned char *xs = xring + (size_t)sx * 2 * p.x_part;
+                        if (leader) {
                             mbar_expect_tx(&fullX[sx], 2 * p.x_part);
                             tt_tma_load_5d(xs, &tm_hi, cb * (F16 ? 64 : 32), kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
                             tt_tma_load_5d(xs + p.x_part, &tm_lo, cb * (F16 ? 64 : 32), kwi - 1, -1, d0 + kdi - pd, n, &fullX[sx]);
-                            if (++sx == kTtXSlots) { sx = 0; phx ^= 1u; }
-                            for (int khi = 0; khi < 3; ++khi) {
-                                const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
-                                mbar_wait(&emptyW[sw], phw ^ 1u);
+                        }
+                        if (++sx == kTtXSlots) { sx = 0; phx ^= 1u; }
+                        for (int khi = 0; khi < 3; ++khi) {
+                            const int kb = ((kdi * 3 + khi) * 3 + kwi) * p.ncb + cb;
+                            mbar_wait(&emptyW[sw], phw ^ 1u);
+                            if (leader) {
                                 mbar_expect_tx(&fullW[sw], 2 * kTtWPart);
                                 bulk_g2s(wring + (size_t)sw * kTtWSlot + kTtWPart, p.wp + (size_t)kb * (2 * kTtWPart / 4), 2 * kTtWPart,
                                          &fullW[sw]);
-                                if (++sw == kTtWSlots) { sw = 0; phw ^= 1u; }
                             }
+                            if (++sw == kTtWSlots) { sw = 0; phw ^= 1u; }
                         }
-            }
+                    }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = tc_idesc<F16>(128, kTtVox);
-            const uint32_t view = (uint32_t)p.bw * 128u;              // bytes per halo row
-            const int ngroups = p.kd * 3 * p.ncb;
-            int sx = 0, sw = 0, acc = 0;
-            uint32_t phx = 0, phw = 0, acc_ph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+        // all 32 lanes run the loops, the elected lane issues the MMAs and commits (tc_elect_one(): descriptors stay in uniform
+        // registers, no per-instruction election loop)
+        const bool leader = tc_elect_one();
+        const uint32_t idesc = tc_idesc<F16>(128, kTtVox);
+        const uint32_t view = (uint32_t)p.bw * 128u;              // bytes per halo row
+        const int ngroups = p.kd * 3 * p.ncb;
+        const uint64_t xdesc0 = tc_smem_desc(smem_u32(xring)), wdesc0 = tc_smem_desc(smem_u32(wring));
+        int sx = 0, sw = 0, acc = 0, cbm = 0;
+        uint32_t phx = 0, phw = 0, acc_ph = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTtVox);
+            for (int g = 0; g < ngroups; ++g) {
+                mbar_wait(&fullX[sx], phx);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTtVox);
-                for (int g = 0; g < ngroups; ++g) {
-                    mbar_wait(&fullX[sx], phx);
+                const uint64_t xs = tc_desc_add(xdesc0, (uint32_t)sx * 2u * p.x_part);
+                const int ksteps = (cbm == p.ncb - 1) ? p.klast : 4;
+                if (++cbm == p.ncb) cbm = 0;
+                for (int khi = 0; khi < 3; ++khi) {
+                    mbar_wait(&fullW[sw], phw);
                     tc_fence_after();
-                    const uint32_t xs = smem_u32(xring + (size_t)sx * 2 * p.x_part);
-                    const int ksteps = (g % p.ncb == p.ncb - 1) ? p.klast : 4;
-                    for (int khi = 0; khi < 3; ++khi) {
-                        mbar_wait(&fullW[sw], phw);
-                        tc_fence_after();
-                        const uint32_t ws = smem_u32(wring + (size_t)sw * kTtWSlot);
-                        const uint32_t xv = xs + (uint32_t)khi * view;
+                    const uint64_t a_zh0 = tc_desc_add(wdesc0, (uint32_t)sw * kTtWSlot);       // [0 ; W_hi]
+                    const uint64_t a_hl0 = tc_desc_add(a_zh0, kTtWPart);                       // [W_hi ; W_lo]
+                    const uint64_t b_hi0 = tc_desc_add(xs, (uint32_t)khi * view), b_lo0 = tc_desc_add(b_hi0, p.x_part);
+                    if (leader) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (k >= ksteps) break;
-                            const uint64_t a_hl = tc_smem_desc(ws + kTtWPart + k * 32);        // [W_hi ; W_lo]
-                            const uint64_t a_zh = tc_smem_desc(ws + k * 32);                   // [0 ; W_hi]
-                            const uint64_t b_hi = tc_smem_desc(xv + k * 32), b_lo = tc_smem_desc(xv + p.x_part + k * 32);
-                            tc_mma<F16>(tmem_d, a_hl, b_hi, idesc, (g | khi | k) != 0 ? 1u : 0u);
-                            tc_mma<F16>(tmem_d, a_zh, b_lo, idesc, 1u);
+                            tc_mma<F16>(tmem_d, tc_desc_add(a_hl0, k * 32), tc_desc_add(b_hi0, k * 32), idesc, (g | khi | k) != 0 ? 1u : 0u);
+                            tc_mma<F16>(tmem_d, tc_desc_add(a_zh0, k * 32), tc_desc_add(b_lo0, k * 32), idesc, 1u);
                         }
                         tc_commit(&emptyW[sw]);
-                        if (++sw == kTtWSlots) { sw = 0; phw ^= 1u; }
                     }
-                    tc_commit(&emptyX[sx]);
-                    if (++sx == kTtXSlots) { sx = 0; phx ^= 1u; }
+                    if (++sw == kTtWSlots) { sw = 0; phw ^= 1u; }
                 }
-                tc_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+                if (leader) tc_commit(&emptyX[sx]);
+                if (++sx == kTtXSlots) { sx = 0; phx ^= 1u; }
             }
+            if (leader) tc_commit(&tmem_full[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
         __syncwarp();
     } else {

@@ -52,6 +52,20 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
     else tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accum);
 }
 
+// One lane of a converged warp, the same one every time for a full mask.  The MMA-issuing warps run their loops with ALL lanes
+// (warp-uniform control flow and operands) and only predicate the tcgen05 instructions on this: with the whole loop inside
+// `if (lane == 0)` the compiler cannot prove the descriptors uniform, moves each of them through R2UR and wraps every
+// tcgen05.mma in an ELECT / BRA.U.ANY loop -- ~45 instructions of one thread per K-step, which (not the tensor core) was the
+// "~115 cycles per MMA whatever N" floor measured in round 1.
+__device__ __forceinline__ bool tc_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// shared-memory descriptor advanced by `bytes` (a multiple of 16 that stays inside the tile: the 14-bit address field cannot carry)
+__device__ __forceinline__ uint64_t tc_desc_add(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
 // "3xFP16" operand split, the fp16 counterpart of the tf32 hi/lo split: x = hi + lo' * 2^-11 with hi = fp16(x) and
 // lo' = fp16((x - hi) * 2^11) -- 11 + 11 significand bits like two tf32 values; the 2^11 keeps lo' out of the fp16
 // subnormals.  hi*hi goes to the main accumulator, hi*lo' + lo'*hi to the cross accumulator, which the epilogue scales by

@@ -21,3 +21,10 @@ for _ in range(3):
     ops.conv3d_tc(hi, lo, wp, Cout, scale=sc, shift=sh, relu=True, full=False, split=True)
 torch.cuda.synchronize()
 print("ok")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.conv3d_tc(hi, lo, wp, Cout, scale=sc, shift=sh, relu=True, full=False, split=True)
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / 10 * 1e3
+print("%dx%dx%dx%d %d->%d %s: %.1f us  %.1f TF/s" % (N, D, H, W, Cin, Cout, fmt, us, 2.0 * N * D * H * W * Cin * Cout * 27 / us / 1e6))

@@ -15,6 +15,7 @@ D = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 wmin = float(sys.argv[3]) if len(sys.argv) > 3 else 16.0
 wmax = float(sys.argv[4]) if len(sys.argv) > 4 else 30.0
 B = 8
+DIFF = os.environ.get("SIDE_CL_DIFF", "0") == "1"       # default: the (L, R)-only volume the network uses
 dev = torch.device("cuda")
 g = torch.Generator().manual_seed(0)
 fL, fR = torch.randn(B, 32, 96, 320, generator=g).to(dev), torch.randn(B, 32, 96, 320, generator=g).to(dev)
@@ -26,12 +27,12 @@ left = torch.stack([b, x1, y1, x1 + w, y1 + h], 1).to(dev)
 right = torch.stack([b, x1 - sh, y1, x1 + w - sh, y1 + h], 1).to(dev)
 fb = torch.full((B,), 384.38, device=dev)
 for _ in range(4):
-    hi, lo, db, xc = ops.inst_costvol_cl(fL, fR, left, right, fb, D, 16, 319.0)
+    hi, lo, db, xc = ops.inst_costvol_cl(fL, fR, left, right, fb, D, 16, 319.0, diff=DIFF)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    ops.inst_costvol_cl(fL, fR, left, right, fb, D, 16, 319.0)
+    ops.inst_costvol_cl(fL, fR, left, right, fb, D, 16, 319.0, diff=DIFF)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
