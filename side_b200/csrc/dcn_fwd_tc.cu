@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
     __shared__ unsigned int s_ticket;
 
     const DcnShape &s = a.s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler as well
     const int N = s.Cout;
     const uint32_t b_part_bytes = (uint32_t)N * 128u;
     const uint32_t a_bytes = SPLIT ? 2 * kATileBytes : kATileBytes;
@@ -367,53 +368,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         }
     } else if (warp == 16) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // all 32 lanes run the loop (uniform operands), the elected lane issues -- see tc_elect_one()
+        {
+            const bool leader = tc_elect_one();
             const uint32_t idesc2 = tc_idesc<F16>(kTcBM, 2 * N <= 256 ? 2 * N : N);
+            const uint64_t desc0 = tc_smem_desc(smem_u32(tiles));
             int st = 0;
             uint32_t fph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full_bar[st], fph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + (size_t)st * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint64_t sa = tc_desc_add(desc0, (uint32_t)st * stage_bytes);
+                const uint64_t sb = tc_desc_add(sa, a_bytes);
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < kTcBK / 8; ++k) {
-                    const uint64_t a_hi = tc_smem_desc(sa + k * 32), b_hi = tc_smem_desc(sb + k * 32);
-                    if (SPLIT && 2 * N <= 256) {
-                        // every tcgen05.mma costs ~115 cycles whatever N is (measured, conv_tct.cu): hi*hi and hi*lo go out as
-                        // ONE instruction of width 2N against the adjacent [B_hi | B_lo] tiles (main -> columns 0..N, cross ->
-                        // N..2N), lo*hi then accumulates onto the cross columns: 2 instructions per k-step instead of 3
-                        const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
-                        tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, 1u);
-                        continue;
+                    for (int k = 0; k < kTcBK / 8; ++k) {
+                        const uint64_t a_hi = tc_desc_add(sa, k * 32), b_hi = tc_desc_add(sb, k * 32);
+                        if (SPLIT && 2 * N <= 256) {
+                            // hi*hi and hi*lo go out as ONE instruction of width 2N against the adjacent [B_hi | B_lo] tiles (main ->
+                            // columns 0..N, cross -> N..2N), lo*hi then accumulates onto the cross columns: 2 instructions per k-step
+                            const uint64_t a_lo = tc_desc_add(sa, kATileBytes + k * 32);
+                            tc_mma<F16>(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0 ? 1u : 0u);
+                            tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, 1u);
+                            continue;
+                        }
+                        tc_mma<F16>(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (SPLIT) {
+                            // The two small cross terms go to a SECOND accumulator (columns N..2N): the tensor core adds
+                            // into fp32 with truncation, ~0.5 ulp of the accumulator per MMA, so keeping them out of the
+                            // main accumulator cuts that systematic bias 3x; the epilogue adds the two.
+                            const uint64_t a_lo = tc_desc_add(sa, kATileBytes + k * 32);
+                            const uint64_t b_lo = tc_desc_add(sb, b_part_bytes + k * 32);
+                            tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                            tc_mma<F16>(tmem_d + (uint32_t)N, a_hi, b_lo, idesc, 1u);
+                        }
                     }
-                    tc_mma<F16>(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                    if (SPLIT) {
-                        // The two small cross terms go to a SECOND accumulator (columns N..2N): the tensor core adds
-                        // into fp32 with truncation, ~0.5 ulp of the accumulator per MMA, so keeping them out of the
-                        // main accumulator cuts that systematic bias 3x; the epilogue adds the two.
-                        const uint64_t a_lo = tc_smem_desc(sa + kATileBytes + k * 32);
-                        const uint64_t b_lo = tc_smem_desc(sb + b_part_bytes + k * 32);
-                        tc_mma<F16>(tmem_d + (uint32_t)N, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_mma<F16>(tmem_d + (uint32_t)N, a_hi, b_lo, idesc, 1u);
-                    }
+                    tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
                 }
-                tc_commit(&empty_bar[st]);     // smem stage reusable once these MMAs have read it
                 if (++st == stages) { st = 0; fph ^= 1u; }
             }
-            tc_commit(&tmem_full_bar);         // accumulator complete
+            if (leader) tc_commit(&tmem_full_bar);         // accumulator complete
         }
         __syncwarp();
     } else {
         // ================= weight loader (TMA bulk copies) =================
-        if (lane == 0) {
+        {
+            const bool leader = tc_elect_one();
             int st = 0;
             uint32_t eph = 1;
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&empty_bar[st], eph);
-                mbar_expect_tx(&full_bar[st], b_bytes);
-                bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)(tap_lo * ncb + kb) * (b_bytes / 4), b_bytes, &full_bar[st]);
+                if (leader) {
+                    mbar_expect_tx(&full_bar[st], b_bytes);
+                    bulk_g2s(tiles + (size_t)st * stage_bytes + a_bytes, wp + (size_t)(tap_lo * ncb + kb) * (b_bytes / 4), b_bytes, &full_bar[st]);
+                }
                 if (++st == stages) { st = 0; eph ^= 1u; }
             }
         }

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kGwStages], empty_bar[kGwStages], tmem_full;
     __shared__ uint32_t tmem_base_smem;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler as well
     unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     // work item of this CTA
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0 && nkb > 0) {
+        // all 32 lanes run the loop (uniform operands), the elected lane issues the copies -- see tc_elect_one()
+        const bool leader = tc_elect_one();
+        if (nkb > 0) {
             const uint32_t bytes = 2 * kGwAPart + 2 * (uint32_t)(Nw / 64) * kGwBChunk;
             int st = 0;
             uint32_t ph = 0;
@@ -137,6 +140,10 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
                 const int bl = kb / kpi, p0 = (kb - bl * kpi) * 64;
                 mbar_wait(&empty_bar[st], ph ^ 1u);
                 unsigned char *sa = tiles + (size_t)st * kGwStage;
+                if (!leader) {
+                    if (++st == kGwStages) { st = 0; ph ^= 1u; }
+                    continue;
+                }
                 mbar_expect_tx(&full_bar[st], bytes);
                 if (p.fused) {
                     // box r of sample bl: output voxels (d0.., h0.., w0..); tap (td, th, tw) of column chunk j shifts the INPUT box
@@ -170,29 +177,33 @@ __global__ void __launch_bounds__(kGwThreads, 1) dcn_gw_tc_kernel(const __grid_c
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && nkb > 0) {
+        // all 32 lanes run the loop, the elected lane issues the MMAs and the commits (tc_elect_one())
+        const bool leader = tc_elect_one();
+        if (nkb > 0) {
             // A: K-major (bit 15 = 0), B: MN-major (bit 16 = 1)
             const uint32_t idesc = tc_idesc_f16(128, Nw) | (1u << 16);
             const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + 256u;
+            const uint64_t adesc0 = tc_smem_desc(smem_u32(tiles)), bdesc0 = gw_desc_mn(smem_u32(tiles) + 2 * kGwAPart, kGwBChunk);
             int st = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + (size_t)st * kGwStage);
-                const uint32_t sb = sa + 2 * kGwAPart;
+                const uint64_t sa = tc_desc_add(adesc0, (uint32_t)st * kGwStage), sb = tc_desc_add(bdesc0, (uint32_t)st * kGwStage);
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {                      // 16 pixels per instruction
-                    const uint64_t a_hi = tc_smem_desc(sa + k * 32), a_lo = tc_smem_desc(sa + kGwAPart + k * 32);
-                    const uint64_t b_hi = gw_desc_mn(sb + k * 2048, kGwBChunk), b_lo = gw_desc_mn(sb + kGwBPart + k * 2048, kGwBChunk);
-                    tc_mma_f16(tmem_d, a_hi, b_hi, idesc, (i | k) != 0 ? 1u : 0u);
-                    tc_mma_f16(tmem_x, a_hi, b_lo, idesc, (i | k) != 0 ? 1u : 0u);
-                    tc_mma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) {                      // 16 pixels per instruction
+                        const uint64_t a_hi = tc_desc_add(sa, k * 32), a_lo = tc_desc_add(sa, kGwAPart + k * 32);
+                        const uint64_t b_hi = tc_desc_add(sb, k * 2048), b_lo = tc_desc_add(sb, kGwBPart + k * 2048);
+                        tc_mma_f16(tmem_d, a_hi, b_hi, idesc, (i | k) != 0 ? 1u : 0u);
+                        tc_mma_f16(tmem_x, a_hi, b_lo, idesc, (i | k) != 0 ? 1u : 0u);
+                        tc_mma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty_bar[st]);
                 }
-                tc_commit(&empty_bar[st]);
                 if (++st == kGwStages) { st = 0; ph ^= 1u; }
             }
-            tc_commit(&tmem_full);
+            if (leader) tc_commit(&tmem_full);
         }
         __syncwarp();
     } else if (nkb > 0) {
