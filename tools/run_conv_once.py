@@ -1,4 +1,4 @@
-"""A few launches of the tcgen05 conv3d at the aggregation network's layer shapes (for ncu).  argv: N D H W Cin Cout [tf32|f16]"""
+"""A few launches of the tcgen05 conv3d at the aggregation network's layer shapes (for ncu).  argv: N D H W Cin Cout [tf32|f16 [mode]]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,6 +6,8 @@ from side_b200 import ops
 N, D, H, W, Cin, Cout = (int(v) for v in sys.argv[1:7])
 fmt = sys.argv[7] if len(sys.argv) > 7 else "tf32"
 ops.set_tc_format(fmt)
+from side_b200 import _lib
+_lib.load().side_conv_tc_set_mode(int(sys.argv[8]) if len(sys.argv) > 8 else 0)      # 32: no role-swapped kernel
 dev = torch.device("cuda")
 torch.manual_seed(0)
 x = torch.randn(N, D, H, W, Cin, device=dev)
