@@ -230,6 +230,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
         float amax = 0.f;
         int st = 0, tp = tap_lo, cb = 0, slot = 0;
         uint32_t eph = 1;                        // parity to wait for on empty_bar[st] (first pass falls through)
+        // swizzled byte offset of this thread's 8 (fp16) / 16 (tf32) bytes inside the A tile, row r0: row r0 + 64 is 8 KB further
+        // (same row & 7), the second 32-channel half of an fp16 k-block flips chunk bit 2 = byte 64.  Computed once -- inside the
+        // loop the compiler rebuilt it from threadIdx every pass (112 registers per thread at 576 threads).
+        const uint32_t off0 = F16 ? sw128(r0, c4 >> 1) + ((c4 & 1) << 3) : sw128(r0, c4);
         for (int kb = 0; kb < nkb * kSub; ++kb) {
             const TapRec *tb = tapbuf + slot * kTcBM;
             float4 v[2];
@@ -242,6 +246,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                 v[i].z = fmaf(w.w, a4.z, fmaf(w.z, a3.z, fmaf(w.y, a2.z, w.x * a1.z)));
                 v[i].w = fmaf(w.w, a4.w, fmaf(w.z, a3.w, fmaf(w.y, a2.w, w.x * a1.w)));
             }
+            // `raw` is dead from here on: the next pass's loads below go into the same registers.  Without this fence the compiler
+            // hoists them above the FMAs into fresh registers and pays 32 register moves per pass at the end of the loop.
+            asm volatile("" ::: "memory");
             // advance (tap, channel block) to the next k-block and start its loads while this one is stored
             int ncbi = cb + 1, ntp = tp, nslot = slot;
             if (ncbi == npass) {
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
             for (int i = 0; i < 2; ++i) {
                 if (F16) {
                     // 4 channels = 8 bytes of the row's 128: chunk 4 half + c4 / 2, upper or lower 8 bytes
-                    const uint32_t off = sw128(r0 + 64 * i, 4 * half + (c4 >> 1)) + ((c4 & 1) << 3);
+                    const uint32_t off = (off0 ^ ((uint32_t)half << 6)) + (uint32_t)i * 8192u;
                     uint2 hi, lo;
                     f16_split2(v[i].x, v[i].y, hi.x, lo.x);
                     f16_split2(v[i].z, v[i].w, hi.y, lo.y);
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) dcn_fwd_tc_kernel(DcnFwdArgs a,
                     *reinterpret_cast<uint2 *>(sa + kATileBytes + off) = lo;
                     continue;
                 }
-                const uint32_t off = sw128(r0 + 64 * i, c4);
+                const uint32_t off = off0 + (uint32_t)i * 8192u;
                 if (SPLIT) {
                     float4 hi, lo;
                     hi.x = tf32_hi(v[i].x); lo.x = v[i].x - hi.x;
