@@ -260,6 +260,16 @@ int side_dw_deconv_fwd(const float *x, const float *w, float *y, int B, int C, i
 int side_dw_deconv_bwd(const float *x, const float *w, const float *gy, float *gx, float *gw, int B, int C, int H, int W,
                        int k, int stride, int pad, void *stream);
 
+/* One IDAUp step between its two deformable convolutions, fused (inference; feature_extraction_dla34.py:380-386):
+ *     sum = up_k(x) + skip            up_k = the depth-wise ConvTranspose2d above with k = 2 * stride, pad = stride / 2
+ * written channels-last [B, H*stride, W*stride, Cpad] three times over: `full` fp32 (what node_k's deformable gather reads,
+ * side_dcn_fwd_cl) and the fp16 operand pairs hi / lo (what node_k's offset convolution reads, side_conv3d_tc_fwd_f16).
+ * Replaces side_dw_deconv_fwd + the elementwise addition + side_ncdhw_to_cl_split_f16; bit-identical to that sequence.
+ *   x [B,C,H,W] (output of proj_k), w [C,1,2*stride,2*stride], skip [B,C,H*stride,W*stride]; stride in {2, 4, 8};
+ *   Cpad >= C, even: channels C..Cpad-1 are written as zeros (Cpad = C rounded up to 32 in the network). */
+int side_idaup_fuse_cl_f16(const float *x, const float *w, const float *skip, float *full, void *hi, void *lo, int B, int C,
+                           int H, int W, int stride, int Cpad, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Aggregation network of the instance-depth branch on the tensor cores.
  * Replaces the cuDNN calls behind cost_volume.dres0 / dres1 / dres2 / classify (stereo_network_old.py:139-171,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "side_conv_tc_prep_weights_f16": (_i, [_vp] * 2 + [_i] * 3 + [_vp]),
     "side_conv3d_tc_fwd_f16": (_i, [_vp] * 9 + [_i] * 11 + [_vp]),
     "side_ncdhw_to_cl_split_f16": (_i, [_vp] * 5 + [_i] * 2 + [_ll, _i, _i, _vp]),
+    "side_idaup_fuse_cl_f16": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
     "side_gate_mul_split_f16": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_maxpool_hw2_cl_f16": (_i, [_vp] * 4 + [_i] * 5 + [_vp]),
     "side_ncdhw_to_cl_split": (_i, [_vp] * 5 + [_i] * 2 + [_ll, _i, _vp]),

@@ -6,7 +6,7 @@
 // micro-batch 4 (41 % of the whole inference step, profiles/r1_launches_step_fp32.md) although the layer moves only
 // tens of MB.  Here: one thread per output pixel, at most ceil(k/s)^2 multiply-adds, fully coalesced along W;
 // HBM-bound (reads x once, writes y once).  Backward: gather form for grad_input, block reduction for grad_weight.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace side {
 
@@ -119,6 +119,68 @@ __global__ void __launch_bounds__(256) dw_deconv_bwd_weight_kernel(const float *
     }
 }
 
+// IDAUp step fused (feature_extraction_dla34.py:380-386):  node_k(up_k(proj_k(layers[i])) + layers[i-1])  -- everything between
+// the two deformable convolutions in ONE pass: the depth-wise transposed convolution of the projected map (k = 2 ST, stride ST,
+// padding ST / 2: at most 2 x 2 taps per output pixel, same tap order as dw_deconv_fwd_v4_kernel), the skip addition, the change to
+// channels-last and the split into the fp16 operand pairs the node's offset convolution reads; the unsplit channels-last copy is
+// what the node's deformable gather reads.  Replaces dw_deconv + at::add + ncdhw_to_cl_split (the up-sampled map and the sum
+// never exist in NCHW).  Block (32, 8): 64 channels x 32 pixels through a shared-memory transpose, a lane owns two adjacent
+// channels so every warp store is 128 contiguous bytes of one pixel's row.
+template <int ST>
+__global__ void __launch_bounds__(256) idaup_fuse_f16_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ skip, float *__restrict__ full,
+                                                            uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, int C, int H, int W,
+                                                            int Cpad, uint32_t *rs)
+{
+    constexpr int k = 2 * ST, pd = ST / 2;
+    __shared__ float tile[64][33];
+    const int Ho = H * ST, Wo = W * ST;
+    const long long S = (long long)Ho * Wo;
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64;
+    const long long p = p0 + threadIdx.x;
+    const int oy = (int)(p / Wo), ox = (int)(p - (long long)oy * Wo);
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const int c = c0 + i;
+        float v = 0.f;
+        if (c < C && p < S) {
+            const float *xp = x + ((size_t)n * C + c) * H * W;
+            const float *wp = w + (size_t)c * k * k;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int ky = (oy + pd) % ST + a * ST, iy = (oy + pd - ky) / ST;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int kx = (ox + pd) % ST + b * ST, ix = (ox + pd - kx) / ST;
+                    if (ix < 0 || ix >= W) continue;
+                    acc = fmaf(__ldg(xp + iy * W + ix), __ldg(wp + ky * k + kx), acc);
+                }
+            }
+            v = acc + __ldg(skip + ((size_t)n * C + c) * S + p);
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int c = c0 + 2 * threadIdx.x;
+    float amax = 0.f;
+    for (int i = threadIdx.y; i < 32 && c < Cpad; i += blockDim.y) {
+        const long long q = p0 + i;
+        if (q >= S) continue;
+        const float a = tile[2 * threadIdx.x][i], b = tile[2 * threadIdx.x + 1][i];
+        const size_t o = (((size_t)n * S + q) * Cpad + c) >> 1;      // index of the channel PAIR
+        uint32_t h, l;
+        amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+        f16_split2(a, b, h, l);
+        hi[o] = h;
+        lo[o] = l;
+        reinterpret_cast<float2 *>(full)[o] = make_float2(a, b);
+    }
+    if (rs) range_commit(rs, amax);
+}
+
 static int dw_check(int B, int C, int H, int W, int k, int s, int p, int &Ho, int &Wo)
 {
     SIDE_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && s > 0 && p >= 0, "dw_deconv: bad shape");
@@ -177,5 +239,23 @@ extern "C" int side_dw_deconv_bwd(const float *x, const float *w, const float *g
         dw_deconv_bwd_weight_kernel<<<grid, 256, 0, st>>>(x, gy, gw, B, C, H, W, Ho, Wo, k, stride, pad);
         SIDE_LAUNCH_CHECK("dw_deconv_bwd_weight_kernel");
     }
+    return SIDE_OK;
+}
+
+extern "C" int side_idaup_fuse_cl_f16(const float *x, const float *w, const float *skip, float *full, void *hi, void *lo, int B,
+                                      int C, int H, int W, int stride, int Cpad, void *stream)
+{
+    SIDE_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && (stride == 2 || stride == 4 || stride == 8),
+                 "side_idaup_fuse_cl_f16: bad shape (stride must be 2, 4 or 8)");
+    SIDE_REQUIRE(Cpad >= C && Cpad % 2 == 0 && B <= 65535 && (Cpad + 63) / 64 <= 65535, "side_idaup_fuse_cl_f16: bad channel padding / batch");
+    SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(skip); SIDE_REQUIRE_DEV(full); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
+    const long long S = (long long)H * stride * W * stride;
+    const dim3 grid((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)B), block(32, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *h = reinterpret_cast<uint32_t *>(hi), *l = reinterpret_cast<uint32_t *>(lo);
+    if (stride == 2) idaup_fuse_f16_kernel<2><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
+    else if (stride == 4) idaup_fuse_f16_kernel<4><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
+    else idaup_fuse_f16_kernel<8><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
+    SIDE_LAUNCH_CHECK("idaup_fuse_f16_kernel");
     return SIDE_OK;
 }

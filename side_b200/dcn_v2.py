@@ -110,6 +110,13 @@ class DCN(DCNv2):
     def _forward_cl(self, input, bn, relu):
         B, C, H, W = input.shape
         full, hi, lo = ops.ncdhw_to_cl_split(input.unsqueeze(2), want_full=True)            # [B, 1, H, W, C]
+        return self.forward_prepared(full, hi, lo, (B, C, H, W), bn, relu)
+
+    def forward_prepared(self, full, hi, lo, shape, bn=None, relu=False):
+        """The channels-last inference path from an input that is already channels-last and split: ``full`` fp32 and the operand
+        pairs ``hi`` / ``lo`` [B, 1, H, W, C] (``ops.ncdhw_to_cl_split(x.unsqueeze(2), want_full=True)`` or ``ops.idaup_fuse_cl``);
+        ``shape`` = (B, C, H, W) of the NCHW tensor they stand for.  Returns NCHW like ``forward``."""
+        B, C, H, W = shape
         wp, bias = self._om_weights()
         om, _, _ = ops.conv3d_tc(hi.view(1, B, H, W, C), lo.view(1, B, H, W, C), wp, 32, ksize=(1, 3, 3), shift=bias,
                                  full=True, split=False)                                       # [1, B, H, W, 32]

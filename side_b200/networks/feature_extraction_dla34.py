@@ -371,11 +371,22 @@ class IDAUp(nn.Module):
             setattr(self, "up_%d" % i, up)
             setattr(self, "node_%d" % i, DeformConv(o, o))
 
+    fuse_up_add = True     # inference: up_k + skip addition + layout change + operand split in one kernel (ops.idaup_fuse_cl)
+
     def forward(self, layers, startp, endp):
         for i in range(startp + 1, endp):
             k = i - startp
-            layers[i] = getattr(self, "up_%d" % k)(getattr(self, "proj_%d" % k)(layers[i]))
-            layers[i] = getattr(self, "node_%d" % k)(layers[i] + layers[i - 1])
+            proj, up, node = getattr(self, "proj_%d" % k), getattr(self, "up_%d" % k), getattr(self, "node_%d" % k)
+            x, skip = proj(layers[i]), layers[i - 1]
+            f, bn = up.stride[0], node.actf[0]
+            if (self.fuse_up_add and not torch.is_grad_enabled() and not bn.training and ops.get_tc_format() == "f16"
+                    and f in (2, 4, 8) and up.kernel_size[0] == 2 * f and up.padding[0] == f // 2 and node.conv._cl_ok(skip)
+                    and tuple(skip.shape) == (x.shape[0], x.shape[1], x.shape[2] * f, x.shape[3] * f)):
+                # everything between the two deformable convolutions in one pass; the up-sampled map and the sum never exist in NCHW
+                full, hi, lo = ops.idaup_fuse_cl(x, up.weight, skip, f)
+                layers[i] = node.conv.forward_prepared(full, hi, lo, tuple(skip.shape), bn=bn, relu=True)
+                continue
+            layers[i] = node(up(x) + skip)
 
 
 class DLAUp(nn.Module):

@@ -742,6 +742,26 @@ def ncdhw_to_cl_split(x, scale=None, want_full=False, fmt=None):
     return (full, hi, lo) if want_full else (hi, lo)
 
 
+def idaup_fuse_cl(x, weight, skip, stride):
+    """One IDAUp step between its two deformable convolutions (reference feature_extraction_dla34.py:380-386), inference, fp16
+    pairs:  up_k(x) + skip  ->  (full fp32, hi, lo fp16) channels-last [B, 1, H*stride, W*stride, Cp] -- what
+    ``ncdhw_to_cl_split((dw_deconv(x, weight, stride, stride // 2) + skip).unsqueeze(2), want_full=True)`` returns, in one pass."""
+    lib = _lib.load()
+    x, weight, skip = _chk(x, "x"), _chk(weight, "weight"), _chk(skip, "skip")
+    B, C, H, W = x.shape
+    Ho, Wo = H * stride, W * stride
+    if tuple(skip.shape) != (B, C, Ho, Wo) or tuple(weight.shape) != (C, 1, 2 * stride, 2 * stride):
+        raise RuntimeError("idaup_fuse_cl: skip must be [B, C, H*stride, W*stride] and weight [C, 1, 2*stride, 2*stride]")
+    _range_guard(x.device)
+    Cp = (C + 31) // 32 * 32
+    full = torch.empty((B, 1, Ho, Wo, Cp), device=x.device, dtype=_F32)
+    hi = torch.empty((B, 1, Ho, Wo, Cp), device=x.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.side_idaup_fuse_cl_f16(x.data_ptr(), weight.data_ptr(), skip.data_ptr(), full.data_ptr(), hi.data_ptr(),
+                                          lo.data_ptr(), B, C, H, W, int(stride), Cp, _stream()), "side_idaup_fuse_cl_f16")
+    return full, hi, lo
+
+
 def split_pairs(x, fmt=None):
     """Operand pairs (hi, lo) of a tensor that already has the consumer's (channels-last) layout, in the given operand format."""
     fmt = fmt or _tc_format

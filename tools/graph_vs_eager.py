@@ -12,6 +12,9 @@ _lib.load()
 ops.set_dcn_precision("3xfp16"); ops.set_tc_format("f16")
 model = bench.build_model().to(dev)
 det = StereoDetector(model, grid_size=28, K=100)
+if os.environ.get('SIDE_NO_IDAUP_FUSE'):
+    from side_b200.networks.feature_extraction_dla34 import IDAUp
+    IDAUp.fuse_up_add = False
 g = torch.Generator().manual_seed(1)
 batch = {'input': torch.randn(mb, 3, 384, 1280, generator=g).to(dev), 'input_right': torch.randn(mb, 3, 384, 1280, generator=g).to(dev),
          'fb': torch.full((mb,), KITTI_FB, device=dev)}
