@@ -9,6 +9,8 @@
 
 namespace side {
 
+int launch_cl_split_tile_f16(const float *x, float *full, void *hi, void *lo, int N, int C, long long S, int Cpad, cudaStream_t st);
+
 __device__ __forceinline__ void split4(const float4 v, float4 &h, float4 &l)
 {
     h.x = tf32_hi(v.x); l.x = v.x - h.x;
@@ -273,6 +275,9 @@ static int ncdhw_to_cl_split_impl(const float *x, const float *scale, float *ful
     if (scale) SIDE_REQUIRE_DEV(scale);
     if (full) SIDE_REQUIRE_DEV(full);
     const int per_d = scale ? (int)(S / D) : 1;
+    if (f16 && !scale && S % 4 == 0 && Cpad % 8 == 0 && N <= 65535 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(full) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0)
+        return launch_cl_split_tile_f16(x, full, hi, lo, N, C, S, Cpad, (cudaStream_t)stream);     // 16-byte loads, 64 x 128 tiles (upsample.cu)
     if (f16 && Cpad % 2 == 0) {
         dim3 g2((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)N);
         ncdhw_to_cl_split_f16_kernel<<<g2, b, 0, (cudaStream_t)stream>>>(x, scale, full, reinterpret_cast<uint32_t *>(hi),

@@ -119,13 +119,7 @@ __global__ void __launch_bounds__(256) dw_deconv_bwd_weight_kernel(const float *
     }
 }
 
-// IDAUp step fused (feature_extraction_dla34.py:380-386):  node_k(up_k(proj_k(layers[i])) + layers[i-1])  -- everything between
-// the two deformable convolutions in ONE pass: the depth-wise transposed convolution of the projected map (k = 2 ST, stride ST,
-// padding ST / 2: at most 2 x 2 taps per output pixel, same tap order as dw_deconv_fwd_v4_kernel), the skip addition, the change to
-// channels-last and the split into the fp16 operand pairs the node's offset convolution reads; the unsplit channels-last copy is
-// what the node's deformable gather reads.  Replaces dw_deconv + at::add + ncdhw_to_cl_split (the up-sampled map and the sum
-// never exist in NCHW).  Block (32, 8): 64 channels x 32 pixels through a shared-memory transpose, a lane owns two adjacent
-// channels so every warp store is 128 contiguous bytes of one pixel's row.
+// scalar fallback of the fused IDAUp step below for output widths that are not a multiple of 4 (one thread per pixel and channel)
 template <int ST>
 __global__ void __launch_bounds__(256) idaup_fuse_f16_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                             const float *__restrict__ skip, float *__restrict__ full,
@@ -177,6 +171,127 @@ __global__ void __launch_bounds__(256) idaup_fuse_f16_kernel(const float *__rest
         hi[o] = h;
         lo[o] = l;
         reinterpret_cast<float2 *>(full)[o] = make_float2(a, b);
+    }
+    if (rs) range_commit(rs, amax);
+}
+
+// NCHW -> channels-last fp16 operand pairs (+ the unsplit fp32 copy), optionally with one IDAUp step fused in front
+// (feature_extraction_dla34.py:380-386):  node_k(up_k(proj_k(layers[i])) + layers[i-1])  -- everything between the two deformable
+// convolutions in ONE pass: the depth-wise transposed convolution of the projected map (k = 2 ST, stride ST, padding ST / 2: at
+// most 2 x 2 taps per output pixel, same tap order as dw_deconv_fwd_v4_kernel), the skip addition, the change to channels-last and
+// the split into the fp16 operand pairs the node's offset convolution reads; the unsplit channels-last copy is what the node's
+// deformable gather reads.  Replaces dw_deconv + at::add + ncdhw_to_cl_split (the up-sampled map and the sum never exist in NCHW).
+// ST = 0: plain layout change + split of `skip` (side_ncdhw_to_cl_split_f16 for S % 4 == 0).
+// Tile = 64 channels x 128 pixels, block (32, 8).  Load phase: a lane reads 4 consecutive pixels of one channel as a 16-byte vector
+// (512 contiguous bytes per warp) and stores them to shared memory at the permuted column (px >> 2) + 32 (px & 3) of a row of 129
+// floats, so the four scalar stores of a vector are conflict-free.  Store phase: a lane owns 8 channels of one pixel and a warp
+// instruction covers the pixels {4 G, 4 G + 4, 4 G + 8, 4 G + 12} + e -- a quarter-warp writes one pixel's 256-byte fp32 row /
+// 128-byte hi and lo rows (2-way bank conflicts on the reads).
+template <int ST>
+__global__ void __launch_bounds__(256) cl_split_tile_f16_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                               const float *__restrict__ skip, float *__restrict__ full,
+                                                               uint32_t *__restrict__ hi, uint32_t *__restrict__ lo, int C, int H, int W,
+                                                               long long S, int Cpad, uint32_t *rs)
+{
+    constexpr int T = ST > 0 ? ST : 2;                 // ST = 0 (plain split): the fused branch is compiled out, T only keeps it well-formed
+    constexpr int k = 2 * T, pd = T / 2;
+    constexpr int kRow = 129;
+    __shared__ float tile[64 * kRow];
+    const int Wo = ST > 0 ? W * ST : 1;
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 128;
+    const int c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long p = p0 + 4 * tx;                   // S % 4 == 0: a vector is inside the plane or outside as a whole
+    int oy = 0, ox0 = 0;
+    if constexpr (ST > 0) { oy = (int)(p / Wo); ox0 = (int)(p - (long long)oy * Wo); }      // Wo % 4 == 0: the 4 pixels share a row
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C && p < S) {
+            v = __ldg(reinterpret_cast<const float4 *>(skip + ((size_t)n * C + c) * S + p));
+            if constexpr (ST > 0) {
+                const float *xp = x + ((size_t)n * C + c) * H * W;
+                const float *wp = w + (size_t)c * k * k;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (T == 2 || T == 4) {
+                    // ox0 % 4 == 0 and 4 % T == 0: the tap columns of the four pixels are compile-time offsets from ox0 / T --
+                    // pixel j uses kx = (j + pd) % T + b ST and input column ox0 / T + (j + pd) / T - b -- so the two input rows
+                    // are read once as a 4-column window and the two weight rows once (same products, same order per pixel)
+                    const int xb = ox0 / T;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int ky = (oy + pd) % T + a * T, iy = (oy + pd - ky) / T;
+                        if (iy < 0 || iy >= H) continue;
+                        float xw[4], wr[2 * T];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int ix = xb - 1 + q;
+                            xw[q] = (ix >= 0 && ix < W) ? __ldg(xp + iy * W + ix) : 0.f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2 * T; ++q) wr[q] = __ldg(wp + ky * k + q);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                const int kx = (j + pd) % T + b * T, dq = (j + pd) / T - b + 1;      // compile-time
+                                const int ix = xb - 1 + dq;
+                                if (ix < 0 || ix >= W) continue;
+                                acc[j] = fmaf(xw[dq], wr[kx], acc[j]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int ky = (oy + pd) % T + a * T, iy = (oy + pd - ky) / T;
+                        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ox = ox0 + j;
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                const int kx = (ox + pd) % T + b * T, ix = (ox + pd - kx) / T;
+                                if (ix < 0 || ix >= W) continue;
+                                acc[j] = fmaf(__ldg(xp + iy * W + ix), __ldg(wp + ky * k + kx), acc[j]);
+                            }
+                        }
+                    }
+                }
+                v.x = acc[0] + v.x; v.y = acc[1] + v.y; v.z = acc[2] + v.z; v.w = acc[3] + v.w;
+            }
+        }
+        float *tr = tile + i * kRow + tx;
+        tr[0] = v.x; tr[32] = v.y; tr[64] = v.z; tr[96] = v.w;
+    }
+    __syncthreads();
+    const int o8 = tx & 7, g4 = tx >> 3;               // 8-channel group, which of the instruction's four pixels
+    const int c = c0 + 8 * o8;
+    float amax = 0.f;
+    if (c < Cpad) {
+#pragma unroll 1
+        for (int it = ty; it < 32; it += 8) {          // it = 4 G' + e: pixels 4 (4 G' + g4) + e
+            const int px = 4 * (4 * (it >> 2) + g4) + (it & 3);
+            const long long q = p0 + px;
+            if (q >= S) continue;
+            const float *tc = tile + (8 * o8) * kRow + (px >> 2) + 32 * (px & 3);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = tc[e * kRow];
+            const size_t o = ((size_t)n * S + q) * Cpad + c;
+            uint4 h, l;
+            f16_split2(v[0], v[1], h.x, l.x); f16_split2(v[2], v[3], h.y, l.y);
+            f16_split2(v[4], v[5], h.z, l.z); f16_split2(v[6], v[7], h.w, l.w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[e]));
+            *reinterpret_cast<uint4 *>(hi + (o >> 1)) = h;
+            *reinterpret_cast<uint4 *>(lo + (o >> 1)) = l;
+            if (full) {
+                *reinterpret_cast<float4 *>(full + o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(full + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
     }
     if (rs) range_commit(rs, amax);
 }
@@ -247,15 +362,40 @@ extern "C" int side_idaup_fuse_cl_f16(const float *x, const float *w, const floa
 {
     SIDE_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && (stride == 2 || stride == 4 || stride == 8),
                  "side_idaup_fuse_cl_f16: bad shape (stride must be 2, 4 or 8)");
-    SIDE_REQUIRE(Cpad >= C && Cpad % 2 == 0 && B <= 65535 && (Cpad + 63) / 64 <= 65535, "side_idaup_fuse_cl_f16: bad channel padding / batch");
+    SIDE_REQUIRE(Cpad >= C && Cpad % 8 == 0 && B <= 65535 && (Cpad + 63) / 64 <= 65535,
+                 "side_idaup_fuse_cl_f16: bad channel padding / batch (Cpad %% 8 == 0)");
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(skip); SIDE_REQUIRE_DEV(full); SIDE_REQUIRE_DEV(hi); SIDE_REQUIRE_DEV(lo);
-    const long long S = (long long)H * stride * W * stride;
-    const dim3 grid((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)B), block(32, 8);
+    SIDE_REQUIRE(((reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(full) | reinterpret_cast<uintptr_t>(hi) |
+                   reinterpret_cast<uintptr_t>(lo)) & 15) == 0, "side_idaup_fuse_cl_f16: skip / full / hi / lo must be 16-byte aligned");
+    const long long S = (long long)H * stride * W * stride;      // (W * stride) % 4 == 0 always holds: stride is even ... times W
+    if ((W * stride) % 4 != 0) {
+        const dim3 g1((unsigned)((S + 31) / 32), (unsigned)((Cpad + 63) / 64), (unsigned)B), b1(32, 8);
+        cudaStream_t s1 = (cudaStream_t)stream;
+        uint32_t *h1 = reinterpret_cast<uint32_t *>(hi), *l1 = reinterpret_cast<uint32_t *>(lo);
+        if (stride == 2) idaup_fuse_f16_kernel<2><<<g1, b1, 0, s1>>>(x, w, skip, full, h1, l1, C, H, W, Cpad, range_slot_next());
+        else if (stride == 4) idaup_fuse_f16_kernel<4><<<g1, b1, 0, s1>>>(x, w, skip, full, h1, l1, C, H, W, Cpad, range_slot_next());
+        else idaup_fuse_f16_kernel<8><<<g1, b1, 0, s1>>>(x, w, skip, full, h1, l1, C, H, W, Cpad, range_slot_next());
+        SIDE_LAUNCH_CHECK("idaup_fuse_f16_kernel");
+        return SIDE_OK;
+    }
+    const dim3 grid((unsigned)((S + 127) / 128), (unsigned)((Cpad + 63) / 64), (unsigned)B), block(32, 8);
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *h = reinterpret_cast<uint32_t *>(hi), *l = reinterpret_cast<uint32_t *>(lo);
-    if (stride == 2) idaup_fuse_f16_kernel<2><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
-    else if (stride == 4) idaup_fuse_f16_kernel<4><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
-    else idaup_fuse_f16_kernel<8><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, Cpad, range_slot_next());
-    SIDE_LAUNCH_CHECK("idaup_fuse_f16_kernel");
+    if (stride == 2) cl_split_tile_f16_kernel<2><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, S, Cpad, range_slot_next());
+    else if (stride == 4) cl_split_tile_f16_kernel<4><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, S, Cpad, range_slot_next());
+    else cl_split_tile_f16_kernel<8><<<grid, block, 0, st>>>(x, w, skip, full, h, l, C, H, W, S, Cpad, range_slot_next());
+    SIDE_LAUNCH_CHECK("cl_split_tile_f16_kernel<fused>");
     return SIDE_OK;
 }
+
+// side_ncdhw_to_cl_split_f16 without a scale, S % 4 == 0, Cpad % 8 == 0, aligned pointers: the tiled kernel above (aggr_ops.cu)
+namespace side {
+int launch_cl_split_tile_f16(const float *x, float *full, void *hi, void *lo, int N, int C, long long S, int Cpad, cudaStream_t st)
+{
+    const dim3 grid((unsigned)((S + 127) / 128), (unsigned)((Cpad + 63) / 64), (unsigned)N), block(32, 8);
+    cl_split_tile_f16_kernel<0><<<grid, block, 0, st>>>(nullptr, nullptr, x, full, reinterpret_cast<uint32_t *>(hi),
+                                                        reinterpret_cast<uint32_t *>(lo), C, 0, 0, S, Cpad, range_slot_next());
+    SIDE_LAUNCH_CHECK("cl_split_tile_f16_kernel");
+    return SIDE_OK;
+}
+}  // namespace side
