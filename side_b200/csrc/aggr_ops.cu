@@ -241,6 +241,60 @@ __global__ void __launch_bounds__(256) conv3d_c1_cl_kernel(const float *__restri
     }
 }
 
+// The same layer for small per-sample volumes (the classifier of the aggregation network: 16 x 4 x 4 voxels per RoI, C = 64).
+// The gather form above reads every voxel's channels 27 times (2.8 GB of L2 traffic for 105 MB of activations: 0.75 ms per 1600
+// RoIs).  Here a CTA owns one sample and a thread one voxel: it reads its C = 64 channels ONCE into registers, projects them on
+// all 27 tap filters (P[tap][voxel], weights broadcast from shared memory), and after one barrier sums the 27 projections of its
+// neighbours:  out[v] = sum_tap P[tap][v + tap].  Same products, summed per tap first (<= 1e-6 relative to the gather form).
+template <int C>
+__global__ void __launch_bounds__(512) conv3d_c1_roi_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                            float *__restrict__ out, int D, int H, int W)
+{
+    extern __shared__ __align__(16) float sm[];       // ws [27][C], then P [27][nv + 1]
+    const int nv = D * H * W, tid = threadIdx.x;
+    float *ws = sm, *P = sm + 27 * C;
+    for (int i = tid; i < 27 * C; i += blockDim.x) {
+        const int tap = i / C, c = i - tap * C;
+        ws[i] = __ldg(w + (size_t)c * 27 + tap);
+    }
+    float xr[C];
+    if (tid < nv) {
+        const float4 *xp = reinterpret_cast<const float4 *>(x + ((size_t)blockIdx.x * nv + tid) * C);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            const float4 v = __ldg(xp + c);
+            xr[4 * c] = v.x; xr[4 * c + 1] = v.y; xr[4 * c + 2] = v.z; xr[4 * c + 3] = v.w;
+        }
+    }
+    __syncthreads();
+    if (tid < nv) {
+#pragma unroll 1
+        for (int tap = 0; tap < 27; ++tap) {
+            const float4 *wp = reinterpret_cast<const float4 *>(ws + tap * C);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C / 4; ++c) {
+                const float4 b = wp[c];
+                a0 = fmaf(xr[4 * c], b.x, a0); a1 = fmaf(xr[4 * c + 1], b.y, a1);
+                a2 = fmaf(xr[4 * c + 2], b.z, a2); a3 = fmaf(xr[4 * c + 3], b.w, a3);
+            }
+            P[tap * (nv + 1) + tid] = (a0 + a1) + (a2 + a3);
+        }
+    }
+    __syncthreads();
+    if (tid < nv) {
+        const int wq = tid % W, hq = (tid / W) % H, dq = tid / (W * H);
+        float acc = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const int dd = dq + tap / 9 - 1, hh = hq + (tap / 3) % 3 - 1, ww = wq + tap % 3 - 1;
+            if (dd < 0 || dd >= D || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            acc += P[tap * (nv + 1) + (dd * H + hh) * W + ww];
+        }
+        out[(size_t)blockIdx.x * nv + tid] = acc;
+    }
+}
+
 }  // namespace side
 
 using namespace side;
@@ -386,6 +440,15 @@ extern "C" int side_conv3d_c1_cl(const float *x, const float *w, float *out, int
     SIDE_REQUIRE_DEV(x); SIDE_REQUIRE_DEV(w); SIDE_REQUIRE_DEV(out);
     const long long nvox = (long long)N * D * H * W;
     SIDE_REQUIRE(C % 4 == 0, "side_conv3d_c1_cl: C %% 4 == 0");
+    const int nv = D * H * W;
+    if (C == 64 && nv <= 512 && N <= (1 << 30) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {       // one sample per CTA, one voxel per thread
+        const size_t smem = sizeof(float) * (27 * 64 + 27 * (size_t)(nv + 1));
+        int rc;
+        if ((rc = set_smem_attr((const void *)conv3d_c1_roi_kernel<64>, smem))) return rc;
+        conv3d_c1_roi_kernel<64><<<(unsigned)N, (unsigned)((nv + 31) / 32 * 32), smem, (cudaStream_t)stream>>>(x, w, out, D, H, W);
+        SIDE_LAUNCH_CHECK("conv3d_c1_roi_kernel");
+        return SIDE_OK;
+    }
     if (C >= 128) conv3d_c1_cl_kernel<32><<<ew_grid(nvox * 32, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
     else if (C >= 64) conv3d_c1_cl_kernel<16><<<ew_grid(nvox * 16, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
     else conv3d_c1_cl_kernel<4><<<ew_grid(nvox * 4, 256), 256, 27 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, out, nvox, D, H, W, C);
