@@ -782,6 +782,13 @@ def main():
         }
         if not args.no_kernels and world == 1:
             line["kernels"] = kernel_rooflines(pk, args.dcn_precision)
+            if line["cost_volume"] is not None:
+                # BASELINE config #2 (64 RoIs x 48 candidates x 64 channels, reference fp32 layout) beside the in-step builder:
+                # stand-alone launches with the L2 flushed, CUDA events around the whole call (see `kernels`)
+                kk = line["kernels"]
+                line["cost_volume"]["config2"] = {
+                    "forward_separable": kk.get("inst_costvol_fwd_separable"), "forward_exact": kk.get("inst_costvol_fwd_exact"),
+                    "backward": kk.get("inst_costvol_bwd"), "peak": pk["hbm"], "unit": "GB/s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
