@@ -36,9 +36,11 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
         const int o = i % COUT, ck = i / COUT;                   // ws[ck][o] = w[o][ck]   (w is [COUT][CIN][K][K])
         ws[i] = __ldg(w + (size_t)o * CIN * K * K + ck);
     }
-    float acc0[COUT], acc1[COUT];
+    // accumulators as channel PAIRS: fma.rn.f32x2 (FFMA2) does two of them per issue slot -- the layer is bound by instruction
+    // issue (1600 FFMA + 294 LDS per input channel and thread), not by the FP32 pipe; same IEEE results
+    float2 acc0[COUT / 2], acc1[COUT / 2];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc0[o] = acc1[o] = 0.f;
+    for (int o = 0; o < COUT / 2; ++o) acc0[o] = acc1[o] = make_float2(0.f, 0.f);
     const float *xb = x + (size_t)b * CIN * H * W;
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
     for (int c0 = 0; c0 < CIN; c0 += CCHUNK) {
@@ -66,13 +68,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
                     // input column tx * S + kx (and 32 * S further right for the second pixel)
                     const int ci = S == 2 ? (kx & 1) * HALF + (kx >> 1) : kx;
                     const float v0 = row[ci], v1 = row[ci + 32];
+                    const float2 v00 = make_float2(v0, v0), v11 = make_float2(v1, v1);
 #pragma unroll
                     for (int o4 = 0; o4 < COUT / 4; ++o4) {
                         const float4 wv = *reinterpret_cast<const float4 *>(wr + kx * COUT + 4 * o4);
-                        acc0[4 * o4] = fmaf(v0, wv.x, acc0[4 * o4]);         acc1[4 * o4] = fmaf(v1, wv.x, acc1[4 * o4]);
-                        acc0[4 * o4 + 1] = fmaf(v0, wv.y, acc0[4 * o4 + 1]); acc1[4 * o4 + 1] = fmaf(v1, wv.y, acc1[4 * o4 + 1]);
-                        acc0[4 * o4 + 2] = fmaf(v0, wv.z, acc0[4 * o4 + 2]); acc1[4 * o4 + 2] = fmaf(v1, wv.z, acc1[4 * o4 + 2]);
-                        acc0[4 * o4 + 3] = fmaf(v0, wv.w, acc0[4 * o4 + 3]); acc1[4 * o4 + 3] = fmaf(v1, wv.w, acc1[4 * o4 + 3]);
+                        const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+                        acc0[2 * o4] = __ffma2_rn(v00, wa, acc0[2 * o4]);         acc1[2 * o4] = __ffma2_rn(v11, wa, acc1[2 * o4]);
+                        acc0[2 * o4 + 1] = __ffma2_rn(v00, wb, acc0[2 * o4 + 1]); acc1[2 * o4 + 1] = __ffma2_rn(v11, wb, acc1[2 * o4 + 1]);
                     }
                 }
             }
@@ -86,12 +88,12 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
             for (int px = 0; px < 2; ++px) {
                 const int xo = ox + 32 * px;
                 if (xo >= Wo) continue;
-                const float *acc = px ? acc1 : acc0;
+                const float2 *acc = px ? acc1 : acc0;
                 uint32_t hh[COUT / 2], ll[COUT / 2];
 #pragma unroll
                 for (int o = 0; o < COUT; o += 2) {
-                    float a = fmaf(acc[o], scale ? __ldg(scale + o) : 1.f, shift ? __ldg(shift + o) : 0.f);
-                    float c = fmaf(acc[o + 1], scale ? __ldg(scale + o + 1) : 1.f, shift ? __ldg(shift + o + 1) : 0.f);
+                    float a = fmaf(acc[o / 2].x, scale ? __ldg(scale + o) : 1.f, shift ? __ldg(shift + o) : 0.f);
+                    float c = fmaf(acc[o / 2].y, scale ? __ldg(scale + o + 1) : 1.f, shift ? __ldg(shift + o + 1) : 0.f);
                     if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
                     amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
                     f16_split2(a, c, hh[o / 2], ll[o / 2]);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
 #pragma unroll
         for (int o = 0; o < COUT; ++o) {
             const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
-            float a = fmaf(acc0[o], sc, sh), c = fmaf(acc1[o], sc, sh);
+            float a = fmaf(o & 1 ? acc0[o / 2].y : acc0[o / 2].x, sc, sh), c = fmaf(o & 1 ? acc1[o / 2].y : acc1[o / 2].x, sc, sh);
             if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             yp[(size_t)o * Ho * Wo] = a;                         // a warp writes 128 contiguous bytes per channel and half tile
             if (two) yp[(size_t)o * Ho * Wo + 32] = c;
