@@ -532,3 +532,18 @@ def test_cl_concat_matches_torch_cat(lib):
     for dt, widths in ((torch.float16, (64, 64, 128)), (torch.float32, (32, 4, 96)), (torch.float16, (64, 12))):   # last: 24-byte rows -> torch.cat
         ts = [torch.randn(2, 3, 5, 7, w, device="cuda").to(dt) for w in widths]
         assert torch.equal(ops.cl_concat(ts), torch.cat(ts, -1))
+
+
+@pytest.mark.parametrize("shape", [(5, 16, 4, 4), (3, 32, 4, 4), (2, 48, 4, 4), (4, 7, 3, 5), (1, 2, 1, 1)])
+def test_conv3d_c1_cl_one_sample_per_cta_kernel(lib, shape):
+    """Conv3d(64 -> 1, 3, padding 1) of the classifier (stereo_network_old.py:161-163): the one-RoI-per-CTA kernel (D*H*W <= 512)
+    and the generic gather kernel (larger volumes) against float64, <= 1e-5 of the output range."""
+    from side_b200 import ops
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(N * 1000 + D)
+    y = torch.randn(N, D, H, W, 64, generator=g)
+    w = torch.randn(1, 64, 3, 3, 3, generator=g) * 0.1
+    out = ops.conv3d_c1_cl(y.cuda(), w.cuda())
+    ref = F.conv3d(y.permute(0, 4, 1, 2, 3).double(), w.double(), padding=1)[:, 0]
+    assert tuple(out.shape) == (N, D, H, W)
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
