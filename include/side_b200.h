@@ -70,7 +70,8 @@ enum {
                                is computed once per RoI into shared memory, every bin is then 4 taps.  Values differ
                                from torchvision's operation order by a few ulp (<= 1e-5 relative);
                                channel placement and L-R stay exact.  Needs P == 16, C % 8 == 0, D <= 256 and
-                               side_inst_costvol_fast_ws_bytes(...) bytes of workspace. */
+                               side_inst_costvol_fast_ws_bytes(...) bytes of workspace (the per-CTA gate-statistics partials;
+                               the features are read in place as NCHW, 16-byte loads along x when W % 4 == 0). */
     SIDE_VOL_XCROSS = 1 << 3, /* with SEPARABLE and without GATE: also return the gate scalar xcross[N, D] computed in the
                                same pass, WITHOUT applying it (the consumer, side_ncdhw_to_cl_split, multiplies) */
     SIDE_VOL_BWD_SCALAR = 1 << 4, /* side_inst_costvol_bwd: force the scalar-atomic kernel (torchvision's roi_align backward
